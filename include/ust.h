@@ -1,0 +1,265 @@
+/*
+ * ust.h — C ABI of libust.so, the B200-native per-node driver-upgrade state machine.
+ *
+ * One call to ust_apply_state*() evaluates, for every node of a cluster snapshot, the transition
+ * that the reference's ClusterUpgradeStateManagerImpl.ApplyState() would make
+ * (reference: pkg/upgrade/upgrade_state.go:171-281), on one B200 (or sharded over the B200s of one
+ * NVSwitch box). The snapshot is a struct-of-arrays encoding of ClusterUpgradeState
+ * (reference: pkg/upgrade/common_manager.go:58-80); the policy is a flat copy of
+ * DriverUpgradePolicySpec (reference: api/upgrade/v1alpha1/upgrade_spec.go:27-110) plus the
+ * manager options (reference: pkg/upgrade/upgrade_state.go:329-350, :94-96).
+ *
+ * The library never evaluates a node on the CPU: every entry point that computes fails with
+ * UST_ERR_CUDA when no sm_100 device / kernel image is available.
+ *
+ * Plain C, no torch types: this header is what a cgo / ctypes / JNI binding binds.
+ */
+#ifndef UST_H_
+#define UST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UST_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------------
+ * Node upgrade-state codes — the value of the node label nvidia.com/<driver>-driver-upgrade-state
+ * (reference: pkg/upgrade/consts.go:49-82, key format consts.go:21).
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  UST_STATE_UNKNOWN = 0,                    /* ""                          consts.go:50 */
+  UST_STATE_UPGRADE_REQUIRED = 1,           /* "upgrade-required"          consts.go:53 */
+  UST_STATE_CORDON_REQUIRED = 2,            /* "cordon-required"           consts.go:55 */
+  UST_STATE_WAIT_FOR_JOBS_REQUIRED = 3,     /* "wait-for-jobs-required"    consts.go:57 */
+  UST_STATE_POD_DELETION_REQUIRED = 4,      /* "pod-deletion-required"     consts.go:59 */
+  UST_STATE_DRAIN_REQUIRED = 5,             /* "drain-required"            consts.go:62 */
+  UST_STATE_NODE_MAINTENANCE_REQUIRED = 6,  /* "node-maintenance-required" consts.go:67 */
+  UST_STATE_POST_MAINTENANCE_REQUIRED = 7,  /* "post-maintenance-required" consts.go:71 */
+  UST_STATE_POD_RESTART_REQUIRED = 8,       /* "pod-restart-required"      consts.go:74 */
+  UST_STATE_VALIDATION_REQUIRED = 9,        /* "validation-required"       consts.go:77 */
+  UST_STATE_UNCORDON_REQUIRED = 10,         /* "uncordon-required"         consts.go:79 */
+  UST_STATE_DONE = 11,                      /* "upgrade-done"              consts.go:81 */
+  UST_STATE_FAILED = 12,                    /* "upgrade-failed"            consts.go:83 */
+  UST_STATE_OTHER = 13,    /* any other label value: bucketed by BuildState (upgrade_state.go:158-160),
+                              counted by GetCurrentUnavailableNodes, never processed */
+  UST_STATE_EXCLUDED = 14, /* driver pod with NodeName=="" && Phase==Pending: BuildState skips it
+                              (upgrade_state.go:149-152) — not part of the snapshot */
+  UST_NUM_STATE_CODES = 16 /* code 15 is reserved and treated like UST_STATE_EXCLUDED */
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * state[i] (uint8): the "hot" byte. Low nibble = state code above. High nibble = the four node
+ * predicates the cluster-wide constraint logic needs, so that the counting phase of the kernel
+ * streams 1 byte per node and everything else is read exactly once.
+ * ---------------------------------------------------------------------------------------------- */
+#define UST_HOT_STATE_MASK 0x0Fu
+#define UST_HOT_NOT_READY 0x10u   /* some NodeReady condition has Status != True   common_manager.go:656-663 */
+#define UST_HOT_SKIP 0x20u        /* label ...-driver-upgrade.skip == "true"       common_manager.go:666-668 */
+#define UST_HOT_UNSCHEDULABLE 0x40u /* node.Spec.Unschedulable                     common_manager.go:651-653 */
+#define UST_HOT_REVISION_HASH_ERROR 0x80u
+/* ^ revision-hash lookup fails for a NON-orphaned driver pod: controller-revision-hash label absent
+ *   (pod_manager.go:84-89) or no ControllerRevision for its DaemonSet (pod_manager.go:108-110).
+ *   ApplyState aborts with an error when it reaches such a node in the unknown / upgrade-done /
+ *   pod-restart-required / upgrade-failed passes (common_manager.go:234-238, :463-467, :533-538). */
+
+/* ------------------------------------------------------------------------------------------------
+ * flags[i] (uint32): one bit per reference predicate on the node / its driver pod.
+ * Bits 0-2, 7 and 8 are reserved for values the kernel derives itself and are ignored on input.
+ * ---------------------------------------------------------------------------------------------- */
+#define UST_F_UPGRADE_REQUESTED (1u << 3)  /* annotation ...-driver-upgrade-requested == "true"  common_manager.go:323-325 */
+#define UST_F_VALIDATION_DONE (1u << 4)    /* ValidationManager.Validate() == true               common_manager.go:587-596 */
+#define UST_F_SAFE_LOAD (1u << 5)          /* annotation ...driver-wait-for-safe-load != ""      safe_driver_load_manager.go:51-53 */
+#define UST_F_POD_ORPHANED (1u << 6)       /* DriverDaemonSet == nil                             common_manager.go:66-68 */
+#define UST_F_POD_READY (1u << 9)          /* Phase==Running && len(ContainerStatuses)!=0 && all Ready   common_manager.go:617-630 */
+#define UST_F_INITIAL_STATE_ANNO (1u << 10) /* annotation ...node-initial-state.unschedulable PRESENT    common_manager.go:545, :680 */
+#define UST_F_REQUESTOR_MODE (1u << 11)    /* annotation ...-driver-upgrade-requestor-mode PRESENT       util.go:135-138 */
+#define UST_F_POD_TERMINATING (1u << 12)   /* !DriverPod.DeletionTimestamp.IsZero()              common_manager.go:472 */
+#define UST_F_POD_FAILING (1u << 13)       /* some (init)container !Ready && RestartCount > 10   common_manager.go:636-648 */
+#define UST_F_WAIT_PODS_RUNNING (1u << 14) /* a wait-selector pod is Running or Pending          pod_manager.go:278-284, :371-391 */
+#define UST_F_WAIT_START_ANNO (1u << 15)   /* annotation ...wait-for-pod-completion-start-time PRESENT   pod_manager.go:336 */
+#define UST_F_WAIT_TIMED_OUT (1u << 16)    /* now > start + timeout                              pod_manager.go:354 */
+#define UST_F_WAIT_START_INVALID (1u << 17) /* start-time annotation does not parse as int64     pod_manager.go:348-353 */
+#define UST_F_NM_PRESENT (1u << 18)        /* NodeUpgradeState.NodeMaintenance != nil            upgrade_requestor.go:420 */
+#define UST_F_NM_READY (1u << 19)          /* NodeMaintenance Ready condition with Reason Ready  upgrade_requestor.go:437-439 */
+#define UST_F_INPUT_MASK 0x000FFE78u
+
+/* ------------------------------------------------------------------------------------------------
+ * pod_flags[p] (uint16): one entry per workload pod of a node (CSR by pod_off), used to evaluate
+ * what the asynchronous actuators would decide (kubectl drain filter chain, k8s.io/kubectl v0.35.1
+ * pkg/drain/filters.go; call sites pod_manager.go:146-157,191 and drain_manager.go:76-96,121).
+ * ---------------------------------------------------------------------------------------------- */
+#define UST_POD_PHASE_MASK 0x0007u
+enum { UST_PHASE_OTHER = 0, UST_PHASE_PENDING = 1, UST_PHASE_RUNNING = 2, UST_PHASE_SUCCEEDED = 3, UST_PHASE_FAILED = 4 };
+#define UST_POD_HAS_CONTROLLER (1u << 3)       /* metav1.GetControllerOf(pod) != nil */
+#define UST_POD_CONTROLLED_BY_DS (1u << 4)     /* ... and its Kind is DaemonSet */
+#define UST_POD_DS_MISSING (1u << 5)           /* that DaemonSet cannot be fetched (NotFound) */
+#define UST_POD_MIRROR (1u << 6)               /* kubernetes.io/config.mirror annotation present */
+#define UST_POD_HAS_EMPTYDIR (1u << 7)         /* a volume with EmptyDir != nil */
+#define UST_POD_MATCH_DELETION_FILTER (1u << 8) /* PodDeletionFilter(pod) == true     pod_manager.go:76,139,179 */
+#define UST_POD_MATCH_WAIT_SELECTOR (1u << 9)  /* matches WaitForCompletionSpec.PodSelector   pod_manager.go:263 */
+#define UST_POD_MATCH_DRAIN_SELECTOR (1u << 10) /* matches DrainSpec.PodSelector       drain_manager.go:86 */
+
+/* ------------------------------------------------------------------------------------------------
+ * actions[i] (uint16): the actuator / provider calls ApplyState makes for node i, in addition to the
+ * label change implied by next_state[i] != state code. One bit per call site.
+ * ---------------------------------------------------------------------------------------------- */
+#define UST_A_SET_STATE (1u << 0)               /* ChangeNodeUpgradeState(next_state) */
+#define UST_A_SET_INITIAL_STATE_ANNO (1u << 1)  /* common_manager.go:253-264 */
+#define UST_A_CLEAR_INITIAL_STATE_ANNO (1u << 2) /* common_manager.go:558-565, :699-706 */
+#define UST_A_CLEAR_UPGRADE_REQUESTED (1u << 3) /* upgrade_inplace.go:72-81, upgrade_requestor.go:285-294 */
+#define UST_A_CORDON (1u << 4)                  /* common_manager.go:366 */
+#define UST_A_UNCORDON (1u << 5)                /* upgrade_inplace.go:133 */
+#define UST_A_SCHEDULE_WAIT_CHECK (1u << 6)     /* node passed to ScheduleCheckOnPodCompletion  common_manager.go:413-414 */
+#define UST_A_SCHEDULE_POD_EVICTION (1u << 7)   /* node passed to SchedulePodEviction           common_manager.go:443-452 */
+#define UST_A_SCHEDULE_DRAIN (1u << 8)          /* node passed to ScheduleNodesDrain            common_manager.go:350-356 */
+#define UST_A_RESTART_DRIVER_POD (1u << 9)      /* pod passed to SchedulePodsRestart            common_manager.go:472-474, :523 */
+#define UST_A_UNBLOCK_SAFE_LOAD (1u << 10)      /* safe_driver_load_manager.go:57-71 */
+#define UST_A_SET_WAIT_START (1u << 11)         /* pod_manager.go:336-345 (actuator evaluation only) */
+#define UST_A_CLEAR_WAIT_START (1u << 12)       /* pod_manager.go:301-302, :360 (actuator evaluation only) */
+#define UST_A_REQUESTOR_ANNO_CHANGE (1u << 13)  /* upgrade_requestor.go:302-306 (set), :476-480 (clear) */
+#define UST_A_NM_CREATE_OR_DELETE (1u << 14)    /* upgrade_requestor.go:296, :482 */
+#define UST_A_ERROR (1u << 15)                  /* ApplyState returns an error at this node */
+
+/* actuator_outcome[i] when no actuator runs for the node */
+#define UST_OUTCOME_NONE 0xFFu
+
+/* ------------------------------------------------------------------------------------------------
+ * Policy: DriverUpgradePolicySpec (upgrade_spec.go:27-110) + manager options, flattened.
+ * ---------------------------------------------------------------------------------------------- */
+enum { UST_MAXUNAVAIL_NIL = 0, UST_MAXUNAVAIL_INT = 1, UST_MAXUNAVAIL_PERCENT = 2, UST_MAXUNAVAIL_INVALID = 3 };
+
+typedef struct ust_policy {
+  int32_t auto_upgrade;            /* AutoUpgrade; 0 => ApplyState is a successful no-op (upgrade_state.go:179-182) */
+  int32_t max_unavailable_kind;    /* UST_MAXUNAVAIL_*: nil / intstr.Int / "NN%" / unparsable string */
+  int64_t max_parallel_upgrades;   /* MaxParallelUpgrades; 0 = unlimited */
+  int64_t max_unavailable_value;   /* IntVal, or NN of "NN%" */
+  int32_t pod_deletion_enabled;    /* WithPodDeletionEnabled(filter != nil)      upgrade_state.go:329-337 */
+  int32_t validation_enabled;      /* WithValidationEnabled(selector != "")      upgrade_state.go:341-350 */
+  int32_t pod_deletion_spec_present; /* PodDeletion != nil */
+  int32_t pod_deletion_force;      /* PodDeletionSpec.Force */
+  int32_t pod_deletion_delete_emptydir; /* PodDeletionSpec.DeleteEmptyDir */
+  int32_t drain_enabled;           /* DrainSpec != nil && DrainSpec.Enable       upgrade_state.go:235 */
+  int32_t drain_force;             /* DrainSpec.Force */
+  int32_t drain_delete_emptydir;   /* DrainSpec.DeleteEmptyDir */
+  int32_t wait_selector_set;       /* WaitForCompletion != nil && PodSelector != ""   common_manager.go:392 */
+  int32_t wait_timeout_nonzero;    /* WaitForCompletionSpec.TimeoutSecond != 0       pod_manager.go:290 */
+  int32_t use_maintenance_operator; /* StateOptions.Requestor.UseMaintenanceOperator  upgrade_state.go:291,302,321 */
+  int32_t evaluate_actuators;      /* 1: also fill actuator_outcome / wait-start actions from the
+                                         WAIT_* flag bits and, when given, the pod lists */
+} ust_policy;
+
+/* ------------------------------------------------------------------------------------------------
+ * Cluster-wide results of one call (what CommonUpgradeStateManager's getters return,
+ * common_manager.go:715-788, plus the slot arithmetic of upgrade_inplace.go:49-62).
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  UST_OK = 0,
+  UST_ERR_INVALID_ARGUMENT = -1,
+  UST_ERR_CUDA = -2,            /* no device, no sm_100 image, launch or copy failure */
+  UST_ERR_NIL_STATE = -3,       /* "currentState should not be empty"           upgrade_state.go:175-177 */
+  UST_ERR_REVISION_HASH = -4,   /* per-node abort, see UST_HOT_REVISION_HASH_ERROR */
+  UST_ERR_MAX_UNAVAILABLE = -5, /* intstr.GetScaledValueFromIntOrPercent fails   upgrade_inplace.go:54-60 */
+  UST_ERR_POD_DELETION_SPEC = -6, /* "pod deletion spec should not be empty"     pod_manager.go:132-134 */
+  UST_ERR_DS_UNSCHEDULED = -7,  /* "driver DaemonSet should not have Unscheduled pods"  upgrade_state.go:128-131 */
+  UST_ERR_COMM = -8             /* multi-GPU exchange failed */
+};
+
+typedef struct ust_counters {
+  int64_t hist[UST_NUM_STATE_CODES]; /* nodes per state code (index 14 = excluded entries) */
+  int64_t unavailable;        /* GetCurrentUnavailableNodes               common_manager.go:146-165 */
+  int64_t candidates;         /* upgrade-required nodes not marked skip */
+  int64_t total_managed;      /* GetTotalManagedNodes                     common_manager.go:715-730 */
+  int64_t in_progress;        /* GetUpgradesInProgress                    common_manager.go:733-739 */
+  int64_t max_unavailable;    /* scaled MaxUnavailable                    upgrade_inplace.go:52-60 */
+  int64_t upgrades_available; /* GetUpgradesAvailable (may be negative)   common_manager.go:748-776 */
+  int64_t error_code;         /* UST_OK or the UST_ERR_* ApplyState aborted with */
+  int64_t error_index;        /* node index it aborted at; -1 for a policy-level error */
+  int64_t error_pass;         /* 0-based position of the aborting Process* pass in upgrade_state.go:205-274 */
+  int64_t reserved[7];
+} ust_counters;
+
+/* Optional per-node workload pod lists (CSR). pod_off has n_nodes+1 entries. */
+typedef struct ust_pods {
+  const int32_t* pod_off;
+  const uint16_t* pod_flags;
+  int64_t n_pods;
+} ust_pods;
+
+typedef struct ust_handle ust_handle;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+
+/* Create a handle bound to CUDA device `device` (>= 0). The handle owns one stream, its staging
+ * buffers (grown geometrically) and a 64 KiB workspace. Not re-entrant; distinct handles are
+ * independent. Returns UST_OK or UST_ERR_CUDA (then *out == NULL). */
+int ust_create(ust_handle** out, int device);
+void ust_destroy(ust_handle* h);
+/* Message for the last non-OK return on this handle (never NULL; valid until the next call). */
+const char* ust_last_error(const ust_handle* h);
+/* Same, for failures of ust_create itself (thread-local). */
+const char* ust_create_error(void);
+int ust_abi_version(void);
+/* Number of kernels this handle has launched so far (for bench.py's gpu_launches). */
+int64_t ust_launch_count(const ust_handle* h);
+
+/* Pinned host memory for the SoA arrays (optional; pageable pointers also work, more slowly). */
+void* ust_host_alloc(size_t bytes);
+void ust_host_free(void* p);
+
+/* ---- ApplyState -------------------------------------------------------------------------------- */
+
+/* Replaces ClusterUpgradeStateManagerImpl.ApplyState (upgrade_state.go:171-281) for a snapshot given
+ * as host arrays. All pointers are caller-owned and are not retained after return.
+ *   policy == NULL or !auto_upgrade  => no-op: next_state = state code, actions = 0, returns UST_OK.
+ *   n_nodes < 0 or NULL arrays       => UST_ERR_NIL_STATE / UST_ERR_INVALID_ARGUMENT.
+ * On a reference-level abort (UST_ERR_REVISION_HASH, _MAX_UNAVAILABLE, _POD_DELETION_SPEC) the outputs
+ * hold exactly what the reference had done before returning the error: nodes the sequential passes
+ * had not reached are left untouched, the aborting node carries UST_A_ERROR. */
+int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n_nodes,
+                    const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev,
+                    const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                    const ust_pods* pods /* nullable */,
+                    uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome /* nullable */,
+                    ust_counters* out /* nullable */);
+
+/* Same computation on arrays already resident in device memory (16-byte aligned), enqueued on the
+ * handle's stream (or `stream`, a cudaStream_t, when non-NULL). Returns after the launch;
+ * `out_device` (nullable) receives the counters in device memory. Use ust_sync() before reading. */
+int ust_apply_state_device(ust_handle* h, const ust_policy* policy, int64_t n_nodes,
+                           const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev,
+                           const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                           const ust_pods* pods /* nullable; device pointers inside */,
+                           uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome,
+                           ust_counters* out_device, void* stream);
+int ust_sync(ust_handle* h);
+
+/* ---- BuildState -------------------------------------------------------------------------------- */
+
+/* The device part of BuildState (upgrade_state.go:99-164): per-DaemonSet count of owned driver pods
+ * against DesiredNumberScheduled (:128-131, counted before the pending-skip of :149-152) and the
+ * bucket sizes. One entry per driver pod; ds_idx < 0 = orphaned pod. Returns UST_ERR_DS_UNSCHEDULED
+ * when some DaemonSet's count differs (counters->error_index = that DaemonSet's index). */
+int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const int32_t* ds_idx,
+                    int32_t n_ds, const int32_t* ds_desired, ust_counters* out);
+
+/* ---- multi-GPU (one process per GPU) ----------------------------------------------------------- */
+
+#define UST_UNIQUE_ID_BYTES 128
+/* Rank 0 calls ust_get_unique_id and distributes the bytes; every rank then calls ust_comm_init.
+ * Nodes are sharded in contiguous index ranges, rank r before rank r+1 (slice order of the
+ * upgrade-required bucket, upgrade_inplace.go:71, is global index order). Afterwards every
+ * ust_apply_state* call is collective: each rank passes its shard and one exchange of the
+ * constraint counters happens per call. */
+int ust_get_unique_id(void* out_bytes);
+int ust_comm_init(ust_handle* h, int rank, int world_size, const void* unique_id_bytes);
+/* exchange mode: 0 = ncclAllReduce between two kernels (default), 1 = fused in-kernel NVLink exchange */
+int ust_comm_set_mode(ust_handle* h, int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UST_H_ */

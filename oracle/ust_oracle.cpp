@@ -1,0 +1,1236 @@
+// ust_oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the reference's pkg/upgrade hot path (NVIDIA/k8s-operator-libs @ 11e747a),
+// written "reference-shaped": heap node / pod objects with string-keyed label and annotation maps,
+// a snapshot bucketed by the state label, and the twelve sequential Process* passes of ApplyState in
+// the reference's order, run against recording mocks with the semantics of the reference's own test
+// suite (pkg/upgrade/upgrade_suit_test.go:114-182). Every function cites the Go it follows.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+// this library; libust.so never links or calls it.
+//
+// Parity pinning: the Go toolchain is not in this image, so the reference itself cannot be run here.
+// This restatement is pinned against every known-answer test the reference holds for the path
+// (pkg/upgrade/upgrade_state_test.go:190-1294, :1296-1784 and pod_manager_test.go:120-429), encoded
+// with file:line provenance in tests/golden/reference_vectors.json and replayed by
+// tests/test_oracle_golden.py. Third-party arithmetic restated from its published source:
+//   * k8s.io/apimachinery v0.35.1 pkg/util/intstr.GetScaledValueFromIntOrPercent (go.mod:13)
+//   * k8s.io/kubectl v0.35.1 pkg/drain filter chain (go.mod:15)
+// The daemonset / mirror / finished-pod branches of the drain filter chain are NOT exercised by any
+// reference test: parity unpinned for those branches (stated in DESIGN.md).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../include/ust.h"
+
+namespace ref {
+
+// ---- consts.go:19-93, util.go:91-155 ------------------------------------------------------------
+static std::string DriverName = "gpu";  // util.go:91-99 (suite sets "gpu", upgrade_suit_test.go:110)
+
+static std::string key(const char* prefix_fmt_tail) { return "nvidia.com/" + DriverName + prefix_fmt_tail; }
+static std::string GetUpgradeStateLabelKey() { return key("-driver-upgrade-state"); }                    // consts.go:21
+static std::string GetUpgradeSkipNodeLabelKey() { return key("-driver-upgrade.skip"); }                  // consts.go:23
+static std::string GetUpgradeDriverWaitForSafeLoadAnnotationKey() { return key("-driver-upgrade.driver-wait-for-safe-load"); }  // consts.go:30
+static std::string GetUpgradeInitialStateAnnotationKey() { return key("-driver-upgrade.node-initial-state.unschedulable"); }     // consts.go:33
+static std::string GetWaitForPodCompletionStartTimeAnnotationKey() { return key("-driver-upgrade-wait-for-pod-completion-start-time"); }  // consts.go:37
+static std::string GetUpgradeRequestedAnnotationKey() { return key("-driver-upgrade-requested"); }       // consts.go:44
+static std::string GetUpgradeRequestorModeAnnotationKey() { return key("-driver-upgrade-requestor-mode"); }  // consts.go:47
+
+static const char* const kStateNames[14] = {
+    "",                        // UpgradeStateUnknown                 consts.go:50
+    "upgrade-required",        // consts.go:53
+    "cordon-required",         // consts.go:55
+    "wait-for-jobs-required",  // consts.go:57
+    "pod-deletion-required",   // consts.go:59
+    "drain-required",          // consts.go:62
+    "node-maintenance-required",  // consts.go:67
+    "post-maintenance-required",  // consts.go:71
+    "pod-restart-required",    // consts.go:74
+    "validation-required",     // consts.go:77
+    "uncordon-required",       // consts.go:79
+    "upgrade-done",            // consts.go:81
+    "upgrade-failed",          // consts.go:83
+    "some-unrecognised-state"};
+static const std::string trueString = "true";  // consts.go:92
+static const std::string nullString = "null";  // consts.go:90
+
+static int stateCode(const std::string& s) {
+  for (int i = 0; i < 13; i++)
+    if (s == kStateNames[i]) return i;
+  return UST_STATE_OTHER;
+}
+
+// ---- minimal object model (corev1.Node / corev1.Pod / appsv1.DaemonSet) --------------------------
+using StrMap = std::unordered_map<std::string, std::string>;
+struct NodeCondition { std::string type, status; };
+struct Node {
+  std::string name;
+  StrMap labels, annotations;
+  bool unschedulable = false;             // Spec.Unschedulable
+  std::vector<NodeCondition> conditions;  // Status.Conditions
+};
+struct ContainerStatus { bool ready; int restartCount; };
+struct Pod {
+  StrMap labels;
+  std::string phase;  // Status.Phase
+  std::vector<ContainerStatus> containerStatuses, initContainerStatuses;
+  bool deletionTimestampSet = false;
+};
+struct DaemonSet {
+  std::string revisionHash;     // what GetDaemonsetControllerRevisionHash returns for it
+  bool revisionMissing = false; // "no revision found for daemonset" pod_manager.go:108-110
+};
+struct NodeMaintenance { bool readyConditionWithReasonReady = false; };
+
+// workload pod as seen by the kubectl drain helper
+struct WorkloadPod {
+  std::string phase;
+  bool hasController = false, controllerIsDaemonSet = false, daemonSetMissing = false;
+  bool mirror = false, emptyDir = false;
+  bool matchDeletionFilter = false, matchWaitSelector = false, matchDrainSelector = false;
+};
+
+// common_manager.go:58-63
+struct NodeUpgradeState {
+  Node* node = nullptr;
+  Pod* driverPod = nullptr;
+  DaemonSet* driverDaemonSet = nullptr;
+  NodeMaintenance* nodeMaintenance = nullptr;
+  // oracle bookkeeping (not part of the reference type)
+  int64_t index = -1;
+  bool validationResult = true;                 // what the mocked ValidationManager.Validate returns
+  bool waitPodsRunning = false, waitStartInvalid = false, waitTimedOut = false;  // pre-evaluated wait predicates
+  const std::vector<WorkloadPod>* workload = nullptr;
+  bool IsOrphanedPod() const { return driverDaemonSet == nullptr; }  // common_manager.go:66-68
+};
+
+// common_manager.go:73-80
+struct ClusterUpgradeState {
+  std::unordered_map<std::string, std::vector<NodeUpgradeState*>> NodeStates;
+};
+
+// upgrade_spec.go:27-110 (only the fields the path reads)
+struct IntOrString { int type; int64_t intVal; std::string strVal; };  // type 0 = Int, 1 = String
+struct WaitForCompletionSpec { std::string podSelector; int timeoutSecond = 0; };
+struct PodDeletionSpec { bool force = false, deleteEmptyDir = false; };
+struct DrainSpec { bool enable = false, force = false, deleteEmptyDir = false; };
+struct DriverUpgradePolicySpec {
+  bool autoUpgrade = false;
+  int64_t maxParallelUpgrades = 0;
+  std::unique_ptr<IntOrString> maxUnavailable;
+  std::unique_ptr<PodDeletionSpec> podDeletion;
+  std::unique_ptr<WaitForCompletionSpec> waitForCompletion;
+  std::unique_ptr<DrainSpec> drainSpec;
+};
+
+struct Error { int code = 0; int64_t index = -1; int pass = -1; };
+#define RETURN_IF(e) do { if ((e).code) return (e); } while (0)
+
+// ---- k8s.io/apimachinery/pkg/util/intstr (v0.35.1) GetScaledValueFromIntOrPercent -----------------
+// Int => IntVal. String must be "<int>%"; value = int(math.Ceil(float64(v) * float64(total) / 100))
+// when roundUp. Anything else is an error. Call site: upgrade_inplace.go:55.
+static bool GetScaledValueFromIntOrPercent(const IntOrString& v, int64_t total, bool roundUp, int64_t* out) {
+  if (v.type == 0) { *out = v.intVal; return true; }
+  const std::string& s = v.strVal;
+  if (s.empty() || s.back() != '%') return false;
+  std::string digits = s.substr(0, s.size() - 1);
+  if (digits.empty()) return false;
+  size_t i = (digits[0] == '-' || digits[0] == '+') ? 1 : 0;
+  if (i >= digits.size()) return false;
+  for (size_t k = i; k < digits.size(); k++)
+    if (digits[k] < '0' || digits[k] > '9') return false;
+  long long pct = std::stoll(digits);
+  volatile double prod = (double)pct * (double)total;  // float64(value) * float64(total)
+  volatile double q = prod / 100.0;
+  *out = (int64_t)(roundUp ? std::ceil(q) : std::floor(q));
+  return true;
+}
+
+// ---- the manager with the suite's mocks wired in -------------------------------------------------
+struct Manager {
+  // options
+  bool podDeletionStateEnabled = false;  // common_manager.go:98, upgrade_state.go:335
+  bool validationStateEnabled = false;   // common_manager.go:99, upgrade_state.go:348
+  bool useMaintenanceOperator = false;   // StateOptions.Requestor.UseMaintenanceOperator
+  bool evaluateActuators = false;        // oracle option: also run the real actuators' decision logic
+  bool waitTimeoutPrecomputed = true;
+
+  // recording (per snapshot index)
+  std::vector<uint16_t> actions;
+  std::vector<uint8_t> outcome;
+
+  void rec(const NodeUpgradeState* ns, unsigned bit) { if (ns->index >= 0) actions[ns->index] |= (uint16_t)bit; }
+
+  // NodeUpgradeStateProvider mock — upgrade_suit_test.go:114-130
+  void ChangeNodeUpgradeState(NodeUpgradeState* ns, const std::string& newState) {
+    ns->node->labels[GetUpgradeStateLabelKey()] = newState;
+    rec(ns, UST_A_SET_STATE);
+  }
+  void ChangeNodeUpgradeAnnotation(NodeUpgradeState* ns, const std::string& k, const std::string& v, unsigned bit) {
+    if (v == nullString) ns->node->annotations.erase(k); else ns->node->annotations[k] = v;
+    rec(ns, bit);
+  }
+  // PodManager revision-hash getters: real semantics (pod_manager.go:84-89) for the pod,
+  // suite-mock-like constant-per-DaemonSet for the DaemonSet (upgrade_suit_test.go:169-171).
+  bool GetPodControllerRevisionHash(const Pod* pod, std::string* out) {
+    auto it = pod->labels.find("controller-revision-hash");  // pod_manager.go:72
+    if (it == pod->labels.end()) return false;
+    *out = it->second;
+    return true;
+  }
+  bool GetDaemonsetControllerRevisionHash(const DaemonSet* ds, std::string* out) {
+    if (ds->revisionMissing) return false;
+    *out = ds->revisionHash;
+    return true;
+  }
+
+  // common_manager.go:323-325
+  bool IsUpgradeRequested(const Node* n) {
+    auto it = n->annotations.find(GetUpgradeRequestedAnnotationKey());
+    return it != n->annotations.end() && it->second == trueString;
+  }
+  // common_manager.go:651-653, :710-712
+  bool IsNodeUnschedulable(const Node* n) { return n->unschedulable; }
+  // common_manager.go:656-663
+  bool isNodeConditionReady(const Node* n) {
+    for (const auto& c : n->conditions)
+      if (c.type == "Ready" && c.status != "True") return false;
+    return true;
+  }
+  // common_manager.go:666-668
+  bool SkipNodeUpgrade(const Node* n) {
+    auto it = n->labels.find(GetUpgradeSkipNodeLabelKey());
+    return it != n->labels.end() && it->second == trueString;
+  }
+  // util.go:135-138
+  bool IsNodeInRequestorMode(const Node* n) { return n->annotations.count(GetUpgradeRequestorModeAnnotationKey()) != 0; }
+  // safe_driver_load_manager.go:51-53
+  bool IsWaitingForSafeDriverLoad(const Node* n) {
+    auto it = n->annotations.find(GetUpgradeDriverWaitForSafeLoadAnnotationKey());
+    return it != n->annotations.end() && !it->second.empty();
+  }
+  // safe_driver_load_manager.go:57-71
+  void UnblockLoading(NodeUpgradeState* ns) {
+    if (!IsWaitingForSafeDriverLoad(ns->node)) return;
+    ChangeNodeUpgradeAnnotation(ns, GetUpgradeDriverWaitForSafeLoadAnnotationKey(), nullString, UST_A_UNBLOCK_SAFE_LOAD);
+  }
+
+  static size_t len(const ClusterUpgradeState& s, int code) {
+    auto it = s.NodeStates.find(kStateNames[code]);
+    return it == s.NodeStates.end() ? 0 : it->second.size();
+  }
+  static const std::vector<NodeUpgradeState*>& bucket(const ClusterUpgradeState& s, int code) {
+    static const std::vector<NodeUpgradeState*> empty;
+    auto it = s.NodeStates.find(kStateNames[code]);
+    return it == s.NodeStates.end() ? empty : it->second;
+  }
+
+  // common_manager.go:715-730
+  int64_t GetTotalManagedNodes(const ClusterUpgradeState& s) {
+    return (int64_t)(len(s, UST_STATE_UNKNOWN) + len(s, UST_STATE_DONE) + len(s, UST_STATE_UPGRADE_REQUIRED) +
+                     len(s, UST_STATE_CORDON_REQUIRED) + len(s, UST_STATE_WAIT_FOR_JOBS_REQUIRED) +
+                     len(s, UST_STATE_POD_DELETION_REQUIRED) + len(s, UST_STATE_FAILED) + len(s, UST_STATE_DRAIN_REQUIRED) +
+                     len(s, UST_STATE_POD_RESTART_REQUIRED) + len(s, UST_STATE_UNCORDON_REQUIRED) +
+                     len(s, UST_STATE_VALIDATION_REQUIRED));
+  }
+  // common_manager.go:733-739
+  int64_t GetUpgradesInProgress(const ClusterUpgradeState& s) {
+    return GetTotalManagedNodes(s) -
+           (int64_t)(len(s, UST_STATE_UNKNOWN) + len(s, UST_STATE_DONE) + len(s, UST_STATE_UPGRADE_REQUIRED));
+  }
+  // common_manager.go:146-165 — iterates over EVERY bucket of the map
+  int64_t GetCurrentUnavailableNodes(const ClusterUpgradeState& s) {
+    int64_t unavailableNodes = 0;
+    for (const auto& kv : s.NodeStates)
+      for (const NodeUpgradeState* ns : kv.second) {
+        if (IsNodeUnschedulable(ns->node)) { unavailableNodes++; continue; }
+        if (!isNodeConditionReady(ns->node)) unavailableNodes++;
+      }
+    return unavailableNodes;
+  }
+  // common_manager.go:748-776
+  int64_t GetUpgradesAvailable(const ClusterUpgradeState& s, int64_t maxParallelUpgrades, int64_t maxUnavailable) {
+    int64_t upgradesInProgress = GetUpgradesInProgress(s);
+    int64_t totalNodes = GetTotalManagedNodes(s);
+    int64_t upgradesAvailable;
+    if (maxParallelUpgrades == 0) upgradesAvailable = (int64_t)len(s, UST_STATE_UPGRADE_REQUIRED);
+    else upgradesAvailable = maxParallelUpgrades - upgradesInProgress;
+    int64_t currentUnavailableNodes = GetCurrentUnavailableNodes(s) + (int64_t)len(s, UST_STATE_CORDON_REQUIRED);
+    if (upgradesAvailable > maxUnavailable) upgradesAvailable = maxUnavailable;
+    if (currentUnavailableNodes >= maxUnavailable) upgradesAvailable = 0;
+    else if (maxUnavailable < totalNodes && currentUnavailableNodes + upgradesAvailable > maxUnavailable)
+      upgradesAvailable = maxUnavailable - currentUnavailableNodes;
+    return upgradesAvailable;
+  }
+
+  // common_manager.go:299-320
+  Error podInSyncWithDS(NodeUpgradeState* ns, bool* isPodSynced, bool* isOrphaned) {
+    *isPodSynced = false;
+    *isOrphaned = ns->IsOrphanedPod();
+    if (*isOrphaned) return {};
+    std::string podRevisionHash, daemonsetRevisionHash;
+    if (!GetPodControllerRevisionHash(ns->driverPod, &podRevisionHash)) return {UST_ERR_REVISION_HASH, ns->index, -1};
+    if (!GetDaemonsetControllerRevisionHash(ns->driverDaemonSet, &daemonsetRevisionHash)) return {UST_ERR_REVISION_HASH, ns->index, -1};
+    *isPodSynced = podRevisionHash == daemonsetRevisionHash;
+    return {};
+  }
+  // common_manager.go:606-634
+  Error isDriverPodInSync(NodeUpgradeState* ns, bool* out) {
+    bool isPodSynced, isOrphaned;
+    *out = false;
+    Error e = podInSyncWithDS(ns, &isPodSynced, &isOrphaned);
+    RETURN_IF(e);
+    if (isOrphaned) return {};
+    if (isPodSynced && ns->driverPod->phase == "Running" && !ns->driverPod->containerStatuses.empty()) {
+      for (const auto& cs : ns->driverPod->containerStatuses)
+        if (!cs.ready) return {};
+      *out = true;
+    }
+    return {};
+  }
+  // common_manager.go:636-648
+  bool isDriverPodFailing(const Pod* pod) {
+    for (const auto& st : pod->initContainerStatuses)
+      if (!st.ready && st.restartCount > 10) return true;
+    for (const auto& st : pod->containerStatuses)
+      if (!st.ready && st.restartCount > 10) return true;
+    return false;
+  }
+  // common_manager.go:673-708
+  void updateNodeToUncordonOrDoneState(NodeUpgradeState* ns) {
+    Node* node = ns->node;
+    std::string newUpgradeState = kStateNames[UST_STATE_UNCORDON_REQUIRED];
+    std::string annotationKey = GetUpgradeInitialStateAnnotationKey();
+    bool isNodeUnderRequestorMode = IsNodeInRequestorMode(node);
+    if (node->annotations.count(annotationKey)) {
+      if (!isNodeUnderRequestorMode) newUpgradeState = kStateNames[UST_STATE_DONE];
+    }
+    ChangeNodeUpgradeState(ns, newUpgradeState);
+    if (newUpgradeState == kStateNames[UST_STATE_DONE] || isNodeUnderRequestorMode)
+      ChangeNodeUpgradeAnnotation(ns, annotationKey, nullString, UST_A_CLEAR_INITIAL_STATE_ANNO);
+  }
+
+  // common_manager.go:229-291
+  Error ProcessDoneOrUnknownNodes(ClusterUpgradeState& s, int nodeStateCode) {
+    for (NodeUpgradeState* ns : bucket(s, nodeStateCode)) {
+      bool isPodSynced, isOrphaned;
+      Error e = podInSyncWithDS(ns, &isPodSynced, &isOrphaned);
+      RETURN_IF(e);
+      bool isUpgradeRequested = IsUpgradeRequested(ns->node);
+      bool isWaitingForSafeDriverLoad = IsWaitingForSafeDriverLoad(ns->node);
+      if ((!isPodSynced && !isOrphaned) || isWaitingForSafeDriverLoad || isUpgradeRequested) {
+        if (IsNodeUnschedulable(ns->node))
+          ChangeNodeUpgradeAnnotation(ns, GetUpgradeInitialStateAnnotationKey(), trueString, UST_A_SET_INITIAL_STATE_ANNO);
+        ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_UPGRADE_REQUIRED]);
+        continue;
+      }
+      if (nodeStateCode == UST_STATE_UNKNOWN) {
+        ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_DONE]);
+        continue;
+      }
+    }
+    return {};
+  }
+
+  // upgrade_inplace.go:44-112
+  int64_t lastTotal = 0, lastInProgress = 0, lastUnavailable = 0, lastMaxUnavailable = 0, lastAvailable = 0;
+  Error InplaceProcessUpgradeRequiredNodes(ClusterUpgradeState& s, const DriverUpgradePolicySpec& policy) {
+    int64_t totalNodes = GetTotalManagedNodes(s);
+    int64_t upgradesInProgress = GetUpgradesInProgress(s);
+    int64_t currentUnavailableNodes = GetCurrentUnavailableNodes(s);
+    int64_t maxUnavailable = totalNodes;
+    if (policy.maxUnavailable) {
+      if (!GetScaledValueFromIntOrPercent(*policy.maxUnavailable, totalNodes, true, &maxUnavailable))
+        return {UST_ERR_MAX_UNAVAILABLE, -1, -1};
+    }
+    int64_t upgradesAvailable = GetUpgradesAvailable(s, policy.maxParallelUpgrades, maxUnavailable);
+    lastTotal = totalNodes; lastInProgress = upgradesInProgress; lastUnavailable = currentUnavailableNodes;
+    lastMaxUnavailable = maxUnavailable; lastAvailable = upgradesAvailable;
+
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_UPGRADE_REQUIRED)) {
+      if (IsUpgradeRequested(ns->node))
+        ChangeNodeUpgradeAnnotation(ns, GetUpgradeRequestedAnnotationKey(), nullString, UST_A_CLEAR_UPGRADE_REQUESTED);
+      if (SkipNodeUpgrade(ns->node)) continue;
+      if (upgradesAvailable <= 0) {
+        if (!IsNodeUnschedulable(ns->node)) continue;  // already-cordoned nodes progress regardless
+      }
+      ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_CORDON_REQUIRED]);
+      upgradesAvailable--;
+    }
+    return {};
+  }
+  // upgrade_requestor.go:277-319
+  Error RequestorProcessUpgradeRequiredNodes(ClusterUpgradeState& s) {
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_UPGRADE_REQUIRED)) {
+      if (IsUpgradeRequested(ns->node))
+        ChangeNodeUpgradeAnnotation(ns, GetUpgradeRequestedAnnotationKey(), nullString, UST_A_CLEAR_UPGRADE_REQUESTED);
+      if (SkipNodeUpgrade(ns->node)) continue;
+      rec(ns, UST_A_NM_CREATE_OR_DELETE);  // createOrUpdateNodeMaintenance  upgrade_requestor.go:296
+      ChangeNodeUpgradeAnnotation(ns, GetUpgradeRequestorModeAnnotationKey(), trueString, UST_A_REQUESTOR_ANNO_CHANGE);
+      ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_NODE_MAINTENANCE_REQUIRED]);
+    }
+    return {};
+  }
+  // upgrade_state.go:287-297
+  Error ProcessUpgradeRequiredNodesWrapper(ClusterUpgradeState& s, const DriverUpgradePolicySpec& policy) {
+    if (useMaintenanceOperator) return RequestorProcessUpgradeRequiredNodes(s);
+    return InplaceProcessUpgradeRequiredNodes(s, policy);
+  }
+
+  // common_manager.go:361-380
+  Error ProcessCordonRequiredNodes(ClusterUpgradeState& s) {
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_CORDON_REQUIRED)) {
+      rec(ns, UST_A_CORDON);  // CordonManager.Cordon (mock: nil)
+      ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_WAIT_FOR_JOBS_REQUIRED]);
+    }
+    return {};
+  }
+
+  // pod_manager.go:371-391
+  static bool IsPodRunningOrPending(const std::string& phase) { return phase == "Running" || phase == "Pending"; }
+
+  // What the real PodManagerImpl.ScheduleCheckOnPodCompletion (pod_manager.go:256-317) and
+  // HandleTimeoutOnPodCompletions (:331-368) decide for one node. Recorded as the actuator outcome;
+  // the node label itself is left alone (the suite's PodManager mock is a no-op).
+  void evalCheckOnPodCompletion(NodeUpgradeState* ns, const WaitForCompletionSpec& spec) {
+    bool running = false;
+    if (ns->workload) {
+      for (const auto& p : *ns->workload) {
+        if (!p.matchWaitSelector) continue;  // ListPods(selector, node)  pod_manager.go:263
+        running = IsPodRunningOrPending(p.phase);
+        if (running) break;
+      }
+    } else {
+      running = ns->waitPodsRunning;
+    }
+    std::string annotationKey = GetWaitForPodCompletionStartTimeAnnotationKey();
+    uint8_t result = UST_STATE_WAIT_FOR_JOBS_REQUIRED;
+    if (running) {
+      if (spec.timeoutSecond != 0) {
+        if (!ns->node->annotations.count(annotationKey)) {
+          rec(ns, UST_A_SET_WAIT_START);
+        } else if (ns->waitStartInvalid) {
+          // strconv.ParseInt fails: event logged, nothing changes  pod_manager.go:348-353, :292-296
+        } else if (ns->waitTimedOut) {  // currentTime > startTime + timeoutSeconds  pod_manager.go:354
+          result = UST_STATE_POD_DELETION_REQUIRED;
+          rec(ns, UST_A_CLEAR_WAIT_START);
+        }
+      }
+    } else {
+      rec(ns, UST_A_CLEAR_WAIT_START);  // pod_manager.go:301-302
+      result = UST_STATE_POD_DELETION_REQUIRED;
+    }
+    outcome[ns->index] = result;
+  }
+
+  // common_manager.go:384-419
+  Error ProcessWaitForJobsRequiredNodes(ClusterUpgradeState& s, const WaitForCompletionSpec* spec) {
+    std::vector<NodeUpgradeState*> nodes;
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_WAIT_FOR_JOBS_REQUIRED)) {
+      nodes.push_back(ns);
+      if (spec == nullptr || spec->podSelector.empty()) {
+        std::string nextState = kStateNames[UST_STATE_POD_DELETION_REQUIRED];
+        if (!podDeletionStateEnabled) nextState = kStateNames[UST_STATE_DRAIN_REQUIRED];
+        ChangeNodeUpgradeState(ns, nextState);
+      }
+    }
+    if (spec == nullptr || spec->podSelector.empty()) return {};
+    if (nodes.empty()) return {};
+    // PodManager.ScheduleCheckOnPodCompletion(config{Nodes: nodes})
+    for (NodeUpgradeState* ns : nodes) {
+      rec(ns, UST_A_SCHEDULE_WAIT_CHECK);
+      if (evaluateActuators) evalCheckOnPodCompletion(ns, *spec);
+    }
+    return {};
+  }
+
+  // ---- k8s.io/kubectl v0.35.1 pkg/drain/filters.go, restated ----
+  enum DeleteStatus { kOkay, kSkip, kWarnDelete, kWarnNoDelete, kError };
+  static bool isFinished(const WorkloadPod& p) { return p.phase == "Succeeded" || p.phase == "Failed"; }
+  // makeFilters(): skipDeleted, daemonSet, mirrorPod, localStorage, unreplicated, then AdditionalFilters;
+  // filterPods() short-circuits at the first status with Delete == false.
+  static DeleteStatus runFilterChain(const WorkloadPod& p, bool force, bool deleteEmptyDirData, bool useCustomFilter) {
+    // skipDeletedFilter: SkipWaitForDeleteTimeoutSeconds is never set by the reference => Okay.
+    // daemonSetFilter (IgnoreAllDaemonSets is always true at both call sites)
+    if (p.hasController && p.controllerIsDaemonSet && !isFinished(p)) {
+      if (p.daemonSetMissing) {
+        if (!force) return kError;
+        // warning, Delete=true: continue down the chain
+      } else {
+        return kWarnNoDelete;
+      }
+    }
+    // mirrorPodFilter
+    if (p.mirror) return kSkip;
+    // localStorageFilter
+    if (p.emptyDir && !isFinished(p)) {
+      if (!deleteEmptyDirData) return kError;
+    }
+    // unreplicatedFilter
+    if (!isFinished(p) && !p.hasController) {
+      if (!force) return kError;
+    }
+    // AdditionalFilters: customDrainFilter  pod_manager.go:138-144
+    if (useCustomFilter && !p.matchDeletionFilter) return kSkip;
+    return kOkay;
+  }
+
+  // Decision of the goroutine body of PodManagerImpl.SchedulePodEviction (pod_manager.go:164-223),
+  // assuming the API calls themselves succeed.
+  void evalPodEviction(NodeUpgradeState* ns, const PodDeletionSpec& spec, bool drainEnabled) {
+    static const std::vector<WorkloadPod> none;
+    const std::vector<WorkloadPod>& pods = ns->workload ? *ns->workload : none;
+    int numPodsToDelete = 0;
+    for (const auto& p : pods)
+      if (p.matchDeletionFilter) numPodsToDelete++;
+    if (numPodsToDelete == 0) { outcome[ns->index] = UST_STATE_POD_RESTART_REQUIRED; return; }
+    int numPodsCanDelete = 0;  // len(podDeleteList.Pods())
+    for (const auto& p : pods) {
+      DeleteStatus st = runFilterChain(p, spec.force, spec.deleteEmptyDir, true);
+      if (st == kOkay || st == kWarnDelete) numPodsCanDelete++;
+    }
+    if (numPodsCanDelete != numPodsToDelete) {
+      // updateNodeToDrainOrFailed  pod_manager.go:393-403
+      outcome[ns->index] = drainEnabled ? UST_STATE_DRAIN_REQUIRED : UST_STATE_FAILED;
+      return;
+    }
+    outcome[ns->index] = UST_STATE_POD_RESTART_REQUIRED;
+  }
+
+  // common_manager.go:424-453
+  Error ProcessPodDeletionRequiredNodes(ClusterUpgradeState& s, const PodDeletionSpec* spec, bool drainEnabled) {
+    if (!podDeletionStateEnabled) {
+      for (NodeUpgradeState* ns : bucket(s, UST_STATE_POD_DELETION_REQUIRED))
+        ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_DRAIN_REQUIRED]);
+      return {};
+    }
+    const auto& nodes = bucket(s, UST_STATE_POD_DELETION_REQUIRED);
+    if (nodes.empty()) return {};
+    // PodManager.SchedulePodEviction: pod_manager.go:125-134
+    if (spec == nullptr) return {UST_ERR_POD_DELETION_SPEC, -1, -1};
+    for (NodeUpgradeState* ns : nodes) {
+      rec(ns, UST_A_SCHEDULE_POD_EVICTION);
+      if (evaluateActuators) evalPodEviction(ns, *spec, drainEnabled);
+    }
+    return {};
+  }
+
+  // Decision of the goroutine body of DrainManagerImpl.ScheduleNodesDrain (drain_manager.go:106-131):
+  // RunNodeDrain fails iff GetPodsForDeletion reports an error-status pod.
+  void evalDrain(NodeUpgradeState* ns, const DrainSpec& spec) {
+    static const std::vector<WorkloadPod> none;
+    const std::vector<WorkloadPod>& pods = ns->workload ? *ns->workload : none;
+    bool anyError = false;
+    for (const auto& p : pods) {
+      if (!p.matchDrainSelector) continue;  // Helper.PodSelector  drain_manager.go:86
+      if (runFilterChain(p, spec.force, spec.deleteEmptyDir, false) == kError) anyError = true;
+    }
+    outcome[ns->index] = anyError ? UST_STATE_FAILED : UST_STATE_POD_RESTART_REQUIRED;
+  }
+
+  // common_manager.go:329-357
+  Error ProcessDrainNodes(ClusterUpgradeState& s, const DrainSpec* drainSpec) {
+    if (drainSpec == nullptr || !drainSpec->enable) {
+      for (NodeUpgradeState* ns : bucket(s, UST_STATE_DRAIN_REQUIRED))
+        ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_POD_RESTART_REQUIRED]);
+      return {};
+    }
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_DRAIN_REQUIRED)) {
+      rec(ns, UST_A_SCHEDULE_DRAIN);  // DrainManager.ScheduleNodesDrain (mock: nil)
+      if (evaluateActuators) evalDrain(ns, *drainSpec);
+    }
+    return {};
+  }
+
+  // upgrade_requestor.go:416-452
+  Error ProcessNodeMaintenanceRequiredNodes(ClusterUpgradeState& s) {
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_NODE_MAINTENANCE_REQUIRED)) {
+      if (ns->nodeMaintenance == nullptr) {
+        ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_UPGRADE_REQUIRED]);
+        continue;
+      }
+      if (ns->nodeMaintenance->readyConditionWithReasonReady)
+        ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_POD_RESTART_REQUIRED]);
+    }
+    return {};
+  }
+
+  // common_manager.go:457-524
+  Error ProcessPodRestartNodes(ClusterUpgradeState& s) {
+    std::vector<NodeUpgradeState*> pods;
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_POD_RESTART_REQUIRED)) {
+      bool isPodSynced, isOrphaned;
+      Error e = podInSyncWithDS(ns, &isPodSynced, &isOrphaned);
+      RETURN_IF(e);  // returns before SchedulePodsRestart: pods collected so far are NOT restarted
+      if (!isPodSynced || isOrphaned) {
+        if (!ns->driverPod->deletionTimestampSet) pods.push_back(ns);
+      } else {
+        UnblockLoading(ns);
+        bool driverPodInSync;
+        e = isDriverPodInSync(ns, &driverPodInSync);
+        RETURN_IF(e);
+        if (driverPodInSync) {
+          if (!validationStateEnabled) { updateNodeToUncordonOrDoneState(ns); continue; }
+          ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_VALIDATION_REQUIRED]);
+        } else {
+          if (!isDriverPodFailing(ns->driverPod)) continue;
+          ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_FAILED]);
+        }
+      }
+    }
+    for (NodeUpgradeState* ns : pods) rec(ns, UST_A_RESTART_DRIVER_POD);  // PodManager.SchedulePodsRestart
+    return {};
+  }
+
+  // common_manager.go:528-570
+  Error ProcessUpgradeFailedNodes(ClusterUpgradeState& s) {
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_FAILED)) {
+      bool driverPodInSync;
+      Error e = isDriverPodInSync(ns, &driverPodInSync);
+      RETURN_IF(e);
+      if (driverPodInSync) {
+        std::string newUpgradeState = kStateNames[UST_STATE_UNCORDON_REQUIRED];
+        std::string annotationKey = GetUpgradeInitialStateAnnotationKey();
+        if (ns->node->annotations.count(annotationKey)) newUpgradeState = kStateNames[UST_STATE_DONE];
+        ChangeNodeUpgradeState(ns, newUpgradeState);
+        if (newUpgradeState == kStateNames[UST_STATE_DONE])
+          ChangeNodeUpgradeAnnotation(ns, annotationKey, nullString, UST_A_CLEAR_INITIAL_STATE_ANNO);
+      }
+    }
+    return {};
+  }
+
+  // common_manager.go:573-604
+  Error ProcessValidationRequiredNodes(ClusterUpgradeState& s) {
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_VALIDATION_REQUIRED)) {
+      UnblockLoading(ns);
+      bool validationDone = ns->validationResult;  // ValidationManager.Validate (mocked per node)
+      if (!validationDone) continue;
+      updateNodeToUncordonOrDoneState(ns);
+    }
+    return {};
+  }
+
+  // upgrade_inplace.go:124-147
+  Error InplaceProcessUncordonRequiredNodes(ClusterUpgradeState& s) {
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_UNCORDON_REQUIRED)) {
+      if (IsNodeInRequestorMode(ns->node)) continue;
+      rec(ns, UST_A_UNCORDON);  // CordonManager.Uncordon (mock: nil)
+      ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_DONE]);
+    }
+    return {};
+  }
+  // upgrade_requestor.go:454-488
+  Error RequestorProcessUncordonRequiredNodes(ClusterUpgradeState& s) {
+    for (NodeUpgradeState* ns : bucket(s, UST_STATE_UNCORDON_REQUIRED)) {
+      if (!IsNodeInRequestorMode(ns->node)) continue;
+      ChangeNodeUpgradeState(ns, kStateNames[UST_STATE_DONE]);
+      ChangeNodeUpgradeAnnotation(ns, GetUpgradeRequestorModeAnnotationKey(), nullString, UST_A_REQUESTOR_ANNO_CHANGE);
+      rec(ns, UST_A_NM_CREATE_OR_DELETE);  // deleteOrUpdateNodeMaintenance  upgrade_requestor.go:482
+    }
+    return {};
+  }
+  // upgrade_state.go:311-325
+  Error ProcessUncordonRequiredNodesWrapper(ClusterUpgradeState& s) {
+    // In-place first; its nodes keep the snapshot label "uncordon-required" in the bucket, but the
+    // requestor pass only touches nodes carrying the requestor-mode annotation, which the in-place
+    // pass skipped — the two passes are disjoint.
+    Error e = InplaceProcessUncordonRequiredNodes(s);
+    RETURN_IF(e);
+    if (useMaintenanceOperator) e = RequestorProcessUncordonRequiredNodes(s);
+    return e;
+  }
+
+  // upgrade_state.go:171-281. `state == nullptr` mirrors the nil check; pass numbering = call order.
+  Error ApplyState(ClusterUpgradeState* currentState, const DriverUpgradePolicySpec* upgradePolicy) {
+    if (currentState == nullptr) return {UST_ERR_NIL_STATE, -1, -1};
+    if (upgradePolicy == nullptr || !upgradePolicy->autoUpgrade) return {};
+    ClusterUpgradeState& s = *currentState;
+    Error e;
+    auto tag = [&](int pass) { if (e.code && e.pass < 0) e.pass = pass; return e.code != 0; };
+    e = ProcessDoneOrUnknownNodes(s, UST_STATE_UNKNOWN);                       if (tag(0)) return e;
+    e = ProcessDoneOrUnknownNodes(s, UST_STATE_DONE);                          if (tag(1)) return e;
+    e = ProcessUpgradeRequiredNodesWrapper(s, *upgradePolicy);                 if (tag(2)) return e;
+    e = ProcessCordonRequiredNodes(s);                                         if (tag(3)) return e;
+    e = ProcessWaitForJobsRequiredNodes(s, upgradePolicy->waitForCompletion.get());  if (tag(4)) return e;
+    bool drainEnabled = upgradePolicy->drainSpec != nullptr && upgradePolicy->drainSpec->enable;
+    e = ProcessPodDeletionRequiredNodes(s, upgradePolicy->podDeletion.get(), drainEnabled);  if (tag(5)) return e;
+    e = ProcessDrainNodes(s, upgradePolicy->drainSpec.get());                  if (tag(6)) return e;
+    if (useMaintenanceOperator) { e = ProcessNodeMaintenanceRequiredNodes(s); if (tag(7)) return e; }  // upgrade_state.go:299-309
+    e = ProcessPodRestartNodes(s);                                             if (tag(8)) return e;
+    e = ProcessUpgradeFailedNodes(s);                                          if (tag(9)) return e;
+    e = ProcessValidationRequiredNodes(s);                                     if (tag(10)) return e;
+    e = ProcessUncordonRequiredNodesWrapper(s);                                if (tag(11)) return e;
+    return {};
+  }
+};
+
+// ---- SoA <-> object model ------------------------------------------------------------------------
+// Inverse of the host encoder: materialise, for every snapshot entry, objects for which each reference
+// predicate evaluates to the corresponding input bit. Where several object shapes give the same
+// predicate value the shape is varied with the index so that all of them get exercised.
+struct World {
+  std::vector<std::unique_ptr<Node>> nodes;
+  std::vector<std::unique_ptr<Pod>> pods;
+  std::vector<std::unique_ptr<DaemonSet>> daemonSets;
+  std::vector<std::unique_ptr<NodeMaintenance>> nms;
+  std::vector<std::unique_ptr<NodeUpgradeState>> entries;
+  std::vector<std::vector<WorkloadPod>> workload;
+  ClusterUpgradeState state;
+  DriverUpgradePolicySpec policy;
+  Manager mgr;
+  int64_t n = 0;
+};
+
+static const char* phaseName(unsigned code) {
+  switch (code) {
+    case UST_PHASE_PENDING: return "Pending";
+    case UST_PHASE_RUNNING: return "Running";
+    case UST_PHASE_SUCCEEDED: return "Succeeded";
+    case UST_PHASE_FAILED: return "Failed";
+    default: return "Unknown";
+  }
+}
+
+static void buildPolicy(World& w, const ust_policy& p) {
+  DriverUpgradePolicySpec& o = w.policy;
+  o.autoUpgrade = p.auto_upgrade != 0;
+  o.maxParallelUpgrades = p.max_parallel_upgrades;
+  if (p.max_unavailable_kind == UST_MAXUNAVAIL_INT) o.maxUnavailable.reset(new IntOrString{0, p.max_unavailable_value, ""});
+  else if (p.max_unavailable_kind == UST_MAXUNAVAIL_PERCENT)
+    o.maxUnavailable.reset(new IntOrString{1, 0, std::to_string(p.max_unavailable_value) + "%"});
+  else if (p.max_unavailable_kind == UST_MAXUNAVAIL_INVALID) o.maxUnavailable.reset(new IntOrString{1, 0, "twenty-five"});
+  if (p.pod_deletion_spec_present) {
+    o.podDeletion.reset(new PodDeletionSpec());
+    o.podDeletion->force = p.pod_deletion_force != 0;
+    o.podDeletion->deleteEmptyDir = p.pod_deletion_delete_emptydir != 0;
+  }
+  // DrainSpec: nil and {Enable:false} are equivalent on the path (common_manager.go:332); alternate.
+  if (p.drain_enabled || p.drain_force || p.drain_delete_emptydir) {
+    o.drainSpec.reset(new DrainSpec());
+    o.drainSpec->enable = p.drain_enabled != 0;
+    o.drainSpec->force = p.drain_force != 0;
+    o.drainSpec->deleteEmptyDir = p.drain_delete_emptydir != 0;
+  }
+  if (p.wait_selector_set) {
+    o.waitForCompletion.reset(new WaitForCompletionSpec());
+    o.waitForCompletion->podSelector = "app=workload";
+    o.waitForCompletion->timeoutSecond = p.wait_timeout_nonzero ? 30 : 0;
+  } else if (p.wait_timeout_nonzero) {
+    o.waitForCompletion.reset(new WaitForCompletionSpec());  // spec present but empty selector
+    o.waitForCompletion->timeoutSecond = 30;
+  }
+  w.mgr.podDeletionStateEnabled = p.pod_deletion_enabled != 0;
+  w.mgr.validationStateEnabled = p.validation_enabled != 0;
+  w.mgr.useMaintenanceOperator = p.use_maintenance_operator != 0;
+  w.mgr.evaluateActuators = p.evaluate_actuators != 0;
+}
+
+static void buildWorld(World& w, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
+                       const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                       const ust_pods* pods) {
+  w.n = n;
+  if (policy) buildPolicy(w, *policy);
+  w.mgr.actions.assign((size_t)n, 0);
+  w.mgr.outcome.assign((size_t)n, UST_OUTCOME_NONE);
+  for (int32_t d = 0; d < n_ds; d++) {
+    auto ds = std::make_unique<DaemonSet>();
+    ds->revisionHash = "rev-" + std::to_string(ds_rev[d]);
+    w.daemonSets.push_back(std::move(ds));
+  }
+  if (pods) w.workload.resize((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    unsigned hot = state[i];
+    unsigned code = hot & UST_HOT_STATE_MASK;
+    if (code >= UST_STATE_EXCLUDED) continue;  // never entered the snapshot  upgrade_state.go:149-152
+    uint32_t f = flags[i];
+    auto node = std::make_unique<Node>();
+    node->name = "node-" + std::to_string(i);
+    if (code == UST_STATE_UNKNOWN) {
+      if (i & 1) node->labels[GetUpgradeStateLabelKey()] = "";  // label absent and label "" bucket alike
+    } else {
+      node->labels[GetUpgradeStateLabelKey()] = kStateNames[code];
+    }
+    node->unschedulable = (hot & UST_HOT_UNSCHEDULABLE) != 0;
+    if (hot & UST_HOT_NOT_READY) {
+      node->conditions.push_back({"MemoryPressure", "False"});
+      node->conditions.push_back({"Ready", (i % 3 == 0) ? "Unknown" : "False"});
+    } else if (i % 4 != 0) {  // no Ready condition at all also counts as ready (common_manager.go:656-663)
+      node->conditions.push_back({"Ready", "True"});
+      if (i % 4 == 2) node->conditions.push_back({"DiskPressure", "False"});
+    }
+    if (hot & UST_HOT_SKIP) node->labels[GetUpgradeSkipNodeLabelKey()] = trueString;
+    else if (i % 5 == 0) node->labels[GetUpgradeSkipNodeLabelKey()] = "false";
+    if (f & UST_F_UPGRADE_REQUESTED) node->annotations[GetUpgradeRequestedAnnotationKey()] = trueString;
+    else if (i % 7 == 0) node->annotations[GetUpgradeRequestedAnnotationKey()] = "false";
+    if (f & UST_F_SAFE_LOAD) node->annotations[GetUpgradeDriverWaitForSafeLoadAnnotationKey()] = (i & 1) ? "true" : "pending";
+    else if (i % 11 == 0) node->annotations[GetUpgradeDriverWaitForSafeLoadAnnotationKey()] = "";
+    if (f & UST_F_INITIAL_STATE_ANNO) node->annotations[GetUpgradeInitialStateAnnotationKey()] = (i % 3 == 0) ? "" : trueString;
+    if (f & UST_F_REQUESTOR_MODE) node->annotations[GetUpgradeRequestorModeAnnotationKey()] = (i % 3 == 1) ? "false" : trueString;
+    if (f & UST_F_WAIT_START_ANNO)
+      node->annotations[GetWaitForPodCompletionStartTimeAnnotationKey()] = (f & UST_F_WAIT_START_INVALID) ? "not-a-number" : "1700000000";
+
+    auto pod = std::make_unique<Pod>();
+    bool orphan = (f & UST_F_POD_ORPHANED) != 0;
+    bool hashErr = (hot & UST_HOT_REVISION_HASH_ERROR) != 0 && !orphan;
+    DaemonSet* ds = nullptr;
+    if (!orphan) {
+      int32_t d = ds_idx[i];
+      if (d < 0 || d >= n_ds) {
+        // contract violation (non-orphan without DaemonSet): materialise a private one that never matches
+        auto own = std::make_unique<DaemonSet>();
+        own->revisionHash = "rev-none";
+        ds = own.get();
+        w.daemonSets.push_back(std::move(own));
+      } else {
+        ds = w.daemonSets[(size_t)d].get();
+      }
+      if (hashErr && (i & 1)) {
+        // the DaemonSet side of the lookup fails: give this entry a private revision-less DaemonSet
+        auto own = std::make_unique<DaemonSet>();
+        own->revisionMissing = true;
+        ds = own.get();
+        w.daemonSets.push_back(std::move(own));
+        pod->labels["controller-revision-hash"] = "rev-" + std::to_string(pod_rev[i]);
+      } else if (!hashErr) {
+        pod->labels["controller-revision-hash"] = "rev-" + std::to_string(pod_rev[i]);
+      }
+    }
+    if (f & UST_F_POD_READY) {
+      pod->phase = "Running";
+      pod->containerStatuses.push_back({true, (int)(i % 13)});
+      if (i & 1) pod->containerStatuses.push_back({true, 0});
+    } else {
+      switch (i % 3) {
+        case 0: pod->phase = "Pending"; pod->containerStatuses.push_back({true, 0}); break;
+        case 1: pod->phase = "Running"; break;  // zero containers
+        default: pod->phase = "Running"; pod->containerStatuses.push_back({true, 0}); pod->containerStatuses.push_back({false, 3}); break;
+      }
+    }
+    if (f & UST_F_POD_FAILING) {
+      if ((f & UST_F_POD_READY) || (i & 1)) pod->initContainerStatuses.push_back({false, 11});
+      else pod->containerStatuses.push_back({false, 11});  // keeps POD_READY false
+    } else {
+      // near-misses: ready with many restarts, not-ready with exactly 10
+      if (i % 5 == 1) pod->initContainerStatuses.push_back({true, 50});
+      if (i % 5 == 2 && !(f & UST_F_POD_READY)) pod->containerStatuses.push_back({false, 10});
+    }
+    pod->deletionTimestampSet = (f & UST_F_POD_TERMINATING) != 0;
+
+    auto e = std::make_unique<NodeUpgradeState>();
+    e->node = node.get();
+    e->driverPod = pod.get();
+    e->driverDaemonSet = ds;
+    e->index = i;
+    e->validationResult = (f & UST_F_VALIDATION_DONE) != 0;
+    e->waitPodsRunning = (f & UST_F_WAIT_PODS_RUNNING) != 0;
+    e->waitStartInvalid = (f & UST_F_WAIT_START_INVALID) != 0;
+    e->waitTimedOut = (f & UST_F_WAIT_TIMED_OUT) != 0;
+    if (f & UST_F_NM_PRESENT) {
+      auto nm = std::make_unique<NodeMaintenance>();
+      nm->readyConditionWithReasonReady = (f & UST_F_NM_READY) != 0;
+      e->nodeMaintenance = nm.get();
+      w.nms.push_back(std::move(nm));
+    }
+    if (pods) {
+      auto& wl = w.workload[(size_t)i];
+      for (int64_t p = pods->pod_off[i]; p < pods->pod_off[i + 1]; p++) {
+        unsigned pf = pods->pod_flags[p];
+        WorkloadPod wp;
+        wp.phase = phaseName(pf & UST_POD_PHASE_MASK);
+        wp.hasController = (pf & UST_POD_HAS_CONTROLLER) != 0;
+        wp.controllerIsDaemonSet = (pf & UST_POD_CONTROLLED_BY_DS) != 0;
+        wp.daemonSetMissing = (pf & UST_POD_DS_MISSING) != 0;
+        wp.mirror = (pf & UST_POD_MIRROR) != 0;
+        wp.emptyDir = (pf & UST_POD_HAS_EMPTYDIR) != 0;
+        wp.matchDeletionFilter = (pf & UST_POD_MATCH_DELETION_FILTER) != 0;
+        wp.matchWaitSelector = (pf & UST_POD_MATCH_WAIT_SELECTOR) != 0;
+        wp.matchDrainSelector = (pf & UST_POD_MATCH_DRAIN_SELECTOR) != 0;
+        wl.push_back(wp);
+      }
+      e->workload = &wl;
+    }
+    // BuildState bucketing: upgrade_state.go:158-160 (key = label value; absent label => "")
+    auto it = node->labels.find(GetUpgradeStateLabelKey());
+    std::string label = it == node->labels.end() ? "" : it->second;
+    w.state.NodeStates[label].push_back(e.get());
+    w.nodes.push_back(std::move(node));
+    w.pods.push_back(std::move(pod));
+    w.entries.push_back(std::move(e));
+  }
+}
+
+static void fillCounters(World& w, const ust_policy* policy, const uint8_t* state, int64_t n, const Error& err, ust_counters* out) {
+  if (!out) return;
+  std::memset(out, 0, sizeof(*out));
+  for (int c = 0; c < 14; c++) out->hist[c] = (int64_t)Manager::len(w.state, c);
+  // the "other" bucket: every key that is not one of the 13 known names
+  int64_t other = 0;
+  for (const auto& kv : w.state.NodeStates)
+    if (stateCode(kv.first) == UST_STATE_OTHER) other += (int64_t)kv.second.size();
+  out->hist[UST_STATE_OTHER] = other;
+  int64_t excluded = 0, cand = 0;
+  for (int64_t i = 0; i < n; i++) {
+    unsigned code = state[i] & UST_HOT_STATE_MASK;
+    if (code >= UST_STATE_EXCLUDED) excluded++;
+  }
+  out->hist[UST_STATE_EXCLUDED] = excluded;
+  for (const NodeUpgradeState* ns : Manager::bucket(w.state, UST_STATE_UPGRADE_REQUIRED))
+    if (!w.mgr.SkipNodeUpgrade(ns->node)) cand++;
+  out->candidates = cand;
+  out->unavailable = w.mgr.GetCurrentUnavailableNodes(w.state);
+  out->total_managed = w.mgr.GetTotalManagedNodes(w.state);
+  out->in_progress = w.mgr.GetUpgradesInProgress(w.state);
+  bool slots = policy && policy->auto_upgrade && !policy->use_maintenance_operator &&
+               !(err.code && err.pass < 2) && err.code != UST_ERR_MAX_UNAVAILABLE;
+  if (slots) {
+    out->max_unavailable = w.mgr.lastMaxUnavailable;
+    out->upgrades_available = w.mgr.lastAvailable;
+  }
+  out->error_code = err.code;
+  out->error_index = err.code ? err.index : -1;
+  out->error_pass = err.code ? err.pass : -1;
+}
+
+}  // namespace ref
+
+// ================================================================================================
+// SoA scalar variant: the same decisions written directly over the encoded arrays (second,
+// independently written restatement; also the "generous" single-core CPU baseline of BASELINE.md §2).
+// ================================================================================================
+namespace soa {
+
+static const int kPassOf[16] = {0, 2, 3, 4, 5, 6, 7, -1, 8, 10, 11, 1, 9, -1, -1, -1};
+
+struct Scalars { int64_t total, inProgress, unavailable, maxUnavailable, available, cand; };
+
+static int run(const ust_policy* pol, int64_t n, const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev,
+               const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev, const ust_pods* pods, uint8_t* next,
+               uint16_t* actions, uint8_t* outcome, ust_counters* out) {
+  ust_counters c;
+  std::memset(&c, 0, sizeof(c));
+  c.error_index = -1;
+  c.error_pass = -1;
+  for (int64_t i = 0; i < n; i++) {
+    unsigned code = state[i] & 15u;
+    if (code == 15) code = 14;
+    next[i] = (uint8_t)(state[i] & 15u);
+    actions[i] = 0;
+    if (outcome) outcome[i] = UST_OUTCOME_NONE;
+    c.hist[code]++;
+    if (code >= 14) continue;
+    if (state[i] & (UST_HOT_UNSCHEDULABLE | UST_HOT_NOT_READY)) c.unavailable++;
+    if (code == 1 && !(state[i] & UST_HOT_SKIP)) c.candidates++;
+  }
+  c.total_managed = c.hist[0] + c.hist[1] + c.hist[2] + c.hist[3] + c.hist[4] + c.hist[5] + c.hist[8] + c.hist[9] +
+                    c.hist[10] + c.hist[11] + c.hist[12];
+  c.in_progress = c.total_managed - c.hist[0] - c.hist[11] - c.hist[1];
+  if (!pol || !pol->auto_upgrade) { if (out) *out = c; return UST_OK; }
+
+  // abort point (pass, index) in the reference's sequential order
+  int errPass = 99; int64_t errIdx = -1; int errCode = 0;
+  auto consider = [&](int pass, int64_t idx, int code) {
+    if (pass < errPass || (pass == errPass && idx < errIdx)) { errPass = pass; errIdx = idx; errCode = code; }
+  };
+  for (int64_t i = 0; i < n; i++) {
+    unsigned code = state[i] & 15u;
+    if ((state[i] & UST_HOT_REVISION_HASH_ERROR) && !(flags[i] & UST_F_POD_ORPHANED) &&
+        (code == 0 || code == 11 || code == 8 || code == 12))
+      consider(kPassOf[code], i, UST_ERR_REVISION_HASH);
+  }
+  int64_t avail = 0;
+  if (!pol->use_maintenance_operator) {
+    if (pol->max_unavailable_kind == UST_MAXUNAVAIL_INVALID) consider(2, -1, UST_ERR_MAX_UNAVAILABLE);
+    int64_t maxUnav = c.total_managed;
+    if (pol->max_unavailable_kind == UST_MAXUNAVAIL_INT) maxUnav = pol->max_unavailable_value;
+    else if (pol->max_unavailable_kind == UST_MAXUNAVAIL_PERCENT) {
+      volatile double prod = (double)pol->max_unavailable_value * (double)c.total_managed;
+      volatile double q = prod / 100.0;
+      maxUnav = (int64_t)std::ceil(q);
+    }
+    avail = pol->max_parallel_upgrades == 0 ? c.hist[1] : pol->max_parallel_upgrades - c.in_progress;
+    int64_t curUnav = c.unavailable + c.hist[2];
+    if (avail > maxUnav) avail = maxUnav;
+    if (curUnav >= maxUnav) avail = 0;
+    else if (maxUnav < c.total_managed && curUnav + avail > maxUnav) avail = maxUnav - curUnav;
+    if (!(errCode && errPass < 2) && pol->max_unavailable_kind != UST_MAXUNAVAIL_INVALID) {
+      c.max_unavailable = maxUnav;
+      c.upgrades_available = avail;
+    }
+  }
+  if (pol->pod_deletion_enabled && !pol->pod_deletion_spec_present && c.hist[4] > 0) consider(5, -1, UST_ERR_POD_DELETION_SPEC);
+
+  int64_t rank = 0;
+  for (int64_t i = 0; i < n; i++) {
+    unsigned hot = state[i], s = hot & 15u;
+    uint32_t f = flags[i];
+    if (s >= 13) continue;
+    int pass = kPassOf[s];
+    if (pass < 0) continue;
+    if (s == 6 && !pol->use_maintenance_operator) continue;
+    if (errCode) {
+      if (pass > errPass || (pass == errPass && i >= errIdx)) {
+        if (pass == errPass && i == errIdx) actions[i] = UST_A_ERROR;
+        if (s == 1 && !(hot & UST_HOT_SKIP)) rank++;
+        continue;
+      }
+    }
+    bool orphan = f & UST_F_POD_ORPHANED;
+    bool synced = false;
+    if (!orphan) {
+      int32_t d = ds_idx[i];
+      synced = d >= 0 && d < n_ds && pod_rev[i] == ds_rev[d];
+    }
+    bool unsched = hot & UST_HOT_UNSCHEDULABLE;
+    unsigned a = 0, nx = s;
+    auto uncordonOrDone = [&]() {
+      nx = 10;
+      bool rq = f & UST_F_REQUESTOR_MODE;
+      if ((f & UST_F_INITIAL_STATE_ANNO) && !rq) nx = 11;
+      if (nx == 11 || rq) a |= UST_A_CLEAR_INITIAL_STATE_ANNO;
+    };
+    switch (s) {
+      case 0: case 11: {
+        bool need = (!synced && !orphan) || (f & UST_F_SAFE_LOAD) || (f & UST_F_UPGRADE_REQUESTED);
+        if (need) { if (unsched) a |= UST_A_SET_INITIAL_STATE_ANNO; nx = 1; }
+        else if (s == 0) nx = 11;
+      } break;
+      case 1: {
+        if (f & UST_F_UPGRADE_REQUESTED) a |= UST_A_CLEAR_UPGRADE_REQUESTED;
+        if (hot & UST_HOT_SKIP) break;
+        if (pol->use_maintenance_operator) { a |= UST_A_NM_CREATE_OR_DELETE | UST_A_REQUESTOR_ANNO_CHANGE; nx = 6; break; }
+        bool granted = rank < (avail > 0 ? avail : 0);
+        rank++;
+        if (granted || unsched) nx = 2;
+      } break;
+      case 2: a |= UST_A_CORDON; nx = 3; break;
+      case 3:
+        if (!pol->wait_selector_set) nx = pol->pod_deletion_enabled ? 4 : 5;
+        else {
+          a |= UST_A_SCHEDULE_WAIT_CHECK;
+          if (pol->evaluate_actuators) {
+            bool running = f & UST_F_WAIT_PODS_RUNNING;
+            if (pods) {
+              running = false;
+              for (int64_t p = pods->pod_off[i]; p < pods->pod_off[i + 1]; p++) {
+                unsigned pf = pods->pod_flags[p];
+                if (!(pf & UST_POD_MATCH_WAIT_SELECTOR)) continue;
+                unsigned ph = pf & UST_POD_PHASE_MASK;
+                if (ph == UST_PHASE_RUNNING || ph == UST_PHASE_PENDING) { running = true; break; }
+              }
+            }
+            uint8_t oc = 3;
+            if (running) {
+              if (pol->wait_timeout_nonzero) {
+                if (!(f & UST_F_WAIT_START_ANNO)) a |= UST_A_SET_WAIT_START;
+                else if (f & UST_F_WAIT_START_INVALID) {}
+                else if (f & UST_F_WAIT_TIMED_OUT) { oc = 4; a |= UST_A_CLEAR_WAIT_START; }
+              }
+            } else { a |= UST_A_CLEAR_WAIT_START; oc = 4; }
+            if (outcome) outcome[i] = oc;
+          }
+        }
+        break;
+      case 4:
+        if (!pol->pod_deletion_enabled) nx = 5;
+        else {
+          a |= UST_A_SCHEDULE_POD_EVICTION;
+          if (pol->evaluate_actuators && outcome) {
+            int toDelete = 0, canDelete = 0;
+            if (pods)
+              for (int64_t p = pods->pod_off[i]; p < pods->pod_off[i + 1]; p++) {
+                unsigned pf = pods->pod_flags[p];
+                if (!(pf & UST_POD_MATCH_DELETION_FILTER)) continue;
+                toDelete++;
+                unsigned ph = pf & UST_POD_PHASE_MASK;
+                bool fin = ph == UST_PHASE_SUCCEEDED || ph == UST_PHASE_FAILED;
+                bool ok = true;
+                if ((pf & UST_POD_HAS_CONTROLLER) && (pf & UST_POD_CONTROLLED_BY_DS) && !fin) {
+                  if (pf & UST_POD_DS_MISSING) { if (!pol->pod_deletion_force) ok = false; }
+                  else ok = false;
+                }
+                if (ok && (pf & UST_POD_MIRROR)) ok = false;
+                if (ok && (pf & UST_POD_HAS_EMPTYDIR) && !fin && !pol->pod_deletion_delete_emptydir) ok = false;
+                if (ok && !fin && !(pf & UST_POD_HAS_CONTROLLER) && !pol->pod_deletion_force) ok = false;
+                if (ok) canDelete++;
+              }
+            if (toDelete == 0) outcome[i] = 8;
+            else if (canDelete != toDelete) outcome[i] = pol->drain_enabled ? 5 : 12;
+            else outcome[i] = 8;
+          }
+        }
+        break;
+      case 5:
+        if (!pol->drain_enabled) nx = 8;
+        else {
+          a |= UST_A_SCHEDULE_DRAIN;
+          if (pol->evaluate_actuators && outcome) {
+            bool anyErr = false;
+            if (pods)
+              for (int64_t p = pods->pod_off[i]; p < pods->pod_off[i + 1]; p++) {
+                unsigned pf = pods->pod_flags[p];
+                if (!(pf & UST_POD_MATCH_DRAIN_SELECTOR)) continue;
+                unsigned ph = pf & UST_POD_PHASE_MASK;
+                bool fin = ph == UST_PHASE_SUCCEEDED || ph == UST_PHASE_FAILED;
+                if ((pf & UST_POD_HAS_CONTROLLER) && (pf & UST_POD_CONTROLLED_BY_DS) && !fin) {
+                  if (pf & UST_POD_DS_MISSING) { if (!pol->drain_force) { anyErr = true; continue; } }
+                  else continue;  // skipped with a warning
+                }
+                if (pf & UST_POD_MIRROR) continue;
+                if ((pf & UST_POD_HAS_EMPTYDIR) && !fin && !pol->drain_delete_emptydir) { anyErr = true; continue; }
+                if (!fin && !(pf & UST_POD_HAS_CONTROLLER) && !pol->drain_force) { anyErr = true; continue; }
+              }
+            outcome[i] = anyErr ? 12 : 8;
+          }
+        }
+        break;
+      case 6:
+        if (!(f & UST_F_NM_PRESENT)) nx = 1;
+        else if (f & UST_F_NM_READY) nx = 8;
+        break;
+      case 8:
+        if (!synced || orphan) {
+          if (!(f & UST_F_POD_TERMINATING)) {
+            // SchedulePodsRestart runs after the loop; an abort inside this pass drops it
+            if (!(errCode && errPass == 8)) a |= UST_A_RESTART_DRIVER_POD;
+          }
+        } else {
+          if (f & UST_F_SAFE_LOAD) a |= UST_A_UNBLOCK_SAFE_LOAD;
+          if (f & UST_F_POD_READY) { if (!pol->validation_enabled) uncordonOrDone(); else nx = 9; }
+          else if (f & UST_F_POD_FAILING) nx = 12;
+        }
+        break;
+      case 12:
+        if (!orphan && synced && (f & UST_F_POD_READY)) {
+          if (f & UST_F_INITIAL_STATE_ANNO) { nx = 11; a |= UST_A_CLEAR_INITIAL_STATE_ANNO; } else nx = 10;
+        }
+        break;
+      case 9:
+        if (f & UST_F_SAFE_LOAD) a |= UST_A_UNBLOCK_SAFE_LOAD;
+        if (f & UST_F_VALIDATION_DONE) uncordonOrDone();
+        break;
+      case 10:
+        if (!(f & UST_F_REQUESTOR_MODE)) { a |= UST_A_UNCORDON; nx = 11; }
+        else if (pol->use_maintenance_operator) { nx = 11; a |= UST_A_REQUESTOR_ANNO_CHANGE | UST_A_NM_CREATE_OR_DELETE; }
+        break;
+      default: break;
+    }
+    if (nx != s) a |= UST_A_SET_STATE;
+    next[i] = (uint8_t)nx;
+    actions[i] = (uint16_t)a;
+  }
+  c.error_code = errCode;
+  c.error_index = errCode ? errIdx : -1;
+  c.error_pass = errCode ? errPass : -1;
+  if (out) *out = c;
+  return errCode;
+}
+
+}  // namespace soa
+
+// ================================================================================================
+// C entry points (ctypes)
+// ================================================================================================
+extern "C" {
+
+// variant 0: reference-shaped object model; variant 1: SoA scalar loop.
+int ust_oracle_apply_state(int variant, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
+                           const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                           const ust_pods* pods, uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome,
+                           ust_counters* out) {
+  if (n < 0 || (n > 0 && (!state || !flags || !pod_rev || !ds_idx || !next_state || !actions))) return UST_ERR_INVALID_ARGUMENT;
+  if (variant == 1) return soa::run(policy, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, pods, next_state, actions, actuator_outcome, out);
+  ref::World w;
+  ref::buildWorld(w, policy, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, pods);
+  ref::Error err = w.mgr.ApplyState(&w.state, policy ? &w.policy : nullptr);
+  if (err.code && err.index >= 0) w.mgr.actions[(size_t)err.index] |= UST_A_ERROR;
+  // read the result back off the objects
+  for (int64_t i = 0; i < n; i++) {
+    next_state[i] = (uint8_t)(state[i] & UST_HOT_STATE_MASK);
+    actions[i] = 0;
+    if (actuator_outcome) actuator_outcome[i] = UST_OUTCOME_NONE;
+  }
+  for (const auto& e : w.entries) {
+    auto it = e->node->labels.find(ref::GetUpgradeStateLabelKey());
+    std::string label = it == e->node->labels.end() ? "" : it->second;
+    int code = ref::stateCode(label);
+    next_state[e->index] = (uint8_t)code;
+    actions[e->index] = w.mgr.actions[(size_t)e->index];
+    if (actuator_outcome) actuator_outcome[e->index] = w.mgr.outcome[(size_t)e->index];
+  }
+  ref::fillCounters(w, policy, state, n, err, out);
+  return err.code;
+}
+
+// Time `reps` ApplyState passes of the reference-shaped variant over a snapshot (objects are rebuilt,
+// untimed, before every pass because ApplyState mutates them). Returns the median seconds per pass.
+double ust_oracle_time_apply_state(int variant, const ust_policy* policy, int64_t n, const uint8_t* state,
+                                   const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds,
+                                   const int32_t* ds_rev, const ust_pods* pods, int reps) {
+  std::vector<double> t;
+  std::vector<uint8_t> nx((size_t)n), oc((size_t)n);
+  std::vector<uint16_t> ac((size_t)n);
+  for (int r = 0; r < reps; r++) {
+    if (variant == 1) {
+      auto t0 = std::chrono::steady_clock::now();
+      soa::run(policy, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, pods, nx.data(), ac.data(), oc.data(), nullptr);
+      auto t1 = std::chrono::steady_clock::now();
+      t.push_back(std::chrono::duration<double>(t1 - t0).count());
+    } else {
+      ref::World w;
+      ref::buildWorld(w, policy, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, pods);
+      auto t0 = std::chrono::steady_clock::now();
+      ref::Error err = w.mgr.ApplyState(&w.state, policy ? &w.policy : nullptr);
+      auto t1 = std::chrono::steady_clock::now();
+      (void)err;
+      t.push_back(std::chrono::duration<double>(t1 - t0).count());
+    }
+  }
+  std::sort(t.begin(), t.end());
+  return t.empty() ? 0.0 : t[t.size() / 2];
+}
+
+// intstr scaling exposed for the known-answer tests (upgrade_state_test.go:384-513)
+int ust_oracle_scaled_value(int is_percent, int64_t value, int64_t total, int64_t* out) {
+  ref::IntOrString v{is_percent ? 1 : 0, value, is_percent ? std::to_string(value) + "%" : ""};
+  return ref::GetScaledValueFromIntOrPercent(v, total, true, out) ? 0 : -1;
+}
+
+// BuildState restatement (upgrade_state.go:99-164) over per-pod arrays: per-DaemonSet owned-pod count
+// vs DesiredNumberScheduled (:128-131), then bucket sizes of the pods that survive the pending-skip.
+int ust_oracle_build_state(int64_t n_pods, const uint8_t* state, const int32_t* ds_idx, int32_t n_ds,
+                           const int32_t* ds_desired, ust_counters* out) {
+  std::vector<int64_t> owned((size_t)std::max(n_ds, 0), 0);
+  ust_counters c;
+  std::memset(&c, 0, sizeof(c));
+  c.error_index = -1;
+  c.error_pass = -1;
+  for (int64_t i = 0; i < n_pods; i++) {
+    int32_t d = ds_idx[i];
+    if (d >= 0 && d < n_ds) owned[(size_t)d]++;  // GetPodsOwnedbyDs  common_manager.go:190-208
+    unsigned code = state[i] & 15u;
+    if (code == 15) code = 14;
+    c.hist[code]++;
+    if (code < 14 && (state[i] & (UST_HOT_UNSCHEDULABLE | UST_HOT_NOT_READY))) c.unavailable++;
+    if (code == 1 && !(state[i] & UST_HOT_SKIP)) c.candidates++;
+  }
+  c.total_managed = c.hist[0] + c.hist[1] + c.hist[2] + c.hist[3] + c.hist[4] + c.hist[5] + c.hist[8] + c.hist[9] +
+                    c.hist[10] + c.hist[11] + c.hist[12];
+  c.in_progress = c.total_managed - c.hist[0] - c.hist[11] - c.hist[1];
+  int rc = UST_OK;
+  for (int32_t d = 0; d < n_ds; d++)
+    if ((int64_t)ds_desired[d] != owned[(size_t)d]) { rc = UST_ERR_DS_UNSCHEDULED; c.error_code = rc; c.error_index = d; break; }
+  if (out) *out = c;
+  return rc;
+}
+
+}  // extern "C"
