@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py — node state-transitions/s of ApplyState on B200 (BASELINE.json metric).
+
+A "step" is one ApplyState pass over one synthetic cluster snapshot. Workload at N=1: BASELINE config C3
+(10 M nodes, MaxParallelUpgrades=100, MaxUnavailable=25%). At N>1 every rank holds one 10 M-node contiguous
+shard of an N x 10 M-node cluster (config C5 at N=8): weak scaling, one exchange of the constraint counters
+per step.
+
+  value      device-resident inputs, CUDA-event time of K steps, max over ranks, whole-job nodes/s
+  e2e        the same step through the host-pointer C ABI (ust_apply_state): pinned host arrays in,
+             H2D + kernel + D2H inside the timed region
+  roofline   dominant kernel (ust_fused_kernel): 16 algorithmic bytes per node / its CUDA-event duration,
+             against the measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline / --impl reference   the oracle's reference-shaped restatement of the Go loop (1 thread —
+             the reference's ApplyState is strictly sequential), bounded sample of the same workload
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "k8s-operator-libs_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+BYTES_PER_NODE = 16  # state 1 + flags 4 + pod_rev 4 + ds_idx 4 read, next_state 1 + actions 2 written
+SHARD_NODES = 10_000_000
+CPU_SAMPLE_NODES = 1_000_000
+L2_BYTES = 126 * 1024 * 1024
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(policy, soa, reps):
+    """Reference-shaped oracle (ApplyState only, objects built untimed) on one host thread. nodes/s."""
+    import helpers
+    n = int(soa["state"].shape[0])
+    sec = helpers.oracle().ust_oracle_time_apply_state(
+        C.c_int(0), C.byref(policy), C.c_int64(n), soa["state"].ctypes.data_as(C.c_void_p),
+        soa["flags"].ctypes.data_as(C.c_void_p), soa["pod_rev"].ctypes.data_as(C.c_void_p),
+        soa["ds_idx"].ctypes.data_as(C.c_void_p), C.c_int32(int(soa["ds_rev"].shape[0])),
+        soa["ds_rev"].ctypes.data_as(C.c_void_p), None, C.c_int(reps))
+    return n / sec, sec
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own (sequential, CPU) ApplyState, represented by the oracle's
+    reference-shaped restatement — Go is not installed here or on the GPU box."""
+    if rank != 0:
+        return
+    from ust import synth
+    cfg = synth.CONFIGS["C3" if world == 1 else "C5"]
+    pol = synth.config_policy("C3")
+    soa = synth.make_nodes(CPU_SAMPLE_NODES, cfg["seed"])
+    cpu_reference_rate(pol, soa, max(1, min(args.warmup, 1)))
+    t0 = time.time()
+    rate, sec = cpu_reference_rate(pol, soa, max(1, args.steps))
+    sample = f"first {CPU_SAMPLE_NODES} nodes of the workload, {max(1, args.steps)} ApplyState passes, median"
+    line = {
+        "impl": "reference", "metric": "node state-transitions/sec", "value": rate, "unit": "nodes/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32", "data": "synthetic",
+        "config": {"workload": workload_name(world), "sample_nodes": CPU_SAMPLE_NODES},
+        "cpu_baseline": {"value": rate, "unit": "nodes/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(world):
+    if world == 1:
+        return "C3: 10M-node synthetic cluster, MaxParallelUpgrades=100, MaxUnavailable=25%, 1xB200"
+    return (f"C5-style: {world}x10M-node contiguous shards ({world * 10}M nodes), MaxParallelUpgrades=100, "
+            f"MaxUnavailable=25%, one exchange of the constraint counters per ApplyState")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ust", choices=["ust", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--nodes", type=int, default=SHARD_NODES, help="nodes per GPU (default: the BASELINE workload)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ust import abi, lib as ustlib, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libust.so has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    warmup = max(args.warmup, 3)
+    n = args.nodes
+    cfg = synth.CONFIGS["C3" if world == 1 else "C5"]
+    pol = synth.config_policy("C3")
+    soa = synth.make_nodes(n, cfg["seed"], start=rank * n)
+    n_ds = int(soa["ds_rev"].shape[0])
+
+    h = ustlib.Handle(local_rank)
+    if world > 1:
+        uid = [ustlib.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(rank, world, uid[0])
+
+    # two rotating buffer sets (2 x 160 MB): consecutive steps never find their inputs in the 126 MB L2
+    SETS = 2
+    bufs = []
+    for _ in range(SETS):
+        d = {k: torch.from_numpy(v).to(dev) for k, v in soa.items()}
+        d["next"] = torch.empty(n, dtype=torch.uint8, device=dev)
+        d["actions"] = torch.empty(n, dtype=torch.int16, device=dev)
+        bufs.append(d)
+    counters = torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i):
+        b = bufs[i % SETS]
+        h.apply_state_device(pol, n, b["state"].data_ptr(), b["flags"].data_ptr(), b["pod_rev"].data_ptr(),
+                             b["ds_idx"].data_ptr(), n_ds, b["ds_rev"].data_ptr(), b["next"].data_ptr(),
+                             b["actions"].data_ptr(), counters=counters.data_ptr(), stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = h.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    for i in range(args.steps):
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    barrier()
+    t_wall = time.time() - t_wall0
+    launches = h.launch_count() - launches0
+    total_ms = ev[0][0].elapsed_time(ev[-1][1])
+    per_step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    clocks = sampler.stop()
+
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    value = world * n * args.steps / (total_ms * 1e-3)
+
+    # verify the outputs of the timed buffers (rank-local properties; full parity lives in tests/)
+    cnt = abi.Counters.from_buffer_copy(counters.cpu().numpy().tobytes()).as_dict()
+    nxt = bufs[0]["next"].cpu().numpy()
+    code = soa["state"] & 15
+    assert cnt["error_code"] == 0
+    assert cnt["total_managed"] == world * n or world > 1
+    assert np.array_equal(nxt[code == 2], np.full(int((code == 2).sum()), 3, np.uint8)), "cordon-required -> wait-for-jobs"
+
+    line = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        kern_ms = float(np.median(per_step_ms))
+        achieved = BYTES_PER_NODE * n / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "node state-transitions/sec", "value": value, "unit": "nodes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32", "data": "synthetic",
+            "config": {"workload": workload_name(world), "nodes_per_gpu": n, "bytes_per_node": BYTES_PER_NODE,
+                       "l2": f"{SETS} rotating buffer sets of {BYTES_PER_NODE * n / 1e6:.0f} MB each (> 126 MB L2 together)",
+                       "exchange": "none" if world == 1 else "ncclAllReduce of 42 int64 lanes between two kernels"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "ust_fused_kernel" if world == 1 else "ust_phase2_kernel",
+                         "kernel_ms": kern_ms, "frac_of_8TBs": achieved / 8000.0},
+            "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
+            "counters": {k: cnt[k] for k in ("total_managed", "in_progress", "unavailable", "max_unavailable", "upgrades_available")},
+        }
+
+    # ---- e2e: host-pointer C ABI with pinned host buffers, H2D + kernel + D2H inside the timed region ----
+    host = {k: ustlib.pinned_array(v.shape, v.dtype) for k, v in soa.items()}
+    for k in soa:
+        host[k][...] = soa[k]
+    out = (ustlib.pinned_array(n, np.uint8), ustlib.pinned_array(n, np.uint16), None)
+    for _ in range(2):
+        h.apply_state(pol, host, want_outcome=False, out=out, check=True)
+    barrier()
+    t0 = time.time()
+    for _ in range(args.e2e_steps):
+        h.apply_state(pol, host, want_outcome=False, out=out, check=True)
+    barrier()
+    e2e_s = time.time() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.e2e_steps / float(te.item())
+    assert np.array_equal(out[0], nxt), "e2e result differs from the device-resident result"
+
+    if rank == 0:
+        line["e2e"] = {"value": e2e_value, "unit": "nodes/s", "h2d_bytes_per_step": 13 * n + 4 * n_ds,
+                       "d2h_bytes_per_step": 3 * n + C.sizeof(abi.Counters), "steps": args.e2e_steps,
+                       "ms_per_step": float(te.item()) / args.e2e_steps * 1e3}
+        # ---- CPU baseline beside it: bounded sample, 1 thread (the reference loop is sequential) ----
+        m = min(CPU_SAMPLE_NODES, n)
+        sample = {k: (v[:m].copy() if k != "ds_rev" else v) for k, v in soa.items()}
+        rate, sec = cpu_reference_rate(pol, sample, 3)
+        line["cpu_baseline"] = {"value": rate, "unit": "nodes/s", "cores": 1, "kind": "port",
+                                "sample": f"first {m} nodes of the workload, ApplyState only, median of 3 passes "
+                                          f"({sec:.2f} s each), reference-shaped oracle (Go unavailable)"}
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -68,24 +68,27 @@ enum {
 
 /* ------------------------------------------------------------------------------------------------
  * flags[i] (uint32): one bit per reference predicate on the node / its driver pod.
- * Bits 0-2, 7 and 8 are reserved for values the kernel derives itself and are ignored on input.
+ * Bits 0-4, 9, 10 and 22-31 are reserved for values the kernel derives itself (skip / unschedulable
+ * from the hot byte, slot grant, pod-in-sync, pod-list summaries) and are ignored on input. The
+ * positions are chosen so that the bits each state's transition reads are contiguous (the kernel
+ * indexes a per-state table with a 9-bit window of this word).
  * ---------------------------------------------------------------------------------------------- */
-#define UST_F_UPGRADE_REQUESTED (1u << 3)  /* annotation ...-driver-upgrade-requested == "true"  common_manager.go:323-325 */
-#define UST_F_VALIDATION_DONE (1u << 4)    /* ValidationManager.Validate() == true               common_manager.go:587-596 */
-#define UST_F_SAFE_LOAD (1u << 5)          /* annotation ...driver-wait-for-safe-load != ""      safe_driver_load_manager.go:51-53 */
-#define UST_F_POD_ORPHANED (1u << 6)       /* DriverDaemonSet == nil                             common_manager.go:66-68 */
-#define UST_F_POD_READY (1u << 9)          /* Phase==Running && len(ContainerStatuses)!=0 && all Ready   common_manager.go:617-630 */
-#define UST_F_INITIAL_STATE_ANNO (1u << 10) /* annotation ...node-initial-state.unschedulable PRESENT    common_manager.go:545, :680 */
-#define UST_F_REQUESTOR_MODE (1u << 11)    /* annotation ...-driver-upgrade-requestor-mode PRESENT       util.go:135-138 */
-#define UST_F_POD_TERMINATING (1u << 12)   /* !DriverPod.DeletionTimestamp.IsZero()              common_manager.go:472 */
-#define UST_F_POD_FAILING (1u << 13)       /* some (init)container !Ready && RestartCount > 10   common_manager.go:636-648 */
-#define UST_F_WAIT_PODS_RUNNING (1u << 14) /* a wait-selector pod is Running or Pending          pod_manager.go:278-284, :371-391 */
-#define UST_F_WAIT_START_ANNO (1u << 15)   /* annotation ...wait-for-pod-completion-start-time PRESENT   pod_manager.go:336 */
-#define UST_F_WAIT_TIMED_OUT (1u << 16)    /* now > start + timeout                              pod_manager.go:354 */
-#define UST_F_WAIT_START_INVALID (1u << 17) /* start-time annotation does not parse as int64     pod_manager.go:348-353 */
-#define UST_F_NM_PRESENT (1u << 18)        /* NodeUpgradeState.NodeMaintenance != nil            upgrade_requestor.go:420 */
-#define UST_F_NM_READY (1u << 19)          /* NodeMaintenance Ready condition with Reason Ready  upgrade_requestor.go:437-439 */
-#define UST_F_INPUT_MASK 0x000FFE78u
+#define UST_F_UPGRADE_REQUESTED (1u << 5)  /* annotation ...-driver-upgrade-requested == "true"  common_manager.go:323-325 */
+#define UST_F_VALIDATION_DONE (1u << 6)    /* ValidationManager.Validate() == true               common_manager.go:587-596 */
+#define UST_F_SAFE_LOAD (1u << 7)          /* annotation ...driver-wait-for-safe-load != ""      safe_driver_load_manager.go:51-53 */
+#define UST_F_POD_ORPHANED (1u << 8)       /* DriverDaemonSet == nil                             common_manager.go:66-68 */
+#define UST_F_POD_READY (1u << 11)         /* Phase==Running && len(ContainerStatuses)!=0 && all Ready   common_manager.go:617-630 */
+#define UST_F_INITIAL_STATE_ANNO (1u << 12) /* annotation ...node-initial-state.unschedulable PRESENT    common_manager.go:545, :680 */
+#define UST_F_REQUESTOR_MODE (1u << 13)    /* annotation ...-driver-upgrade-requestor-mode PRESENT       util.go:135-138 */
+#define UST_F_POD_TERMINATING (1u << 14)   /* !DriverPod.DeletionTimestamp.IsZero()              common_manager.go:472 */
+#define UST_F_POD_FAILING (1u << 15)       /* some (init)container !Ready && RestartCount > 10   common_manager.go:636-648 */
+#define UST_F_WAIT_PODS_RUNNING (1u << 16) /* a wait-selector pod is Running or Pending          pod_manager.go:278-284, :371-391 */
+#define UST_F_WAIT_START_ANNO (1u << 17)   /* annotation ...wait-for-pod-completion-start-time PRESENT   pod_manager.go:336 */
+#define UST_F_WAIT_TIMED_OUT (1u << 18)    /* now > start + timeout                              pod_manager.go:354 */
+#define UST_F_WAIT_START_INVALID (1u << 19) /* start-time annotation does not parse as int64     pod_manager.go:348-353 */
+#define UST_F_NM_PRESENT (1u << 20)        /* NodeUpgradeState.NodeMaintenance != nil            upgrade_requestor.go:420 */
+#define UST_F_NM_READY (1u << 21)          /* NodeMaintenance Ready condition with Reason Ready  upgrade_requestor.go:437-439 */
+#define UST_F_INPUT_MASK 0x003FF9E0u
 
 /* ------------------------------------------------------------------------------------------------
  * pod_flags[p] (uint16): one entry per workload pod of a node (CSR by pod_off), used to evaluate
@@ -245,6 +248,17 @@ int ust_sync(ust_handle* h);
  * when some DaemonSet's count differs (counters->error_index = that DaemonSet's index). */
 int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const int32_t* ds_idx,
                     int32_t n_ds, const int32_t* ds_desired, ust_counters* out);
+
+/* ---- introspection ----------------------------------------------------------------------------- */
+
+/* The kernel evaluates a node by one lookup in a per-policy table indexed by (state code, 9-bit window
+ * of the node's predicate word w = flags | derived bits). These two calls expose that table (host side,
+ * no device needed) so that it can be audited entry by entry:
+ *   ust_table_entry: bits 0-15 actions, 16-23 next state, 24-31 actuator outcome (0xFF = none) for a
+ *   node in state `state_code` whose predicate word is `w` (only the bits of the state's window matter);
+ *   ust_table_window_shift: first bit of the window that state reads. */
+uint32_t ust_table_entry(const ust_policy* policy, unsigned state_code, uint32_t w);
+int ust_table_window_shift(unsigned state_code);
 
 /* ---- multi-GPU (one process per GPU) ----------------------------------------------------------- */
 

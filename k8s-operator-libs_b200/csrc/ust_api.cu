@@ -1,0 +1,500 @@
+// ust_api.cu — host side of libust.so: the C ABI of include/ust.h over the kernels of ust_kernels.cu.
+// No node is ever evaluated on the CPU here; without an sm_100 device every computing call fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only; the library is resolved with dlopen when ust_comm_init is called
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "ust_dev.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string* err) {
+    if (lib) return true;
+    // prefer a copy already mapped into the process (e.g. the one PyTorch ships), then the system one
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);
+      if (lib) break;
+    }
+    for (const char* n : names) {
+      if (lib) break;
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!lib) { *err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { *err = "libnccl lacks required symbols"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = cap ? cap : 1024;
+    while (want < n) want += want / 2 + 1024;  // geometric growth
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p) cudaFree(p);
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct ust_handle {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::string err;
+  int64_t launches = 0;
+  int ctas_per_sm = 0, num_sms = 0;
+  bool ws_dirty = false;
+
+  UstWorkspace* ws = nullptr;
+  uint32_t* lut_dev = nullptr;      // UST_LUT_ENTRIES + 32 words
+  uint8_t* podlut_dev = nullptr;
+  uint32_t* lut_host = nullptr;     // pinned staging copy
+  uint8_t* podlut_host = nullptr;   // pinned
+  ust_policy lut_policy;            // policy the device tables were built for
+  bool lut_valid = false;
+  ust_counters* counters_dev = nullptr;
+  ust_counters* counters_host = nullptr;  // pinned
+  long long* xchg_dev = nullptr;
+  unsigned long long* ds_count_dev = nullptr;
+  size_t ds_count_cap = 0;
+
+  // staging for the host-pointer API
+  DevBuf<uint8_t> s_hot, s_next, s_outcome;
+  DevBuf<uint32_t> s_flags;
+  DevBuf<int32_t> s_rev, s_ds, s_dsrev, s_podoff, s_dsdesired;
+  DevBuf<uint16_t> s_actions, s_podflags;
+
+  // multi-GPU
+  int rank = 0, world = 1, comm_mode = 0;
+  ncclComm_t comm = nullptr;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define UST_CUDA(h, call)                                                                                   \
+  do {                                                                                                      \
+    cudaError_t e_ = (call);                                                                                \
+    if (e_ != cudaSuccess) return (h)->fail(UST_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static bool policy_active(const ust_policy* p) { return p != nullptr && p->auto_upgrade != 0; }
+
+// tables depend on these fields only
+static ust_policy table_key(const ust_policy* p) {
+  ust_policy k;
+  memset(&k, 0, sizeof(k));
+  if (!policy_active(p)) return k;  // all-noop tables
+  k = *p;
+  k.max_parallel_upgrades = 0;
+  k.max_unavailable_kind = 0;
+  k.max_unavailable_value = 0;
+  return k;
+}
+
+static int ensure_tables(ust_handle* h, const ust_policy* p, cudaStream_t st) {
+  const ust_policy key = table_key(p);
+  if (h->lut_valid && memcmp(&key, &h->lut_policy, sizeof(key)) == 0) return UST_OK;
+  UST_CUDA(h, cudaStreamSynchronize(st));  // the pinned staging copy may still be in flight
+  if (policy_active(p)) {
+    ust_build_lut(&key, h->lut_host);
+    ust_build_pod_lut(&key, h->podlut_host);
+  } else {
+    for (unsigned s = 0; s < 16; s++)
+      for (unsigned k = 0; k < UST_LUT_WINDOW; k++) h->lut_host[s * UST_LUT_WINDOW + k] = ust_lut_pack(s, s, 0, 0xFF);
+    memset(h->podlut_host, 0, UST_PODLUT_ENTRIES);
+  }
+  for (unsigned s = 0; s < 16; s++) {
+    h->lut_host[UST_LUT_ENTRIES + 2 * s] = (uint32_t)(ust_window_shift[s] - 2);
+    h->lut_host[UST_LUT_ENTRIES + 2 * s + 1] = s * UST_LUT_WINDOW * 4u;
+  }
+  UST_CUDA(h, cudaMemcpyAsync(h->lut_dev, h->lut_host, (UST_LUT_ENTRIES + 32) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  UST_CUDA(h, cudaMemcpyAsync(h->podlut_dev, h->podlut_host, UST_PODLUT_ENTRIES, cudaMemcpyHostToDevice, st));
+  h->lut_policy = key;
+  h->lut_valid = true;
+  return UST_OK;
+}
+
+static int pick_grid(const ust_handle* h, int64_t n) {
+  const int64_t max_grid = (int64_t)h->ctas_per_sm * h->num_sms;
+  int64_t g = n / 8192;
+  if (g < 1) g = 1;
+  if (g > max_grid) g = max_grid;
+  if (g > UST_MAX_CTAS) g = UST_MAX_CTAS;
+  return (int)g;
+}
+
+static int check_aligned(ust_handle* h, const void* p, const char* what) {
+  if (((uintptr_t)p & 15u) != 0) return h->fail(UST_ERR_INVALID_ARGUMENT, "%s must be 16-byte aligned", what);
+  return UST_OK;
+}
+
+// core: everything device-resident, enqueue on `st`
+static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
+                        const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                        const int32_t* pod_off, const uint16_t* pod_flags, uint8_t* next_state, uint16_t* actions,
+                        uint8_t* outcome, ust_counters* out_dev, cudaStream_t st) {
+  if (n < 0) return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
+  if (n > 0 && (!state || !flags || !pod_rev || !ds_idx || !next_state || !actions))
+    return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
+  if (n_ds < 0 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table");
+  if (n >= (1LL << 48)) return h->fail(UST_ERR_INVALID_ARGUMENT, "too many nodes");
+  const void* ptrs[] = {state, flags, pod_rev, ds_idx, next_state, actions, outcome};
+  const char* names[] = {"state", "flags", "pod_rev", "ds_idx", "next_state", "actions", "actuator_outcome"};
+  for (int i = 0; i < 7; i++)
+    if (ptrs[i]) { int rc = check_aligned(h, ptrs[i], names[i]); if (rc) return rc; }
+  UST_CUDA(h, cudaSetDevice(h->device));
+  if (h->ws_dirty) {
+    UST_CUDA(h, cudaMemsetAsync(h->ws, 0, sizeof(UstWorkspace), st));
+    h->ws_dirty = false;
+  }
+  int rc = ensure_tables(h, policy, st);
+  if (rc) return rc;
+
+  const bool active = policy_active(policy);
+  UstParams P;
+  memset(&P, 0, sizeof(P));
+  P.n = n;
+  P.hot = state; P.flags = flags; P.pod_rev = pod_rev; P.ds_idx = ds_idx;
+  P.ds_rev = ds_rev; P.n_ds = n_ds;
+  P.pod_off = pod_off; P.pod_flags = pod_flags;
+  P.next = next_state; P.actions = actions; P.outcome = outcome;
+  P.lut = h->lut_dev; P.podlut = h->podlut_dev;
+  P.ws = h->ws; P.xchg = h->xchg_dev;
+  P.out = out_dev ? out_dev : h->counters_dev;
+  P.active = active ? 1 : 0;
+  if (active) {
+    P.max_parallel = policy->max_parallel_upgrades;
+    P.max_unav_value = policy->max_unavailable_value;
+    P.max_unav_kind = policy->max_unavailable_kind;
+    P.requestor = policy->use_maintenance_operator != 0;
+    P.pd_enabled = policy->pod_deletion_enabled != 0;
+    P.pd_spec_present = policy->pod_deletion_spec_present != 0;
+    P.eval_pods = (policy->evaluate_actuators != 0 && pod_off && pod_flags) ? 1 : 0;
+  }
+  P.rank = h->rank;
+  P.world = h->world;
+  const int grid = pick_grid(h, n);
+  P.grid_chunks = grid;
+  P.chunk_begin = 0;
+
+  h->ws_dirty = true;  // cleared again once every launch of this call has been enqueued successfully
+  if (h->world == 1) {
+    int e = ust_launch_fused(P, grid, st);
+    if (e) return h->fail(UST_ERR_CUDA, "fused kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->launches += 1;
+  } else {
+    int e = ust_launch_phase1(P, grid, st);
+    if (e) return h->fail(UST_ERR_CUDA, "phase-1 kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    ncclResult_t r = g_nccl.AllReduce(h->xchg_dev, h->xchg_dev, UST_V_LEN, ncclInt64, ncclSum, h->comm, st);
+    if (r != ncclSuccess) return h->fail(UST_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    e = ust_launch_phase2(P, grid, st);
+    if (e) return h->fail(UST_ERR_CUDA, "phase-2 kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->launches += 2;
+  }
+  h->ws_dirty = false;
+  return UST_OK;
+}
+
+static int finish_with_counters(ust_handle* h, cudaStream_t st, ust_counters* out) {
+  UST_CUDA(h, cudaMemcpyAsync(h->counters_host, h->counters_dev, sizeof(ust_counters), cudaMemcpyDeviceToHost, st));
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    h->ws_dirty = true;
+    return h->fail(UST_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
+  }
+  if (out) *out = *h->counters_host;
+  const int code = (int)h->counters_host->error_code;
+  if (code != UST_OK) {
+    switch (code) {
+      case UST_ERR_REVISION_HASH:
+        return h->fail(code, "failed to get daemonset template/pod revision hash (node index %lld, pass %lld)",
+                       (long long)h->counters_host->error_index, (long long)h->counters_host->error_pass);
+      case UST_ERR_MAX_UNAVAILABLE: return h->fail(code, "failed to compute maxUnavailable from the current total nodes");
+      case UST_ERR_POD_DELETION_SPEC: return h->fail(code, "pod deletion spec should not be empty");
+      case UST_ERR_DS_UNSCHEDULED: return h->fail(code, "driver DaemonSet should not have Unscheduled pods");
+      default: return h->fail(code, "ApplyState aborted with code %d", code);
+    }
+  }
+  return UST_OK;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int ust_abi_version(void) { return UST_ABI_VERSION; }
+const char* ust_create_error(void) { return g_create_error.c_str(); }
+const char* ust_last_error(const ust_handle* h) { return h ? h->err.c_str() : "null handle"; }
+int64_t ust_launch_count(const ust_handle* h) { return h ? h->launches : 0; }
+
+int ust_create(ust_handle** out, int device) {
+  if (!out) return UST_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return UST_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) { g_create_error = "device index out of range"; return UST_ERR_INVALID_ARGUMENT; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return UST_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = "libust.so carries sm_100a code only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return UST_ERR_CUDA;
+  }
+  ust_handle* h = new ust_handle();
+  h->device = device;
+  auto bail = [&](const char* what, cudaError_t err) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    ust_destroy(h);
+    return UST_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaMalloc(&h->ws, sizeof(UstWorkspace))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemset(h->ws, 0, sizeof(UstWorkspace))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMalloc(&h->lut_dev, (UST_LUT_ENTRIES + 32) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->podlut_dev, UST_PODLUT_ENTRIES)) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMallocHost(&h->lut_host, (UST_LUT_ENTRIES + 32) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost(&h->podlut_host, UST_PODLUT_ENTRIES)) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMalloc(&h->counters_dev, sizeof(ust_counters))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMallocHost(&h->counters_host, sizeof(ust_counters))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMalloc(&h->xchg_dev, UST_V_LEN * sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemset(h->xchg_dev, 0, UST_V_LEN * sizeof(long long))) != cudaSuccess) return bail("cudaMemset", e);
+  int rc = ust_max_coresident_ctas(device, &h->ctas_per_sm, &h->num_sms);
+  if (rc != 0 || h->ctas_per_sm < 1) {
+    g_create_error = std::string("no sm_100a kernel image usable on this device: ") + cudaGetErrorString((cudaError_t)rc);
+    ust_destroy(h);
+    return UST_ERR_CUDA;
+  }
+  *out = h;
+  return UST_OK;
+}
+
+void ust_destroy(ust_handle* h) {
+  if (!h) return;
+  if (h->device >= 0) cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->ws) cudaFree(h->ws);
+  if (h->lut_dev) cudaFree(h->lut_dev);
+  if (h->podlut_dev) cudaFree(h->podlut_dev);
+  if (h->lut_host) cudaFreeHost(h->lut_host);
+  if (h->podlut_host) cudaFreeHost(h->podlut_host);
+  if (h->counters_dev) cudaFree(h->counters_dev);
+  if (h->counters_host) cudaFreeHost(h->counters_host);
+  if (h->xchg_dev) cudaFree(h->xchg_dev);
+  if (h->ds_count_dev) cudaFree(h->ds_count_dev);
+  h->s_hot.release(); h->s_next.release(); h->s_outcome.release(); h->s_flags.release();
+  h->s_rev.release(); h->s_ds.release(); h->s_dsrev.release(); h->s_podoff.release(); h->s_dsdesired.release();
+  h->s_actions.release(); h->s_podflags.release();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+void* ust_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void ust_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int ust_sync(ust_handle* h) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  UST_CUDA(h, cudaSetDevice(h->device));
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { h->ws_dirty = true; return h->fail(UST_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e)); }
+  return UST_OK;
+}
+
+int ust_apply_state_device(ust_handle* h, const ust_policy* policy, int64_t n_nodes, const uint8_t* state,
+                           const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds,
+                           const int32_t* ds_rev, const ust_pods* pods, uint8_t* next_state, uint16_t* actions,
+                           uint8_t* actuator_outcome, ust_counters* out_device, void* stream) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  return apply_device(h, policy, n_nodes, state, flags, pod_rev, ds_idx, n_ds, ds_rev, pods ? pods->pod_off : nullptr,
+                      pods ? pods->pod_flags : nullptr, next_state, actions, actuator_outcome, out_device, st);
+}
+
+int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
+                    const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                    const ust_pods* pods, uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome,
+                    ust_counters* out) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  if (n < 0 || (n > 0 && (!state || !flags || !pod_rev || !ds_idx || !next_state || !actions)))
+    return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
+  if (n_ds < 0 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table");
+  if (pods && (!pods->pod_off || pods->n_pods < 0 || (pods->n_pods > 0 && !pods->pod_flags)))
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "bad pod lists");
+  UST_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t N = (size_t)n;
+  UST_CUDA(h, h->s_hot.reserve(N + 16));
+  UST_CUDA(h, h->s_flags.reserve(N + 4));
+  UST_CUDA(h, h->s_rev.reserve(N + 4));
+  UST_CUDA(h, h->s_ds.reserve(N + 4));
+  UST_CUDA(h, h->s_next.reserve(N + 16));
+  UST_CUDA(h, h->s_actions.reserve(N + 8));
+  UST_CUDA(h, h->s_dsrev.reserve((size_t)n_ds + 1));
+  if (actuator_outcome) UST_CUDA(h, h->s_outcome.reserve(N + 16));
+  if (pods) {
+    UST_CUDA(h, h->s_podoff.reserve(N + 1));
+    UST_CUDA(h, h->s_podflags.reserve((size_t)pods->n_pods + 8));
+  }
+  if (N) {
+    UST_CUDA(h, cudaMemcpyAsync(h->s_hot.p, state, N, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->s_flags.p, flags, N * 4, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->s_rev.p, pod_rev, N * 4, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->s_ds.p, ds_idx, N * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsrev.p, ds_rev, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
+  if (pods) {
+    UST_CUDA(h, cudaMemcpyAsync(h->s_podoff.p, pods->pod_off, (N + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (pods->n_pods) UST_CUDA(h, cudaMemcpyAsync(h->s_podflags.p, pods->pod_flags, (size_t)pods->n_pods * 2, cudaMemcpyHostToDevice, st));
+  }
+  int rc = apply_device(h, policy, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, n_ds, h->s_dsrev.p,
+                        pods ? h->s_podoff.p : nullptr, pods ? h->s_podflags.p : nullptr, h->s_next.p, h->s_actions.p,
+                        actuator_outcome ? h->s_outcome.p : nullptr, nullptr, st);
+  if (rc) return rc;
+  if (N) {
+    UST_CUDA(h, cudaMemcpyAsync(next_state, h->s_next.p, N, cudaMemcpyDeviceToHost, st));
+    UST_CUDA(h, cudaMemcpyAsync(actions, h->s_actions.p, N * 2, cudaMemcpyDeviceToHost, st));
+    if (actuator_outcome) UST_CUDA(h, cudaMemcpyAsync(actuator_outcome, h->s_outcome.p, N, cudaMemcpyDeviceToHost, st));
+  }
+  return finish_with_counters(h, st, out);
+}
+
+int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const int32_t* ds_idx, int32_t n_ds,
+                    const int32_t* ds_desired, ust_counters* out) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  if (n_pods < 0 || (n_pods > 0 && (!state || !ds_idx)) || n_ds < 0 || (n_ds > 0 && !ds_desired))
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
+  UST_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t N = (size_t)n_pods;
+  UST_CUDA(h, h->s_hot.reserve(N + 16));
+  UST_CUDA(h, h->s_ds.reserve(N + 4));
+  UST_CUDA(h, h->s_dsdesired.reserve((size_t)n_ds + 1));
+  if ((size_t)n_ds + 1 > h->ds_count_cap) {
+    if (h->ds_count_dev) cudaFree(h->ds_count_dev);
+    h->ds_count_cap = (size_t)n_ds + 64;
+    UST_CUDA(h, cudaMalloc(&h->ds_count_dev, h->ds_count_cap * sizeof(unsigned long long)));
+    UST_CUDA(h, cudaMemsetAsync(h->ds_count_dev, 0, h->ds_count_cap * sizeof(unsigned long long), st));
+  }
+  if (h->ws_dirty) { UST_CUDA(h, cudaMemsetAsync(h->ws, 0, sizeof(UstWorkspace), st)); h->ws_dirty = false; }
+  if (N) {
+    UST_CUDA(h, cudaMemcpyAsync(h->s_hot.p, state, N, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->s_ds.p, ds_idx, N * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsdesired.p, ds_desired, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
+  int64_t grid = (n_pods + 4095) / 4096;
+  if (grid < 1) grid = 1;
+  if (grid > 4 * h->num_sms) grid = 4 * h->num_sms;
+  h->ws_dirty = true;
+  int e = ust_launch_build_state(n_pods, h->s_hot.p, h->s_ds.p, n_ds, h->s_dsdesired.p, h->ds_count_dev, h->ws, h->counters_dev, (int)grid, st);
+  if (e) return h->fail(UST_ERR_CUDA, "build-state kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  h->ws_dirty = false;
+  h->launches += 2;
+  return finish_with_counters(h, st, out);
+}
+
+uint32_t ust_table_entry(const ust_policy* policy, unsigned state_code, uint32_t w) {
+  state_code &= 15u;
+  if (!policy_active(policy)) return ust_lut_pack(state_code, state_code, 0, 0xFF);
+  const ust_policy key = table_key(policy);
+  const int sh = ust_window_shift[state_code];
+  const uint32_t window = (uint32_t)(((uint64_t)(UST_LUT_WINDOW - 1) << sh) & 0xFFFFFFFFull);
+  return ust_transition(state_code, w & window, &key);
+}
+int ust_table_window_shift(unsigned state_code) { return ust_window_shift[state_code & 15u]; }
+
+int ust_get_unique_id(void* out_bytes) {
+  if (!out_bytes) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(g_nccl_mu);
+  std::string err;
+  if (!g_nccl.load(&err)) { g_create_error = err; return UST_ERR_COMM; }
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == UST_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return UST_ERR_COMM; }
+  memcpy(out_bytes, &id, sizeof(id));
+  return UST_OK;
+}
+
+int ust_comm_init(ust_handle* h, int rank, int world_size, const void* unique_id_bytes) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  if (world_size < 1 || world_size > UST_MAX_WORLD || rank < 0 || rank >= world_size)
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "world size must be 1..%d", UST_MAX_WORLD);
+  if (world_size == 1) { h->rank = 0; h->world = 1; return UST_OK; }
+  if (!unique_id_bytes) return h->fail(UST_ERR_INVALID_ARGUMENT, "unique id required");
+  {
+    std::lock_guard<std::mutex> g2(g_nccl_mu);
+    std::string err;
+    if (!g_nccl.load(&err)) return h->fail(UST_ERR_COMM, "%s", err.c_str());
+  }
+  UST_CUDA(h, cudaSetDevice(h->device));
+  ncclUniqueId id;
+  memcpy(&id, unique_id_bytes, sizeof(id));
+  ncclResult_t r = g_nccl.CommInitRank(&h->comm, world_size, id, rank);
+  if (r != ncclSuccess) return h->fail(UST_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  h->rank = rank;
+  h->world = world_size;
+  return UST_OK;
+}
+
+int ust_comm_set_mode(ust_handle* h, int mode) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  if (mode != 0) return h->fail(UST_ERR_INVALID_ARGUMENT, "exchange mode %d is not available in this build", mode);
+  h->comm_mode = mode;
+  return UST_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,76 @@
+// ust_dev.h — structures shared by the host side of libust.so (ust_api.cu) and its kernels.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/ust.h"
+#include "ust_lut.h"
+
+#define UST_THREADS 256
+#define UST_MAX_CTAS 4096
+#define UST_MAX_WORLD 8
+#define UST_DS_SMEM_MAX 1024
+
+// Exchange vector (int64 lanes): what one shard contributes to / learns from the cluster-wide
+// constraint arithmetic (upgrade_inplace.go:49-62). Summed across shards; per-rank slots are one-hot,
+// so the sum doubles as an all-gather.
+#define UST_V_HIST 0                         /* 16 lanes: nodes per state code */
+#define UST_V_UNAVAILABLE 16
+#define UST_V_CANDIDATES 17
+#define UST_V_RANK_CAND (18)                 /* UST_MAX_WORLD lanes */
+#define UST_V_RANK_NODES (18 + UST_MAX_WORLD)
+#define UST_V_RANK_ERRINV (18 + 2 * UST_MAX_WORLD) /* ~abort key of the rank, 0 = none */
+#define UST_V_LEN (18 + 3 * UST_MAX_WORLD)
+
+// Device workspace owned by a handle. Invariant: acc / errinv / arrive / depart are zero between launches.
+struct UstWorkspace {
+  unsigned long long acc[18];   // hist[0..15], unavailable, candidates (this shard)
+  unsigned long long errinv;    // ~min abort key seen by phase 1, 0 = none
+  unsigned int arrive;
+  unsigned int depart;
+  unsigned int cand_cta[UST_MAX_CTAS];  // candidates per CTA chunk (written by phase 1, read by phase 2)
+};
+
+// abort key: (pass << 56) | (global node index + 1); policy-level aborts use index part 0
+#define UST_KEY(pass, gidx_plus1) ((((unsigned long long)(pass)) << 56) | (unsigned long long)(gidx_plus1))
+
+struct UstParams {
+  long long n;  // nodes in this shard
+  const uint8_t* hot;
+  const uint32_t* flags;
+  const int32_t* pod_rev;
+  const int32_t* ds_idx;
+  const int32_t* ds_rev;
+  int n_ds;
+  const int32_t* pod_off;     // nullable
+  const uint16_t* pod_flags;  // nullable
+  uint8_t* next;
+  uint16_t* actions;
+  uint8_t* outcome;  // nullable
+  const uint32_t* lut;    // UST_LUT_ENTRIES words, then 16 uint2 {shift-2, state*2048}
+  const uint8_t* podlut;  // UST_PODLUT_ENTRIES bytes
+  UstWorkspace* ws;
+  long long* xchg;        // UST_V_LEN lanes (split mode: phase 1 writes, phase 2 reads the reduced copy)
+  ust_counters* out;      // device
+  // policy (flattened; see include/ust.h)
+  long long max_parallel;
+  long long max_unav_value;
+  int max_unav_kind;
+  int active;             // policy != nil && AutoUpgrade (upgrade_state.go:179-182); 0 => every node is a no-op
+  int requestor;
+  int pd_enabled;
+  int pd_spec_present;
+  int eval_pods;          // pod lists present and evaluate_actuators
+  // sharding
+  int rank;
+  int world;
+  int grid_chunks;        // number of CTA chunks the shard is cut into (same for phase 1 and phase 2)
+  int chunk_begin;        // phase-2 sub-range launches: first chunk handled by blockIdx.x == 0
+};
+
+// kernel launchers (ust_kernels.cu); all return cudaError_t as int
+int ust_launch_fused(const UstParams& p, int grid, void* stream);
+int ust_launch_phase1(const UstParams& p, int grid, void* stream);
+int ust_launch_phase2(const UstParams& p, int grid, void* stream);
+int ust_launch_build_state(long long n, const uint8_t* hot, const int32_t* ds_idx, int n_ds, const int32_t* ds_desired,
+                           unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream);
+int ust_max_coresident_ctas(int device, int* ctas_per_sm, int* num_sms);

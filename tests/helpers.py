@@ -23,7 +23,8 @@ def oracle():
     global _oracle
     if _oracle is None:
         src = os.path.join(ROOT, "oracle", "ust_oracle.cpp")
-        if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        newest = max(os.path.getmtime(src), os.path.getmtime(abi.HEADER))
+        if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < newest:
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
         lib = C.CDLL(ORACLE_SO)
         lib.ust_oracle_apply_state.restype = C.c_int
@@ -294,7 +295,7 @@ def random_soa(rng, n, n_ds=3, p_err=0.0, with_pods=False, all_states=True, wild
             p = 0.15 if k == "UST_F_POD_ORPHANED" else 0.5
             flags |= np.where(rng.random(n) < p, np.uint32(v), np.uint32(0))
     if wild:
-        flags |= (rng.integers(0, 2, size=n).astype(np.uint32) * np.uint32(0x187))  # reserved bits set: must be ignored
+        flags |= (rng.integers(0, 2, size=n).astype(np.uint32) * np.uint32(0xFFC0061F))  # reserved bits set: must be ignored
     ds_rev = rng.integers(1, 4, size=n_ds).astype(np.int32)
     ds_idx = rng.integers(0, n_ds, size=n).astype(np.int32)
     if wild:

@@ -1,0 +1,200 @@
+"""Parity of the CUDA path (through the C ABI of libust.so) against the oracle. Bit-exact: this is integer
+and index work. Run on the B200 box: python -m pytest tests -m gpu"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import abi
+from ust import lib as ustlib, synth
+
+pytestmark = pytest.mark.gpu
+
+G = helpers.load_golden()
+
+
+@pytest.fixture(scope="module")
+def handle():
+    h = ustlib.Handle(0)  # raises (never skips) when the extension or the device is missing
+    yield h
+    h.close()
+
+
+def gpu_apply(handle, pol, soa, pods=None, nil_policy=False):
+    return handle.apply_state(None if nil_policy else pol, soa, pods, want_outcome=True)
+
+
+# ---- the reference's own known-answer tests, through the kernel ------------------------------------
+
+VEC = [v for v in G["apply_state"] if not v.get("nil_state")]
+
+
+@pytest.mark.parametrize("v", VEC, ids=[v["ref"].split("/")[-1] for v in VEC])
+def test_reference_vector(handle, v):
+    pol = helpers.policy_from_vector(v)
+    soa, pods = helpers.encode_nodes(v["nodes"], G["daemonset_hash"], v.get("policy"))
+    rc, nxt, act, oc, cnt = gpu_apply(handle, pol, soa, pods, nil_policy=pol is None)
+    assert helpers.check_vector(v, soa, rc, nxt, act, oc) > 0 or v.get("actuator_error")
+    helpers.check_derived(v, nxt)
+    # and identical to the oracle in every output, not only in what the Go test asserts
+    ref = helpers.oracle_apply(pol if pol is not None else abi.Policy(), soa, pods, variant=0, nil_policy=pol is None)
+    helpers.assert_same((rc, nxt, act, oc, cnt), ref, v["name"])
+
+
+def test_nil_state_is_an_error(handle):
+    # upgrade_state.go:175-177
+    pol = abi.make_policy()
+    rc = ustlib.load().ust_apply_state(handle._h, C.addressof(pol), 4, None, None, None, None, 0, None, None, None, None, None, None)
+    assert rc == abi.UST_ERR_NIL_STATE
+    assert "currentState should not be empty" in handle.last_error()
+
+
+@pytest.mark.parametrize("b", G["build_state"], ids=lambda b: b["name"][:40])
+def test_build_state_vector(handle, b):
+    pods = b["pods"]
+    n = len(pods)
+    state = np.zeros(max(n, 1), np.uint8)[:n]
+    ds_idx = np.full(max(n, 1), -1, np.int32)[:n]
+    for i, p in enumerate(pods):
+        code = abi.STATE_CODE.get(p["node_state"], abi.UST_STATE_OTHER)
+        if p["node_name"] == "" and p["phase"] == "Pending":
+            code = abi.UST_STATE_EXCLUDED
+        state[i] = code
+        ds_idx[i] = -1 if p["ds"] is None else p["ds"]
+    desired = np.array([d["desired"] for d in b["daemonsets"]], np.int32)
+    rc, cnt = handle.build_state(state, ds_idx, desired)
+    ocnt = abi.Counters()
+    orc = helpers.oracle().ust_oracle_build_state(
+        C.c_int64(n), state.ctypes.data_as(C.c_void_p), ds_idx.ctypes.data_as(C.c_void_p), C.c_int32(len(desired)),
+        desired.ctypes.data_as(C.c_void_p), C.byref(ocnt))
+    assert rc == orc
+    if b["expect_error"]:
+        assert rc == abi.K["UST_ERR_" + b["expect_error"]]
+    else:
+        assert rc == 0
+        got = {abi.STATE_NAMES[c]: cnt["hist"][c] for c in range(13) if cnt["hist"][c]}
+        assert got == b["expect_buckets"]
+    assert cnt == ocnt.as_dict()
+
+
+# ---- random snapshots: every flag bit, abort paths, requestor mode, pod lists ------------------------
+
+SIZES = [0, 1, 3, 4, 5, 127, 128, 129, 1023, 1024, 1025, 4095, 4096, 4097, 8191, 8192, 20_000, 70_001, 300_000]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_random_snapshot_matches_reference_shaped_oracle(handle, n):
+    rng = np.random.default_rng(4242 + n)
+    for rep in range(3):
+        soa, pods = helpers.random_soa(rng, n, n_ds=int(rng.integers(1, 6)), p_err=(0.0, 0.0005, 0.02)[rep],
+                                       with_pods=(rep == 1))
+        pol = helpers.random_policy(rng)
+        got = gpu_apply(handle, pol, soa, pods)
+        ref = helpers.oracle_apply(pol, soa, pods, variant=0)
+        helpers.assert_same(got, ref, f"n={n} rep={rep}")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_slot_budget_cut_positions(handle, seed):
+    """The ordered slot allocation (upgrade_inplace.go:71-109) with the budget cut falling at the start,
+    inside and at the end of a chunk, with maxUnavailable percent / int / nil."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([9000, 33_000, 150_000, 600_000]))
+    soa, _ = helpers.random_soa(rng, n, all_states=False, wild=False)
+    pick = rng.random(n)
+    soa["state"] = np.where(pick < 0.6, (soa["state"] & 0xF0) | 1, soa["state"]).astype(np.uint8)
+    soa["state"] &= np.uint8(0x7F)
+    cands = int(np.sum(((soa["state"] & 15) == 1) & ((soa["state"] & abi.UST_HOT_SKIP) == 0)))
+    for max_par, unav in ((0, None), (0, "100%"), (0, f"{int(rng.integers(20, 60))}%"), (int(rng.integers(1, 200)), None),
+                          (cands // 2 + n, int(n)), (0, int(rng.integers(0, n))), (1, 0), (10**9, "37%")):
+        pol = abi.make_policy(max_parallel_upgrades=max_par, max_unavailable=unav)
+        got = gpu_apply(handle, pol, soa)
+        ref = helpers.oracle_apply(pol, soa, variant=1)
+        helpers.assert_same(got, ref, f"seed={seed} maxPar={max_par} maxUnav={unav}")
+
+
+def test_many_daemonsets_use_the_global_table(handle):
+    rng = np.random.default_rng(99)
+    n, n_ds = 50_000, 3000  # > UST_DS_SMEM_MAX
+    soa, _ = helpers.random_soa(rng, n, n_ds=n_ds)
+    pol = abi.make_policy(max_parallel_upgrades=7, max_unavailable="25%")
+    helpers.assert_same(gpu_apply(handle, pol, soa), helpers.oracle_apply(pol, soa, variant=0), "n_ds=3000")
+
+
+def test_disabled_and_nil_policy(handle):
+    rng = np.random.default_rng(5)
+    soa, _ = helpers.random_soa(rng, 10_000, p_err=0.01)
+    off = abi.make_policy(auto_upgrade=False, max_parallel_upgrades=3)
+    for nil in (False, True):
+        got = gpu_apply(handle, off, soa, nil_policy=nil)
+        ref = helpers.oracle_apply(off, soa, variant=0, nil_policy=nil)
+        helpers.assert_same(got, ref, f"nil={nil}")
+        assert got[0] == 0 and not got[2].any()
+
+
+def test_idempotent_and_stateless(handle):
+    """ApplyState is stateless (upgrade_state.go:166-170): same snapshot, same answer, whatever ran before."""
+    rng = np.random.default_rng(17)
+    soa, pods = helpers.random_soa(rng, 40_000, with_pods=True)
+    pol = helpers.random_policy(rng)
+    a = gpu_apply(handle, pol, soa, pods)
+    soa2, _ = helpers.random_soa(rng, 1234, p_err=0.05)
+    gpu_apply(handle, helpers.random_policy(rng), soa2)  # an aborting call in between
+    b = gpu_apply(handle, pol, soa, pods)
+    helpers.assert_same(a, b, "repeat")
+
+
+# ---- BASELINE.json configurations at full size ------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3"])
+def test_baseline_config_bit_exact(handle, name):
+    cfg = synth.CONFIGS[name]
+    soa = synth.make_nodes(cfg["n"], cfg["seed"])
+    pol = synth.config_policy(name)
+    got = gpu_apply(handle, pol, soa)
+    ref = helpers.oracle_apply(pol, soa, variant=1)  # SoA oracle: seconds at 10 M nodes
+    helpers.assert_same(got, ref, name)
+    if cfg["n"] <= 1_000_000:
+        helpers.assert_same(got, helpers.oracle_apply(pol, soa, variant=0), name + " (reference-shaped)")
+    rc, nxt, act, oc, cnt = got
+    # size-independent properties
+    code = soa["state"] & 15
+    assert cnt["hist"][:14] == [int(np.sum(code == c)) for c in range(14)]
+    granted = int(np.sum((code == 1) & (nxt == 2) & ((soa["state"] & abi.UST_HOT_UNSCHEDULABLE) == 0)))
+    assert granted <= max(cnt["upgrades_available"], 0)
+    assert np.all((act & abi.UST_A_SET_STATE != 0) == (nxt != code))
+
+
+def test_c4_pod_lists_sample(handle):
+    """C4 (pod-list actuators) on a 300 k-node sample against the reference-shaped oracle."""
+    cfg = synth.CONFIGS["C4"]
+    n = 300_000
+    soa = synth.make_nodes(n, cfg["seed"])
+    pods = synth.make_pods(n, cfg["seed"])
+    pol = synth.config_policy("C4")
+    helpers.assert_same(gpu_apply(handle, pol, soa, pods), helpers.oracle_apply(pol, soa, pods, variant=0), "C4 sample")
+
+
+def test_device_resident_entry_point(handle):
+    """ust_apply_state_device on torch-owned device buffers (plumbing only) == host entry point."""
+    import torch
+    cfg = synth.CONFIGS["C2"]
+    soa = synth.make_nodes(cfg["n"], cfg["seed"])
+    pol = synth.config_policy("C2")
+    dev = torch.device("cuda:0")
+    t = {k: torch.from_numpy(v).to(dev) for k, v in soa.items()}
+    n = cfg["n"]
+    nxt = torch.empty(n, dtype=torch.uint8, device=dev)
+    act = torch.empty(n, dtype=torch.int16, device=dev)
+    cnt = torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)
+    handle.apply_state_device(pol, n, t["state"].data_ptr(), t["flags"].data_ptr(), t["pod_rev"].data_ptr(),
+                              t["ds_idx"].data_ptr(), 4, t["ds_rev"].data_ptr(), nxt.data_ptr(), act.data_ptr(),
+                              counters=cnt.data_ptr())
+    handle.sync()
+    ref = helpers.oracle_apply(pol, soa, variant=1)
+    assert np.array_equal(nxt.cpu().numpy(), ref[1])
+    assert np.array_equal(act.cpu().numpy().view(np.uint16), ref[2])
+    c = abi.Counters.from_buffer_copy(cnt.cpu().numpy().tobytes())
+    assert c.as_dict() == ref[4]
