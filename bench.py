@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--impl", default="ust", choices=["ust", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--nodes", type=int, default=SHARD_NODES, help="nodes per GPU (default: the BASELINE workload)")
+    ap.add_argument("--sets", type=int, default=16, help="rotating input/output buffer sets (L2 defeat)")
+    ap.add_argument("--quick", action="store_true", help="tuning: device-resident timing only (no e2e / cpu baseline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -175,8 +177,10 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         h.comm_init(rank, world, uid[0])
 
-    # two rotating buffer sets (2 x 160 MB): consecutive steps never find their inputs in the 126 MB L2
-    SETS = 2
+    # Rotating buffer sets: a step never finds more than 126 MB / (SETS x 160 MB) of its inputs in L2.
+    # (Two sets are NOT enough: the streaming loads are evict-first, so L2 keeps a fixed ~126 MB subset of
+    # the 320 MB alive and half of every step would be L2 hits — measured in round 1, profiles/README.md.)
+    SETS = max(2, args.sets)
     bufs = []
     for _ in range(SETS):
         d = {k: torch.from_numpy(v).to(dev) for k, v in soa.items()}
@@ -184,18 +188,39 @@ def main():
         d["actions"] = torch.empty(n, dtype=torch.int16, device=dev)
         bufs.append(d)
     counters = torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated stream: torch's default stream has handle 0, which the C ABI reads as "use the handle's own
+    # stream" — events recorded on torch's stream would then not bracket the kernels (round-1 lesson)
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    # pre-bound ctypes arguments per buffer set: the launch loop must not be the bottleneck (a step is ~40 us)
+    fn = ustlib.load().ust_apply_state_device
+    pol_p = C.c_void_p(C.addressof(pol))
+    cnt_p = C.c_void_p(counters.data_ptr())
+    st_p = C.c_void_p(stream)
+    bound = []
+    for b in bufs:
+        bound.append((h._h, pol_p, C.c_int64(n), C.c_void_p(b["state"].data_ptr()), C.c_void_p(b["flags"].data_ptr()),
+                      C.c_void_p(b["pod_rev"].data_ptr()), C.c_void_p(b["ds_idx"].data_ptr()), C.c_int32(n_ds),
+                      C.c_void_p(b["ds_rev"].data_ptr()), None, C.c_void_p(b["next"].data_ptr()),
+                      C.c_void_p(b["actions"].data_ptr()), None, cnt_p, st_p))
 
     def step(i):
-        b = bufs[i % SETS]
-        h.apply_state_device(pol, n, b["state"].data_ptr(), b["flags"].data_ptr(), b["pod_rev"].data_ptr(),
-                             b["ds_idx"].data_ptr(), n_ds, b["ds_rev"].data_ptr(), b["next"].data_ptr(),
-                             b["actions"].data_ptr(), counters=counters.data_ptr(), stream=stream)
+        rc = fn(*bound[i % SETS])
+        if rc:
+            raise ustlib.UstError(rc, h.last_error())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def blocker():
+        # ~1.5 ms of GPU spinning: the host queues the timed launches behind it, so the CUDA events bracket
+        # back-to-back GPU execution rather than the Python launch rate
+        torch.cuda._sleep(3_000_000)
 
     for i in range(warmup):
         step(i)
@@ -204,17 +229,27 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = h.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
+    blocker()
+    e_start.record()
     for i in range(args.steps):
+        step(i)
+    e_end.record()
+    barrier()
+    t_wall = time.time() - t_wall0
+    launches = h.launch_count() - launches0
+    total_ms = e_start.elapsed_time(e_end)
+    # dominant-kernel duration: per-step event pairs over a second, shorter run of the same steps
+    ksteps = min(args.steps, 20)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
+    blocker()
+    for i in range(ksteps):
         ev[i][0].record()
         step(i)
         ev[i][1].record()
     barrier()
-    t_wall = time.time() - t_wall0
-    launches = h.launch_count() - launches0
-    total_ms = ev[0][0].elapsed_time(ev[-1][1])
     per_step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     clocks = sampler.stop()
 
@@ -235,21 +270,43 @@ def main():
     line = None
     if rank == 0:
         peak, peak_src = peaks()
-        kern_ms = float(np.median(per_step_ms))
+        # one step == one launch of the dominant kernel: its average duration over the timed region; the
+        # per-step event pairs (each pair adds ~2 us of event latency) are reported alongside
+        kern_ms = total_ms / args.steps
         achieved = BYTES_PER_NODE * n / (kern_ms * 1e-3) / 1e9
         line = {
             "metric": "node state-transitions/sec", "value": value, "unit": "nodes/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32", "data": "synthetic",
             "config": {"workload": workload_name(world), "nodes_per_gpu": n, "bytes_per_node": BYTES_PER_NODE,
-                       "l2": f"{SETS} rotating buffer sets of {BYTES_PER_NODE * n / 1e6:.0f} MB each (> 126 MB L2 together)",
+                       "l2": f"inputs larger than L2: {SETS} rotating buffer sets of {BYTES_PER_NODE * n / 1e6:.0f} MB each "
+                             f"({SETS * BYTES_PER_NODE * n / 1e9:.2f} GB vs 126 MB L2, at most {100 * 126e6 / (SETS * BYTES_PER_NODE * n):.0f}% of a step can hit)",
                        "exchange": "none" if world == 1 else "ncclAllReduce of 42 int64 lanes between two kernels"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "ust_fused_kernel" if world == 1 else "ust_phase2_kernel",
-                         "kernel_ms": kern_ms, "frac_of_8TBs": achieved / 8000.0},
+                         "kernel_ms": kern_ms, "kernel_ms_event_pairs_median": float(np.median(per_step_ms)),
+                         "frac_of_8TBs": achieved / 8000.0},
             "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
             "counters": {k: cnt[k] for k in ("total_managed", "in_progress", "unavailable", "max_unavailable", "upgrades_available")},
         }
+
+    if args.quick:
+        if rank == 0 and os.environ.get("UST_STAMPS"):
+            g = int(os.environ["UST_STAMPS"])
+            st = (C.c_uint64 * (4 * g))()
+            ustlib.load().ust_debug_stamps(h._h, st, g)
+            a = np.array(st, dtype=np.int64).reshape(g, 4)
+            t0 = a[:, 0].min()
+            a = a - t0
+            print("stamps us: entry[min,max]=%.1f,%.1f stream_end[min,med,max]=%.1f,%.1f,%.1f barrier_release[min,max]=%.1f,%.1f "
+                  "exit[min,max]=%.1f,%.1f stream_dur[min,med,max]=%.1f,%.1f,%.1f" % (
+                      a[:, 0].min() / 1e3, a[:, 0].max() / 1e3, a[:, 1].min() / 1e3, np.median(a[:, 1]) / 1e3, a[:, 1].max() / 1e3,
+                      a[:, 2].min() / 1e3, a[:, 2].max() / 1e3, a[:, 3].min() / 1e3, a[:, 3].max() / 1e3,
+                      (a[:, 1] - a[:, 0]).min() / 1e3, np.median(a[:, 1] - a[:, 0]) / 1e3, (a[:, 1] - a[:, 0]).max() / 1e3), flush=True)
+        if rank == 0:
+            print(json.dumps({k: line[k] for k in ("value", "ms_per_step", "roofline", "clocks")}), flush=True)
+        h.close()
+        return
 
     # ---- e2e: host-pointer C ABI with pinned host buffers, H2D + kernel + D2H inside the timed region ----
     host = {k: ustlib.pinned_array(v.shape, v.dtype) for k, v in soa.items()}

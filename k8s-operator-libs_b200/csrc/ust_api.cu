@@ -214,6 +214,10 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
   }
   P.rank = h->rank;
   P.world = h->world;
+  // Speculative slot grant (verified in-kernel after the grid barrier, so only speed depends on it):
+  // with no MaxParallelUpgrades / MaxUnavailable limit every candidate gets a slot (upgrade_inplace.go:49-62);
+  // with limits the budget is normally tiny next to the number of candidates.
+  P.spec_cut_chunk = (active && policy->max_parallel_upgrades == 0 && policy->max_unavailable_kind == UST_MAXUNAVAIL_NIL) ? 0x7FFFFFFF : 0;
   const int grid = pick_grid(h, n);
   P.grid_chunks = grid;
   P.chunk_begin = 0;
@@ -453,6 +457,16 @@ uint32_t ust_table_entry(const ust_policy* policy, unsigned state_code, uint32_t
   return ust_transition(state_code, w & window, &key);
 }
 int ust_table_window_shift(unsigned state_code) { return ust_window_shift[state_code & 15u]; }
+
+// diagnostics (not in include/ust.h): %globaltimer stamps taken by CTA 0 of the last fused launch
+int ust_debug_stamps(ust_handle* h, unsigned long long* out, int n_ctas) {
+  if (!h || !out || n_ctas < 1 || n_ctas > UST_MAX_CTAS) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  UST_CUDA(h, cudaSetDevice(h->device));
+  UST_CUDA(h, cudaDeviceSynchronize());
+  UST_CUDA(h, cudaMemcpy(out, h->ws->dbg, (size_t)n_ctas * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return UST_OK;
+}
 
 int ust_get_unique_id(void* out_bytes) {
   if (!out_bytes) return UST_ERR_INVALID_ARGUMENT;

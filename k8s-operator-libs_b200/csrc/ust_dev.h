@@ -28,6 +28,7 @@ struct UstWorkspace {
   unsigned int arrive;
   unsigned int depart;
   unsigned int cand_cta[UST_MAX_CTAS];  // candidates per CTA chunk (written by phase 1, read by phase 2)
+  unsigned long long dbg[UST_MAX_CTAS][4];  // %globaltimer stamps per CTA: entry, stream end, barrier release, exit (diagnostics)
 };
 
 // abort key: (pass << 56) | (global node index + 1); policy-level aborts use index part 0
@@ -60,6 +61,7 @@ struct UstParams {
   int pd_enabled;
   int pd_spec_present;
   int eval_pods;          // pod lists present and evaluate_actuators
+  int spec_cut_chunk;     // speculation: chunks before this index assume every upgrade candidate gets a slot
   // sharding
   int rank;
   int world;

@@ -28,16 +28,28 @@ namespace {
 
 constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kStep = kThreads * 4;  // nodes per CTA step in phase 2 (4 per thread)
-constexpr int kUnroll = 4;           // steps in flight per thread in the fast path
+constexpr int kStep = kThreads * 4;   // nodes per CTA step in phase 2 (4 per thread)
+#ifndef UST_UNROLL
+#define UST_UNROLL 2
+#endif
+#ifndef UST_MIN_CTAS
+#define UST_MIN_CTAS 2
+#endif
+constexpr int kUnroll = UST_UNROLL;            // steps in flight per thread in the fast path
+constexpr int kTile = kStep * kUnroll;
+constexpr int kPrefetchTiles = 2;     // L2 prefetch distance of the phase-2 stream, in tiles
+constexpr int kP1Unroll = 4;          // 16-byte hot loads in flight per thread in phase 1
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr uint32_t kLutBytes = (UST_LUT_ENTRIES + 32) * sizeof(uint32_t);  // table + 16 {shift, base} pairs
 
-struct __align__(16) Shared {
-  uint32_t lut[UST_LUT_ENTRIES];
-  uint4 hotlut[256];
+struct __align__(128) Shared {
+  uint32_t lut[UST_LUT_ENTRIES];  // + meta directly behind it: filled by ONE bulk (TMA) copy
   uint2 meta[16];
+  uint4 hotent[256];             // per hot byte: {window shift - 2, table base, sixteen 4-bit one-hot count increments}
   int dsrev[UST_DS_SMEM_MAX + 1];
   unsigned int cnt[16];
   unsigned long long errinv;
+  unsigned long long mbar;       // mbarrier the bulk copy completes on
   long long V[UST_V_LEN];
   // derived, CTA-uniform
   unsigned long long abort_key;  // ~0 = none
@@ -46,9 +58,9 @@ struct __align__(16) Shared {
   long long max_unav;
   long long node_offset;         // global index of this shard's node 0
   long long cand_prefix;         // candidates before this chunk (global order)
+  long long part[kWarps];
   unsigned int warp_tot[kWarps];
-  unsigned int chunk_cand;
-  int red_scratch[kWarps];
+  int last;
 };
 
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
@@ -71,39 +83,62 @@ __device__ __forceinline__ int pass_of_state(unsigned code) {
 __device__ __forceinline__ long long chunk_bound(long long n, int c, int chunks) {
   if (c >= chunks) return n;
   long long b = (n * (long long)c) / chunks;
-  return b & ~127LL;  // chunks start on 128-node boundaries: 128 B of hot bytes, 512 B of each int32 array
+  return b & ~127LL;  // chunks start on 128-node boundaries: a warp's 128-node span never straddles two chunks
 }
 
 // ------------------------------------------------------------------------------------------------
-// table staging
+// table staging: the per-policy transition table (DriverUpgradePolicySpec + manager options, compiled
+// to 32 KiB by ust_lut.h) goes global -> shared with one TMA bulk copy that completes on an mbarrier;
+// nothing waits for it until phase 2 starts.
 // ------------------------------------------------------------------------------------------------
-__device__ void stage_tables(const UstParams& P, Shared& S) {
+__device__ __forceinline__ void stamp(const UstParams& P, int k) {
+  if (threadIdx.x == 0 && k < 4) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.ws->dbg[blockIdx.x][k] = t;
+  }
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ void p1_build_table(Shared& S);
+
+__device__ void stage_tables_begin(const UstParams& P, Shared& S) {
   const int t = threadIdx.x;
-  const uint4* src = reinterpret_cast<const uint4*>(P.lut);
-  uint4* dst = reinterpret_cast<uint4*>(S.lut);
-  for (int i = t; i < (int)(UST_LUT_ENTRIES / 4); i += kThreads) dst[i] = __ldg(src + i);
-  if (t < 16) S.meta[t] = __ldg(reinterpret_cast<const uint2*>(P.lut + UST_LUT_ENTRIES) + t);
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&S.mbar)), "r"(kLutBytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(S.lut)), "l"(P.lut), "r"(kLutBytes), "r"(smem_u32(&S.mbar)) : "memory");
+  }
   if (P.n_ds <= UST_DS_SMEM_MAX)
     for (int i = t; i <= P.n_ds; i += kThreads) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
-  // hot-byte -> byte-sliced counter increments: field j<14 = (code==j), field 14 = unavailable
-  // (GetCurrentUnavailableNodes, common_manager.go:146-165), field 15 = upgrade candidate
-  // (upgrade-required and not skip, upgrade_inplace.go:82)
-  {
-    const unsigned b = t, code = b & 15u;
-    unsigned w[4] = {0, 0, 0, 0};
-    if (code < 14) {
-      w[code >> 2] |= 1u << (8 * (code & 3));
-      if (b & (UST_HOT_UNSCHEDULABLE | UST_HOT_NOT_READY)) w[3] |= 1u << 16;
-      if (code == UST_STATE_UPGRADE_REQUIRED && !(b & UST_HOT_SKIP)) w[3] |= 1u << 24;
-    }
-    S.hotlut[b] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
+  p1_build_table(S);
   if (t < 16) S.cnt[t] = 0;
-  if (t == 0) S.errinv = 0;
+  if (t == 32) { S.errinv = 0; S.abort_key = ~0ull; }
+}
+
+__device__ __forceinline__ void stage_tables_wait(Shared& S) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(&S.mbar)) : "memory");
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // phase 1: counts over the hot bytes of [b0, b1)
+//
+// Byte-sliced SIMD-in-register counting. A 256-entry shared-memory table maps a hot byte to sixteen
+// 4-bit one-hot increments packed in 64 bits (fields 0-13: state code, 14: unavailable, 15: upgrade
+// candidate); a thread sums the entries of 8 nodes (no field can exceed 8), widens the nibbles to byte
+// lanes, and keeps going. Per node: one 8-byte LDS, two shifts/masks for the address, one add. No
+// atomics until the end of the chunk: one REDUX per counter per warp, 16 global atomics per CTA.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void p1_error_byte(const UstParams& P, Shared& S, unsigned b, long long i) {
   const unsigned code = b & 15u;
@@ -114,59 +149,98 @@ __device__ __forceinline__ void p1_error_byte(const UstParams& P, Shared& S, uns
   atomicMax(&S.errinv, ~key);
 }
 
-__device__ __forceinline__ void p1_word(const UstParams& P, Shared& S, uint32_t x, long long i, uint4& acc) {
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const uint4 inc = S.hotlut[(x >> (8 * k)) & 0xFFu];
-    acc.x += inc.x; acc.y += inc.y; acc.z += inc.z; acc.w += inc.w;
+// window shift (minus 2) of every state code, 8 bits each — compile-time copy of ust_window_shift[]
+constexpr unsigned long long pack_shifts(int from) {
+  unsigned long long v = 0;
+  for (int i = 0; i < 8; i++) v |= (unsigned long long)(ust_window_shift[from + i] - 2) << (8 * i);
+  return v;
+}
+constexpr unsigned long long kShiftLo = pack_shifts(0), kShiftHi = pack_shifts(8);
+
+__device__ void p1_build_table(Shared& S) {
+  // GetCurrentUnavailableNodes (common_manager.go:146-165) counts every snapshot entry that is cordoned or
+  // not ready; an upgrade candidate is upgrade-required and not marked skip (upgrade_inplace.go:82)
+  const unsigned b = threadIdx.x, code = b & 15u;
+  unsigned long long v = 0;
+  if (code < 14) {
+    v = 1ull << (4 * code);
+    if (b & (UST_HOT_UNSCHEDULABLE | UST_HOT_NOT_READY)) v |= 1ull << 56;
+    if (code == UST_STATE_UPGRADE_REQUIRED && !(b & UST_HOT_SKIP)) v |= 1ull << 60;
   }
-  if (x & 0x80808080u) {
-#pragma unroll
-    for (int k = 0; k < 4; k++) p1_error_byte(P, S, (x >> (8 * k)) & 0xFFu, i + k);
-  }
+  const unsigned shift = (unsigned)(((code < 8 ? kShiftLo : kShiftHi) >> (8 * (code & 7))) & 0xFFull);
+  S.hotent[b] = make_uint4(shift, code * (UST_LUT_WINDOW * 4u), (uint32_t)v, (uint32_t)(v >> 32));
 }
 
-__device__ __forceinline__ void p1_spill_thread(Shared& S, uint4& acc) {
-  const uint32_t w[4] = {acc.x, acc.y, acc.z, acc.w};
+// byte lanes: B[0] = fields 0,2,4,6  B[1] = fields 1,3,5,7  B[2] = fields 8,10,12,14  B[3] = fields 9,11,13,15
+__device__ __forceinline__ unsigned p1_field(const uint32_t (&B)[4], int f) {
+  return (B[(f >> 3) * 2 + (f & 1)] >> (8 * ((f & 7) >> 1))) & 0xFFu;
+}
+
+__device__ __forceinline__ void p1_words(const Shared& S, uint32_t x, uint32_t y, uint32_t (&B)[4]) {
+  uint32_t lo = 0, hi = 0;
 #pragma unroll
-  for (int f = 0; f < 16; f++) {
-    const unsigned v = (w[f >> 2] >> (8 * (f & 3))) & 0xFFu;
-    if (v) atomicAdd(&S.cnt[f], v);
+  for (int k = 0; k < 4; k++) {
+    const uint2 a = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(S.hotent) + (((x >> (8 * k)) & 0xFFu) << 4) + 8);
+    const uint2 c = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(S.hotent) + (((y >> (8 * k)) & 0xFFu) << 4) + 8);
+    lo += a.x + c.x;
+    hi += a.y + c.y;
   }
-  acc = make_uint4(0, 0, 0, 0);
+  B[0] += lo & 0x0F0F0F0Fu;
+  B[1] += (lo >> 4) & 0x0F0F0F0Fu;
+  B[2] += hi & 0x0F0F0F0Fu;
+  B[3] += (hi >> 4) & 0x0F0F0F0Fu;
 }
 
 __device__ void phase1(const UstParams& P, Shared& S, long long b0, long long b1) {
   const int t = threadIdx.x;
-  uint4 acc = make_uint4(0, 0, 0, 0);
+  uint32_t B[4] = {0, 0, 0, 0};
   int pending = 0;
-  for (long long i = b0 + 16LL * t; i < b1; i += 16LL * kThreads) {
-    if (i + 16 <= b1) {
-      const uint4 h = __ldg(reinterpret_cast<const uint4*>(P.hot + i));
-      p1_word(P, S, h.x, i, acc);
-      p1_word(P, S, h.y, i + 4, acc);
-      p1_word(P, S, h.z, i + 8, acc);
-      p1_word(P, S, h.w, i + 12, acc);
-    } else {
-      for (long long j = i; j < b1; j++) {  // ragged end of the array
-        const unsigned b = P.hot[j];
-        const uint4 inc = S.hotlut[b];
-        acc.x += inc.x; acc.y += inc.y; acc.z += inc.z; acc.w += inc.w;
-        p1_error_byte(P, S, b, j);
+  constexpr uint32_t kFill = 0x0E0E0E0Eu;  // "excluded": contributes to no counter
+  for (long long base = b0; base < b1; base += 16LL * kThreads * kP1Unroll) {
+    uint4 h[kP1Unroll];
+#pragma unroll
+    for (int u = 0; u < kP1Unroll; u++) {
+      const long long i = base + (long long)u * 16 * kThreads + 16LL * t;
+      if (i + 16 <= b1) {
+        h[u] = __ldg(reinterpret_cast<const uint4*>(P.hot + i));
+      } else {
+        uint32_t w[4] = {kFill, kFill, kFill, kFill};
+        for (long long j = i; j < b1; j++) {  // ragged end of the array (at most 15 bytes, one lane)
+          const int q = (int)(j - i);
+          w[q >> 2] = (w[q >> 2] & ~(0xFFu << (8 * (q & 3)))) | ((uint32_t)P.hot[j] << (8 * (q & 3)));
+        }
+        h[u] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
-    pending += 16;
-    if (pending > 255 - 16) { p1_spill_thread(S, acc); pending = 0; }  // byte lanes hold at most 255
+#pragma unroll
+    for (int u = 0; u < kP1Unroll; u++) {
+      if ((h[u].x | h[u].y | h[u].z | h[u].w) & 0x80808080u) {  // rare: a revision-hash error bit among these 16 nodes
+        const uint32_t w[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
+        const long long i = base + (long long)u * 16 * kThreads + 16LL * t;
+        for (int q = 0; q < 16; q++) {
+          const unsigned b = (w[q >> 2] >> (8 * (q & 3))) & 0xFFu;
+          if ((b & 15u) < UST_STATE_EXCLUDED) p1_error_byte(P, S, b, i + q);
+        }
+      }
+      p1_words(S, h[u].x, h[u].y, B);
+      p1_words(S, h[u].z, h[u].w, B);
+    }
+    pending += 16 * kP1Unroll;
+    if (pending > 255 - 16 * kP1Unroll) {  // byte lanes hold at most 255: spill (thread-serial, rare)
+#pragma unroll
+      for (int f = 0; f < 16; f++) {
+        const unsigned v = p1_field(B, f);
+        if (v) atomicAdd(&S.cnt[f], v);
+      }
+      B[0] = B[1] = B[2] = B[3] = 0;
+      pending = 0;
+    }
   }
   // all threads converged: one REDUX per counter per warp, one shared atomic per warp
-  {
-    const uint32_t w[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-    for (int f = 0; f < 16; f++) {
-      unsigned v = (w[f >> 2] >> (8 * (f & 3))) & 0xFFu;
-      v = __reduce_add_sync(0xFFFFFFFFu, v);
-      if ((t & 31) == 0 && v) atomicAdd(&S.cnt[f], v);
-    }
+  for (int f = 0; f < 16; f++) {
+    const unsigned v = __reduce_add_sync(kFull, p1_field(B, f));
+    if ((t & 31) == 0 && v) atomicAdd(&S.cnt[f], v);
   }
   __syncthreads();
   UstWorkspace* ws = P.ws;
@@ -261,18 +335,19 @@ __device__ void write_counters(const UstParams& P, const Shared& S) {
 // ------------------------------------------------------------------------------------------------
 // phase 2: per-node transition
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int load_dsrev(const UstParams& P, const Shared& S, uint32_t di) {
-  if (P.n_ds <= UST_DS_SMEM_MAX) return S.dsrev[min(di, (uint32_t)P.n_ds)];
-  return di < (uint32_t)P.n_ds ? __ldg(P.ds_rev + di) : 0;
+template <bool DS_SMEM>
+__device__ __forceinline__ bool pod_synced(const UstParams& P, const Shared& S, int rev, uint32_t di) {
+  // podRevisionHash == daemonsetRevisionHash (common_manager.go:318); a missing DaemonSet never matches
+  if (DS_SMEM) return (di < (uint32_t)P.n_ds) && (rev == S.dsrev[min(di, (uint32_t)P.n_ds)]);
+  return di < (uint32_t)P.n_ds && rev == __ldg(P.ds_rev + di);
 }
 
 // table entry for one node. hb = hot byte, extra = derived bits (slot grant, pod-list summaries)
+template <bool DS_SMEM>
 __device__ __forceinline__ uint32_t node_entry(const UstParams& P, const Shared& S, uint32_t hb, uint32_t fl, int rev,
                                                uint32_t di, uint32_t extra) {
-  const int dsr = load_dsrev(P, S, di);
-  const bool synced = (di < (uint32_t)P.n_ds) && (rev == dsr);  // podRevisionHash == daemonsetRevisionHash (common_manager.go:318)
   uint32_t w = (fl & UST_F_INPUT_MASK) | ((hb >> 3) & (UST_W_SKIP | UST_W_UNSCHEDULABLE)) | extra;
-  if (synced) w |= UST_W_SYNCED;
+  if (pod_synced<DS_SMEM>(P, S, rev, di)) w |= UST_W_SYNCED;
   const uint2 m = S.meta[hb & 15u];
   const uint32_t off = (__funnelshift_r(w, 0u, m.x) & 0x7FCu) | m.y;
   return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(S.lut) + off);
@@ -327,33 +402,187 @@ __device__ __forceinline__ void pack4(const uint32_t e[4], uint32_t& next4, uint
   out4 = __byte_perm(hi01, hi23, 0x7531);
 }
 
-// fast path: full steps, CTA on one side of the slot budget, no abort, no pod lists
-__device__ __forceinline__ void fast_tile(const UstParams& P, const Shared& S, long long base, uint32_t grant) {
-  const int t = threadIdx.x;
+// One tile = kUnroll steps of kStep nodes; thread t owns nodes base + j*kStep + 4t .. +3. `lim` is a
+// multiple of 128 (or the tile is full), so validity is uniform per warp and per j.
+struct Tile {
   uint32_t h[kUnroll];
   uint4 f[kUnroll], r[kUnroll], d[kUnroll];
+};
+
+// Chunk-relative addressing: the chunk's base pointers are CTA-uniform; a thread addresses 4-node groups
+// with a 32-bit group index q (thread t of the CTA owns groups done/4 + j*kStepQ + t of a tile).
+struct Cursor {
+  const uint32_t* h;
+  const uint4* f;
+  const uint4* r;
+  const uint4* d;
+  uint32_t* nx;
+  uint2* ac;
+  uint32_t* oc;
+  int q;
+};
+constexpr int kStepQ = kStep / 4;  // a step in units of 4-node groups
+constexpr int kTileQ = kTile / 4;
+
+__device__ __forceinline__ Cursor cursor_at(const UstParams& P, long long base) {
+  Cursor c;
+  c.h = reinterpret_cast<const uint32_t*>(P.hot + base);
+  c.f = reinterpret_cast<const uint4*>(P.flags + base);
+  c.r = reinterpret_cast<const uint4*>(P.pod_rev + base);
+  c.d = reinterpret_cast<const uint4*>(P.ds_idx + base);
+  c.nx = reinterpret_cast<uint32_t*>(P.next + base);
+  c.ac = reinterpret_cast<uint2*>(P.actions + base);
+  c.oc = P.outcome ? reinterpret_cast<uint32_t*>(P.outcome + base) : nullptr;
+  c.q = threadIdx.x;
+  return c;
+}
+__device__ __forceinline__ void cursor_advance(Cursor& c) { c.q += kTileQ; }
+
+// `room` = nodes left in the chunk from this thread's first node of the tile; chunk ends are multiples of
+// 128 nodes, so for a partial tile validity is uniform per warp and per step.
+template <bool FULL>
+__device__ __forceinline__ void tile_load(const Cursor& c, int room, Tile& T) {
 #pragma unroll
   for (int j = 0; j < kUnroll; j++) {
-    const long long i = base + (long long)j * kStep + 4 * t;
-    h[j] = ld_keep_u32(P.hot + i);
-    f[j] = ld_stream_u4(P.flags + i);
-    r[j] = ld_stream_u4(P.pod_rev + i);
-    d[j] = ld_stream_u4(P.ds_idx + i);
+    if (FULL || j * kStep + 4 <= room) {
+      T.h[j] = __ldg(c.h + c.q + j * kStepQ);
+      T.f[j] = __ldcs(c.f + c.q + j * kStepQ);
+      T.r[j] = __ldcs(c.r + c.q + j * kStepQ);
+      T.d[j] = __ldcs(c.d + c.q + j * kStepQ);
+    }
   }
+}
+
+// pull the int32 arrays of the tile `ahead` tiles further on into L2 (one request per 128-byte line)
+__device__ __forceinline__ void tile_prefetch_l2(const Cursor& c, int ahead, int room) {
+  if ((threadIdx.x & 7) != 0) return;
 #pragma unroll
   for (int j = 0; j < kUnroll; j++) {
-    const long long i = base + (long long)j * kStep + 4 * t;
-    uint32_t e[4];
-    e[0] = node_entry(P, S, h[j] & 0xFFu, f[j].x, (int)r[j].x, d[j].x, grant);
-    e[1] = node_entry(P, S, (h[j] >> 8) & 0xFFu, f[j].y, (int)r[j].y, d[j].y, grant);
-    e[2] = node_entry(P, S, (h[j] >> 16) & 0xFFu, f[j].z, (int)r[j].z, d[j].z, grant);
-    e[3] = node_entry(P, S, h[j] >> 24, f[j].w, (int)r[j].w, d[j].w, grant);
-    uint32_t next4, out4;
-    uint2 act4;
-    pack4(e, next4, act4, out4);
-    __stcs(reinterpret_cast<uint32_t*>(P.next + i), next4);
-    __stcs(reinterpret_cast<uint2*>(P.actions + i), act4);
-    if (P.outcome) __stcs(reinterpret_cast<uint32_t*>(P.outcome + i), out4);
+    if (ahead * kTile + j * kStep + 4 <= room) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(c.f + c.q + ahead * kTileQ + j * kStepQ));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(c.r + c.q + ahead * kTileQ + j * kStepQ));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(c.d + c.q + ahead * kTileQ + j * kStepQ));
+    }
+  }
+}
+
+// revision-hash error seen while streaming (flags word already in registers)
+__device__ __forceinline__ void spec_error_byte(const UstParams& P, Shared& S, unsigned b, uint32_t fl, long long i) {
+  const unsigned code = b & 15u;
+  if (!(b & UST_HOT_REVISION_HASH_ERROR) || !P.active) return;
+  if (!(code == UST_STATE_UNKNOWN || code == UST_STATE_DONE || code == UST_STATE_POD_RESTART_REQUIRED || code == UST_STATE_FAILED)) return;
+  if (fl & UST_F_POD_ORPHANED) return;
+  atomicMax(&S.errinv, ~UST_KEY(pass_of_state(code), (unsigned long long)i + 1ull));
+}
+
+__device__ __forceinline__ void widen(uint32_t& lo, uint32_t& hi, uint32_t (&B)[4]) {
+  B[0] += lo & 0x0F0F0F0Fu;
+  B[1] += (lo >> 4) & 0x0F0F0F0Fu;
+  B[2] += hi & 0x0F0F0F0Fu;
+  B[3] += (hi >> 4) & 0x0F0F0F0Fu;
+  lo = hi = 0;
+}
+
+__device__ __forceinline__ void spill_thread(Shared& S, uint32_t (&B)[4]) {
+#pragma unroll
+  for (int f = 0; f < 16; f++) {
+    const unsigned v = p1_field(B, f);
+    if (v) atomicAdd(&S.cnt[f], v);
+  }
+  B[0] = B[1] = B[2] = B[3] = 0;
+}
+
+// One node of the streaming pass. `xs` = the node's hot byte moved to bits 4..11 of a word (so it indexes
+// the 16-byte hotent table directly), `ws` = its SKIP / UNSCHEDULABLE bits already at w positions 2, 3.
+template <bool DS_SMEM>
+__device__ __forceinline__ uint32_t stream_node(const UstParams& P, const Shared& S, uint32_t tab_off, uint32_t wbits,
+                                                uint32_t fl, int rev, uint32_t di, uint32_t grant, uint32_t& lo,
+                                                uint32_t& hi) {
+  const uint4 m = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(S.hotent) + tab_off);
+  lo += m.z;
+  hi += m.w;
+  uint32_t w = (fl & UST_F_INPUT_MASK) | wbits | grant;
+  if (pod_synced<DS_SMEM>(P, S, rev, di)) w |= UST_W_SYNCED;
+  const uint32_t off = (__funnelshift_r(w, 0u, m.x) & 0x7FCu) | m.y;
+  return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(S.lut) + off);
+}
+
+// The single streaming pass: for one tile, count (byte-sliced) AND evaluate every node with the chunk's
+// speculative slot grant, writing next_state / actions. Whether the speculation was right is only known
+// after the grid barrier; chunks on the wrong side of the cut are redone exactly there.
+template <bool FULL, bool DS_SMEM, bool OUTCOME>
+__device__ __forceinline__ void spec_tile(const UstParams& P, Shared& S, const Cursor& c, int room, long long i0,
+                                          const Tile& T, uint32_t grant, uint32_t (&B)[4]) {
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int j = 0; j < kUnroll; j++) {
+    if (FULL || j * kStep + 4 <= room) {
+      const uint32_t x = T.h[j];
+      if (x & 0x80808080u) {  // rare
+        const long long i = i0 + j * kStep;
+        spec_error_byte(P, S, x & 0xFFu, T.f[j].x, i);
+        spec_error_byte(P, S, (x >> 8) & 0xFFu, T.f[j].y, i + 1);
+        spec_error_byte(P, S, (x >> 16) & 0xFFu, T.f[j].z, i + 2);
+        spec_error_byte(P, S, x >> 24, T.f[j].w, i + 3);
+      }
+      constexpr uint32_t kW = UST_W_SKIP | UST_W_UNSCHEDULABLE;
+      uint32_t e[4];
+      e[0] = stream_node<DS_SMEM>(P, S, (x << 4) & 0xFF0u, (x >> 3) & kW, T.f[j].x, (int)T.r[j].x, T.d[j].x, grant, lo, hi);
+      e[1] = stream_node<DS_SMEM>(P, S, (x >> 4) & 0xFF0u, (x >> 11) & kW, T.f[j].y, (int)T.r[j].y, T.d[j].y, grant, lo, hi);
+      e[2] = stream_node<DS_SMEM>(P, S, (x >> 12) & 0xFF0u, (x >> 19) & kW, T.f[j].z, (int)T.r[j].z, T.d[j].z, grant, lo, hi);
+      e[3] = stream_node<DS_SMEM>(P, S, (x >> 20) & 0xFF0u, (x >> 27) & kW, T.f[j].w, (int)T.r[j].w, T.d[j].w, grant, lo, hi);
+      uint32_t next4, out4;
+      uint2 act4;
+      pack4(e, next4, act4, out4);
+      __stcs(c.nx + c.q + j * kStepQ, next4);
+      __stcs(c.ac + c.q + j * kStepQ, act4);
+      if (OUTCOME) __stcs(c.oc + c.q + j * kStepQ, out4);
+    }
+    if (j & 1) widen(lo, hi, B);  // at most 8 per nibble so far
+  }
+  if (kUnroll & 1) widen(lo, hi, B);
+}
+
+// The chunk loop is software-pipelined over two register tiles: tile i+1's loads are issued before tile i
+// is evaluated, so HBM always has a full tile per thread in flight while the SM computes.
+template <bool DS_SMEM, bool OUTCOME>
+__device__ void spec_chunk(const UstParams& P, Shared& S, long long b0, long long lim, uint32_t grant, uint32_t (&B)[4]) {
+  const long long span = lim - b0;  // CTA-uniform, a multiple of 128
+  const int t4 = 4 * threadIdx.x;
+  auto room_at = [&](long long done) -> int {  // nodes from this thread's first node of the tile to the chunk end
+    const long long r = span - done - t4;
+    return r > (1LL << 30) ? (1 << 30) : (r < 0 ? 0 : (int)r);
+  };
+  Cursor c = cursor_at(P, b0);
+  long long i0 = b0 + t4;
+  Tile TA, TB;
+  auto load = [&](Tile& T, long long done) {  // loads of the tile starting `done` nodes into the chunk; c.q points at it
+    if (done >= span) return;
+    if (span - done >= kTile) tile_load<true>(c, 0, T); else tile_load<false>(c, room_at(done), T);
+  };
+  auto eval = [&](const Tile& T, long long done) {  // c.q points at the tile being evaluated
+    const int room = room_at(done);
+    if (span - done >= kTile) spec_tile<true, DS_SMEM, OUTCOME>(P, S, c, room, i0, T, grant, B);
+    else spec_tile<false, DS_SMEM, OUTCOME>(P, S, c, room, i0, T, grant, B);
+  };
+  // the first tile's loads go out before anything waits on the table copy
+  load(TA, 0);
+  stage_tables_wait(S);
+  __syncthreads();
+  int tiles = 0;
+  for (long long done = 0; done < span; done += 2 * kTile) {
+    c.q += kTileQ; load(TB, done + kTile); c.q -= kTileQ;      // next tile in flight ...
+    eval(TA, done);                                            // ... while this one is evaluated
+    cursor_advance(c);
+    i0 += kTile;
+    if (done + kTile < span) {
+      c.q += kTileQ; load(TA, done + 2 * kTile); c.q -= kTileQ;
+      eval(TB, done + kTile);
+      cursor_advance(c);
+      i0 += kTile;
+    }
+    tiles += 2;
+    if (tiles >= 14) { spill_thread(S, B); tiles = 0; }  // byte lanes: 16 per tile, 255 max
   }
 }
 
@@ -402,7 +631,7 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
     unsigned incl = tc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      const unsigned v = __shfl_up_sync(kFull, incl, o);
       if ((t & 31) >= o) incl += v;
     }
     if ((t & 31) == 31) S.warp_tot[t >> 5] = incl;
@@ -425,6 +654,7 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
   }
 
   if (nvalid == 0) return;
+  const bool ds_smem = P.n_ds <= UST_DS_SMEM_MAX;
   uint32_t e[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -434,7 +664,7 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
       extra |= pod_summary(P, hb[k], i0 + k, clear_mask);
       f &= ~clear_mask;
     }
-    e[k] = node_entry(P, S, hb[k], f, rev[k], di[k], extra);
+    e[k] = ds_smem ? node_entry<true>(P, S, hb[k], f, rev[k], di[k], extra) : node_entry<false>(P, S, hb[k], f, rev[k], di[k], extra);
     if (aborting) e[k] = apply_abort(S, e[k], hb[k], S.node_offset + i0 + k);
   }
   uint32_t next4, out4;
@@ -453,24 +683,81 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
   }
 }
 
-__device__ void phase2(const UstParams& P, Shared& S, long long b0, long long b1, unsigned chunk_cand) {
-  // where does this chunk sit relative to the slot budget?
+// exact / abort / pod-list evaluation of a whole chunk (the verification step falls back to this)
+__device__ void general_chunk(const UstParams& P, Shared& S, long long b0, long long b1, unsigned chunk_cand) {
   const long long lo = S.cand_prefix, hi = S.cand_prefix + chunk_cand;
   const bool slotted = P.active && !P.requestor;
   const bool exact = slotted && chunk_cand != 0 && lo < S.budget && hi > S.budget;
   const uint32_t grant = (slotted && chunk_cand != 0 && hi <= S.budget) ? UST_W_GRANTED : 0u;
-  const bool general = exact || S.abort_key != ~0ull || P.eval_pods;
-  long long base = b0;
-  if (!general) {
-    for (; base + (long long)kStep * kUnroll <= b1; base += (long long)kStep * kUnroll) fast_tile(P, S, base, grant);
-    long long running = 0;
-    for (; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
-  } else if (!exact) {
-    long long running = 0;
-    for (; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
+  long long running = 0;
+  if (!exact) {
+    for (long long base = b0; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
   } else {
+    for (long long base = b0; base < b1; base += kStep) general_step<true>(P, S, base, b1, 0u, running);
+  }
+}
+
+// speculative grant of a chunk: chunks before P.spec_cut_chunk assume every candidate gets a slot
+__device__ __forceinline__ uint32_t spec_grant(const UstParams& P, int chunk) {
+  return (P.active && !P.requestor && chunk < P.spec_cut_chunk) ? UST_W_GRANTED : 0u;
+}
+
+// was the speculation right for this chunk? (called after derive_scalars + prefix)
+__device__ __forceinline__ bool spec_holds(const UstParams& P, const Shared& S, int chunk, unsigned chunk_cand) {
+  if (S.abort_key != ~0ull) return false;
+  if (!(P.active && !P.requestor) || chunk_cand == 0) return true;
+  const long long lo = S.cand_prefix, hi = S.cand_prefix + chunk_cand;
+  return spec_grant(P, chunk) ? (hi <= S.budget) : (lo >= S.budget);
+}
+
+// streaming pass over one chunk: counts + speculative outputs (or counts only when pod lists are evaluated)
+__device__ void stream_chunk(const UstParams& P, Shared& S, int chunk, long long b0, long long b1) {
+  if (P.eval_pods) {
+    phase1(P, S, b0, b1);
+    return;
+  }
+  const int t = threadIdx.x;
+  const long long lim = b1 & ~127LL;  // == b1 except for the ragged end of the whole array
+  const uint32_t grant = spec_grant(P, chunk);
+  uint32_t B[4] = {0, 0, 0, 0};
+  const bool ds_smem = P.n_ds <= UST_DS_SMEM_MAX;
+  if (ds_smem) {
+    if (P.outcome) spec_chunk<true, true>(P, S, b0, lim, grant, B);
+    else spec_chunk<true, false>(P, S, b0, lim, grant, B);
+  } else {
+    if (P.outcome) spec_chunk<false, true>(P, S, b0, lim, grant, B);
+    else spec_chunk<false, false>(P, S, b0, lim, grant, B);
+  }
+  if (lim < b1) {  // ragged end (< 128 nodes, last chunk only)
     long long running = 0;
-    for (; base < b1; base += kStep) general_step<true>(P, S, base, b1, 0u, running);
+    general_step<false>(P, S, lim, b1, grant, running);
+    for (long long j = lim + t; j < b1; j += kThreads) {
+      const unsigned b = P.hot[j];
+      uint32_t lo = S.hotent[b].z, hi = S.hotent[b].w;
+      widen(lo, hi, B);
+      spec_error_byte(P, S, b, P.flags[j], j);
+    }
+  }
+  // all threads converged: one REDUX per counter per warp, one shared atomic per warp, 16 global atomics per CTA
+#pragma unroll
+  for (int f = 0; f < 16; f++) {
+    const unsigned v = __reduce_add_sync(kFull, p1_field(B, f));
+    if ((t & 31) == 0 && v) atomicAdd(&S.cnt[f], v);
+  }
+  __syncthreads();
+  UstWorkspace* ws = P.ws;
+  if (t < 14) {
+    if (S.cnt[t]) atomicAdd(&ws->acc[t], (unsigned long long)S.cnt[t]);
+  } else if (t == 14) {
+    unsigned long long in = 0;
+    for (int f = 0; f < 14; f++) in += S.cnt[f];
+    const unsigned long long excluded = (unsigned long long)(b1 - b0) - in;
+    if (excluded) atomicAdd(&ws->acc[UST_STATE_EXCLUDED], excluded);
+  } else if (t == 15) {
+    if (S.cnt[14]) atomicAdd(&ws->acc[UST_V_UNAVAILABLE], (unsigned long long)S.cnt[14]);
+    if (S.cnt[15]) atomicAdd(&ws->acc[UST_V_CANDIDATES], (unsigned long long)S.cnt[15]);
+  } else if (t == 32) {
+    if (S.errinv) atomicMax(&ws->errinv, S.errinv);
   }
 }
 
@@ -479,12 +766,11 @@ __device__ long long block_sum_cand_before(const UstParams& P, Shared& S, int ch
   const int t = threadIdx.x;
   long long s = 0;
   for (int c = t; c < chunk; c += kThreads) s += __ldcg(&P.ws->cand_cta[c]);
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-  __shared__ long long part[kWarps];
-  if ((t & 31) == 0) part[t >> 5] = s;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+  if ((t & 31) == 0) S.part[t >> 5] = s;
   __syncthreads();
   long long tot = 0;
-  for (int w = 0; w < kWarps; w++) tot += part[w];
+  for (int w = 0; w < kWarps; w++) tot += S.part[w];
   __syncthreads();
   return tot;
 }
@@ -523,50 +809,57 @@ __device__ void finish(const UstParams& P, Shared& S, int chunks, bool reset_ws)
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2) ust_fused_kernel(const __grid_constant__ UstParams P) {
+__global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_fused_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
   const int chunk = blockIdx.x, chunks = gridDim.x;
   const long long b0 = chunk_bound(P.n, chunk, chunks), b1 = chunk_bound(P.n, chunk + 1, chunks);
-  stage_tables(P, S);
+  stamp(P, 0);
+  stage_tables_begin(P, S);
   __syncthreads();
-  phase1(P, S, b0, b1);
-  if (threadIdx.x == 0) P.ws->cand_cta[chunk] = S.cnt[15];
-  // grid-wide barrier: every CTA is co-resident (cooperative launch)
+  stream_chunk(P, S, chunk, b0, b1);
+  stamp(P, 1);
+  // grid-wide barrier (every CTA is co-resident: cooperative launch). After it the cluster-wide
+  // counters are final and each chunk can check its speculation.
   __syncthreads();
   if (threadIdx.x == 0) {
+    P.ws->cand_cta[chunk] = S.cnt[15];
     __threadfence();
     atomicAdd(&P.ws->arrive, 1u);
-    while (ld_acquire_u32(&P.ws->arrive) < (unsigned)chunks) __nanosleep(40);
+    while (ld_acquire_u32(&P.ws->arrive) < (unsigned)chunks) __nanosleep(20);
     __threadfence();
   }
   __syncthreads();
+  stamp(P, 2);
   load_local_vector(P, S);
   __syncthreads();
   if (threadIdx.x == 0) derive_scalars(P, S);
   const long long before = block_sum_cand_before(P, S, chunk);
   if (threadIdx.x == 0) S.cand_prefix += before;
   __syncthreads();
-  phase2(P, S, b0, b1, S.cnt[15]);
+  if (P.eval_pods || !spec_holds(P, S, chunk, S.cnt[15])) {
+    if (P.eval_pods) { stage_tables_wait(S); __syncthreads(); }
+    general_chunk(P, S, b0, b1, S.cnt[15]);
+  }
   finish(P, S, chunks, true);
+  stamp(P, 3);
 }
 
-// split mode (multi-GPU with a host-launched collective between the phases, or pipelined uploads)
-__global__ void __launch_bounds__(kThreads, 2) ust_phase1_kernel(const __grid_constant__ UstParams P) {
+// split mode (multi-GPU with a host-launched collective between the kernels): streaming pass ...
+__global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase1_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
   const int chunk = blockIdx.x, chunks = gridDim.x;
   const long long b0 = chunk_bound(P.n, chunk, chunks), b1 = chunk_bound(P.n, chunk + 1, chunks);
-  stage_tables(P, S);
+  stage_tables_begin(P, S);
   __syncthreads();
-  phase1(P, S, b0, b1);
-  if (threadIdx.x == 0) P.ws->cand_cta[chunk] = S.cnt[15];
+  stream_chunk(P, S, chunk, b0, b1);
   __syncthreads();
-  __shared__ int last;
   if (threadIdx.x == 0) {
+    P.ws->cand_cta[chunk] = S.cnt[15];
     __threadfence();
-    last = atomicAdd(&P.ws->depart, 1u) == (unsigned)chunks - 1u;
+    S.last = atomicAdd(&P.ws->depart, 1u) == (unsigned)chunks - 1u;
   }
   __syncthreads();
-  if (last) {  // publish this shard's lanes of the exchange vector, restore the workspace invariant
+  if (S.last) {  // publish this shard's lanes of the exchange vector, restore the workspace invariant
     __threadfence();
     load_local_vector(P, S);
     __syncthreads();
@@ -575,20 +868,24 @@ __global__ void __launch_bounds__(kThreads, 2) ust_phase1_kernel(const __grid_co
     if (threadIdx.x < 18) P.ws->acc[threadIdx.x] = 0;
     if (threadIdx.x == 0) { P.ws->errinv = 0; P.ws->depart = 0; }
   }
+  if (P.eval_pods) stage_tables_wait(S);  // never leave a bulk copy in flight at CTA exit
 }
 
-__global__ void __launch_bounds__(kThreads, 2) ust_phase2_kernel(const __grid_constant__ UstParams P) {
+// ... and verification: redo, exactly, the chunks whose speculation did not hold
+__global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase2_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
   const int chunk = P.chunk_begin + blockIdx.x, chunks = P.grid_chunks;
   const long long b0 = chunk_bound(P.n, chunk, chunks), b1 = chunk_bound(P.n, chunk + 1, chunks);
-  stage_tables(P, S);
+  stage_tables_begin(P, S);
   if (threadIdx.x < UST_V_LEN) S.V[threadIdx.x] = P.xchg[threadIdx.x];
   __syncthreads();
   if (threadIdx.x == 0) derive_scalars(P, S);
   const long long before = block_sum_cand_before(P, S, chunk);
   if (threadIdx.x == 0) S.cand_prefix += before;
+  stage_tables_wait(S);
   __syncthreads();
-  phase2(P, S, b0, b1, __ldcg(&P.ws->cand_cta[chunk]));
+  const unsigned chunk_cand = __ldcg(&P.ws->cand_cta[chunk]);
+  if (P.eval_pods || !spec_holds(P, S, chunk, chunk_cand)) general_chunk(P, S, b0, b1, chunk_cand);
   finish(P, S, (int)gridDim.x, false);
 }
 

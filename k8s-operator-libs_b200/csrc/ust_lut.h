@@ -29,7 +29,7 @@
 
 // first bit of the window each state's transition reads (always >= 2: the kernel shifts by sh-2 so the
 // table index comes out pre-multiplied by 4)
-static const int ust_window_shift[16] = {
+static constexpr int ust_window_shift[16] = {
     /* 0 unknown            */ 3,   // UNSCHED, UPG_REQ, SAFE_LOAD, ORPHANED, SYNCED
     /* 1 upgrade-required   */ 2,   // SKIP, UNSCHED, GRANTED, UPG_REQ
     /* 2 cordon-required    */ 2,

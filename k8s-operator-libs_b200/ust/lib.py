@@ -7,7 +7,7 @@ import numpy as np
 from . import abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(os.path.dirname(HERE), "libust.so")
+SO_PATH = os.environ.get("UST_LIB") or os.path.join(os.path.dirname(HERE), "libust.so")  # UST_LIB: tuning experiments only
 
 _lib = None
 
