@@ -155,13 +155,20 @@ static int ensure_tables(ust_handle* h, const ust_policy* p, cudaStream_t st) {
   return UST_OK;
 }
 
-static int pick_grid(const ust_handle* h, int64_t n) {
+// The shard is cut into contiguous chunks that CTAs claim with an atomic ticket. Measured on B200 (round 1,
+// profiles/README.md): one chunk per co-resident CTA beats finer dynamic chunks, because every chunk start
+// exposes one full HBM latency before its first tile arrives — so chunks == grid unless the snapshot is small.
+static int pick_chunks(const ust_handle* h, int64_t n) {
   const int64_t max_grid = (int64_t)h->ctas_per_sm * h->num_sms;
-  int64_t g = n / 8192;
-  if (g < 1) g = 1;
-  if (g > max_grid) g = max_grid;
-  if (g > UST_MAX_CTAS) g = UST_MAX_CTAS;
-  return (int)g;
+  int64_t c = n / 8192;
+  if (c < 1) c = 1;
+  if (c > max_grid) c = max_grid;
+  if (c > UST_MAX_CTAS) c = UST_MAX_CTAS;
+  return (int)c;
+}
+static int pick_grid(const ust_handle* h, int chunks) {
+  const int64_t max_grid = (int64_t)h->ctas_per_sm * h->num_sms;
+  return (int)(chunks < max_grid ? chunks : max_grid);
 }
 
 static int check_aligned(ust_handle* h, const void* p, const char* what) {
@@ -218,8 +225,10 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
   // with no MaxParallelUpgrades / MaxUnavailable limit every candidate gets a slot (upgrade_inplace.go:49-62);
   // with limits the budget is normally tiny next to the number of candidates.
   P.spec_cut_chunk = (active && policy->max_parallel_upgrades == 0 && policy->max_unavailable_kind == UST_MAXUNAVAIL_NIL) ? 0x7FFFFFFF : 0;
-  const int grid = pick_grid(h, n);
-  P.grid_chunks = grid;
+  int chunks = pick_chunks(h, n);
+  int grid = pick_grid(h, chunks);
+  if (P.eval_pods) chunks = grid;  // pod-list evaluation keeps one static chunk per CTA
+  P.grid_chunks = chunks;
   P.chunk_begin = 0;
 
   h->ws_dirty = true;  // cleared again once every launch of this call has been enqueued successfully

@@ -27,6 +27,8 @@ struct UstWorkspace {
   unsigned long long errinv;    // ~min abort key seen by phase 1, 0 = none
   unsigned int arrive;
   unsigned int depart;
+  unsigned int ticket;   // dynamic chunk claiming
+  unsigned int pad_;
   unsigned int cand_cta[UST_MAX_CTAS];  // candidates per CTA chunk (written by phase 1, read by phase 2)
   unsigned long long dbg[UST_MAX_CTAS][4];  // %globaltimer stamps per CTA: entry, stream end, barrier release, exit (diagnostics)
 };
@@ -65,7 +67,7 @@ struct UstParams {
   // sharding
   int rank;
   int world;
-  int grid_chunks;        // number of CTA chunks the shard is cut into (same for phase 1 and phase 2)
+  int grid_chunks;        // number of chunks the shard is cut into (>= grid size; claimed dynamically)
   int chunk_begin;        // phase-2 sub-range launches: first chunk handled by blockIdx.x == 0
 };
 

@@ -30,7 +30,10 @@ constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStep = kThreads * 4;   // nodes per CTA step in phase 2 (4 per thread)
 #ifndef UST_UNROLL
-#define UST_UNROLL 2
+#define UST_UNROLL 4
+#endif
+#ifndef UST_DOUBLE_BUFFER
+#define UST_DOUBLE_BUFFER 0
 #endif
 #ifndef UST_MIN_CTAS
 #define UST_MIN_CTAS 2
@@ -59,6 +62,8 @@ struct __align__(128) Shared {
   long long node_offset;         // global index of this shard's node 0
   long long cand_prefix;         // candidates before this chunk (global order)
   long long part[kWarps];
+  unsigned int chunk_cand;       // candidates of the chunk being streamed
+  int next_chunk;                // next claimed chunk
   unsigned int warp_tot[kWarps];
   int last;
 };
@@ -117,7 +122,7 @@ __device__ void stage_tables_begin(const UstParams& P, Shared& S) {
     for (int i = t; i <= P.n_ds; i += kThreads) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
   p1_build_table(S);
   if (t < 16) S.cnt[t] = 0;
-  if (t == 32) { S.errinv = 0; S.abort_key = ~0ull; }
+  if (t == 32) { S.errinv = 0; S.abort_key = ~0ull; S.chunk_cand = 0; }
 }
 
 __device__ __forceinline__ void stage_tables_wait(Shared& S) {
@@ -191,7 +196,7 @@ __device__ __forceinline__ void p1_words(const Shared& S, uint32_t x, uint32_t y
   B[3] += (hi >> 4) & 0x0F0F0F0Fu;
 }
 
-__device__ void phase1(const UstParams& P, Shared& S, long long b0, long long b1) {
+__device__ void phase1_count(const UstParams& P, Shared& S, long long b0, long long b1) {
   const int t = threadIdx.x;
   uint32_t B[4] = {0, 0, 0, 0};
   int pending = 0;
@@ -241,21 +246,6 @@ __device__ void phase1(const UstParams& P, Shared& S, long long b0, long long b1
   for (int f = 0; f < 16; f++) {
     const unsigned v = __reduce_add_sync(kFull, p1_field(B, f));
     if ((t & 31) == 0 && v) atomicAdd(&S.cnt[f], v);
-  }
-  __syncthreads();
-  UstWorkspace* ws = P.ws;
-  if (t < 14) {
-    if (S.cnt[t]) atomicAdd(&ws->acc[t], (unsigned long long)S.cnt[t]);
-  } else if (t == 14) {
-    unsigned long long in = 0;
-    for (int f = 0; f < 14; f++) in += S.cnt[f];
-    const unsigned long long excluded = (unsigned long long)(b1 - b0) - in;
-    if (excluded) atomicAdd(&ws->acc[UST_STATE_EXCLUDED], excluded);
-  } else if (t == 15) {
-    if (S.cnt[14]) atomicAdd(&ws->acc[UST_V_UNAVAILABLE], (unsigned long long)S.cnt[14]);
-    if (S.cnt[15]) atomicAdd(&ws->acc[UST_V_CANDIDATES], (unsigned long long)S.cnt[15]);
-  } else if (t == 32) {
-    if (S.errinv) atomicMax(&ws->errinv, S.errinv);
   }
 }
 
@@ -483,13 +473,22 @@ __device__ __forceinline__ void widen(uint32_t& lo, uint32_t& hi, uint32_t (&B)[
   lo = hi = 0;
 }
 
-__device__ __forceinline__ void spill_thread(Shared& S, uint32_t (&B)[4]) {
+// per-thread counting state of the streaming phase (lives across the chunks a CTA claims)
+struct Acc {
+  uint32_t B[4];           // sixteen byte-lane counters
+  int tiles;               // tiles accumulated since the last spill (byte lanes hold 255)
+  unsigned cand_spilled;   // candidates already spilled: cand_spilled + field 15 of B is monotonic per thread
+};
+
+__device__ __forceinline__ void spill_thread(Shared& S, Acc& A) {
 #pragma unroll
   for (int f = 0; f < 16; f++) {
-    const unsigned v = p1_field(B, f);
+    const unsigned v = p1_field(A.B, f);
     if (v) atomicAdd(&S.cnt[f], v);
   }
-  B[0] = B[1] = B[2] = B[3] = 0;
+  A.cand_spilled += p1_field(A.B, 15);
+  A.B[0] = A.B[1] = A.B[2] = A.B[3] = 0;
+  A.tiles = 0;
 }
 
 // One node of the streaming pass. `xs` = the node's hot byte moved to bits 4..11 of a word (so it indexes
@@ -546,7 +545,8 @@ __device__ __forceinline__ void spec_tile(const UstParams& P, Shared& S, const C
 // The chunk loop is software-pipelined over two register tiles: tile i+1's loads are issued before tile i
 // is evaluated, so HBM always has a full tile per thread in flight while the SM computes.
 template <bool DS_SMEM, bool OUTCOME>
-__device__ void spec_chunk(const UstParams& P, Shared& S, long long b0, long long lim, uint32_t grant, uint32_t (&B)[4]) {
+__device__ __forceinline__ void spec_chunk(const UstParams& P, Shared& S, long long b0, long long lim, uint32_t grant, Acc& A,
+                           bool wait_for_table) {
   const long long span = lim - b0;  // CTA-uniform, a multiple of 128
   const int t4 = 4 * threadIdx.x;
   auto room_at = [&](long long done) -> int {  // nodes from this thread's first node of the tile to the chunk end
@@ -555,34 +555,23 @@ __device__ void spec_chunk(const UstParams& P, Shared& S, long long b0, long lon
   };
   Cursor c = cursor_at(P, b0);
   long long i0 = b0 + t4;
-  Tile TA, TB;
-  auto load = [&](Tile& T, long long done) {  // loads of the tile starting `done` nodes into the chunk; c.q points at it
-    if (done >= span) return;
+  Tile T;
+  auto load = [&](long long done) {  // loads of the tile starting `done` nodes into the chunk; c.q points at it
     if (span - done >= kTile) tile_load<true>(c, 0, T); else tile_load<false>(c, room_at(done), T);
   };
-  auto eval = [&](const Tile& T, long long done) {  // c.q points at the tile being evaluated
+  if (span > 0) load(0);  // the first tile's loads go out before anything waits on the table copy
+  if (wait_for_table) {
+    stage_tables_wait(S);
+    __syncthreads();
+  }
+  for (long long done = 0; done < span; done += kTile) {
+    if (done) load(done);
     const int room = room_at(done);
-    if (span - done >= kTile) spec_tile<true, DS_SMEM, OUTCOME>(P, S, c, room, i0, T, grant, B);
-    else spec_tile<false, DS_SMEM, OUTCOME>(P, S, c, room, i0, T, grant, B);
-  };
-  // the first tile's loads go out before anything waits on the table copy
-  load(TA, 0);
-  stage_tables_wait(S);
-  __syncthreads();
-  int tiles = 0;
-  for (long long done = 0; done < span; done += 2 * kTile) {
-    c.q += kTileQ; load(TB, done + kTile); c.q -= kTileQ;      // next tile in flight ...
-    eval(TA, done);                                            // ... while this one is evaluated
+    if (span - done >= kTile) spec_tile<true, DS_SMEM, OUTCOME>(P, S, c, room, i0, T, grant, A.B);
+    else spec_tile<false, DS_SMEM, OUTCOME>(P, S, c, room, i0, T, grant, A.B);
     cursor_advance(c);
     i0 += kTile;
-    if (done + kTile < span) {
-      c.q += kTileQ; load(TA, done + 2 * kTile); c.q -= kTileQ;
-      eval(TB, done + kTile);
-      cursor_advance(c);
-      i0 += kTile;
-    }
-    tiles += 2;
-    if (tiles >= 14) { spill_thread(S, B); tiles = 0; }  // byte lanes: 16 per tile, 255 max
+    if (++A.tiles >= 14) spill_thread(S, A);  // byte lanes: at most 16 per tile, 255 max
   }
 }
 
@@ -710,48 +699,89 @@ __device__ __forceinline__ bool spec_holds(const UstParams& P, const Shared& S, 
   return spec_grant(P, chunk) ? (hi <= S.budget) : (lo >= S.budget);
 }
 
-// streaming pass over one chunk: counts + speculative outputs (or counts only when pod lists are evaluated)
-__device__ void stream_chunk(const UstParams& P, Shared& S, int chunk, long long b0, long long b1) {
-  if (P.eval_pods) {
-    phase1(P, S, b0, b1);
-    return;
-  }
+// The chunk loop of the streaming phase: chunks (contiguous node ranges, chunk order == slice order) are
+// claimed with an atomic ticket, so CTAs that HBM serves faster take more of them and all CTAs reach the
+// grid barrier together. Per chunk: counts + speculative outputs; the chunk's candidate count is published
+// for the ordered slot allocation. Returns the number of nodes this CTA streamed.
+template <bool DS_SMEM, bool OUTCOME>
+__device__ long long stream_loop(const UstParams& P, Shared& S) {
   const int t = threadIdx.x;
-  const long long lim = b1 & ~127LL;  // == b1 except for the ragged end of the whole array
-  const uint32_t grant = spec_grant(P, chunk);
-  uint32_t B[4] = {0, 0, 0, 0};
-  const bool ds_smem = P.n_ds <= UST_DS_SMEM_MAX;
-  if (ds_smem) {
-    if (P.outcome) spec_chunk<true, true>(P, S, b0, lim, grant, B);
-    else spec_chunk<true, false>(P, S, b0, lim, grant, B);
-  } else {
-    if (P.outcome) spec_chunk<false, true>(P, S, b0, lim, grant, B);
-    else spec_chunk<false, false>(P, S, b0, lim, grant, B);
-  }
-  if (lim < b1) {  // ragged end (< 128 nodes, last chunk only)
-    long long running = 0;
-    general_step<false>(P, S, lim, b1, grant, running);
-    for (long long j = lim + t; j < b1; j += kThreads) {
-      const unsigned b = P.hot[j];
-      uint32_t lo = S.hotent[b].z, hi = S.hotent[b].w;
-      widen(lo, hi, B);
-      spec_error_byte(P, S, b, P.flags[j], j);
+  const int n_chunks = P.grid_chunks;
+  UstWorkspace* ws = P.ws;
+  long long nodes_seen = 0;
+  Acc A;
+  A.B[0] = A.B[1] = A.B[2] = A.B[3] = 0;
+  A.tiles = 0;
+  A.cand_spilled = 0;
+  bool first = true;
+  int chunk = blockIdx.x;
+  while (chunk < n_chunks) {
+    if (t == 0) S.next_chunk = (int)(atomicAdd(&ws->ticket, 1u) + gridDim.x);  // claimed early: its latency hides behind the chunk
+    const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
+    const long long lim = b1 & ~127LL;  // == b1 except for the ragged end of the whole array
+    const uint32_t grant = spec_grant(P, chunk);
+    const unsigned cand0 = A.cand_spilled + p1_field(A.B, 15);
+    spec_chunk<DS_SMEM, OUTCOME>(P, S, b0, lim, grant, A, first);
+    first = false;
+    if (lim < b1) {  // ragged end (< 128 nodes, last chunk only)
+      long long running = 0;
+      general_step<false>(P, S, lim, b1, grant, running);
+      for (long long j = lim + t; j < b1; j += kThreads) {
+        const unsigned b = P.hot[j];
+        uint32_t lo = S.hotent[b].z, hi = S.hotent[b].w;
+        widen(lo, hi, A.B);
+        spec_error_byte(P, S, b, P.flags[j], j);
+      }
     }
+    const unsigned mine = A.cand_spilled + p1_field(A.B, 15) - cand0;
+    const unsigned warp_cand = __reduce_add_sync(kFull, mine);
+    if ((t & 31) == 0 && warp_cand) atomicAdd(&S.chunk_cand, warp_cand);
+    __syncthreads();
+    const int next = S.next_chunk;
+    if (t == 0) { ws->cand_cta[chunk] = S.chunk_cand; S.chunk_cand = 0; }
+    __syncthreads();
+    nodes_seen += b1 - b0;
+    chunk = next;
   }
-  // all threads converged: one REDUX per counter per warp, one shared atomic per warp, 16 global atomics per CTA
+  if (first) stage_tables_wait(S);  // no chunk for this CTA: still never exit with the bulk copy in flight
+  // all threads converged: one REDUX per counter per warp, one shared atomic per warp
 #pragma unroll
   for (int f = 0; f < 16; f++) {
-    const unsigned v = __reduce_add_sync(kFull, p1_field(B, f));
+    const unsigned v = __reduce_add_sync(kFull, p1_field(A.B, f));
     if ((t & 31) == 0 && v) atomicAdd(&S.cnt[f], v);
   }
-  __syncthreads();
+  return nodes_seen;
+}
+
+// Streaming phase of one CTA.
+__device__ void stream_phase(const UstParams& P, Shared& S) {
+  const int t = threadIdx.x;
+  const int n_chunks = P.grid_chunks;
   UstWorkspace* ws = P.ws;
+  long long nodes_seen = 0;
+  if (P.eval_pods) {
+    // pod lists are evaluated by the exact path after the barrier: count only, one static chunk per CTA
+    const int chunk = blockIdx.x;
+    if (chunk < n_chunks) {
+      const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
+      phase1_count(P, S, b0, b1);
+      nodes_seen = b1 - b0;
+      __syncthreads();
+      if (t == 0) ws->cand_cta[chunk] = S.cnt[15];
+    }
+  } else if (P.n_ds <= UST_DS_SMEM_MAX) {
+    nodes_seen = P.outcome ? stream_loop<true, true>(P, S) : stream_loop<true, false>(P, S);
+  } else {
+    nodes_seen = P.outcome ? stream_loop<false, true>(P, S) : stream_loop<false, false>(P, S);
+  }
+  __syncthreads();
+  // 16 global atomics per CTA
   if (t < 14) {
     if (S.cnt[t]) atomicAdd(&ws->acc[t], (unsigned long long)S.cnt[t]);
   } else if (t == 14) {
     unsigned long long in = 0;
     for (int f = 0; f < 14; f++) in += S.cnt[f];
-    const unsigned long long excluded = (unsigned long long)(b1 - b0) - in;
+    const unsigned long long excluded = (unsigned long long)nodes_seen - in;
     if (excluded) atomicAdd(&ws->acc[UST_STATE_EXCLUDED], excluded);
   } else if (t == 15) {
     if (S.cnt[14]) atomicAdd(&ws->acc[UST_V_UNAVAILABLE], (unsigned long long)S.cnt[14]);
@@ -788,16 +818,17 @@ __device__ void load_local_vector(const UstParams& P, Shared& S) {
   }
 }
 
-__device__ void finish(const UstParams& P, Shared& S, int chunks, bool reset_ws) {
+__device__ void finish(const UstParams& P, Shared& S, bool reset_ws) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned prev = atomicAdd(&P.ws->depart, 1u);
-    if (prev == (unsigned)chunks - 1u) {  // last CTA out: publish counters, restore the workspace invariant
+    if (prev == gridDim.x - 1u) {  // last CTA out: publish counters, restore the workspace invariant
       write_counters(P, S);
       if (reset_ws) {
         for (int i = 0; i < 18; i++) P.ws->acc[i] = 0;
         P.ws->errinv = 0;
+        P.ws->ticket = 0;
       }
       P.ws->arrive = 0;
       P.ws->depart = 0;
@@ -806,26 +837,51 @@ __device__ void finish(const UstParams& P, Shared& S, int chunks, bool reset_ws)
   }
 }
 
+// Is any chunk's speculation possibly wrong? O(1) from the cluster-wide scalars: with "nobody gets a
+// slot" the speculation only fails if there is a budget at all, with "everybody gets one" only if the
+// budget is smaller than the number of candidates.
+__device__ __forceinline__ bool verification_needed(const UstParams& P, const Shared& S) {
+  if (P.eval_pods || S.abort_key != ~0ull) return true;
+  if (!(P.active && !P.requestor)) return false;
+  const long long cands = S.V[UST_V_CANDIDATES];
+  if (cands == 0) return false;
+  return P.spec_cut_chunk ? (S.budget < cands) : (S.budget > 0);
+}
+
+// redo, exactly, every chunk of this CTA's share whose speculation did not hold (or that needs pod lists)
+__device__ void verify_phase(const UstParams& P, Shared& S) {
+  const int n_chunks = P.grid_chunks;
+  const long long rank_base = S.cand_prefix;  // candidates on lower ranks
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const long long before = block_sum_cand_before(P, S, chunk);
+    const unsigned chunk_cand = __ldcg(&P.ws->cand_cta[chunk]);
+    if (threadIdx.x == 0) S.cand_prefix = rank_base + before;
+    __syncthreads();
+    if (P.eval_pods || !spec_holds(P, S, chunk, chunk_cand)) {
+      const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
+      general_chunk(P, S, b0, b1, chunk_cand);
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_fused_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
-  const int chunk = blockIdx.x, chunks = gridDim.x;
-  const long long b0 = chunk_bound(P.n, chunk, chunks), b1 = chunk_bound(P.n, chunk + 1, chunks);
   stamp(P, 0);
   stage_tables_begin(P, S);
   __syncthreads();
-  stream_chunk(P, S, chunk, b0, b1);
+  stream_phase(P, S);
   stamp(P, 1);
   // grid-wide barrier (every CTA is co-resident: cooperative launch). After it the cluster-wide
-  // counters are final and each chunk can check its speculation.
+  // counters are final and the speculation can be checked.
   __syncthreads();
   if (threadIdx.x == 0) {
-    P.ws->cand_cta[chunk] = S.cnt[15];
     __threadfence();
     atomicAdd(&P.ws->arrive, 1u);
-    while (ld_acquire_u32(&P.ws->arrive) < (unsigned)chunks) __nanosleep(20);
+    while (ld_acquire_u32(&P.ws->arrive) < gridDim.x) __nanosleep(20);
     __threadfence();
   }
   __syncthreads();
@@ -833,30 +889,25 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_fused_kernel(const
   load_local_vector(P, S);
   __syncthreads();
   if (threadIdx.x == 0) derive_scalars(P, S);
-  const long long before = block_sum_cand_before(P, S, chunk);
-  if (threadIdx.x == 0) S.cand_prefix += before;
   __syncthreads();
-  if (P.eval_pods || !spec_holds(P, S, chunk, S.cnt[15])) {
+  if (verification_needed(P, S)) {
     if (P.eval_pods) { stage_tables_wait(S); __syncthreads(); }
-    general_chunk(P, S, b0, b1, S.cnt[15]);
+    verify_phase(P, S);
   }
-  finish(P, S, chunks, true);
+  finish(P, S, true);
   stamp(P, 3);
 }
 
-// split mode (multi-GPU with a host-launched collective between the kernels): streaming pass ...
+// split mode (multi-GPU with a host-launched collective between the kernels): streaming phase ...
 __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase1_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
-  const int chunk = blockIdx.x, chunks = gridDim.x;
-  const long long b0 = chunk_bound(P.n, chunk, chunks), b1 = chunk_bound(P.n, chunk + 1, chunks);
   stage_tables_begin(P, S);
   __syncthreads();
-  stream_chunk(P, S, chunk, b0, b1);
+  stream_phase(P, S);
   __syncthreads();
   if (threadIdx.x == 0) {
-    P.ws->cand_cta[chunk] = S.cnt[15];
     __threadfence();
-    S.last = atomicAdd(&P.ws->depart, 1u) == (unsigned)chunks - 1u;
+    S.last = atomicAdd(&P.ws->depart, 1u) == gridDim.x - 1u;
   }
   __syncthreads();
   if (S.last) {  // publish this shard's lanes of the exchange vector, restore the workspace invariant
@@ -866,7 +917,7 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase1_kernel(cons
     if (threadIdx.x < UST_V_LEN) P.xchg[threadIdx.x] = S.V[threadIdx.x];
     __syncthreads();
     if (threadIdx.x < 18) P.ws->acc[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { P.ws->errinv = 0; P.ws->depart = 0; }
+    if (threadIdx.x == 0) { P.ws->errinv = 0; P.ws->depart = 0; P.ws->ticket = 0; }
   }
   if (P.eval_pods) stage_tables_wait(S);  // never leave a bulk copy in flight at CTA exit
 }
@@ -874,19 +925,15 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase1_kernel(cons
 // ... and verification: redo, exactly, the chunks whose speculation did not hold
 __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase2_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
-  const int chunk = P.chunk_begin + blockIdx.x, chunks = P.grid_chunks;
-  const long long b0 = chunk_bound(P.n, chunk, chunks), b1 = chunk_bound(P.n, chunk + 1, chunks);
   stage_tables_begin(P, S);
   if (threadIdx.x < UST_V_LEN) S.V[threadIdx.x] = P.xchg[threadIdx.x];
   __syncthreads();
   if (threadIdx.x == 0) derive_scalars(P, S);
-  const long long before = block_sum_cand_before(P, S, chunk);
-  if (threadIdx.x == 0) S.cand_prefix += before;
+  __syncthreads();
   stage_tables_wait(S);
   __syncthreads();
-  const unsigned chunk_cand = __ldcg(&P.ws->cand_cta[chunk]);
-  if (P.eval_pods || !spec_holds(P, S, chunk, chunk_cand)) general_chunk(P, S, b0, b1, chunk_cand);
-  finish(P, S, (int)gridDim.x, false);
+  if (verification_needed(P, S)) verify_phase(P, S);
+  finish(P, S, false);
 }
 
 // BuildState's device part (upgrade_state.go:126-133, :158-160): owned pods per DaemonSet and bucket sizes
