@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -72,6 +73,11 @@ struct DevBuf {
 struct ust_handle {
   int device = -1;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_d2h = nullptr;   // pipelined host path: downloads, kernels and uploads on three streams
+  cudaStream_t stream_h2d = nullptr;
+  cudaEvent_t seg_done[16] = {};
+  cudaEvent_t seg_up[16] = {};
+  cudaEvent_t d2h_done = nullptr;
   std::mutex mu;
   std::string err;
   int64_t launches = 0;
@@ -176,28 +182,10 @@ static int check_aligned(ust_handle* h, const void* p, const char* what) {
   return UST_OK;
 }
 
-// core: everything device-resident, enqueue on `st`
-static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
+static void fill_params(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
                         const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
                         const int32_t* pod_off, const uint16_t* pod_flags, uint8_t* next_state, uint16_t* actions,
-                        uint8_t* outcome, ust_counters* out_dev, cudaStream_t st) {
-  if (n < 0) return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
-  if (n > 0 && (!state || !flags || !pod_rev || !ds_idx || !next_state || !actions))
-    return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
-  if (n_ds < 0 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table");
-  if (n >= (1LL << 48)) return h->fail(UST_ERR_INVALID_ARGUMENT, "too many nodes");
-  const void* ptrs[] = {state, flags, pod_rev, ds_idx, next_state, actions, outcome};
-  const char* names[] = {"state", "flags", "pod_rev", "ds_idx", "next_state", "actions", "actuator_outcome"};
-  for (int i = 0; i < 7; i++)
-    if (ptrs[i]) { int rc = check_aligned(h, ptrs[i], names[i]); if (rc) return rc; }
-  UST_CUDA(h, cudaSetDevice(h->device));
-  if (h->ws_dirty) {
-    UST_CUDA(h, cudaMemsetAsync(h->ws, 0, sizeof(UstWorkspace), st));
-    h->ws_dirty = false;
-  }
-  int rc = ensure_tables(h, policy, st);
-  if (rc) return rc;
-
+                        uint8_t* outcome, ust_counters* out_dev, UstParams* out, int* grid_out) {
   const bool active = policy_active(policy);
   UstParams P;
   memset(&P, 0, sizeof(P));
@@ -230,6 +218,38 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
   if (P.eval_pods) chunks = grid;  // pod-list evaluation keeps one static chunk per CTA
   P.grid_chunks = chunks;
   P.chunk_begin = 0;
+  P.chunk_end = chunks;
+  P.publish = 1;
+  *out = P;
+  *grid_out = grid;
+}
+
+// core: everything device-resident, enqueue on `st`
+static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
+                        const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                        const int32_t* pod_off, const uint16_t* pod_flags, uint8_t* next_state, uint16_t* actions,
+                        uint8_t* outcome, ust_counters* out_dev, cudaStream_t st) {
+  if (n < 0) return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
+  if (n > 0 && (!state || !flags || !pod_rev || !ds_idx || !next_state || !actions))
+    return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
+  if (n_ds < 0 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table");
+  if (n >= (1LL << 48)) return h->fail(UST_ERR_INVALID_ARGUMENT, "too many nodes");
+  const void* ptrs[] = {state, flags, pod_rev, ds_idx, next_state, actions, outcome};
+  const char* names[] = {"state", "flags", "pod_rev", "ds_idx", "next_state", "actions", "actuator_outcome"};
+  for (int i = 0; i < 7; i++)
+    if (ptrs[i]) { int rc = check_aligned(h, ptrs[i], names[i]); if (rc) return rc; }
+  UST_CUDA(h, cudaSetDevice(h->device));
+  if (h->ws_dirty) {
+    UST_CUDA(h, cudaMemsetAsync(h->ws, 0, sizeof(UstWorkspace), st));
+    h->ws_dirty = false;
+  }
+  int rc = ensure_tables(h, policy, st);
+  if (rc) return rc;
+
+  UstParams P;
+  int grid = 0;
+  fill_params(h, policy, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, pod_off, pod_flags, next_state, actions, outcome,
+              out_dev, &P, &grid);
 
   h->ws_dirty = true;  // cleared again once every launch of this call has been enqueued successfully
   if (h->world == 1) {
@@ -273,6 +293,95 @@ static int finish_with_counters(ust_handle* h, cudaStream_t st, ust_counters* ou
 }
 
 #pragma GCC visibility push(default)
+// host mirror of chunk_bound() in ust_kernels.cu
+static int64_t host_chunk_bound(int64_t n, int c, int chunks) {
+  if (c >= chunks) return n;
+  return ((n * (int64_t)c) / chunks) & ~(int64_t)127;
+}
+
+// Pipelined host path: the snapshot is cut into segments of whole chunks; segment s+1 uploads while segment
+// s streams through the kernel and segment s-1's results download (PCIe is full duplex). The streaming pass
+// is speculative, so a segment's outputs are final unless the end-of-call verification had to redo chunks —
+// then (rare) the outputs are downloaded again.
+static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
+                           const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, uint8_t* next_state,
+                           uint16_t* actions, uint8_t* outcome, ust_counters* out) {
+  cudaStream_t up = h->stream, down = h->stream_d2h, h2d = h->stream_h2d;  // up = compute stream of the call
+  if (h->ws_dirty) {
+    UST_CUDA(h, cudaMemsetAsync(h->ws, 0, sizeof(UstWorkspace), up));
+    h->ws_dirty = false;
+  }
+  int rc = ensure_tables(h, policy, up);
+  if (rc) return rc;
+  UstParams P;
+  int grid = 0;
+  fill_params(h, policy, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, n_ds, h->s_dsrev.p, nullptr, nullptr,
+              h->s_next.p, h->s_actions.p, outcome ? h->s_outcome.p : nullptr, nullptr, &P, &grid);
+  const int chunks = P.grid_chunks;
+  const int kSegments = 8;
+  const int per = (chunks + kSegments - 1) / kSegments;
+  h->ws_dirty = true;
+  const bool dbg = getenv("UST_DEBUG_PIPE") != nullptr;
+  cudaEvent_t ev[4];
+  if (dbg) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], up); }
+  // uploads start once the compute stream has reached this call (tables, DaemonSet table, previous call's reads)
+  UST_CUDA(h, cudaEventRecord(h->d2h_done, up));
+  UST_CUDA(h, cudaStreamWaitEvent(h2d, h->d2h_done, 0));
+  int seg = 0;
+  for (int c0 = 0; c0 < chunks; c0 += per, seg++) {
+    const int c1 = c0 + per < chunks ? c0 + per : chunks;
+    const int64_t n0 = host_chunk_bound(n, c0, chunks), n1 = host_chunk_bound(n, c1, chunks);
+    const size_t len = (size_t)(n1 - n0);
+    if (len) {
+      UST_CUDA(h, cudaMemcpyAsync(h->s_hot.p + n0, state + n0, len, cudaMemcpyHostToDevice, h2d));
+      UST_CUDA(h, cudaMemcpyAsync(h->s_flags.p + n0, flags + n0, len * 4, cudaMemcpyHostToDevice, h2d));
+      UST_CUDA(h, cudaMemcpyAsync(h->s_rev.p + n0, pod_rev + n0, len * 4, cudaMemcpyHostToDevice, h2d));
+      UST_CUDA(h, cudaMemcpyAsync(h->s_ds.p + n0, ds_idx + n0, len * 4, cudaMemcpyHostToDevice, h2d));
+    }
+    UST_CUDA(h, cudaEventRecord(h->seg_up[seg], h2d));
+    UST_CUDA(h, cudaStreamWaitEvent(up, h->seg_up[seg], 0));
+    UstParams Ps = P;
+    Ps.chunk_begin = c0;
+    Ps.chunk_end = c1;
+    Ps.publish = c1 == chunks;
+    int e = ust_launch_phase1(Ps, c1 - c0, up);
+    if (e) return h->fail(UST_ERR_CUDA, "streaming kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->launches += 1;
+    UST_CUDA(h, cudaEventRecord(h->seg_done[seg], up));
+    UST_CUDA(h, cudaStreamWaitEvent(down, h->seg_done[seg], 0));
+    if (len) {
+      UST_CUDA(h, cudaMemcpyAsync(next_state + n0, h->s_next.p + n0, len, cudaMemcpyDeviceToHost, down));
+      UST_CUDA(h, cudaMemcpyAsync(actions + n0, h->s_actions.p + n0, len * 2, cudaMemcpyDeviceToHost, down));
+      if (outcome) UST_CUDA(h, cudaMemcpyAsync(outcome + n0, h->s_outcome.p + n0, len, cudaMemcpyDeviceToHost, down));
+    }
+  }
+  if (dbg) { cudaEventRecord(ev[1], up); }
+  int e = ust_launch_phase2(P, grid, up);
+  if (e) return h->fail(UST_ERR_CUDA, "verification kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  h->launches += 1;
+  h->ws_dirty = false;
+  UST_CUDA(h, cudaMemcpyAsync(h->counters_host, h->counters_dev, sizeof(ust_counters), cudaMemcpyDeviceToHost, up));
+  if (dbg) { cudaEventRecord(ev[2], up); cudaEventRecord(ev[3], down); }
+  cudaError_t ce = cudaStreamSynchronize(up);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(down);
+  if (dbg) {
+    float a, b, c;
+    cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[0], ev[2]); cudaEventElapsedTime(&c, ev[0], ev[3]);
+    fprintf(stderr, "[ust pipe] uploads+stream kernels done %.3f ms, verify+counters %.3f ms, downloads done %.3f ms\n", a, b, c);
+    for (auto& e2 : ev) cudaEventDestroy(e2);
+  }
+  if (ce != cudaSuccess) {
+    h->ws_dirty = true;
+    return h->fail(UST_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(ce));
+  }
+  if (h->counters_host->reserved[0] != 0) {  // the verification redid chunks: fetch the final outputs
+    UST_CUDA(h, cudaMemcpyAsync(next_state, h->s_next.p, (size_t)n, cudaMemcpyDeviceToHost, up));
+    UST_CUDA(h, cudaMemcpyAsync(actions, h->s_actions.p, (size_t)n * 2, cudaMemcpyDeviceToHost, up));
+    if (outcome) UST_CUDA(h, cudaMemcpyAsync(outcome, h->s_outcome.p, (size_t)n, cudaMemcpyDeviceToHost, up));
+  }
+  return finish_with_counters(h, up, out);
+}
+
 extern "C" {
 
 int ust_abi_version(void) { return UST_ABI_VERSION; }
@@ -305,6 +414,13 @@ int ust_create(ust_handle** out, int device) {
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&h->stream_d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&h->stream_h2d, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (auto& ev : h->seg_up)
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  for (auto& ev : h->seg_done)
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&h->d2h_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&h->ws, sizeof(UstWorkspace))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(h->ws, 0, sizeof(UstWorkspace))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = cudaMalloc(&h->lut_dev, (UST_LUT_ENTRIES + 32) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -342,6 +458,11 @@ void ust_destroy(ust_handle* h) {
   h->s_hot.release(); h->s_next.release(); h->s_outcome.release(); h->s_flags.release();
   h->s_rev.release(); h->s_ds.release(); h->s_dsrev.release(); h->s_podoff.release(); h->s_dsdesired.release();
   h->s_actions.release(); h->s_podflags.release();
+  for (auto& ev : h->seg_done) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : h->seg_up) if (ev) cudaEventDestroy(ev);
+  if (h->stream_h2d) cudaStreamDestroy(h->stream_h2d);
+  if (h->d2h_done) cudaEventDestroy(h->d2h_done);
+  if (h->stream_d2h) cudaStreamDestroy(h->stream_d2h);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -399,13 +520,15 @@ int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const ui
     UST_CUDA(h, h->s_podoff.reserve(N + 1));
     UST_CUDA(h, h->s_podflags.reserve((size_t)pods->n_pods + 8));
   }
+  if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsrev.p, ds_rev, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
+  if (!pods && h->world == 1 && n >= (1 << 19))
+    return apply_pipelined(h, policy, n, state, flags, pod_rev, ds_idx, n_ds, next_state, actions, actuator_outcome, out);
   if (N) {
     UST_CUDA(h, cudaMemcpyAsync(h->s_hot.p, state, N, cudaMemcpyHostToDevice, st));
     UST_CUDA(h, cudaMemcpyAsync(h->s_flags.p, flags, N * 4, cudaMemcpyHostToDevice, st));
     UST_CUDA(h, cudaMemcpyAsync(h->s_rev.p, pod_rev, N * 4, cudaMemcpyHostToDevice, st));
     UST_CUDA(h, cudaMemcpyAsync(h->s_ds.p, ds_idx, N * 4, cudaMemcpyHostToDevice, st));
   }
-  if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsrev.p, ds_rev, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
   if (pods) {
     UST_CUDA(h, cudaMemcpyAsync(h->s_podoff.p, pods->pod_off, (N + 1) * 4, cudaMemcpyHostToDevice, st));
     if (pods->n_pods) UST_CUDA(h, cudaMemcpyAsync(h->s_podflags.p, pods->pod_flags, (size_t)pods->n_pods * 2, cudaMemcpyHostToDevice, st));

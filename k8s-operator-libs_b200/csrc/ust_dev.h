@@ -28,7 +28,7 @@ struct UstWorkspace {
   unsigned int arrive;
   unsigned int depart;
   unsigned int ticket;   // dynamic chunk claiming
-  unsigned int pad_;
+  unsigned int fixups;   // chunks redone by the verification phase of the current call
   unsigned int cand_cta[UST_MAX_CTAS];  // candidates per CTA chunk (written by phase 1, read by phase 2)
   unsigned long long dbg[UST_MAX_CTAS][4];  // %globaltimer stamps per CTA: entry, stream end, barrier release, exit (diagnostics)
 };
@@ -68,7 +68,9 @@ struct UstParams {
   int rank;
   int world;
   int grid_chunks;        // number of chunks the shard is cut into (>= grid size; claimed dynamically)
-  int chunk_begin;        // phase-2 sub-range launches: first chunk handled by blockIdx.x == 0
+  int chunk_begin;        // streaming sub-range launches (pipelined uploads): chunks [chunk_begin, chunk_end)
+  int chunk_end;
+  int publish;            // split mode: this streaming launch is the last one of the call (publish + reset)
 };
 
 // kernel launchers (ust_kernels.cu); all return cudaError_t as int

@@ -319,6 +319,7 @@ __device__ void write_counters(const UstParams& P, const Shared& S) {
   c.max_unavailable = slots ? S.max_unav : 0;
   c.upgrades_available = slots ? S.avail : 0;
   for (int i = 0; i < 7; i++) c.reserved[i] = 0;
+  c.reserved[0] = (long long)__ldcg(&P.ws->fixups);  // chunks the verification phase had to redo (diagnostic)
   *P.out = c;
 }
 
@@ -714,9 +715,9 @@ __device__ long long stream_loop(const UstParams& P, Shared& S) {
   A.tiles = 0;
   A.cand_spilled = 0;
   bool first = true;
-  int chunk = blockIdx.x;
-  while (chunk < n_chunks) {
-    if (t == 0) S.next_chunk = (int)(atomicAdd(&ws->ticket, 1u) + gridDim.x);  // claimed early: its latency hides behind the chunk
+  int chunk = P.chunk_begin + blockIdx.x;
+  while (chunk < P.chunk_end) {
+    if (t == 0) S.next_chunk = P.chunk_begin + (int)(atomicAdd(&ws->ticket, 1u) + gridDim.x);  // claimed early: its latency hides behind the chunk
     const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
     const long long lim = b1 & ~127LL;  // == b1 except for the ragged end of the whole array
     const uint32_t grant = spec_grant(P, chunk);
@@ -761,8 +762,8 @@ __device__ void stream_phase(const UstParams& P, Shared& S) {
   long long nodes_seen = 0;
   if (P.eval_pods) {
     // pod lists are evaluated by the exact path after the barrier: count only, one static chunk per CTA
-    const int chunk = blockIdx.x;
-    if (chunk < n_chunks) {
+    const int chunk = P.chunk_begin + blockIdx.x;
+    if (chunk < P.chunk_end) {
       const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
       phase1_count(P, S, b0, b1);
       nodes_seen = b1 - b0;
@@ -825,6 +826,7 @@ __device__ void finish(const UstParams& P, Shared& S, bool reset_ws) {
     const unsigned prev = atomicAdd(&P.ws->depart, 1u);
     if (prev == gridDim.x - 1u) {  // last CTA out: publish counters, restore the workspace invariant
       write_counters(P, S);
+      P.ws->fixups = 0;
       if (reset_ws) {
         for (int i = 0; i < 18; i++) P.ws->acc[i] = 0;
         P.ws->errinv = 0;
@@ -860,6 +862,7 @@ __device__ void verify_phase(const UstParams& P, Shared& S) {
     if (P.eval_pods || !spec_holds(P, S, chunk, chunk_cand)) {
       const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
       general_chunk(P, S, b0, b1, chunk_cand);
+      if (threadIdx.x == 0) atomicAdd(&P.ws->fixups, 1u);
     }
     __syncthreads();
   }
@@ -910,14 +913,17 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase1_kernel(cons
     S.last = atomicAdd(&P.ws->depart, 1u) == gridDim.x - 1u;
   }
   __syncthreads();
-  if (S.last) {  // publish this shard's lanes of the exchange vector, restore the workspace invariant
+  if (S.last) {  // last CTA of this launch
     __threadfence();
-    load_local_vector(P, S);
-    __syncthreads();
-    if (threadIdx.x < UST_V_LEN) P.xchg[threadIdx.x] = S.V[threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x < 18) P.ws->acc[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { P.ws->errinv = 0; P.ws->depart = 0; P.ws->ticket = 0; }
+    if (P.publish) {  // ... and last streaming launch of the call: publish this shard's lanes, restore the invariant
+      load_local_vector(P, S);
+      __syncthreads();
+      if (threadIdx.x < UST_V_LEN) P.xchg[threadIdx.x] = S.V[threadIdx.x];
+      __syncthreads();
+      if (threadIdx.x < 18) P.ws->acc[threadIdx.x] = 0;
+      if (threadIdx.x == 0) P.ws->errinv = 0;
+    }
+    if (threadIdx.x == 0) { P.ws->depart = 0; P.ws->ticket = 0; }
   }
   if (P.eval_pods) stage_tables_wait(S);  // never leave a bulk copy in flight at CTA exit
 }

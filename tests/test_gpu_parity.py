@@ -115,6 +115,24 @@ def test_slot_budget_cut_positions(handle, seed):
         helpers.assert_same(got, ref, f"seed={seed} maxPar={max_par} maxUnav={unav}")
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_pipelined_host_path(handle, seed):
+    """Snapshots >= 2^19 nodes take the segmented upload/compute/download pipeline of ust_apply_state; the
+    speculative outputs of early segments must be replaced when the verification redoes chunks (aborts, budgets
+    that cut through the middle, requestor mode)."""
+    rng = np.random.default_rng(700 + seed)
+    n = 700_001 + 1000 * seed
+    soa, _ = helpers.random_soa(rng, n, p_err=(0.0, 1e-6, 1e-5)[seed % 3], wild=bool(seed % 2))
+    pol = helpers.random_policy(rng)
+    if seed == 3:
+        pol = abi.make_policy(max_parallel_upgrades=0, max_unavailable="30%")
+    if seed == 4:
+        pol = abi.make_policy(max_parallel_upgrades=60_000)
+    got = gpu_apply(handle, pol, soa)
+    ref = helpers.oracle_apply(pol, soa, variant=1)
+    helpers.assert_same(got, ref, f"pipelined seed={seed}")
+
+
 def test_many_daemonsets_use_the_global_table(handle):
     rng = np.random.default_rng(99)
     n, n_ds = 50_000, 3000  # > UST_DS_SMEM_MAX
