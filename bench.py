@@ -35,6 +35,21 @@ CPU_SAMPLE_NODES = 1_000_000
 L2_BYTES = 126 * 1024 * 1024
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
+    ncu capture (profiles/rNN_ncu_traffic.json); None when there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None
+    try:
+        with open(files[-1]) as f:
+            d = json.load(f)
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -283,7 +298,8 @@ def main():
                              f"({SETS * BYTES_PER_NODE * n / 1e9:.2f} GB vs 126 MB L2, at most {100 * 126e6 / (SETS * BYTES_PER_NODE * n):.0f}% of a step can hit)",
                        "exchange": "none" if world == 1 else "ncclAllReduce of 42 int64 lanes between two kernels"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "ust_fused_kernel" if world == 1 else "ust_phase2_kernel",
+                         "traffic": ncu_traffic() if (world == 1 and n == SHARD_NODES) else None, "peak_source": peak_src,
+                         "kernel": "ust_fused_kernel" if world == 1 else "ust_phase1_kernel",
                          "kernel_ms": kern_ms, "kernel_ms_event_pairs_median": float(np.median(per_step_ms)),
                          "frac_of_8TBs": achieved / 8000.0},
             "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall,

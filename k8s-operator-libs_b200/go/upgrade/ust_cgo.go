@@ -1,0 +1,242 @@
+// Package upgrade — cgo shim over libust.so for github.com/NVIDIA/k8s-operator-libs/pkg/upgrade.
+//
+// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Go toolchain (DESIGN.md §1). The file shows the
+// binding a maintainer adds next to pkg/upgrade/upgrade_state.go so that ClusterUpgradeStateManagerImpl keeps its
+// interface (upgrade_state.go:35-53), its types (common_manager.go:58-80) and the UpgradeState* constants
+// (consts.go:49-82) while ApplyState's decisions come from the B200 kernel. The same call sequence is exercised,
+// compiled, by tests/ through ctypes.
+package upgrade
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../include
+#cgo LDFLAGS: -L${SRCDIR}/../.. -lust
+#include <stdlib.h>
+#include "ust.h"
+*/
+import "C"
+
+import (
+	"context"
+	"fmt"
+	"unsafe"
+
+	corev1 "k8s.io/api/core/v1"
+
+	"github.com/NVIDIA/k8s-operator-libs/api/upgrade/v1alpha1"
+)
+
+// passOrder is the order in which ApplyState walks the buckets (upgrade_state.go:205-274).
+var passOrder = []string{
+	UpgradeStateUnknown, UpgradeStateDone, UpgradeStateUpgradeRequired, UpgradeStateCordonRequired,
+	UpgradeStateWaitForJobsRequired, UpgradeStatePodDeletionRequired, UpgradeStateDrainRequired,
+	UpgradeStateNodeMaintenanceRequired, UpgradeStatePodRestartRequired, UpgradeStateFailed,
+	UpgradeStateValidationRequired, UpgradeStateUncordonRequired,
+}
+
+var stateCode = map[string]C.uint8_t{
+	UpgradeStateUnknown: C.UST_STATE_UNKNOWN, UpgradeStateUpgradeRequired: C.UST_STATE_UPGRADE_REQUIRED,
+	UpgradeStateCordonRequired: C.UST_STATE_CORDON_REQUIRED, UpgradeStateWaitForJobsRequired: C.UST_STATE_WAIT_FOR_JOBS_REQUIRED,
+	UpgradeStatePodDeletionRequired: C.UST_STATE_POD_DELETION_REQUIRED, UpgradeStateDrainRequired: C.UST_STATE_DRAIN_REQUIRED,
+	UpgradeStateNodeMaintenanceRequired: C.UST_STATE_NODE_MAINTENANCE_REQUIRED,
+	UpgradeStatePostMaintenanceRequired: C.UST_STATE_POST_MAINTENANCE_REQUIRED,
+	UpgradeStatePodRestartRequired: C.UST_STATE_POD_RESTART_REQUIRED, UpgradeStateValidationRequired: C.UST_STATE_VALIDATION_REQUIRED,
+	UpgradeStateUncordonRequired: C.UST_STATE_UNCORDON_REQUIRED, UpgradeStateDone: C.UST_STATE_DONE, UpgradeStateFailed: C.UST_STATE_FAILED,
+}
+var stateName = func() map[C.uint8_t]string {
+	m := map[C.uint8_t]string{}
+	for k, v := range stateCode {
+		m[v] = k
+	}
+	return m
+}()
+
+// Accelerator owns one ust_handle (one GPU). Not re-entrant, like the reference's single reconcile loop
+// (node_upgrade_state_provider.go:92-99).
+type Accelerator struct{ h *C.ust_handle }
+
+func NewAccelerator(device int) (*Accelerator, error) {
+	var h *C.ust_handle
+	if rc := C.ust_create(&h, C.int(device)); rc != C.UST_OK {
+		return nil, fmt.Errorf("ust_create: %s", C.GoString(C.ust_create_error()))
+	}
+	return &Accelerator{h: h}, nil
+}
+func (a *Accelerator) Close() { C.ust_destroy(a.h) }
+
+// flatten DriverUpgradePolicySpec + manager options (upgrade_spec.go:27-110, upgrade_state.go:329-350)
+func (m *ClusterUpgradeStateManagerImpl) policy(p *v1alpha1.DriverUpgradePolicySpec) C.ust_policy {
+	var c C.ust_policy
+	b := func(v bool) C.int32_t {
+		if v {
+			return 1
+		}
+		return 0
+	}
+	c.auto_upgrade = b(p.AutoUpgrade)
+	c.max_parallel_upgrades = C.int64_t(p.MaxParallelUpgrades)
+	if p.MaxUnavailable != nil {
+		// same parsing as intstr.GetScaledValueFromIntOrPercent: Int, "NN%", or error
+		c.max_unavailable_kind, c.max_unavailable_value = encodeIntOrPercent(p.MaxUnavailable)
+	}
+	c.pod_deletion_enabled = b(m.IsPodDeletionEnabled())
+	c.validation_enabled = b(m.IsValidationEnabled())
+	if p.PodDeletion != nil {
+		c.pod_deletion_spec_present, c.pod_deletion_force, c.pod_deletion_delete_emptydir = 1, b(p.PodDeletion.Force), b(p.PodDeletion.DeleteEmptyDir)
+	}
+	if p.DrainSpec != nil {
+		c.drain_enabled, c.drain_force, c.drain_delete_emptydir = b(p.DrainSpec.Enable), b(p.DrainSpec.Force), b(p.DrainSpec.DeleteEmptyDir)
+	}
+	if p.WaitForCompletion != nil {
+		c.wait_selector_set, c.wait_timeout_nonzero = b(p.WaitForCompletion.PodSelector != ""), b(p.WaitForCompletion.TimeoutSecond != 0)
+	}
+	c.use_maintenance_operator = b(m.opts.Requestor.UseMaintenanceOperator)
+	return c
+}
+
+// encodeNode evaluates each reference predicate once and packs it (bit meanings: include/ust.h).
+func (m *ClusterUpgradeStateManagerImpl) encodeNode(ns *NodeUpgradeState, code C.uint8_t, intern func(string) int32,
+	dsIndex func(*NodeUpgradeState) int32) (hot C.uint8_t, flags C.uint32_t, podRev, ds C.int32_t) {
+	n := ns.Node
+	hot = code
+	if m.IsNodeUnschedulable(n) {
+		hot |= C.UST_HOT_UNSCHEDULABLE
+	}
+	if !m.isNodeConditionReady(n) {
+		hot |= C.UST_HOT_NOT_READY
+	}
+	if m.SkipNodeUpgrade(n) {
+		hot |= C.UST_HOT_SKIP
+	}
+	if m.IsUpgradeRequested(n) {
+		flags |= C.UST_F_UPGRADE_REQUESTED
+	}
+	if n.Annotations[GetUpgradeDriverWaitForSafeLoadAnnotationKey()] != "" {
+		flags |= C.UST_F_SAFE_LOAD
+	}
+	if _, ok := n.Annotations[GetUpgradeInitialStateAnnotationKey()]; ok {
+		flags |= C.UST_F_INITIAL_STATE_ANNO
+	}
+	if IsNodeInRequestorMode(n) {
+		flags |= C.UST_F_REQUESTOR_MODE
+	}
+	ds = -1
+	if ns.IsOrphanedPod() {
+		flags |= C.UST_F_POD_ORPHANED
+	} else {
+		ds = C.int32_t(dsIndex(ns))
+		if hash, err := m.PodManager.GetPodControllerRevisionHash(ns.DriverPod); err != nil {
+			hot |= C.UST_HOT_REVISION_HASH_ERROR
+		} else {
+			podRev = C.int32_t(intern(hash))
+		}
+	}
+	if p := ns.DriverPod; p != nil {
+		ready := p.Status.Phase == corev1.PodRunning && len(p.Status.ContainerStatuses) != 0
+		for i := range p.Status.ContainerStatuses {
+			ready = ready && p.Status.ContainerStatuses[i].Ready
+		}
+		if ready {
+			flags |= C.UST_F_POD_READY
+		}
+		if m.isDriverPodFailing(p) {
+			flags |= C.UST_F_POD_FAILING
+		}
+		if !p.DeletionTimestamp.IsZero() {
+			flags |= C.UST_F_POD_TERMINATING
+		}
+	}
+	if ns.NodeMaintenance != nil {
+		flags |= C.UST_F_NM_PRESENT // + UST_F_NM_READY from the Ready condition, upgrade_requestor.go:437-439
+	}
+	return
+}
+
+// ApplyState keeps the reference signature (upgrade_state.go:171-172).
+func (m *ClusterUpgradeStateManagerImpl) ApplyStateAccelerated(ctx context.Context, acc *Accelerator,
+	currentState *ClusterUpgradeState, upgradePolicy *v1alpha1.DriverUpgradePolicySpec) error {
+	if currentState == nil {
+		return fmt.Errorf("currentState should not be empty") // upgrade_state.go:175-177
+	}
+	if upgradePolicy == nil || !upgradePolicy.AutoUpgrade {
+		return nil // upgrade_state.go:179-182
+	}
+	// 1. encode the snapshot bucket by bucket in pass order: SoA index order == replay order, and the
+	//    upgrade-required bucket keeps its slice order (upgrade_inplace.go:71).
+	var entries []*NodeUpgradeState
+	var hot []C.uint8_t
+	var flags []C.uint32_t
+	var rev, ds []C.int32_t
+	// ... (intern table, DaemonSet table with GetDaemonsetControllerRevisionHash per DaemonSet, buckets not in
+	//      passOrder appended last so that GetCurrentUnavailableNodes still sees them)
+	for _, name := range passOrder {
+		for _, ns := range currentState.NodeStates[name] {
+			h, f, r, d := m.encodeNode(ns, stateCode[name], nil, nil)
+			entries, hot, flags, rev, ds = append(entries, ns), append(hot, h), append(flags, f), append(rev, r), append(ds, d)
+		}
+	}
+	n := len(entries)
+	next := make([]C.uint8_t, n)
+	actions := make([]C.uint16_t, n)
+	var dsRev []C.int32_t
+	var counters C.ust_counters
+	pol := m.policy(upgradePolicy)
+	// 2. one call; Go memory is only borrowed for its duration (cgo pointer rules)
+	rc := C.ust_apply_state(acc.h, &pol, C.int64_t(n), (*C.uint8_t)(unsafe.Pointer(&hot[0])), (*C.uint32_t)(unsafe.Pointer(&flags[0])),
+		(*C.int32_t)(unsafe.Pointer(&rev[0])), (*C.int32_t)(unsafe.Pointer(&ds[0])), C.int32_t(len(dsRev)), (*C.int32_t)(unsafe.Pointer(&dsRev[0])),
+		nil, (*C.uint8_t)(unsafe.Pointer(&next[0])), (*C.uint16_t)(unsafe.Pointer(&actions[0])), nil, &counters)
+	// 3. replay through the unchanged L1/L2 interfaces, in order, stopping at the first error exactly like the
+	//    sequential loops. On a reference-level abort the kernel already left the unreached nodes untouched.
+	var restart []*corev1.Pod
+	for i, ns := range entries {
+		a := actions[i]
+		if a&C.UST_A_ERROR != 0 {
+			return fmt.Errorf("%s", C.GoString(C.ust_last_error(acc.h)))
+		}
+		if a&C.UST_A_CLEAR_UPGRADE_REQUESTED != 0 {
+			if err := m.NodeUpgradeStateProvider.ChangeNodeUpgradeAnnotation(ctx, ns.Node, GetUpgradeRequestedAnnotationKey(), "null"); err != nil {
+				return err
+			}
+		}
+		if a&C.UST_A_SET_INITIAL_STATE_ANNO != 0 {
+			if err := m.NodeUpgradeStateProvider.ChangeNodeUpgradeAnnotation(ctx, ns.Node, GetUpgradeInitialStateAnnotationKey(), trueString); err != nil {
+				return err
+			}
+		}
+		if a&C.UST_A_CORDON != 0 {
+			if err := m.CordonManager.Cordon(ctx, ns.Node); err != nil {
+				return err
+			}
+		}
+		if a&C.UST_A_UNCORDON != 0 {
+			if err := m.CordonManager.Uncordon(ctx, ns.Node); err != nil {
+				return err
+			}
+		}
+		if a&C.UST_A_UNBLOCK_SAFE_LOAD != 0 {
+			if err := m.SafeDriverLoadManager.UnblockLoading(ctx, ns.Node); err != nil {
+				return err
+			}
+		}
+		if a&C.UST_A_SET_STATE != 0 {
+			if err := m.NodeUpgradeStateProvider.ChangeNodeUpgradeState(ctx, ns.Node, stateName[next[i]]); err != nil {
+				return err
+			}
+		}
+		if a&C.UST_A_CLEAR_INITIAL_STATE_ANNO != 0 {
+			if err := m.NodeUpgradeStateProvider.ChangeNodeUpgradeAnnotation(ctx, ns.Node, GetUpgradeInitialStateAnnotationKey(), "null"); err != nil {
+				return err
+			}
+		}
+		if a&C.UST_A_RESTART_DRIVER_POD != 0 {
+			restart = append(restart, ns.DriverPod)
+		}
+		// UST_A_SCHEDULE_WAIT_CHECK / _POD_EVICTION / _DRAIN: collect node lists and make ONE PodManager /
+		// DrainManager call per pass, as common_manager.go:413-414, :443-452, :350-356 do.
+	}
+	if rc != C.UST_OK {
+		return fmt.Errorf("%s", C.GoString(C.ust_last_error(acc.h)))
+	}
+	return m.PodManager.SchedulePodsRestart(ctx, restart) // common_manager.go:523
+}
+
+func encodeIntOrPercent(interface{}) (C.int32_t, C.int64_t) { return C.UST_MAXUNAVAIL_NIL, 0 }
