@@ -1,0 +1,446 @@
+// upgrade.cpp — see upgrade.hpp. Encode -> ust_apply_state (B200) -> Replay.
+#include "upgrade.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace upgrade {
+
+const char* const UpgradeStateUnknown = "";
+const char* const UpgradeStateUpgradeRequired = "upgrade-required";
+const char* const UpgradeStateCordonRequired = "cordon-required";
+const char* const UpgradeStateWaitForJobsRequired = "wait-for-jobs-required";
+const char* const UpgradeStatePodDeletionRequired = "pod-deletion-required";
+const char* const UpgradeStateDrainRequired = "drain-required";
+const char* const UpgradeStateNodeMaintenanceRequired = "node-maintenance-required";
+const char* const UpgradeStatePostMaintenanceRequired = "post-maintenance-required";
+const char* const UpgradeStatePodRestartRequired = "pod-restart-required";
+const char* const UpgradeStateValidationRequired = "validation-required";
+const char* const UpgradeStateUncordonRequired = "uncordon-required";
+const char* const UpgradeStateDone = "upgrade-done";
+const char* const UpgradeStateFailed = "upgrade-failed";
+const char* const PodControllerRevisionHashLabelKey = "controller-revision-hash";
+
+static const char* const kNullString = "null";  // consts.go:90
+static const char* const kTrueString = "true";  // consts.go:92
+static std::string g_driver_name;                 // util.go:91-99
+
+void SetDriverName(const std::string& driver) { g_driver_name = driver; }
+static std::string key(const char* tail) { return "nvidia.com/" + g_driver_name + tail; }
+std::string GetUpgradeStateLabelKey() { return key("-driver-upgrade-state"); }
+std::string GetUpgradeSkipNodeLabelKey() { return key("-driver-upgrade.skip"); }
+std::string GetUpgradeDriverWaitForSafeLoadAnnotationKey() { return key("-driver-upgrade.driver-wait-for-safe-load"); }
+std::string GetUpgradeRequestedAnnotationKey() { return key("-driver-upgrade-requested"); }
+std::string GetUpgradeRequestorModeAnnotationKey() { return key("-driver-upgrade-requestor-mode"); }
+std::string GetUpgradeInitialStateAnnotationKey() { return key("-driver-upgrade.node-initial-state.unschedulable"); }
+std::string GetWaitForPodCompletionStartTimeAnnotationKey() { return key("-driver-upgrade-wait-for-pod-completion-start-time"); }
+
+bool IsOrphanedPod(const Pod& pod) { return pod.OwnerReferences.empty(); }
+bool IsNodeInRequestorMode(const Node& node) { return node.Annotations.count(GetUpgradeRequestorModeAnnotationKey()) != 0; }
+ClusterUpgradeState NewClusterUpgradeState() { return ClusterUpgradeState(); }
+
+static const char* const kStateNames[13] = {
+    UpgradeStateUnknown, UpgradeStateUpgradeRequired, UpgradeStateCordonRequired, UpgradeStateWaitForJobsRequired,
+    UpgradeStatePodDeletionRequired, UpgradeStateDrainRequired, UpgradeStateNodeMaintenanceRequired,
+    UpgradeStatePostMaintenanceRequired, UpgradeStatePodRestartRequired, UpgradeStateValidationRequired,
+    UpgradeStateUncordonRequired, UpgradeStateDone, UpgradeStateFailed};
+const char* StateNameOfCode(unsigned code) { return code < 13 ? kStateNames[code] : nullptr; }
+int StateCodeOfLabel(const std::string& label) {
+  for (int i = 0; i < 13; i++)
+    if (label == kStateNames[i]) return i;
+  return UST_STATE_OTHER;
+}
+
+// buckets in the order ApplyState walks them (upgrade_state.go:205-274)
+static const int kPassOrder[12] = {UST_STATE_UNKNOWN, UST_STATE_DONE, UST_STATE_UPGRADE_REQUIRED, UST_STATE_CORDON_REQUIRED,
+                                   UST_STATE_WAIT_FOR_JOBS_REQUIRED, UST_STATE_POD_DELETION_REQUIRED, UST_STATE_DRAIN_REQUIRED,
+                                   UST_STATE_NODE_MAINTENANCE_REQUIRED, UST_STATE_POD_RESTART_REQUIRED, UST_STATE_FAILED,
+                                   UST_STATE_VALIDATION_REQUIRED, UST_STATE_UNCORDON_REQUIRED};
+
+static size_t len(const ClusterUpgradeState& s, const char* name) {
+  auto it = s.NodeStates.find(name);
+  return it == s.NodeStates.end() ? 0 : it->second.size();
+}
+
+// ---- construction -------------------------------------------------------------------------------------------
+Error ClusterUpgradeStateManagerImpl::New(int device, StateOptions opts, std::unique_ptr<ClusterUpgradeStateManagerImpl>* out) {
+  std::unique_ptr<ClusterUpgradeStateManagerImpl> m(new ClusterUpgradeStateManagerImpl());
+  m->opts_ = opts;
+  if (ust_create(&m->handle_, device) != UST_OK)
+    return Errorf(std::string("failed to create upgrade state manager: ") + ust_create_error());
+  *out = std::move(m);
+  return std::nullopt;
+}
+std::unique_ptr<ClusterUpgradeStateManagerImpl> ClusterUpgradeStateManagerImpl::NewDetached(StateOptions opts) {
+  std::unique_ptr<ClusterUpgradeStateManagerImpl> m(new ClusterUpgradeStateManagerImpl());
+  m->opts_ = opts;
+  return m;
+}
+ClusterUpgradeStateManagerImpl::~ClusterUpgradeStateManagerImpl() { if (handle_) ust_destroy(handle_); }
+
+ClusterUpgradeStateManager& ClusterUpgradeStateManagerImpl::WithPodDeletionEnabled(PodDeletionFilter filter) {
+  if (!filter) return *this;  // "Cannot enable PodDeletion state as PodDeletionFilter is nil"  upgrade_state.go:330-333
+  filter_ = std::move(filter);
+  podDeletionStateEnabled_ = true;
+  return *this;
+}
+ClusterUpgradeStateManager& ClusterUpgradeStateManagerImpl::WithValidationEnabled(const std::string& podSelector) {
+  if (podSelector.empty()) return *this;  // upgrade_state.go:342-345
+  validationSelector_ = podSelector;
+  validationStateEnabled_ = true;
+  return *this;
+}
+
+// ---- predicates ---------------------------------------------------------------------------------------------
+bool ClusterUpgradeStateManagerImpl::IsUpgradeRequested(const Node& n) const {
+  auto it = n.Annotations.find(GetUpgradeRequestedAnnotationKey());
+  return it != n.Annotations.end() && it->second == kTrueString;
+}
+bool ClusterUpgradeStateManagerImpl::IsNodeUnschedulable(const Node& n) const { return n.Unschedulable; }
+bool ClusterUpgradeStateManagerImpl::isNodeConditionReady(const Node& n) const {
+  for (const auto& c : n.Conditions)
+    if (c.Type == "Ready" && c.Status != "True") return false;
+  return true;
+}
+bool ClusterUpgradeStateManagerImpl::SkipNodeUpgrade(const Node& n) const {
+  auto it = n.Labels.find(GetUpgradeSkipNodeLabelKey());
+  return it != n.Labels.end() && it->second == kTrueString;
+}
+bool ClusterUpgradeStateManagerImpl::isDriverPodFailing(const Pod& p) const {
+  for (const auto& st : p.InitContainerStatuses)
+    if (!st.Ready && st.RestartCount > 10) return true;
+  for (const auto& st : p.ContainerStatuses)
+    if (!st.Ready && st.RestartCount > 10) return true;
+  return false;
+}
+
+// ---- counters (common_manager.go:146-165, :715-788) ---------------------------------------------------------
+int ClusterUpgradeStateManagerImpl::GetTotalManagedNodes(const ClusterUpgradeState& s) const {
+  return (int)(len(s, UpgradeStateUnknown) + len(s, UpgradeStateDone) + len(s, UpgradeStateUpgradeRequired) +
+               len(s, UpgradeStateCordonRequired) + len(s, UpgradeStateWaitForJobsRequired) +
+               len(s, UpgradeStatePodDeletionRequired) + len(s, UpgradeStateFailed) + len(s, UpgradeStateDrainRequired) +
+               len(s, UpgradeStatePodRestartRequired) + len(s, UpgradeStateUncordonRequired) +
+               len(s, UpgradeStateValidationRequired));
+}
+int ClusterUpgradeStateManagerImpl::GetUpgradesInProgress(const ClusterUpgradeState& s) const {
+  return GetTotalManagedNodes(s) - (int)(len(s, UpgradeStateUnknown) + len(s, UpgradeStateDone) + len(s, UpgradeStateUpgradeRequired));
+}
+int ClusterUpgradeStateManagerImpl::GetUpgradesDone(const ClusterUpgradeState& s) const { return (int)len(s, UpgradeStateDone); }
+int ClusterUpgradeStateManagerImpl::GetUpgradesFailed(const ClusterUpgradeState& s) const { return (int)len(s, UpgradeStateFailed); }
+int ClusterUpgradeStateManagerImpl::GetUpgradesPending(const ClusterUpgradeState& s) const { return (int)len(s, UpgradeStateUpgradeRequired); }
+int ClusterUpgradeStateManagerImpl::GetCurrentUnavailableNodes(const ClusterUpgradeState& s) const {
+  int unavailable = 0;
+  for (const auto& kv : s.NodeStates)
+    for (const NodeUpgradeState* ns : kv.second) {
+      if (IsNodeUnschedulable(*ns->Node)) { unavailable++; continue; }
+      if (!isNodeConditionReady(*ns->Node)) unavailable++;
+    }
+  return unavailable;
+}
+int ClusterUpgradeStateManagerImpl::GetUpgradesAvailable(const ClusterUpgradeState& s, int maxParallelUpgrades, int maxUnavailable) const {
+  const int inProgress = GetUpgradesInProgress(s), total = GetTotalManagedNodes(s);
+  int available = maxParallelUpgrades == 0 ? (int)len(s, UpgradeStateUpgradeRequired) : maxParallelUpgrades - inProgress;
+  const int currentUnavailable = GetCurrentUnavailableNodes(s) + (int)len(s, UpgradeStateCordonRequired);
+  if (available > maxUnavailable) available = maxUnavailable;
+  if (currentUnavailable >= maxUnavailable) available = 0;
+  else if (maxUnavailable < total && currentUnavailable + available > maxUnavailable) available = maxUnavailable - currentUnavailable;
+  return available;
+}
+
+// ---- BuildState (upgrade_state.go:99-164) --------------------------------------------------------------------
+Error ClusterUpgradeStateManagerImpl::BuildState(const std::string& ns, const StringMap& driverLabels,
+                                                 std::unique_ptr<ClusterUpgradeState>* out) {
+  if (handle_ == nullptr) return Errorf("no B200 device bound to this manager: BuildState has no CPU path");
+  std::vector<DaemonSet*> dsList;
+  if (Error e = K8sClient->ListDaemonSets(ns, driverLabels, &dsList)) return Errorf("error getting DaemonSet list: " + *e);
+  std::map<std::string, DaemonSet*> daemonSets;  // UID -> DaemonSet  (common_manager.go:180-186)
+  for (DaemonSet* ds : dsList) daemonSets[ds->UID] = ds;
+  std::vector<Pod*> podList;
+  if (Error e = K8sClient->ListPods(ns, driverLabels, &podList)) return e;
+
+  // owner join on the host (string UIDs); the per-DaemonSet count check and the bucket sizes run on the GPU
+  std::map<std::string, int> dsIndex;
+  std::vector<int32_t> desired;
+  for (const auto& kv : daemonSets) { dsIndex[kv.first] = (int)desired.size(); desired.push_back(kv.second->DesiredNumberScheduled); }
+  std::vector<Pod*> filtered;
+  for (const auto& kv : daemonSets)  // GetPodsOwnedbyDs  common_manager.go:190-208
+    for (Pod* p : podList)
+      if (!IsOrphanedPod(*p) && p->OwnerReferences[0].UID == kv.first) filtered.push_back(p);
+  for (Pod* p : podList)
+    if (IsOrphanedPod(*p)) filtered.push_back(p);  // GetOrphanedPods  common_manager.go:211-221
+
+  std::vector<Node*> nodes(filtered.size(), nullptr);
+  std::vector<uint8_t> state(filtered.size() + 1);
+  std::vector<int32_t> ds_idx(filtered.size() + 1);
+  for (size_t i = 0; i < filtered.size(); i++) {
+    Pod* pod = filtered[i];
+    ds_idx[i] = IsOrphanedPod(*pod) ? -1 : dsIndex[pod->OwnerReferences[0].UID];
+    if (pod->NodeName.empty() && pod->Phase == "Pending") { state[i] = UST_STATE_EXCLUDED; continue; }  // upgrade_state.go:149-152
+    state[i] = UST_STATE_OTHER;  // label resolved below; the count check does not depend on it
+  }
+  ust_counters c;
+  int rc = ust_build_state(handle_, (int64_t)filtered.size(), state.data(), ds_idx.data(), (int32_t)desired.size(), desired.data(), &c);
+  if (rc == UST_ERR_DS_UNSCHEDULED) return Errorf("driver DaemonSet should not have Unscheduled pods");  // upgrade_state.go:128-131
+  if (rc != UST_OK) return Errorf(ust_last_error(handle_));
+
+  auto st = std::make_unique<ClusterUpgradeState>();
+  const std::string labelKey = GetUpgradeStateLabelKey();
+  for (size_t i = 0; i < filtered.size(); i++) {
+    Pod* pod = filtered[i];
+    if (state[i] == UST_STATE_EXCLUDED) continue;
+    Node* node = nullptr;
+    if (Error e = NodeUpgradeStateProvider->GetNode(pod->NodeName, &node)) return Errorf("unable to get node " + pod->NodeName + ": " + *e);
+    auto nus = std::make_unique<NodeUpgradeState>();
+    nus->Node = node;
+    nus->DriverPod = pod;
+    nus->DriverDaemonSet = IsOrphanedPod(*pod) ? nullptr : daemonSets[pod->OwnerReferences[0].UID];
+    if (opts_.Requestor.UseMaintenanceOperator)
+      if (Error e = K8sClient->GetNodeMaintenance(node->Name, &nus->NodeMaintenance)) return Errorf("failed while trying to fetch nodeMaintennace obj: " + *e);
+    auto it = node->Labels.find(labelKey);
+    st->NodeStates[it == node->Labels.end() ? "" : it->second].push_back(nus.get());
+    st->owned.push_back(std::move(nus));
+  }
+  *out = std::move(st);
+  return std::nullopt;
+}
+
+// ---- ApplyState = Encode -> kernel -> Replay -------------------------------------------------------------------
+static void flatten_policy(const DriverUpgradePolicySpec& p, bool podDeletionEnabled, bool validationEnabled, bool useMaintenanceOperator,
+                           ust_policy* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->auto_upgrade = p.AutoUpgrade;
+  c->max_parallel_upgrades = p.MaxParallelUpgrades;
+  if (p.MaxUnavailable) {
+    // intstr.GetScaledValueFromIntOrPercent: Int => IntVal; String must be "<int>%"; anything else is an error
+    if (p.MaxUnavailable->Type == IntOrString::Int) {
+      c->max_unavailable_kind = UST_MAXUNAVAIL_INT;
+      c->max_unavailable_value = p.MaxUnavailable->IntVal;
+    } else {
+      const std::string& s = p.MaxUnavailable->StrVal;
+      bool ok = s.size() >= 2 && s.back() == '%';
+      size_t i = ok && (s[0] == '-' || s[0] == '+') ? 1 : 0;
+      ok = ok && i < s.size() - 1;
+      for (size_t k = i; ok && k + 1 < s.size(); k++) ok = s[k] >= '0' && s[k] <= '9';
+      if (ok) {
+        c->max_unavailable_kind = UST_MAXUNAVAIL_PERCENT;
+        c->max_unavailable_value = std::stoll(s.substr(0, s.size() - 1));
+      } else {
+        c->max_unavailable_kind = UST_MAXUNAVAIL_INVALID;
+      }
+    }
+  }
+  c->pod_deletion_enabled = podDeletionEnabled;
+  c->validation_enabled = validationEnabled;
+  // a nil PodDeletionSpec is the PodManager's error to raise (pod_manager.go:132-134): the actuator gets the nil
+  c->pod_deletion_spec_present = 1;
+  if (p.PodDeletion) { c->pod_deletion_force = p.PodDeletion->Force; c->pod_deletion_delete_emptydir = p.PodDeletion->DeleteEmptyDir; }
+  if (p.DrainSpec) { c->drain_enabled = p.DrainSpec->Enable; c->drain_force = p.DrainSpec->Force; c->drain_delete_emptydir = p.DrainSpec->DeleteEmptyDir; }
+  if (p.WaitForCompletion) { c->wait_selector_set = !p.WaitForCompletion->PodSelector.empty(); c->wait_timeout_nonzero = p.WaitForCompletion->TimeoutSecond != 0; }
+  c->use_maintenance_operator = useMaintenanceOperator;
+}
+
+Error ClusterUpgradeStateManagerImpl::Encode(const ClusterUpgradeState& s, const DriverUpgradePolicySpec& policy, EncodedSnapshot* out) {
+  EncodedSnapshot& e = *out;
+  e = EncodedSnapshot();
+  flatten_policy(policy, podDeletionStateEnabled_, validationStateEnabled_, opts_.Requestor.UseMaintenanceOperator, &e.policy);
+  std::map<std::string, int32_t> intern;
+  std::map<const DaemonSet*, int32_t> dsIndex;
+  std::vector<bool> dsHashError;
+  auto internHash = [&](const std::string& h) { return intern.emplace(h, (int32_t)intern.size() + 1).first->second; };
+  auto add = [&](NodeUpgradeState* ns, int code) -> Error {
+    const Node& n = *ns->Node;
+    uint8_t hot = (uint8_t)code;
+    uint32_t f = 0;
+    if (IsNodeUnschedulable(n)) hot |= UST_HOT_UNSCHEDULABLE;
+    if (!isNodeConditionReady(n)) hot |= UST_HOT_NOT_READY;
+    if (SkipNodeUpgrade(n)) hot |= UST_HOT_SKIP;
+    if (IsUpgradeRequested(n)) f |= UST_F_UPGRADE_REQUESTED;
+    bool waiting = false;
+    if (Error err = SafeDriverLoadManager->IsWaitingForSafeDriverLoad(&n, &waiting)) return err;
+    if (waiting) f |= UST_F_SAFE_LOAD;
+    if (n.Annotations.count(GetUpgradeInitialStateAnnotationKey())) f |= UST_F_INITIAL_STATE_ANNO;
+    if (IsNodeInRequestorMode(n)) f |= UST_F_REQUESTOR_MODE;
+    // ValidationManager.Validate is an actuator with side effects: Replay calls it, at the reference's point in
+    // the pass order, and drops the transition when it reports "not done" (common_manager.go:587-596)
+    f |= UST_F_VALIDATION_DONE;
+    int32_t rev = 0, ds = -1;
+    if (ns->IsOrphanedPod()) {
+      f |= UST_F_POD_ORPHANED;
+    } else {
+      auto it = dsIndex.find(ns->DriverDaemonSet);
+      if (it == dsIndex.end()) {
+        std::string dsHash;
+        const bool bad = (bool)PodManager->GetDaemonsetControllerRevisionHash(ns->DriverDaemonSet, &dsHash);  // once per DaemonSet
+        it = dsIndex.emplace(ns->DriverDaemonSet, (int32_t)e.ds_rev.size()).first;
+        e.ds_rev.push_back(bad ? 0 : internHash(dsHash));
+        dsHashError.push_back(bad);
+      }
+      ds = it->second;
+      std::string podHash;
+      if (ns->DriverPod == nullptr || PodManager->GetPodControllerRevisionHash(ns->DriverPod, &podHash) || dsHashError[(size_t)ds])
+        hot |= UST_HOT_REVISION_HASH_ERROR;  // pod_manager.go:84-89, :108-110
+      else
+        rev = internHash(podHash);
+    }
+    if (const Pod* p = ns->DriverPod) {
+      bool ready = p->Phase == "Running" && !p->ContainerStatuses.empty();  // common_manager.go:617-630
+      for (const auto& cs : p->ContainerStatuses) ready = ready && cs.Ready;
+      if (ready) f |= UST_F_POD_READY;
+      if (isDriverPodFailing(*p)) f |= UST_F_POD_FAILING;
+      if (p->DeletionTimestampSet) f |= UST_F_POD_TERMINATING;
+    }
+    if (ns->NodeMaintenance) {
+      f |= UST_F_NM_PRESENT;
+      if (ns->NodeMaintenance->ReadyConditionWithReasonReady) f |= UST_F_NM_READY;
+    }
+    e.entries.push_back(ns);
+    e.state.push_back(hot);
+    e.flags.push_back(f);
+    e.pod_rev.push_back(rev);
+    e.ds_idx.push_back(ds);
+    return std::nullopt;
+  };
+  // buckets in pass order: SoA index order == replay order, and the upgrade-required bucket keeps its slice order
+  for (int code : kPassOrder) {
+    auto it = s.NodeStates.find(kStateNames[code]);
+    if (it == s.NodeStates.end()) continue;
+    for (NodeUpgradeState* ns : it->second)
+      if (Error err = add(ns, code)) return err;
+  }
+  // every other bucket still counts towards GetCurrentUnavailableNodes (common_manager.go:149)
+  for (const auto& kv : s.NodeStates) {
+    const int code = StateCodeOfLabel(kv.first);
+    if (code != UST_STATE_OTHER && code != UST_STATE_POST_MAINTENANCE_REQUIRED) continue;
+    for (NodeUpgradeState* ns : kv.second)
+      if (Error err = add(ns, code)) return err;
+  }
+  return std::nullopt;
+}
+
+Error ClusterUpgradeStateManagerImpl::Replay(const EncodedSnapshot& enc, const DriverUpgradePolicySpec& policy,
+                                             const uint8_t* next_state, const uint16_t* actions, int abi_rc,
+                                             const ust_counters& counters) {
+  const size_t n = enc.entries.size();
+  const bool drainEnabled = policy.DrainSpec && policy.DrainSpec->Enable;
+  const bool waitSelector = policy.WaitForCompletion && !policy.WaitForCompletion->PodSelector.empty();
+  const bool requestor = opts_.Requestor.UseMaintenanceOperator;
+  auto setState = [&](size_t i) { return NodeUpgradeStateProvider->ChangeNodeUpgradeState(enc.entries[i]->Node, StateNameOfCode(next_state[i])); };
+  auto anno = [&](size_t i, const std::string& k, const char* v) { return NodeUpgradeStateProvider->ChangeNodeUpgradeAnnotation(enc.entries[i]->Node, k, v); };
+  auto abortError = [&]() -> Error { return Errorf(ust_last_error(handle_)); };
+
+  size_t i = 0;
+  for (int pass = 0; pass < 12; pass++) {
+    const int code = kPassOrder[pass];
+    // policy-level abort raised at the start of a pass (intstr parse error, upgrade_inplace.go:54-60)
+    if (abi_rc != UST_OK && counters.error_index < 0 && counters.error_pass == pass) return abortError();
+    if (code == UST_STATE_NODE_MAINTENANCE_REQUIRED && !requestor) {  // upgrade_state.go:299-309
+      while (i < n && (int)(enc.state[i] & UST_HOT_STATE_MASK) == code) i++;
+      continue;
+    }
+    const size_t begin = i;
+    std::vector<Node*> batchNodes;
+    std::vector<Pod*> restartPods;
+    for (; i < n && (int)(enc.state[i] & UST_HOT_STATE_MASK) == code; i++) {
+      if (code == UST_STATE_UNCORDON_REQUIRED) continue;  // two sub-passes below
+      const unsigned a = actions[i];
+      Node* node = enc.entries[i]->Node;
+      if (a & UST_A_ERROR) return abortError();
+      if (a & UST_A_CLEAR_UPGRADE_REQUESTED)
+        if (Error e = anno(i, GetUpgradeRequestedAnnotationKey(), kNullString)) return e;
+      if (a & UST_A_SET_INITIAL_STATE_ANNO)
+        if (Error e = anno(i, GetUpgradeInitialStateAnnotationKey(), kTrueString)) return e;
+      if (a & UST_A_CORDON)
+        if (Error e = CordonManager->Cordon(node)) return e;
+      if (a & UST_A_UNBLOCK_SAFE_LOAD)
+        if (Error e = SafeDriverLoadManager->UnblockLoading(node)) return e;
+      if (code == UST_STATE_VALIDATION_REQUIRED) {
+        bool done = false;
+        if (Error e = ValidationManager->Validate(node, &done)) return e;
+        if (!done) continue;  // "Validations not complete on the node"
+      }
+      if (a & UST_A_NM_CREATE_OR_DELETE) {}  // NodeMaintenance CRUD is the requestor's own client call (upgrade_requestor.go:296)
+      if ((a & UST_A_REQUESTOR_ANNO_CHANGE) && code == UST_STATE_UPGRADE_REQUIRED)
+        if (Error e = anno(i, GetUpgradeRequestorModeAnnotationKey(), kTrueString)) return Errorf("failed annotate node for 'upgrade-requestor-mode'. " + *e);
+      if (a & UST_A_SET_STATE) {
+        Error e = setState(i);
+        // common_manager.go:399, :432 deliberately ignore this error in the wait-for-jobs / pod-deletion passes
+        if (e && code != UST_STATE_WAIT_FOR_JOBS_REQUIRED && code != UST_STATE_POD_DELETION_REQUIRED) return e;
+      }
+      if (a & UST_A_CLEAR_INITIAL_STATE_ANNO)
+        if (Error e = anno(i, GetUpgradeInitialStateAnnotationKey(), kNullString)) return e;
+      if (a & (UST_A_SCHEDULE_WAIT_CHECK | UST_A_SCHEDULE_POD_EVICTION | UST_A_SCHEDULE_DRAIN)) batchNodes.push_back(node);
+      if (a & UST_A_RESTART_DRIVER_POD) restartPods.push_back(enc.entries[i]->DriverPod);
+    }
+    const bool cut = abi_rc != UST_OK && counters.error_pass == pass;  // the kernel stopped inside this pass
+    switch (code) {
+      case UST_STATE_WAIT_FOR_JOBS_REQUIRED:
+        if (waitSelector && !batchNodes.empty()) {  // common_manager.go:404-418
+          PodManagerConfig cfg;
+          cfg.WaitForCompletionSpec = &*policy.WaitForCompletion;
+          cfg.Nodes = batchNodes;
+          if (Error e = PodManager->ScheduleCheckOnPodCompletion(cfg)) return e;
+        }
+        break;
+      case UST_STATE_POD_DELETION_REQUIRED:
+        if (podDeletionStateEnabled_ && !batchNodes.empty()) {  // common_manager.go:437-452
+          PodManagerConfig cfg;
+          cfg.DeletionSpec = policy.PodDeletion ? &*policy.PodDeletion : nullptr;
+          cfg.DrainEnabled = drainEnabled;
+          cfg.Nodes = batchNodes;
+          if (Error e = PodManager->SchedulePodEviction(cfg)) return e;
+        }
+        break;
+      case UST_STATE_DRAIN_REQUIRED:
+        if (drainEnabled) {  // common_manager.go:346-356 (called even with an empty node list)
+          DrainConfiguration cfg;
+          cfg.Spec = &*policy.DrainSpec;
+          cfg.Nodes = batchNodes;
+          if (Error e = DrainManager->ScheduleNodesDrain(cfg)) return e;
+        }
+        break;
+      case UST_STATE_POD_RESTART_REQUIRED:
+        if (!cut)  // an abort inside the pass returns before SchedulePodsRestart (common_manager.go:462-523)
+          if (Error e = PodManager->SchedulePodsRestart(restartPods)) return e;
+        break;
+      case UST_STATE_UNCORDON_REQUIRED: {
+        // in-place flow first, then the requestor flow (upgrade_state.go:311-325)
+        for (size_t k = begin; k < i; k++) {
+          if (actions[k] & UST_A_UNCORDON) {
+            if (Error e = CordonManager->Uncordon(enc.entries[k]->Node)) return e;
+            if (Error e = setState(k)) return e;
+          }
+        }
+        for (size_t k = begin; k < i; k++) {
+          if ((actions[k] & UST_A_REQUESTOR_ANNO_CHANGE) && !(actions[k] & UST_A_UNCORDON)) {
+            if (Error e = setState(k)) return e;
+            if (Error e = anno(k, GetUpgradeRequestorModeAnnotationKey(), kNullString))
+              return Errorf("failed to remove '" + GetUpgradeRequestorModeAnnotationKey() + "' annotation . " + *e);
+          }
+        }
+      } break;
+      default: break;
+    }
+  }
+  if (abi_rc != UST_OK) return abortError();
+  return std::nullopt;
+}
+
+Error ClusterUpgradeStateManagerImpl::ApplyState(ClusterUpgradeState* currentState, const DriverUpgradePolicySpec* upgradePolicy) {
+  if (currentState == nullptr) return Errorf("currentState should not be empty");  // upgrade_state.go:175-177
+  if (upgradePolicy == nullptr || !upgradePolicy->AutoUpgrade) return std::nullopt;  // upgrade_state.go:179-182
+  if (handle_ == nullptr) return Errorf("no B200 device bound to this manager: ApplyState has no CPU path");
+  EncodedSnapshot enc;
+  if (Error e = Encode(*currentState, *upgradePolicy, &enc)) return e;
+  const size_t n = enc.entries.size();
+  std::vector<uint8_t> next(n + 1);
+  std::vector<uint16_t> actions(n + 1);
+  enc.state.push_back(0); enc.flags.push_back(0); enc.pod_rev.push_back(0); enc.ds_idx.push_back(0);  // never pass NULL for n == 0
+  enc.ds_rev.push_back(0);
+  const int rc = ust_apply_state(handle_, &enc.policy, (int64_t)n, enc.state.data(), enc.flags.data(), enc.pod_rev.data(),
+                                 enc.ds_idx.data(), (int32_t)enc.ds_rev.size() - 1, enc.ds_rev.data(), nullptr, next.data(),
+                                 actions.data(), nullptr, &last_);
+  if (rc == UST_ERR_CUDA || rc == UST_ERR_INVALID_ARGUMENT || rc == UST_ERR_NIL_STATE) return Errorf(ust_last_error(handle_));
+  return Replay(enc, *upgradePolicy, next.data(), actions.data(), rc, last_);
+}
+
+}  // namespace upgrade

@@ -1,0 +1,270 @@
+// upgrade.hpp — host-side mirror of github.com/NVIDIA/k8s-operator-libs/pkg/upgrade for the ApplyState /
+// BuildState path, written in C++ because the build image has no Go toolchain. Names, argument
+// meaning and error behaviour follow the reference so that callers (and tests) read like the Go:
+//
+//   ClusterUpgradeStateManager      pkg/upgrade/upgrade_state.go:35-53
+//   CommonUpgradeStateManager       pkg/upgrade/common_manager.go:23-41
+//   NodeUpgradeState / ClusterUpgradeState   common_manager.go:58-80
+//   UpgradeState* constants, key getters     consts.go:19-93, util.go:91-155
+//   DriverUpgradePolicySpec & sub-specs      api/upgrade/v1alpha1/upgrade_spec.go:27-110
+//   actuator interfaces: NodeUpgradeStateProvider (node_upgrade_state_provider.go:33-37), CordonManager
+//   (cordon_manager.go:33-36), DrainManager (drain_manager.go:48-50), PodManager (pod_manager.go:53-60),
+//   ValidationManager (validation_manager.go:48-50), SafeDriverLoadManager (safe_driver_load_manager.go:74-79)
+//
+// Decisions are NOT made here: ApplyState encodes the snapshot into the struct-of-arrays of include/ust.h, calls
+// ust_apply_state (B200 kernel) and replays the returned per-node action bitmasks through the actuator interfaces
+// in the reference's pass order. Without libust.so / a B200 every ApplyState returns an error.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "../../include/ust.h"
+
+namespace upgrade {
+
+// ---- errors: Go's `error` ---------------------------------------------------------------------------
+using Error = std::optional<std::string>;  // nullopt == nil
+inline Error Errorf(std::string s) { return Error(std::move(s)); }
+
+// ---- consts.go:49-82 ----------------------------------------------------------------------------------
+extern const char* const UpgradeStateUnknown;
+extern const char* const UpgradeStateUpgradeRequired;
+extern const char* const UpgradeStateCordonRequired;
+extern const char* const UpgradeStateWaitForJobsRequired;
+extern const char* const UpgradeStatePodDeletionRequired;
+extern const char* const UpgradeStateDrainRequired;
+extern const char* const UpgradeStateNodeMaintenanceRequired;
+extern const char* const UpgradeStatePostMaintenanceRequired;
+extern const char* const UpgradeStatePodRestartRequired;
+extern const char* const UpgradeStateValidationRequired;
+extern const char* const UpgradeStateUncordonRequired;
+extern const char* const UpgradeStateDone;
+extern const char* const UpgradeStateFailed;
+extern const char* const PodControllerRevisionHashLabelKey;  // pod_manager.go:72
+
+// util.go:91-155
+void SetDriverName(const std::string& driver);
+std::string GetUpgradeStateLabelKey();
+std::string GetUpgradeSkipNodeLabelKey();
+std::string GetUpgradeDriverWaitForSafeLoadAnnotationKey();
+std::string GetUpgradeRequestedAnnotationKey();
+std::string GetUpgradeRequestorModeAnnotationKey();
+std::string GetUpgradeInitialStateAnnotationKey();
+std::string GetWaitForPodCompletionStartTimeAnnotationKey();
+
+// ---- the slice of corev1 / appsv1 the path reads --------------------------------------------------------
+using StringMap = std::map<std::string, std::string>;
+struct NodeCondition { std::string Type, Status; };
+struct Node {
+  std::string Name;
+  StringMap Labels, Annotations;
+  bool Unschedulable = false;            // Spec.Unschedulable
+  std::vector<NodeCondition> Conditions;  // Status.Conditions
+};
+struct ContainerStatus { bool Ready = false; int RestartCount = 0; };
+struct OwnerReference { std::string Kind, Name, UID; };
+struct Pod {
+  std::string Name, Namespace, NodeName;  // Spec.NodeName
+  StringMap Labels;
+  std::vector<OwnerReference> OwnerReferences;
+  std::string Phase;                      // Status.Phase
+  std::vector<ContainerStatus> ContainerStatuses, InitContainerStatuses;
+  bool DeletionTimestampSet = false;      // !DeletionTimestamp.IsZero()
+};
+struct DaemonSet {
+  std::string Name, Namespace, UID;
+  int DesiredNumberScheduled = 0;         // Status.DesiredNumberScheduled
+};
+struct NodeMaintenance {                   // maintenance-operator api v0.3.0, the fields the path reads
+  std::string Name;
+  bool ReadyConditionWithReasonReady = false;  // upgrade_requestor.go:437-439
+};
+bool IsOrphanedPod(const Pod& pod);        // common_manager.go:223-225
+bool IsNodeInRequestorMode(const Node& node);  // util.go:135-138
+
+// ---- api/upgrade/v1alpha1 --------------------------------------------------------------------------------
+struct IntOrString {
+  enum Kind { Int, String } Type = Int;
+  int64_t IntVal = 0;
+  std::string StrVal;
+  static IntOrString FromInt(int64_t v) { IntOrString x; x.Type = Int; x.IntVal = v; return x; }
+  static IntOrString FromString(std::string s) { IntOrString x; x.Type = String; x.StrVal = std::move(s); return x; }
+};
+struct WaitForCompletionSpec { std::string PodSelector; int TimeoutSecond = 0; };
+struct PodDeletionSpec { bool Force = false; int TimeoutSecond = 300; bool DeleteEmptyDir = false; };
+struct DrainSpec { bool Enable = false, Force = false; std::string PodSelector; int TimeoutSecond = 300; bool DeleteEmptyDir = false; };
+struct DriverUpgradePolicySpec {
+  bool AutoUpgrade = false;
+  int64_t MaxParallelUpgrades = 0;
+  std::optional<IntOrString> MaxUnavailable;
+  std::optional<PodDeletionSpec> PodDeletion;
+  std::optional<WaitForCompletionSpec> WaitForCompletion;
+  std::optional<upgrade::DrainSpec> DrainSpec;
+};
+
+// ---- common_manager.go:58-80 ------------------------------------------------------------------------------
+struct NodeUpgradeState {
+  upgrade::Node* Node = nullptr;
+  Pod* DriverPod = nullptr;
+  DaemonSet* DriverDaemonSet = nullptr;
+  upgrade::NodeMaintenance* NodeMaintenance = nullptr;
+  bool IsOrphanedPod() const { return DriverDaemonSet == nullptr; }
+};
+struct ClusterUpgradeState {
+  std::map<std::string, std::vector<NodeUpgradeState*>> NodeStates;
+  std::vector<std::unique_ptr<NodeUpgradeState>> owned;  // BuildState keeps its entries alive here
+};
+ClusterUpgradeState NewClusterUpgradeState();
+
+// ---- actuator interfaces (stay host-side; driven by the kernel's action bits) --------------------------
+struct NodeUpgradeStateProvider {
+  virtual ~NodeUpgradeStateProvider() = default;
+  virtual Error GetNode(const std::string& nodeName, Node** out) = 0;
+  virtual Error ChangeNodeUpgradeState(Node* node, const std::string& newNodeState) = 0;
+  virtual Error ChangeNodeUpgradeAnnotation(Node* node, const std::string& key, const std::string& value) = 0;  // "null" deletes
+};
+struct CordonManager {
+  virtual ~CordonManager() = default;
+  virtual Error Cordon(Node* node) = 0;
+  virtual Error Uncordon(Node* node) = 0;
+};
+struct DrainConfiguration { const upgrade::DrainSpec* Spec = nullptr; std::vector<Node*> Nodes; };
+struct DrainManager {
+  virtual ~DrainManager() = default;
+  virtual Error ScheduleNodesDrain(const DrainConfiguration& drainConfig) = 0;
+};
+using PodDeletionFilter = std::function<bool(const Pod&)>;
+struct PodManagerConfig {
+  std::vector<Node*> Nodes;
+  const PodDeletionSpec* DeletionSpec = nullptr;
+  const upgrade::WaitForCompletionSpec* WaitForCompletionSpec = nullptr;
+  bool DrainEnabled = false;
+};
+struct PodManager {
+  virtual ~PodManager() = default;
+  virtual Error ScheduleCheckOnPodCompletion(const PodManagerConfig& config) = 0;
+  virtual Error SchedulePodsRestart(const std::vector<Pod*>& pods) = 0;
+  virtual Error SchedulePodEviction(const PodManagerConfig& config) = 0;
+  virtual PodDeletionFilter GetPodDeletionFilter() = 0;
+  virtual Error GetPodControllerRevisionHash(const Pod* pod, std::string* hash) = 0;
+  virtual Error GetDaemonsetControllerRevisionHash(const DaemonSet* daemonset, std::string* hash) = 0;
+};
+struct ValidationManager {
+  virtual ~ValidationManager() = default;
+  virtual Error Validate(Node* node, bool* done) = 0;
+};
+struct SafeDriverLoadManager {
+  virtual ~SafeDriverLoadManager() = default;
+  virtual Error IsWaitingForSafeDriverLoad(const Node* node, bool* waiting) = 0;
+  virtual Error UnblockLoading(Node* node) = 0;
+};
+// what BuildState lists (controller-runtime client in the reference, upgrade_state.go:105-119)
+struct K8sClient {
+  virtual ~K8sClient() = default;
+  virtual Error ListDaemonSets(const std::string& ns, const StringMap& labels, std::vector<DaemonSet*>* out) = 0;
+  virtual Error ListPods(const std::string& ns, const StringMap& labels, std::vector<Pod*>* out) = 0;
+  virtual Error GetNodeMaintenance(const std::string& nodeName, NodeMaintenance** out) { *out = nullptr; return std::nullopt; }
+};
+
+struct RequestorOptions { bool UseMaintenanceOperator = false; };  // upgrade_requestor.go:527-546 (the switch only)
+struct StateOptions { RequestorOptions Requestor; };               // upgrade_state.go:94-96
+
+// ---- the encoded snapshot (include/ust.h layout) and its replay ------------------------------------------
+struct EncodedSnapshot {
+  std::vector<NodeUpgradeState*> entries;  // SoA index -> snapshot entry, buckets in ApplyState's pass order
+  std::vector<uint8_t> state;
+  std::vector<uint32_t> flags;
+  std::vector<int32_t> pod_rev, ds_idx, ds_rev;
+  ust_policy policy{};
+};
+
+// ---- common_manager.go:23-41 --------------------------------------------------------------------------------
+class CommonUpgradeStateManager {
+ public:
+  virtual ~CommonUpgradeStateManager() = default;
+  virtual int GetTotalManagedNodes(const ClusterUpgradeState& s) const = 0;
+  virtual int GetUpgradesInProgress(const ClusterUpgradeState& s) const = 0;
+  virtual int GetUpgradesDone(const ClusterUpgradeState& s) const = 0;
+  virtual int GetUpgradesAvailable(const ClusterUpgradeState& s, int maxParallelUpgrades, int maxUnavailable) const = 0;
+  virtual int GetUpgradesFailed(const ClusterUpgradeState& s) const = 0;
+  virtual int GetUpgradesPending(const ClusterUpgradeState& s) const = 0;
+  virtual bool IsPodDeletionEnabled() const = 0;
+  virtual bool IsValidationEnabled() const = 0;
+};
+
+// ---- upgrade_state.go:35-53 -----------------------------------------------------------------------------------
+class ClusterUpgradeStateManager : public CommonUpgradeStateManager {
+ public:
+  virtual ClusterUpgradeStateManager& WithPodDeletionEnabled(PodDeletionFilter filter) = 0;
+  virtual ClusterUpgradeStateManager& WithValidationEnabled(const std::string& podSelector) = 0;
+  virtual Error BuildState(const std::string& ns, const StringMap& driverLabels, std::unique_ptr<ClusterUpgradeState>* out) = 0;
+  virtual Error ApplyState(ClusterUpgradeState* currentState, const DriverUpgradePolicySpec* upgradePolicy) = 0;
+};
+
+class ClusterUpgradeStateManagerImpl : public ClusterUpgradeStateManager {
+ public:
+  // exported fields operators and tests overwrite (common_manager.go:84-100)
+  upgrade::K8sClient* K8sClient = nullptr;
+  upgrade::DrainManager* DrainManager = nullptr;
+  upgrade::PodManager* PodManager = nullptr;
+  upgrade::CordonManager* CordonManager = nullptr;
+  upgrade::NodeUpgradeStateProvider* NodeUpgradeStateProvider = nullptr;
+  upgrade::ValidationManager* ValidationManager = nullptr;
+  upgrade::SafeDriverLoadManager* SafeDriverLoadManager = nullptr;
+
+  // NewClusterUpgradeStateManager (upgrade_state.go:65-92): binds CUDA device `device` through ust_create
+  static Error New(int device, StateOptions opts, std::unique_ptr<ClusterUpgradeStateManagerImpl>* out);
+  // A manager without a device: Encode / Replay work (recording, auditing), ApplyState and BuildState fail loudly.
+  static std::unique_ptr<ClusterUpgradeStateManagerImpl> NewDetached(StateOptions opts);
+  ~ClusterUpgradeStateManagerImpl() override;
+
+  ClusterUpgradeStateManager& WithPodDeletionEnabled(PodDeletionFilter filter) override;  // upgrade_state.go:329-337
+  ClusterUpgradeStateManager& WithValidationEnabled(const std::string& podSelector) override;  // :341-350
+  Error BuildState(const std::string& ns, const StringMap& driverLabels, std::unique_ptr<ClusterUpgradeState>* out) override;
+  Error ApplyState(ClusterUpgradeState* currentState, const DriverUpgradePolicySpec* upgradePolicy) override;
+
+  int GetTotalManagedNodes(const ClusterUpgradeState& s) const override;
+  int GetUpgradesInProgress(const ClusterUpgradeState& s) const override;
+  int GetUpgradesDone(const ClusterUpgradeState& s) const override;
+  int GetUpgradesAvailable(const ClusterUpgradeState& s, int maxParallelUpgrades, int maxUnavailable) const override;
+  int GetUpgradesFailed(const ClusterUpgradeState& s) const override;
+  int GetUpgradesPending(const ClusterUpgradeState& s) const override;
+  int GetCurrentUnavailableNodes(const ClusterUpgradeState& s) const;
+  bool IsPodDeletionEnabled() const override { return podDeletionStateEnabled_; }
+  bool IsValidationEnabled() const override { return validationStateEnabled_; }
+
+  // predicates (same names as the Go methods)
+  bool IsUpgradeRequested(const Node& n) const;     // common_manager.go:323-325
+  bool IsNodeUnschedulable(const Node& n) const;    // :651-653
+  bool isNodeConditionReady(const Node& n) const;   // :656-663
+  bool SkipNodeUpgrade(const Node& n) const;        // :666-668
+  bool isDriverPodFailing(const Pod& p) const;      // :636-648
+
+  // The two halves of ApplyState around the kernel call. Public so that they can be audited separately:
+  // Encode evaluates every reference predicate once and fills the struct-of-arrays; Replay performs the calls
+  // named by the action bits, in the reference's pass order, stopping at the first error.
+  Error Encode(const ClusterUpgradeState& s, const DriverUpgradePolicySpec& policy, EncodedSnapshot* out);
+  Error Replay(const EncodedSnapshot& enc, const DriverUpgradePolicySpec& policy, const uint8_t* next_state,
+               const uint16_t* actions, int abi_rc, const ust_counters& counters);
+
+  const ust_counters& LastCounters() const { return last_; }
+
+ private:
+  ClusterUpgradeStateManagerImpl() = default;
+  ust_handle* handle_ = nullptr;
+  StateOptions opts_;
+  bool podDeletionStateEnabled_ = false, validationStateEnabled_ = false;
+  PodDeletionFilter filter_;
+  std::string validationSelector_;
+  ust_counters last_{};
+};
+
+const char* StateNameOfCode(unsigned code);  // "" for unknown; nullptr for codes without a label
+int StateCodeOfLabel(const std::string& label);
+
+}  // namespace upgrade

@@ -1,0 +1,42 @@
+// Host halves only (no GPU): Encode -> ORACLE -> Replay. The oracle stands in for the kernel here purely as a
+// checker of the encoder / replayer logic; the product's ApplyState never does this (it fails without a device).
+#include <cstring>
+
+#include "upgrade_state_spec.hpp"
+
+extern "C" int ust_oracle_apply_state(int variant, const ust_policy* policy, int64_t n, const uint8_t* state,
+                                      const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds,
+                                      const int32_t* ds_rev, const ust_pods* pods, uint8_t* next_state, uint16_t* actions,
+                                      uint8_t* actuator_outcome, ust_counters* out);
+
+int main() {
+  mocks::Runner R;
+  spec::MakeFn make = [](upgrade::StateOptions o) { return upgrade::ClusterUpgradeStateManagerImpl::NewDetached(o); };
+  spec::ApplyFn apply = [](spec::Env& e, upgrade::ClusterUpgradeState* s, const upgrade::DriverUpgradePolicySpec* p) -> upgrade::Error {
+    if (s == nullptr) return upgrade::Errorf("currentState should not be empty");
+    if (p == nullptr || !p->AutoUpgrade) return std::nullopt;
+    upgrade::EncodedSnapshot enc;
+    if (auto err = e.m->Encode(*s, *p, &enc)) return err;
+    const size_t n = enc.entries.size();
+    std::vector<uint8_t> next(n + 1);
+    std::vector<uint16_t> actions(n + 1);
+    enc.state.push_back(0); enc.flags.push_back(0); enc.pod_rev.push_back(0); enc.ds_idx.push_back(0); enc.ds_rev.push_back(0);
+    ust_counters c;
+    const int rc = ust_oracle_apply_state(0, &enc.policy, (int64_t)n, enc.state.data(), enc.flags.data(), enc.pod_rev.data(),
+                                          enc.ds_idx.data(), (int32_t)enc.ds_rev.size() - 1, enc.ds_rev.data(), nullptr,
+                                          next.data(), actions.data(), nullptr, &c);
+    return e.m->Replay(enc, *p, next.data(), actions.data(), rc, c);
+  };
+  spec::run(R, make, apply);
+  // the detached manager must refuse to decide anything by itself
+  R.it("a manager without a device refuses ApplyState (no CPU path)", [&] {
+    auto m = upgrade::ClusterUpgradeStateManagerImpl::NewDetached({});
+    upgrade::ClusterUpgradeState s;
+    upgrade::DriverUpgradePolicySpec p;
+    p.AutoUpgrade = true;
+    auto err = m->ApplyState(&s, &p);
+    EXPECT(R, err.has_value());
+  });
+  std::printf("# %d passed, %d failed\n", R.passed, R.failed);
+  return R.failed == 0 ? 0 : 1;
+}
