@@ -270,7 +270,10 @@ int ust_table_window_shift(unsigned state_code);
  * constraint counters happens per call. */
 int ust_get_unique_id(void* out_bytes);
 int ust_comm_init(ust_handle* h, int rank, int world_size, const void* unique_id_bytes);
-/* exchange mode: 0 = ncclAllReduce between two kernels (default), 1 = fused in-kernel NVLink exchange */
+/* exchange mode: 0 = ncclAllReduce between two kernels (default), 1 = fused: each rank runs ONE kernel that pushes
+ * its counters into every peer's mailbox over NVLink (CUDA IPC peer memory) and reads the peers' from its own.
+ * Mode 1 returns UST_ERR_COMM when the peer mailboxes could not be mapped at ust_comm_init. All ranks must use the
+ * same mode. */
 int ust_comm_set_mode(ust_handle* h, int mode);
 
 #ifdef __cplusplus

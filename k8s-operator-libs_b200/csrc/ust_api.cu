@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "ust_dev.h"
 
@@ -22,6 +23,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string* err) {
@@ -40,6 +42,7 @@ struct NcclApi {
     GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
     if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { *err = "libnccl lacks required symbols"; return false; }
@@ -106,6 +109,11 @@ struct ust_handle {
   // multi-GPU
   int rank = 0, world = 1, comm_mode = 0;
   ncclComm_t comm = nullptr;
+  // fused exchange: own mailbox + the peers' mailboxes mapped through CUDA IPC
+  UstMailbox* mbox_own = nullptr;
+  UstMailbox* mbox[UST_MAX_WORLD] = {};
+  bool mbox_ready = false;
+  long long epoch = 0;
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -209,6 +217,10 @@ static void fill_params(ust_handle* h, const ust_policy* policy, int64_t n, cons
   }
   P.rank = h->rank;
   P.world = h->world;
+  if (h->world > 1 && h->comm_mode == 1 && h->mbox_ready) {
+    P.fused_exchange = 1;
+    for (int r = 0; r < h->world; r++) P.mbox[r] = h->mbox[r];
+  }
   // Speculative slot grant (verified in-kernel after the grid barrier, so only speed depends on it):
   // with no MaxParallelUpgrades / MaxUnavailable limit every candidate gets a slot (upgrade_inplace.go:49-62);
   // with limits the budget is normally tiny next to the number of candidates.
@@ -252,7 +264,8 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
               out_dev, &P, &grid);
 
   h->ws_dirty = true;  // cleared again once every launch of this call has been enqueued successfully
-  if (h->world == 1) {
+  if (h->world == 1 || P.fused_exchange) {
+    if (P.fused_exchange) P.epoch = ++h->epoch;  // collective call number: identical on every rank
     int e = ust_launch_fused(P, grid, st);
     if (e) return h->fail(UST_ERR_CUDA, "fused kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
     h->launches += 1;
@@ -445,6 +458,9 @@ void ust_destroy(ust_handle* h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int r = 0; r < UST_MAX_WORLD; r++)
+    if (h->mbox[r] && h->mbox[r] != h->mbox_own) cudaIpcCloseMemHandle(h->mbox[r]);
+  if (h->mbox_own) cudaFree(h->mbox_own);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->ws) cudaFree(h->ws);
   if (h->lut_dev) cudaFree(h->lut_dev);
@@ -631,13 +647,43 @@ int ust_comm_init(ust_handle* h, int rank, int world_size, const void* unique_id
   if (r != ncclSuccess) return h->fail(UST_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   h->rank = rank;
   h->world = world_size;
+  // Mailboxes for the fused exchange: allocate, all-gather the CUDA IPC handles over the new communicator, map the
+  // peers' buffers. Any failure leaves the NCCL exchange (mode 0) as the only mode.
+  h->mbox_ready = false;
+  do {
+    if (!g_nccl.AllGather) break;
+    if (cudaMalloc(&h->mbox_own, sizeof(UstMailbox)) != cudaSuccess) break;
+    if (cudaMemset(h->mbox_own, 0, sizeof(UstMailbox)) != cudaSuccess) break;
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, h->mbox_own) != cudaSuccess) { cudaGetLastError(); break; }
+    cudaIpcMemHandle_t* dev = nullptr;
+    if (cudaMalloc(&dev, sizeof(cudaIpcMemHandle_t) * (size_t)(world_size + 1)) != cudaSuccess) break;
+    cudaMemcpy(dev + world_size, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+    ncclResult_t g = g_nccl.AllGather(dev + world_size, dev, sizeof(mine), ncclChar, h->comm, h->stream);
+    cudaError_t ce = cudaStreamSynchronize(h->stream);
+    std::vector<cudaIpcMemHandle_t> all((size_t)world_size);
+    if (g == ncclSuccess && ce == cudaSuccess) cudaMemcpy(all.data(), dev, sizeof(mine) * (size_t)world_size, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (g != ncclSuccess || ce != cudaSuccess) break;
+    bool ok = true;
+    for (int r = 0; r < world_size && ok; r++) {
+      if (r == rank) { h->mbox[r] = h->mbox_own; continue; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      h->mbox[r] = (UstMailbox*)p;
+    }
+    h->mbox_ready = ok;
+  } while (0);
+  h->epoch = 0;
   return UST_OK;
 }
 
 int ust_comm_set_mode(ust_handle* h, int mode) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
-  if (mode != 0) return h->fail(UST_ERR_INVALID_ARGUMENT, "exchange mode %d is not available in this build", mode);
+  if (mode != 0 && mode != 1) return h->fail(UST_ERR_INVALID_ARGUMENT, "unknown exchange mode %d", mode);
+  if (mode == 1 && !(h->world > 1 && h->mbox_ready))
+    return h->fail(UST_ERR_COMM, "fused exchange unavailable: peer mailboxes could not be mapped (CUDA IPC)");
   h->comm_mode = mode;
   return UST_OK;
 }

@@ -21,6 +21,14 @@
 #define UST_V_RANK_ERRINV (18 + 2 * UST_MAX_WORLD) /* ~abort key of the rank, 0 = none */
 #define UST_V_LEN (18 + 3 * UST_MAX_WORLD)
 
+// Peer mailboxes of the fused multi-GPU exchange: rank s writes its lanes into slot[epoch & 1][s] of EVERY rank's
+// mailbox over NVLink (CUDA IPC mapping), then releases the flag lane with the epoch number.
+#define UST_MBOX_FLAG UST_V_LEN
+#define UST_MBOX_LANES (UST_V_LEN + 6)  /* 48 lanes = 384 B per slot */
+struct UstMailbox {
+  long long slot[2][UST_MAX_WORLD][UST_MBOX_LANES];
+};
+
 // Device workspace owned by a handle. Invariant: acc / errinv / arrive / depart are zero between launches.
 struct UstWorkspace {
   unsigned long long acc[18];   // hist[0..15], unavailable, candidates (this shard)
@@ -29,6 +37,10 @@ struct UstWorkspace {
   unsigned int depart;
   unsigned int ticket;   // dynamic chunk claiming
   unsigned int fixups;   // chunks redone by the verification phase of the current call
+  unsigned long long go; // fused exchange: epoch whose cluster-wide vector CTA 0 has published in gv[]
+  long long gv[UST_V_LEN];
+  unsigned int comm_timeout;  // set when a peer did not show up (kernel gives up instead of hanging)
+  unsigned int pad_;
   unsigned int cand_cta[UST_MAX_CTAS];  // candidates per CTA chunk (written by phase 1, read by phase 2)
   unsigned long long dbg[UST_MAX_CTAS][4];  // %globaltimer stamps per CTA: entry, stream end, barrier release, exit (diagnostics)
 };
@@ -71,6 +83,10 @@ struct UstParams {
   int chunk_begin;        // streaming sub-range launches (pipelined uploads): chunks [chunk_begin, chunk_end)
   int chunk_end;
   int publish;            // split mode: this streaming launch is the last one of the call (publish + reset)
+  // fused multi-GPU exchange (world > 1): mailboxes of all ranks as mapped into this process, call number
+  int fused_exchange;
+  long long epoch;
+  UstMailbox* mbox[UST_MAX_WORLD];
 };
 
 // kernel launchers (ust_kernels.cu); all return cudaError_t as int

@@ -319,6 +319,7 @@ __device__ void write_counters(const UstParams& P, const Shared& S) {
   c.max_unavailable = slots ? S.max_unav : 0;
   c.upgrades_available = slots ? S.avail : 0;
   for (int i = 0; i < 7; i++) c.reserved[i] = 0;
+  if (__ldcg(&P.ws->comm_timeout)) { c.error_code = UST_ERR_COMM; c.error_index = -1; c.error_pass = -1; }
   c.reserved[0] = (long long)__ldcg(&P.ws->fixups);  // chunks the verification phase had to redo (diagnostic)
   *P.out = c;
 }
@@ -819,6 +820,86 @@ __device__ void load_local_vector(const UstParams& P, Shared& S) {
   }
 }
 
+// ---- system-scope accessors for the NVLink mailbox exchange -------------------------------------------------
+__device__ __forceinline__ void st_relaxed_sys(long long* p, long long v) { asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) { asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long ld_relaxed_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kCommTimeoutNs = 4000000000ull;  // give up on a missing peer after 4 s
+
+// Cluster-wide vector for world > 1 without leaving the kernel: CTA 0 waits for the local CTAs, pushes this
+// shard's lanes into every rank's mailbox over NVLink, waits for every rank's lanes in its own mailbox, sums,
+// and publishes the result to the other local CTAs. One-hot per-rank lanes make the sum an all-gather.
+__device__ void fused_exchange(const UstParams& P, Shared& S) {
+  const int t = threadIdx.x;
+  UstWorkspace* ws = P.ws;
+  const int par = (int)(P.epoch & 1);
+  if (blockIdx.x == 0) {
+    if (t == 0) {
+      while (ld_acquire_u32(&ws->arrive) < gridDim.x) __nanosleep(20);
+      __threadfence();
+    }
+    __syncthreads();
+    load_local_vector(P, S);
+    __syncthreads();
+    if (t < UST_V_LEN) {
+      for (int r = 0; r < P.world; r++) st_relaxed_sys(&P.mbox[r]->slot[par][P.rank][t], S.V[t]);
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (t < P.world) st_release_sys(&P.mbox[t]->slot[par][P.rank][UST_MBOX_FLAG], P.epoch);
+    if (t < P.world) {
+      const unsigned long long t0 = now_ns();
+      while (ld_acquire_sys(&P.mbox[P.rank]->slot[par][t][UST_MBOX_FLAG]) != P.epoch) {
+        if (now_ns() - t0 > kCommTimeoutNs) { ws->comm_timeout = 1; break; }
+        __nanosleep(50);
+      }
+    }
+    __syncthreads();
+    if (t < UST_V_LEN) {
+      long long sum = 0;
+      for (int r = 0; r < P.world; r++) sum += ld_relaxed_sys(&P.mbox[P.rank]->slot[par][r][t]);
+      S.V[t] = sum;
+      ws->gv[t] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&ws->go), "l"((unsigned long long)P.epoch) : "memory");
+    }
+  } else {
+    if (t == 0) {
+      const unsigned long long t0 = now_ns();
+      while (ld_acquire_u64(&ws->go) != (unsigned long long)P.epoch) {
+        if (now_ns() - t0 > kCommTimeoutNs + 1000000000ull) break;
+        __nanosleep(50);
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    if (t < UST_V_LEN) S.V[t] = __ldcg(&ws->gv[t]);
+  }
+  __syncthreads();
+}
+
 __device__ void finish(const UstParams& P, Shared& S, bool reset_ws) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -827,6 +908,7 @@ __device__ void finish(const UstParams& P, Shared& S, bool reset_ws) {
     if (prev == gridDim.x - 1u) {  // last CTA out: publish counters, restore the workspace invariant
       write_counters(P, S);
       P.ws->fixups = 0;
+      P.ws->comm_timeout = 0;
       if (reset_ws) {
         for (int i = 0; i < 18; i++) P.ws->acc[i] = 0;
         P.ws->errinv = 0;
@@ -881,16 +963,25 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_fused_kernel(const
   // grid-wide barrier (every CTA is co-resident: cooperative launch). After it the cluster-wide
   // counters are final and the speculation can be checked.
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(&P.ws->arrive, 1u);
-    while (ld_acquire_u32(&P.ws->arrive) < gridDim.x) __nanosleep(20);
-    __threadfence();
+  if (P.fused_exchange) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&P.ws->arrive, 1u);
+    }
+    fused_exchange(P, S);
+    stamp(P, 2);
+  } else {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&P.ws->arrive, 1u);
+      while (ld_acquire_u32(&P.ws->arrive) < gridDim.x) __nanosleep(20);
+      __threadfence();
+    }
+    __syncthreads();
+    stamp(P, 2);
+    load_local_vector(P, S);
+    __syncthreads();
   }
-  __syncthreads();
-  stamp(P, 2);
-  load_local_vector(P, S);
-  __syncthreads();
   if (threadIdx.x == 0) derive_scalars(P, S);
   __syncthreads();
   if (verification_needed(P, S)) {

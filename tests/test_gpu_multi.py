@@ -14,7 +14,7 @@ from ust import synth
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, cases, q):
+def _worker(rank, world, port, cases, q, mode):
     import torch
     import torch.distributed as dist
     from ust import lib as ustlib
@@ -26,6 +26,7 @@ def _worker(rank, world, port, cases, q):
     uid = [ustlib.get_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     h.comm_init(rank, world, uid[0])
+    h.comm_set_mode(mode)  # 0 = NCCL all-reduce between two kernels, 1 = fused NVLink mailbox exchange
     results = []
     for (n, seed, p_err, pol_kwargs) in cases:
         pol = abi.make_policy(**pol_kwargs)
@@ -50,16 +51,17 @@ CASES = [
 ]
 
 
-def test_two_ranks_match_unsharded_oracle():
+@pytest.mark.parametrize("mode", [0, 1], ids=["nccl", "fused-nvlink"])
+def test_two_ranks_match_unsharded_oracle(mode):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
-    world = 2
+    world = min(int(os.environ.get("UST_TEST_WORLD", "2")), torch.cuda.device_count())
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, CASES, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port + mode, CASES, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     gathered = q.get(timeout=600)
