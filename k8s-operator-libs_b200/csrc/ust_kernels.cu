@@ -716,6 +716,7 @@ __device__ long long stream_loop(const UstParams& P, Shared& S) {
   A.tiles = 0;
   A.cand_spilled = 0;
   bool first = true;
+  unsigned cand_published = 0;
   int chunk = P.chunk_begin + blockIdx.x;
   while (chunk < P.chunk_end) {
     if (t == 0) S.next_chunk = P.chunk_begin + (int)(atomicAdd(&ws->ticket, 1u) + gridDim.x);  // claimed early: its latency hides behind the chunk
@@ -740,7 +741,11 @@ __device__ long long stream_loop(const UstParams& P, Shared& S) {
     if ((t & 31) == 0 && warp_cand) atomicAdd(&S.chunk_cand, warp_cand);
     __syncthreads();
     const int next = S.next_chunk;
-    if (t == 0) { ws->cand_cta[chunk] = S.chunk_cand; S.chunk_cand = 0; }
+    if (t == 0) {  // S.chunk_cand only ever grows: no shared write between the two barriers
+      const unsigned total = S.chunk_cand;
+      ws->cand_cta[chunk] = total - cand_published;
+      cand_published = total;
+    }
     __syncthreads();
     nodes_seen += b1 - b0;
     chunk = next;
