@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--nodes", type=int, default=SHARD_NODES, help="nodes per GPU (default: the BASELINE workload)")
     ap.add_argument("--sets", type=int, default=16, help="rotating input/output buffer sets (L2 defeat)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="N>1: counter exchange mechanism")
+    ap.add_argument("--maxpar", type=int, default=None, help="tuning: override MaxParallelUpgrades")
+    ap.add_argument("--maxunav", default=None, help="tuning: override MaxUnavailable ('nil', int or 'NN%%')")
     ap.add_argument("--quick", action="store_true", help="tuning: device-resident timing only (no e2e / cpu baseline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -184,6 +186,11 @@ def main():
     n = args.nodes
     cfg = synth.CONFIGS["C3" if world == 1 else "C5"]
     pol = synth.config_policy("C3")
+    if args.maxpar is not None or args.maxunav is not None:
+        mu = {"nil": None}.get(args.maxunav, args.maxunav) if args.maxunav is not None else "25%"
+        if isinstance(mu, str) and mu.isdigit():
+            mu = int(mu)
+        pol = abi.make_policy(max_parallel_upgrades=args.maxpar if args.maxpar is not None else 100, max_unavailable=mu)
     soa = synth.make_nodes(n, cfg["seed"], start=rank * n)
     n_ds = int(soa["ds_rev"].shape[0])
 
@@ -295,6 +302,9 @@ def main():
     assert cnt["error_code"] == 0
     assert cnt["total_managed"] == world * n or world > 1
     assert np.array_equal(nxt[code == 2], np.full(int((code == 2).sum()), 3, np.uint8)), "cordon-required -> wait-for-jobs"
+    if args.quick and rank == 0:
+        print("counters:", {k: cnt[k] for k in ("candidates", "upgrades_available", "max_unavailable")},
+              "redone chunks:", abi.Counters.from_buffer_copy(counters.cpu().numpy().tobytes()).reserved[0], flush=True)
 
     line = None
     if rank == 0:
@@ -323,9 +333,9 @@ def main():
     if args.quick:
         if rank == 0 and os.environ.get("UST_STAMPS"):
             g = int(os.environ["UST_STAMPS"])
-            st = (C.c_uint64 * (4 * g))()
+            st = (C.c_uint64 * (8 * g))()
             ustlib.load().ust_debug_stamps(h._h, st, g)
-            a = np.array(st, dtype=np.int64).reshape(g, 4)
+            a = np.array(st, dtype=np.int64).reshape(g, 8)
             t0 = a[:, 0].min()
             a = a - t0
             print("stamps us: entry[min,max]=%.1f,%.1f stream_end[min,med,max]=%.1f,%.1f,%.1f barrier_release[min,max]=%.1f,%.1f "
@@ -333,6 +343,11 @@ def main():
                       a[:, 0].min() / 1e3, a[:, 0].max() / 1e3, a[:, 1].min() / 1e3, np.median(a[:, 1]) / 1e3, a[:, 1].max() / 1e3,
                       a[:, 2].min() / 1e3, a[:, 2].max() / 1e3, a[:, 3].min() / 1e3, a[:, 3].max() / 1e3,
                       (a[:, 1] - a[:, 0]).min() / 1e3, np.median(a[:, 1] - a[:, 0]) / 1e3, (a[:, 1] - a[:, 0]).max() / 1e3), flush=True)
+            tail = (a[:, 3] - a[:, 2]) / 1e3
+            w = int(tail.argmax())
+            print("after-barrier us: median %.1f max %.1f (CTA %d)" % (np.median(tail), tail.max(), w), flush=True)
+            print("slowest CTA stamps us (entry, stream end, barrier, exit, piece begin, rank known, pre-pass done, piece end):",
+                  [round(float(v) / 1e3, 1) for v in a[w]], flush=True)
         if rank == 0:
             print(json.dumps({k: line[k] for k in ("value", "ms_per_step", "roofline", "clocks")}), flush=True)
         h.close()

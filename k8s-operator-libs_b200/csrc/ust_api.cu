@@ -86,6 +86,7 @@ struct ust_handle {
   int64_t launches = 0;
   int ctas_per_sm = 0, num_sms = 0;
   bool ws_dirty = false;
+  bool no_hint = false;  // UST_NO_HINT=1 (tuning): every call speculates from the policy default, never from the previous call
 
   UstWorkspace* ws = nullptr;
   uint32_t* lut_dev = nullptr;      // UST_LUT_ENTRIES + 32 words
@@ -227,6 +228,13 @@ static void fill_params(ust_handle* h, const ust_policy* policy, int64_t n, cons
   P.spec_cut_chunk = (active && policy->max_parallel_upgrades == 0 && policy->max_unavailable_kind == UST_MAXUNAVAIL_NIL) ? 0x7FFFFFFF : 0;
   int chunks = pick_chunks(h, n);
   int grid = pick_grid(h, chunks);
+  if (active && !P.requestor && !h->no_hint) {
+    // signature of everything the cut position depends on besides the data itself (FNV-1a)
+    unsigned long long sig = 1469598103934665603ull;
+    const long long parts[6] = {n, chunks, policy->max_parallel_upgrades, policy->max_unavailable_kind, policy->max_unavailable_value, h->world * 64 + h->rank};
+    for (long long v : parts) { sig ^= (unsigned long long)v; sig *= 1099511628211ull; }
+    P.spec_sig = sig ? sig : 1;
+  }
   if (P.eval_pods) chunks = grid;  // pod-list evaluation keeps one static chunk per CTA
   P.grid_chunks = chunks;
   P.chunk_begin = 0;
@@ -420,6 +428,7 @@ int ust_create(ust_handle** out, int device) {
   }
   ust_handle* h = new ust_handle();
   h->device = device;
+  h->no_hint = getenv("UST_NO_HINT") != nullptr;
   auto bail = [&](const char* what, cudaError_t err) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
     ust_destroy(h);
@@ -612,7 +621,7 @@ int ust_debug_stamps(ust_handle* h, unsigned long long* out, int n_ctas) {
   std::lock_guard<std::mutex> g(h->mu);
   UST_CUDA(h, cudaSetDevice(h->device));
   UST_CUDA(h, cudaDeviceSynchronize());
-  UST_CUDA(h, cudaMemcpy(out, h->ws->dbg, (size_t)n_ctas * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  UST_CUDA(h, cudaMemcpy(out, h->ws->dbg, (size_t)n_ctas * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return UST_OK;
 }
 

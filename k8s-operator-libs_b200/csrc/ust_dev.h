@@ -40,9 +40,14 @@ struct UstWorkspace {
   unsigned long long go; // fused exchange: epoch whose cluster-wide vector CTA 0 has published in gv[]
   long long gv[UST_V_LEN];
   unsigned int comm_timeout;  // set when a peer did not show up (kernel gives up instead of hanging)
-  unsigned int pad_;
+  unsigned int pad0_;
+  // Speculation hint carried from call to call (results never depend on it, only how many chunks are redone):
+  // the previous call's cut chunk, valid for calls with the same signature (size, chunking, slot policy).
+  unsigned long long hint_sig;
+  int hint_cut;
+  int pad_;
   unsigned int cand_cta[UST_MAX_CTAS];  // candidates per CTA chunk (written by phase 1, read by phase 2)
-  unsigned long long dbg[UST_MAX_CTAS][4];  // %globaltimer stamps per CTA: entry, stream end, barrier release, exit (diagnostics)
+  unsigned long long dbg[UST_MAX_CTAS][8];  // %globaltimer stamps per CTA: entry, stream end, barrier release, exit; 4..7 = redo path (diagnostics)
 };
 
 // abort key: (pass << 56) | (global node index + 1); policy-level aborts use index part 0
@@ -76,6 +81,7 @@ struct UstParams {
   int pd_spec_present;
   int eval_pods;          // pod lists present and evaluate_actuators
   int spec_cut_chunk;     // speculation: chunks before this index assume every upgrade candidate gets a slot
+  unsigned long long spec_sig;  // signature under which a device-resident hint from the previous call applies (0 = none)
   // sharding
   int rank;
   int world;

@@ -43,6 +43,8 @@ constexpr int kTile = kStep * kUnroll;
 constexpr int kPrefetchTiles = 2;     // L2 prefetch distance of the phase-2 stream, in tiles
 constexpr int kP1Unroll = 4;          // 16-byte hot loads in flight per thread in phase 1
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kScanSlots = 512;       // prefix table of the per-chunk candidate counts: one entry per chunk up to 512 chunks
+constexpr int kMaxExactSteps = 256;   // steps per block of the exact (ordered) path: 256 x 1024 nodes
 constexpr uint32_t kLutBytes = (UST_LUT_ENTRIES + 32) * sizeof(uint32_t);  // table + 16 {shift, base} pairs
 
 struct __align__(128) Shared {
@@ -62,6 +64,12 @@ struct __align__(128) Shared {
   long long node_offset;         // global index of this shard's node 0
   long long cand_prefix;         // candidates before this chunk (global order)
   long long part[kWarps];
+  int spec_cut;                  // effective speculative cut of this call (hint or default)
+  int cut;                       // where the budget really cut: first chunk that is not fully granted (INT_MAX = none)
+  int wrong_lo, wrong_hi;        // chunks whose speculation did not hold all lie in [wrong_lo, wrong_hi]
+  long long tbase[kScanSlots];   // candidates before chunk slot * ceil(chunks / kScanSlots), shard-local
+  unsigned int step_base[kMaxExactSteps];     // exact path: candidates before each step of the block
+  unsigned char wtot[kMaxExactSteps][kWarps];  // ... and per warp within the step
   unsigned int chunk_cand;       // candidates of the chunk being streamed
   int next_chunk;                // next claimed chunk
   unsigned int warp_tot[kWarps];
@@ -97,7 +105,7 @@ __device__ __forceinline__ long long chunk_bound(long long n, int c, int chunks)
 // nothing waits for it until phase 2 starts.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void stamp(const UstParams& P, int k) {
-  if (threadIdx.x == 0 && k < 4) {
+  if (threadIdx.x == 0 && k < 8) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     P.ws->dbg[blockIdx.x][k] = t;
@@ -122,7 +130,12 @@ __device__ void stage_tables_begin(const UstParams& P, Shared& S) {
     for (int i = t; i <= P.n_ds; i += kThreads) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
   p1_build_table(S);
   if (t < 16) S.cnt[t] = 0;
-  if (t == 32) { S.errinv = 0; S.abort_key = ~0ull; S.chunk_cand = 0; }
+  if (t == 32) {
+    S.errinv = 0; S.abort_key = ~0ull; S.chunk_cand = 0;
+    // speculative cut: the previous call's, when it was made under the same signature; else the policy default
+    const bool hinted = P.spec_sig != 0 && __ldcg(&P.ws->hint_sig) == P.spec_sig;
+    S.spec_cut = hinted ? __ldcg(&P.ws->hint_cut) : P.spec_cut_chunk;
+  }
 }
 
 __device__ __forceinline__ void stage_tables_wait(Shared& S) {
@@ -436,12 +449,13 @@ template <bool FULL>
 __device__ __forceinline__ void tile_load(const Cursor& c, int room, Tile& T) {
 #pragma unroll
   for (int j = 0; j < kUnroll; j++) {
-    if (FULL || j * kStep + 4 <= room) {
-      T.h[j] = __ldg(c.h + c.q + j * kStepQ);
-      T.f[j] = __ldcs(c.f + c.q + j * kStepQ);
-      T.r[j] = __ldcs(c.r + c.q + j * kStepQ);
-      T.d[j] = __ldcs(c.d + c.q + j * kStepQ);
-    }
+    // every element is assigned on every path, so that the tile stays in registers (no stack copy)
+    const bool valid = FULL || j * kStep + 4 <= room;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    T.h[j] = valid ? __ldg(c.h + c.q + j * kStepQ) : 0x0E0E0E0Eu;
+    T.f[j] = valid ? __ldcs(c.f + c.q + j * kStepQ) : zero;
+    T.r[j] = valid ? __ldcs(c.r + c.q + j * kStepQ) : zero;
+    T.d[j] = valid ? __ldcs(c.d + c.q + j * kStepQ) : zero;
   }
 }
 
@@ -508,30 +522,66 @@ __device__ __forceinline__ uint32_t stream_node(const UstParams& P, const Shared
   return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(S.lut) + off);
 }
 
-// The single streaming pass: for one tile, count (byte-sliced) AND evaluate every node with the chunk's
-// speculative slot grant, writing next_state / actions. Whether the speculation was right is only known
-// after the grid barrier; chunks on the wrong side of the cut are redone exactly there.
-template <bool FULL, bool DS_SMEM, bool OUTCOME>
+// candidate bytes of a hot word: bit 7 of byte k set iff node k is upgrade-required and not marked skip
+__device__ __forceinline__ uint32_t cand_mask4(uint32_t x) {
+  const uint32_t y = (x & 0x2F2F2F2Fu) ^ 0x01010101u;  // zero byte <=> code == 1 && !SKIP
+  return ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u;
+}
+
+struct ExactCtx {
+  int s0;              // step index (within the block) of the tile's first step
+  unsigned int limit;  // candidates of the block that get a slot (rank < limit), block-relative
+};
+
+// One tile of the streaming pass: evaluate every node (one table lookup) and write next_state / actions;
+// COUNT adds the byte-sliced counting, EXACT replaces the chunk-uniform slot grant by the ordered one: a
+// candidate's rank in slice order = candidates before its step (S.step_base) + before its warp within the step
+// (S.wtot) + a warp-shuffle exclusive scan — no block barrier in the loop (upgrade_inplace.go:71-109).
+template <bool FULL, bool DS_SMEM, bool OUTCOME, bool COUNT, bool EXACT>
 __device__ __forceinline__ void spec_tile(const UstParams& P, Shared& S, const Cursor& c, int room, long long i0,
-                                          const Tile& T, uint32_t grant, uint32_t (&B)[4]) {
+                                          const Tile& T, uint32_t grant, uint32_t (&B)[4], ExactCtx ex) {
   uint32_t lo = 0, hi = 0;
 #pragma unroll
   for (int j = 0; j < kUnroll; j++) {
     if (FULL || j * kStep + 4 <= room) {
       const uint32_t x = T.h[j];
-      if (x & 0x80808080u) {  // rare
+      if (COUNT && (x & 0x80808080u)) {  // rare
         const long long i = i0 + j * kStep;
         spec_error_byte(P, S, x & 0xFFu, T.f[j].x, i);
         spec_error_byte(P, S, (x >> 8) & 0xFFu, T.f[j].y, i + 1);
         spec_error_byte(P, S, (x >> 16) & 0xFFu, T.f[j].z, i + 2);
         spec_error_byte(P, S, x >> 24, T.f[j].w, i + 3);
       }
+      uint32_t g[4] = {grant, grant, grant, grant};
+      if (EXACT) {
+        const uint32_t cm = cand_mask4(x);
+        const unsigned tc = __popc(cm);
+        unsigned incl = tc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned v = __shfl_up_sync(kFull, incl, o);
+          if ((threadIdx.x & 31) >= o) incl += v;
+        }
+        const int s = ex.s0 + j, warp = threadIdx.x >> 5;
+        unsigned rank = S.step_base[s] + incl - tc;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++)
+          if (w < warp) rank += S.wtot[s][w];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const unsigned isc = (cm >> (8 * k + 7)) & 1u;
+          g[k] = (isc && rank < ex.limit) ? UST_W_GRANTED : 0u;
+          rank += isc;
+        }
+      }
       constexpr uint32_t kW = UST_W_SKIP | UST_W_UNSCHEDULABLE;
       uint32_t e[4];
-      e[0] = stream_node<DS_SMEM>(P, S, (x << 4) & 0xFF0u, (x >> 3) & kW, T.f[j].x, (int)T.r[j].x, T.d[j].x, grant, lo, hi);
-      e[1] = stream_node<DS_SMEM>(P, S, (x >> 4) & 0xFF0u, (x >> 11) & kW, T.f[j].y, (int)T.r[j].y, T.d[j].y, grant, lo, hi);
-      e[2] = stream_node<DS_SMEM>(P, S, (x >> 12) & 0xFF0u, (x >> 19) & kW, T.f[j].z, (int)T.r[j].z, T.d[j].z, grant, lo, hi);
-      e[3] = stream_node<DS_SMEM>(P, S, (x >> 20) & 0xFF0u, (x >> 27) & kW, T.f[j].w, (int)T.r[j].w, T.d[j].w, grant, lo, hi);
+      uint32_t dlo = 0, dhi = 0;
+      e[0] = stream_node<DS_SMEM>(P, S, (x << 4) & 0xFF0u, (x >> 3) & kW, T.f[j].x, (int)T.r[j].x, T.d[j].x, g[0], dlo, dhi);
+      e[1] = stream_node<DS_SMEM>(P, S, (x >> 4) & 0xFF0u, (x >> 11) & kW, T.f[j].y, (int)T.r[j].y, T.d[j].y, g[1], dlo, dhi);
+      e[2] = stream_node<DS_SMEM>(P, S, (x >> 12) & 0xFF0u, (x >> 19) & kW, T.f[j].z, (int)T.r[j].z, T.d[j].z, g[2], dlo, dhi);
+      e[3] = stream_node<DS_SMEM>(P, S, (x >> 20) & 0xFF0u, (x >> 27) & kW, T.f[j].w, (int)T.r[j].w, T.d[j].w, g[3], dlo, dhi);
+      if (COUNT) { lo += dlo; hi += dhi; }
       uint32_t next4, out4;
       uint2 act4;
       pack4(e, next4, act4, out4);
@@ -539,42 +589,163 @@ __device__ __forceinline__ void spec_tile(const UstParams& P, Shared& S, const C
       __stcs(c.ac + c.q + j * kStepQ, act4);
       if (OUTCOME) __stcs(c.oc + c.q + j * kStepQ, out4);
     }
-    if (j & 1) widen(lo, hi, B);  // at most 8 per nibble so far
+    if (COUNT && (j & 1)) widen(lo, hi, B);  // at most 8 per nibble so far
   }
-  if (kUnroll & 1) widen(lo, hi, B);
+  if (COUNT && (kUnroll & 1)) widen(lo, hi, B);
 }
 
-// The chunk loop is software-pipelined over two register tiles: tile i+1's loads are issued before tile i
-// is evaluated, so HBM always has a full tile per thread in flight while the SM computes.
-template <bool DS_SMEM, bool OUTCOME>
-__device__ __forceinline__ void spec_chunk(const UstParams& P, Shared& S, long long b0, long long lim, uint32_t grant, Acc& A,
-                           bool wait_for_table) {
-  const long long span = lim - b0;  // CTA-uniform, a multiple of 128
+// Pre-pass of the ordered path over one block of steps [blk0, blk1): hot bytes only (they are L2-resident or
+// about to be), all loads in flight at once; leaves per-step/per-warp candidate totals and the per-step exclusive
+// prefix in shared memory. Returns the block's candidate total; `before` gets the candidates among the nodes
+// [count_from, blk0) (the part of the chunk that precedes the block; same batch of loads, no extra round trip).
+__device__ unsigned exact_prepass(const UstParams& P, Shared& S, long long blk0, long long blk1, long long count_from,
+                                  long long& before) {
+  const int t = threadIdx.x, warp = t >> 5;
+  const int nsteps = (int)((blk1 - blk0 + kStep - 1) / kStep);
+  unsigned pre = 0;
+  for (long long a = count_from; a < blk0; a += 8LL * 16 * kThreads) {  // 16 nodes per load, 8 loads in flight
+    uint4 x[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const long long i = a + (long long)u * 16 * kThreads + 16 * t;     // count_from, blk0: multiples of 128
+      x[u] = i < blk0 ? __ldg(reinterpret_cast<const uint4*>(P.hot + i)) : make_uint4(0x0E0E0E0Eu, 0x0E0E0E0Eu, 0x0E0E0E0Eu, 0x0E0E0E0Eu);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      pre += __popc(cand_mask4(x[u].x)) + __popc(cand_mask4(x[u].y)) + __popc(cand_mask4(x[u].z)) + __popc(cand_mask4(x[u].w));
+  }
+  for (int s0 = 0; s0 < nsteps; s0 += 8) {
+    uint32_t x[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const long long i = blk0 + (long long)(s0 + u) * kStep + 4 * t;
+      x[u] = (s0 + u < nsteps && i + 4 <= blk1) ? __ldg(reinterpret_cast<const uint32_t*>(P.hot + i)) : 0x0E0E0E0Eu;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const unsigned w = __reduce_add_sync(kFull, (unsigned)__popc(cand_mask4(x[u])));
+      if ((t & 31) == 0 && s0 + u < nsteps) S.wtot[s0 + u][warp] = (unsigned char)w;  // <= 128
+    }
+  }
+  pre = __reduce_add_sync(kFull, pre);
+  if ((t & 31) == 0) S.part[warp] = pre;
+  __syncthreads();
+  // exclusive prefix over the steps of the block (kMaxExactSteps == kThreads: one step per thread)
+  unsigned tot = 0;
+  if (t < nsteps)
+    for (int w = 0; w < kWarps; w++) tot += S.wtot[t][w];
+  unsigned incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(kFull, incl, o);
+    if ((t & 31) >= o) incl += v;
+  }
+  if ((t & 31) == 31) S.warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned before_steps = 0, total = 0;
+  long long pre_all = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; w++) {
+    const unsigned v = S.warp_tot[w];
+    if (w < warp) before_steps += v;
+    total += v;
+    pre_all += S.part[w];
+  }
+  if (t < nsteps) S.step_base[t] = before_steps + incl - tot;
+  __syncthreads();
+  before = pre_all;
+  return total;
+}
+
+// Evaluate the block [blk0, blk1) of a chunk through the 4-deep tile pipeline. ORDERED: `limit` slots are left
+// for the candidates from node `count_from` (<= blk0) on, in slice order (pre-pass + per-node ranks); otherwise
+// the slot grant is uniform (`grant`). Returns the candidates in [count_from, blk1) (ORDERED only).
+template <bool DS_SMEM, bool OUTCOME, bool COUNT, bool ORDERED>
+__device__ __forceinline__ long long spec_block(const UstParams& P, Shared& S, long long blk0, long long blk1, uint32_t grant,
+                                                long long limit, long long count_from, Acc& A, bool wait_for_table) {
+  const long long span = blk1 - blk0;  // CTA-uniform, a multiple of 128 (or <= 0 for an empty chunk)
+  // the streaming fast path has a specialised body for full tiles; the out-of-line variants keep one (predicated) body
+  constexpr bool kFullVariant = COUNT && !ORDERED;
   const int t4 = 4 * threadIdx.x;
-  auto room_at = [&](long long done) -> int {  // nodes from this thread's first node of the tile to the chunk end
+  auto room_at = [&](long long done) -> int {  // nodes from this thread's first node of the tile to the block end
     const long long r = span - done - t4;
     return r > (1LL << 30) ? (1 << 30) : (r < 0 ? 0 : (int)r);
   };
-  Cursor c = cursor_at(P, b0);
-  long long i0 = b0 + t4;
+  Cursor c = cursor_at(P, blk0);
+  long long i0 = blk0 + t4;
   Tile T;
-  auto load = [&](long long done) {  // loads of the tile starting `done` nodes into the chunk; c.q points at it
-    if (span - done >= kTile) tile_load<true>(c, 0, T); else tile_load<false>(c, room_at(done), T);
+  auto load = [&](long long done) {  // loads of the tile starting `done` nodes into the block; c.q points at it
+    if (kFullVariant && span - done >= kTile) tile_load<true>(c, 0, T); else tile_load<false>(c, room_at(done), T);
   };
-  if (span > 0) load(0);  // the first tile's loads go out before anything waits on the table copy
+  if (span > 0) load(0);  // the first tile's loads go out before anything waits (table copy, pre-pass)
   if (wait_for_table) {
     stage_tables_wait(S);
     __syncthreads();
   }
+  ExactCtx ex{0, 0};
+  long long blk_cand = 0;  // candidates in [count_from, blk1)
+  if (ORDERED && span > 0) {
+    long long before = 0;
+    blk_cand = exact_prepass(P, S, blk0, blk1, count_from, before);
+    stamp(P, 6);
+    limit -= before;  // `limit` slots were left at count_from
+    blk_cand += before;
+    ex.limit = limit <= 0 ? 0u : (limit > 0x7FFFFFFFLL ? 0x7FFFFFFFu : (unsigned)limit);
+  }
+#pragma unroll 1
   for (long long done = 0; done < span; done += kTile) {
     if (done) load(done);
     const int room = room_at(done);
-    if (span - done >= kTile) spec_tile<true, DS_SMEM, OUTCOME>(P, S, c, room, i0, T, grant, A.B);
-    else spec_tile<false, DS_SMEM, OUTCOME>(P, S, c, room, i0, T, grant, A.B);
+    if (ORDERED) ex.s0 = (int)(done / kStep);
+    if (kFullVariant && span - done >= kTile) spec_tile<true, DS_SMEM, OUTCOME, COUNT, ORDERED>(P, S, c, room, i0, T, grant, A.B, ex);
+    else spec_tile<false, DS_SMEM, OUTCOME, COUNT, ORDERED>(P, S, c, room, i0, T, grant, A.B, ex);
     cursor_advance(c);
     i0 += kTile;
-    if (++A.tiles >= 14) spill_thread(S, A);  // byte lanes: at most 16 per tile, 255 max
+    if (COUNT && ++A.tiles >= 14) spill_thread(S, A);  // byte lanes: at most 16 per tile, 255 max
   }
+  return blk_cand;
+}
+
+// The streaming fast path: uniform grant, counting, inlined into the chunk loop.
+template <bool DS_SMEM, bool OUTCOME>
+__device__ __forceinline__ void spec_chunk(const UstParams& P, Shared& S, long long b0, long long lim, uint32_t grant, Acc& A,
+                                           bool wait_for_table) {
+  spec_block<DS_SMEM, OUTCOME, true, false>(P, S, b0, lim, grant, 0, b0, A, wait_for_table);
+}
+
+// The ordered variant lives out of line so that it cannot cost the fast path registers: blocks of
+// kMaxExactSteps steps; `slots` slots are left for the candidates from node `count_from` (<= b0, same chunk) on.
+// Counts (COUNT) go straight to the CTA's shared counters; returns the candidates in [count_from, lim).
+template <bool DS_SMEM, bool OUTCOME, bool COUNT>
+__device__ __forceinline__ long long ordered_range(const UstParams& P, Shared& S, long long b0, long long lim, long long slots,
+                                                long long count_from, bool wait_for_table) {
+  Acc A;
+  A.B[0] = A.B[1] = A.B[2] = A.B[3] = 0;
+  A.tiles = 0;
+  A.cand_spilled = 0;
+  constexpr long long kBlk = (long long)kMaxExactSteps * kStep;
+  long long seen = 0;
+  long long blk0 = b0;
+  do {
+    const long long blk1 = blk0 + kBlk < lim ? blk0 + kBlk : lim;
+    seen += spec_block<DS_SMEM, OUTCOME, COUNT, true>(P, S, blk0, blk1, 0u, slots - seen, blk0 == b0 ? count_from : blk0, A,
+                                                      wait_for_table);
+    wait_for_table = false;
+    __syncthreads();  // step_base / wtot are rewritten by the next block's pre-pass
+    blk0 = blk1;
+  } while (blk0 < lim);
+  if (COUNT) spill_thread(S, A);
+  return seen;
+}
+
+// ... and so does the uniform-grant variant without counting (redo of chunks whose every candidate, or none, gets a slot)
+template <bool DS_SMEM, bool OUTCOME>
+__device__ __forceinline__ void uniform_range(const UstParams& P, Shared& S, long long b0, long long lim, uint32_t grant) {
+  Acc A;
+  A.B[0] = A.B[1] = A.B[2] = A.B[3] = 0;
+  A.tiles = 0;
+  A.cand_spilled = 0;
+  spec_block<DS_SMEM, OUTCOME, false, false>(P, S, b0, lim, grant, 0, b0, A, false);
 }
 
 // general path: one step of kStep nodes, bounds-checked; optional exact ordered slot allocation,
@@ -674,31 +845,28 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
   }
 }
 
-// exact / abort / pod-list evaluation of a whole chunk (the verification step falls back to this)
+// how many candidates of a chunk get a slot, given the cluster-wide budget and the candidates before the chunk
+__device__ __forceinline__ long long required_local(const Shared& S, unsigned chunk_cand) {
+  long long l = S.budget - S.cand_prefix;
+  if (l < 0) l = 0;
+  return l > (long long)chunk_cand ? (long long)chunk_cand : l;
+}
+__device__ __forceinline__ uint32_t spec_grant(const UstParams& P, const Shared& S, int chunk) {
+  return (P.active && !P.requestor && chunk < S.spec_cut) ? UST_W_GRANTED : 0u;
+}
+// Redo one chunk through the bounds-checked step path: aborts (nodes of later passes keep their state) and
+// pod lists (per-node CSR walk) need it; the slot grant is exact here too.
 __device__ void general_chunk(const UstParams& P, Shared& S, long long b0, long long b1, unsigned chunk_cand) {
-  const long long lo = S.cand_prefix, hi = S.cand_prefix + chunk_cand;
   const bool slotted = P.active && !P.requestor;
-  const bool exact = slotted && chunk_cand != 0 && lo < S.budget && hi > S.budget;
-  const uint32_t grant = (slotted && chunk_cand != 0 && hi <= S.budget) ? UST_W_GRANTED : 0u;
+  const long long need = slotted ? required_local(S, chunk_cand) : 0;
+  const bool ordered = slotted && chunk_cand != 0 && need > 0 && need < (long long)chunk_cand;
+  const uint32_t grant = (slotted && chunk_cand != 0 && need == (long long)chunk_cand) ? UST_W_GRANTED : 0u;
   long long running = 0;
-  if (!exact) {
+  if (!ordered) {
     for (long long base = b0; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
   } else {
     for (long long base = b0; base < b1; base += kStep) general_step<true>(P, S, base, b1, 0u, running);
   }
-}
-
-// speculative grant of a chunk: chunks before P.spec_cut_chunk assume every candidate gets a slot
-__device__ __forceinline__ uint32_t spec_grant(const UstParams& P, int chunk) {
-  return (P.active && !P.requestor && chunk < P.spec_cut_chunk) ? UST_W_GRANTED : 0u;
-}
-
-// was the speculation right for this chunk? (called after derive_scalars + prefix)
-__device__ __forceinline__ bool spec_holds(const UstParams& P, const Shared& S, int chunk, unsigned chunk_cand) {
-  if (S.abort_key != ~0ull) return false;
-  if (!(P.active && !P.requestor) || chunk_cand == 0) return true;
-  const long long lo = S.cand_prefix, hi = S.cand_prefix + chunk_cand;
-  return spec_grant(P, chunk) ? (hi <= S.budget) : (lo >= S.budget);
 }
 
 // The chunk loop of the streaming phase: chunks (contiguous node ranges, chunk order == slice order) are
@@ -722,7 +890,7 @@ __device__ long long stream_loop(const UstParams& P, Shared& S) {
     if (t == 0) S.next_chunk = P.chunk_begin + (int)(atomicAdd(&ws->ticket, 1u) + gridDim.x);  // claimed early: its latency hides behind the chunk
     const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
     const long long lim = b1 & ~127LL;  // == b1 except for the ragged end of the whole array
-    const uint32_t grant = spec_grant(P, chunk);
+    const uint32_t grant = spec_grant(P, S, chunk);
     const unsigned cand0 = A.cand_spilled + p1_field(A.B, 15);
     spec_chunk<DS_SMEM, OUTCOME>(P, S, b0, lim, grant, A, first);
     first = false;
@@ -796,20 +964,6 @@ __device__ void stream_phase(const UstParams& P, Shared& S) {
   } else if (t == 32) {
     if (S.errinv) atomicMax(&ws->errinv, S.errinv);
   }
-}
-
-__device__ long long block_sum_cand_before(const UstParams& P, Shared& S, int chunk) {
-  // exclusive prefix of per-chunk candidate counts (chunk order == slice order)
-  const int t = threadIdx.x;
-  long long s = 0;
-  for (int c = t; c < chunk; c += kThreads) s += __ldcg(&P.ws->cand_cta[c]);
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
-  if ((t & 31) == 0) S.part[t >> 5] = s;
-  __syncthreads();
-  long long tot = 0;
-  for (int w = 0; w < kWarps; w++) tot += S.part[w];
-  __syncthreads();
-  return tot;
 }
 
 __device__ void load_local_vector(const UstParams& P, Shared& S) {
@@ -905,6 +1059,8 @@ __device__ void fused_exchange(const UstParams& P, Shared& S) {
   __syncthreads();
 }
 
+__device__ __forceinline__ bool verification_needed(const UstParams& P, const Shared& S);
+
 __device__ void finish(const UstParams& P, Shared& S, bool reset_ws) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -912,6 +1068,12 @@ __device__ void finish(const UstParams& P, Shared& S, bool reset_ws) {
     const unsigned prev = atomicAdd(&P.ws->depart, 1u);
     if (prev == gridDim.x - 1u) {  // last CTA out: publish counters, restore the workspace invariant
       write_counters(P, S);
+      if (P.spec_sig != 0 && P.active && !P.requestor && S.abort_key == ~0ull) {
+        // where the budget really cut this time = next call's speculation
+        const int cut = verification_needed(P, S) ? S.cut : S.spec_cut;  // else: all-or-nothing guess that held
+        P.ws->hint_cut = cut;
+        P.ws->hint_sig = P.spec_sig;
+      }
       P.ws->fixups = 0;
       P.ws->comm_timeout = 0;
       if (reset_ws) {
@@ -934,24 +1096,194 @@ __device__ __forceinline__ bool verification_needed(const UstParams& P, const Sh
   if (!(P.active && !P.requestor)) return false;
   const long long cands = S.V[UST_V_CANDIDATES];
   if (cands == 0) return false;
-  return P.spec_cut_chunk ? (S.budget < cands) : (S.budget > 0);
+  if (S.spec_cut > 0 && S.spec_cut < P.grid_chunks) return true;  // hint in the middle: check chunk by chunk
+  return S.spec_cut ? (S.budget < cands) : (S.budget > 0);
 }
 
-// redo, exactly, every chunk of this CTA's share whose speculation did not hold (or that needs pod lists)
-__device__ void verify_phase(const UstParams& P, Shared& S) {
+// Per-chunk candidate counts of the chunks a thread scans: thread t owns the chunks [t * cpt, (t + 1) * cpt),
+// cpt = 2 * ceil(chunks / kScanSlots). Loaded right after the grid barrier, together with the exchange vector.
+constexpr int kScanRegs = 4;
+struct ChunkCands { unsigned int v[kScanRegs]; };
+__device__ __forceinline__ int scan_slot_chunks(const UstParams& P) { return (P.grid_chunks + kScanSlots - 1) / kScanSlots; }
+__device__ __forceinline__ ChunkCands load_chunk_cands(const UstParams& P) {
+  ChunkCands r;
+  const int cpt = 2 * scan_slot_chunks(P), c0 = threadIdx.x * cpt;
+#pragma unroll
+  for (int k = 0; k < kScanRegs; k++) r.v[k] = (k < cpt && c0 + k < P.grid_chunks) ? __ldcg(&P.ws->cand_cta[c0 + k]) : 0u;
+  return r;
+}
+
+// Every CTA scans the per-chunk candidate counts once: where the budget really cuts, and the interval of chunks
+// whose speculation did not hold. Leaves prefix bases in shared memory for chunk_prefix().
+__device__ void scan_chunks(const UstParams& P, Shared& S, long long rank_base, const ChunkCands& held) {
+  const int t = threadIdx.x, n_chunks = P.grid_chunks;
+  const int spt = scan_slot_chunks(P), cpt = 2 * spt;
+  const int c0 = t * cpt < n_chunks ? t * cpt : n_chunks, c1 = c0 + cpt < n_chunks ? c0 + cpt : n_chunks;
+  const bool in_regs = cpt <= kScanRegs;
+  auto cand_of = [&](int c) -> long long { return __ldcg(&P.ws->cand_cta[c]); };
+  if (t == 0) { S.wrong_lo = 0x7FFFFFFF; S.wrong_hi = -1; S.cut = 0x7FFFFFFF; }
+  long long mine = 0;
+  if (in_regs) {
+#pragma unroll
+    for (int k = 0; k < kScanRegs; k++) mine += held.v[k];
+  } else {
+    for (int c = c0; c < c1; c++) mine += cand_of(c);
+  }
+  long long incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long v = __shfl_up_sync(kFull, incl, o);
+    if ((t & 31) >= o) incl += v;
+  }
+  if ((t & 31) == 31) S.part[t >> 5] = incl;
+  __syncthreads();
+  long long before = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; w++)
+    if (w < (t >> 5)) before += S.part[w];
+  const bool slotted = P.active && !P.requestor;
+  int lo = 0x7FFFFFFF, hi = -1, cut = 0x7FFFFFFF;
+  long long local = before + incl - mine;  // shard-local candidates before chunk c
+  auto visit = [&](int c, long long cand) {
+    if ((c - c0) % spt == 0) S.tbase[c / spt] = local;
+    const long long pre = rank_base + local;
+    if (cand != 0 && slotted) {
+      long long req = S.budget - pre;
+      req = req < 0 ? 0 : (req > cand ? cand : req);
+      const long long spec = c < S.spec_cut ? cand : 0;
+      if (req != spec) { lo = lo < c ? lo : c; hi = c; }
+      if (pre + cand > S.budget && c < cut) cut = c;
+    }
+    local += cand;
+  };
+  if (in_regs) {
+#pragma unroll
+    for (int k = 0; k < kScanRegs; k++)
+      if (c0 + k < c1) visit(c0 + k, held.v[k]);
+  } else {
+    for (int c = c0; c < c1; c++) visit(c, cand_of(c));
+  }
+  lo = __reduce_min_sync(kFull, lo);
+  hi = __reduce_max_sync(kFull, hi);
+  cut = __reduce_min_sync(kFull, cut);
+  if ((t & 31) == 0) {
+    if (hi >= 0) { atomicMin(&S.wrong_lo, lo); atomicMax(&S.wrong_hi, hi); }
+    atomicMin(&S.cut, cut);
+  }
+  __syncthreads();
+}
+
+// shard-local candidates before chunk c (after scan_chunks); no loads up to kScanSlots chunks
+__device__ __forceinline__ long long chunk_prefix(const UstParams& P, const Shared& S, int c) {
+  const int spt = scan_slot_chunks(P);
+  const int slot = c / spt;
+  long long v = S.tbase[slot];
+  for (int k = slot * spt; k < c; k++) v += __ldcg(&P.ws->cand_cta[k]);
+  return v;
+}
+
+// pull the first tile of a piece towards L2 while its starting rank is still being worked out
+__device__ __forceinline__ void prefetch_piece(const UstParams& P, long long p0, long long p1) {
+  const long long end = p1 - p0 > kTile ? p0 + kTile : p1;
+  for (long long i = p0 + 32LL * threadIdx.x; i < end; i += 32LL * kThreads) {  // 32 nodes = one 128-byte line of an int32 array
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.flags + i));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pod_rev + i));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.ds_idx + i));
+  }
+}
+
+// The slot speculation was wrong for the chunks in [wrong_lo, wrong_hi] (a contiguous node range): re-evaluate
+// them with the ordered grant (global candidate rank < budget). The range is cut into pieces that are spread
+// over ALL CTAs of the grid - a single CTA would be latency-bound - each piece finding its starting rank from
+// the per-chunk counts plus a hot-byte count of the part of its chunk that precedes it.
+__device__ void redo_wrong_chunks(const UstParams& P, Shared& S, long long rank_base) {
+  const int lo = S.wrong_lo, hi = S.wrong_hi, n_chunks = P.grid_chunks;
+  if (lo > hi) return;
+  const int m = hi - lo + 1;
+  const long long max_len = P.n / n_chunks + 256;                 // no chunk is longer (chunk_bound rounds to 128)
+  const int max_steps = (int)((max_len + kStep - 1) / kStep);
+  int pieces = (int)gridDim.x / m;                                  // at most one piece per CTA when that is possible
+  pieces = pieces < 1 ? 1 : (pieces > max_steps ? max_steps : pieces);
+  const int variant = (P.n_ds <= UST_DS_SMEM_MAX ? 2 : 0) | (P.outcome ? 1 : 0);
+  const long long items = (long long)m * pieces;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int chunk = lo + (int)(item / pieces), j = (int)(item % pieces);
+    const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
+    const long long lim = b1 & ~127LL;
+    const long long steps = (b1 - b0 + kStep - 1) / kStep, per = (steps + pieces - 1) / pieces;
+    const long long p0 = b0 + (long long)j * per * kStep;
+    long long p1 = p0 + per * kStep;
+    if (p0 >= b1) continue;   // CTA-uniform
+    const bool last = p1 >= b1;
+    if (last) p1 = lim;
+    stamp(P, 4);
+    prefetch_piece(P, p0, p1);
+    const long long slots = S.budget - (rank_base + chunk_prefix(P, S, chunk));  // left at the start of the chunk
+    const long long cand = __ldcg(&P.ws->cand_cta[chunk]);
+    stamp(P, 5);
+    long long seen = 0;  // candidates in [b0, p1)
+    if (slots <= 0 || slots >= cand) {  // nobody / everybody in this chunk gets a slot: no ranks needed
+      const uint32_t grant = (cand != 0 && slots >= cand) ? UST_W_GRANTED : 0u;
+      if (p1 > p0) {
+        switch (variant) {
+          case 3: uniform_range<true, true>(P, S, p0, p1, grant); break;
+          case 2: uniform_range<true, false>(P, S, p0, p1, grant); break;
+          case 1: uniform_range<false, true>(P, S, p0, p1, grant); break;
+          default: uniform_range<false, false>(P, S, p0, p1, grant); break;
+        }
+      }
+      if (last && lim < b1) {
+        long long running = 0;
+        general_step<false>(P, S, lim, b1, grant, running);
+      }
+      continue;
+    }
+    if (p1 > p0) {
+      switch (variant) {
+        case 3: seen = ordered_range<true, true, false>(P, S, p0, p1, slots, b0, false); break;
+        case 2: seen = ordered_range<true, false, false>(P, S, p0, p1, slots, b0, false); break;
+        case 1: seen = ordered_range<false, true, false>(P, S, p0, p1, slots, b0, false); break;
+        default: seen = ordered_range<false, false, false>(P, S, p0, p1, slots, b0, false); break;
+      }
+    }
+    stamp(P, 7);
+    if (last && lim < b1) {  // ragged end of the whole array (< 128 nodes); p1 == lim
+      long long running = 0;
+      if (p1 > p0) {
+        running = seen;
+      } else {  // the piece is nothing but the ragged end: count what precedes it in the chunk
+        long long before = 0;
+        exact_prepass(P, S, p0, p0, b0, before);
+        running = before;
+      }
+      if (threadIdx.x == 0) S.cand_prefix = rank_base + chunk_prefix(P, S, chunk);
+      __syncthreads();
+      general_step<true>(P, S, lim, b1, 0u, running);
+      __syncthreads();
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.ws->fixups, (unsigned)m);
+}
+
+// After the grid barrier: redo what the streaming phase could not know. Aborts and pod lists: every CTA redoes
+// its own chunks through the step path. Otherwise only a wrong slot speculation is left to repair.
+__device__ void verify_phase(const UstParams& P, Shared& S, const ChunkCands& held) {
   const int n_chunks = P.grid_chunks;
   const long long rank_base = S.cand_prefix;  // candidates on lower ranks
+  scan_chunks(P, S, rank_base, held);
+  if (!(P.eval_pods || S.abort_key != ~0ull)) {
+    redo_wrong_chunks(P, S, rank_base);
+    return;
+  }
   for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const long long before = block_sum_cand_before(P, S, chunk);
     const unsigned chunk_cand = __ldcg(&P.ws->cand_cta[chunk]);
+    const long long before = chunk_prefix(P, S, chunk);
+    __syncthreads();
     if (threadIdx.x == 0) S.cand_prefix = rank_base + before;
     __syncthreads();
-    if (P.eval_pods || !spec_holds(P, S, chunk, chunk_cand)) {
-      const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
-      general_chunk(P, S, b0, b1, chunk_cand);
-      if (threadIdx.x == 0) atomicAdd(&P.ws->fixups, 1u);
-    }
-    __syncthreads();
+    const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
+    general_chunk(P, S, b0, b1, chunk_cand);
+    if (threadIdx.x == 0) atomicAdd(&P.ws->fixups, 1u);
   }
 }
 
@@ -968,6 +1300,7 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_fused_kernel(const
   // grid-wide barrier (every CTA is co-resident: cooperative launch). After it the cluster-wide
   // counters are final and the speculation can be checked.
   __syncthreads();
+  ChunkCands held;
   if (P.fused_exchange) {
     if (threadIdx.x == 0) {
       __threadfence();
@@ -975,6 +1308,7 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_fused_kernel(const
     }
     fused_exchange(P, S);
     stamp(P, 2);
+    held = load_chunk_cands(P);
   } else {
     if (threadIdx.x == 0) {
       __threadfence();
@@ -984,6 +1318,7 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_fused_kernel(const
     }
     __syncthreads();
     stamp(P, 2);
+    held = load_chunk_cands(P);  // same round trip as the vector
     load_local_vector(P, S);
     __syncthreads();
   }
@@ -991,7 +1326,7 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_fused_kernel(const
   __syncthreads();
   if (verification_needed(P, S)) {
     if (P.eval_pods) { stage_tables_wait(S); __syncthreads(); }
-    verify_phase(P, S);
+    verify_phase(P, S, held);
   }
   finish(P, S, true);
   stamp(P, 3);
@@ -1029,12 +1364,13 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase2_kernel(cons
   __shared__ Shared S;
   stage_tables_begin(P, S);
   if (threadIdx.x < UST_V_LEN) S.V[threadIdx.x] = P.xchg[threadIdx.x];
+  const ChunkCands held = load_chunk_cands(P);
   __syncthreads();
   if (threadIdx.x == 0) derive_scalars(P, S);
   __syncthreads();
   stage_tables_wait(S);
   __syncthreads();
-  if (verification_needed(P, S)) verify_phase(P, S);
+  if (verification_needed(P, S)) verify_phase(P, S, held);
   finish(P, S, false);
 }
 

@@ -115,6 +115,23 @@ def test_slot_budget_cut_positions(handle, seed):
         helpers.assert_same(got, ref, f"seed={seed} maxPar={max_par} maxUnav={unav}")
 
 
+@pytest.mark.parametrize("n", [300_000, 1_000_037, 2_500_063])
+def test_speculation_hint_never_changes_results(handle, n):
+    """The kernel speculates where the slot budget cuts and carries the observed cut to the next call with the
+    same size and policy. Whatever the hint (none, exact, stale because the snapshot changed, cut moved to the
+    ragged end), the grants must be the ordered ones of upgrade_inplace.go:71-109."""
+    pol = abi.make_policy(max_parallel_upgrades=0, max_unavailable="30%")
+    for rep, frac in enumerate((0.6, 0.6, 0.95, 0.31, 0.02, 0.6)):
+        rng = np.random.default_rng(4000 + rep if rep != 1 else 4000)   # rep 1 repeats rep 0: exact hint
+        soa, _ = helpers.random_soa(rng, n, all_states=False, wild=False)
+        pick = rng.random(n)
+        soa["state"] = np.where(pick < frac, (soa["state"] & 0xF0) | 1, soa["state"]).astype(np.uint8)
+        soa["state"] &= np.uint8(0x7F)
+        got = gpu_apply(handle, pol, soa)
+        ref = helpers.oracle_apply(pol, soa, variant=1)
+        helpers.assert_same(got, ref, f"n={n} rep={rep} frac={frac}")
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_pipelined_host_path(handle, seed):
     """Snapshots >= 2^19 nodes take the segmented upload/compute/download pipeline of ust_apply_state; the
@@ -216,3 +233,32 @@ def test_device_resident_entry_point(handle):
     assert np.array_equal(act.cpu().numpy().view(np.uint16), ref[2])
     c = abi.Counters.from_buffer_copy(cnt.cpu().numpy().tobytes())
     assert c.as_dict() == ref[4]
+
+
+def test_device_entry_point_with_moving_budget_cut(handle):
+    """One fused launch over 2.5 M device-resident nodes, the slot budget cutting through the middle of the
+    array; consecutive calls share the size and policy (so the second and later ones run on the previous call's
+    cut), the snapshots differ."""
+    import torch
+    dev = torch.device("cuda:0")
+    n = 2_500_063
+    pol = abi.make_policy(max_parallel_upgrades=0, max_unavailable="30%")
+    nxt = torch.empty(n, dtype=torch.uint8, device=dev)
+    act = torch.empty(n, dtype=torch.int16, device=dev)
+    cnt = torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)
+    for rep, frac in enumerate((0.6, 0.6, 0.9, 0.32, 0.6)):
+        rng = np.random.default_rng(5000 + (rep if rep != 1 else 0))
+        soa, _ = helpers.random_soa(rng, n, all_states=False, wild=False)
+        pick = rng.random(n)
+        soa["state"] = np.where(pick < frac, (soa["state"] & 0xF0) | 1, soa["state"]).astype(np.uint8)
+        soa["state"] &= np.uint8(0x7F)
+        t = {k: torch.from_numpy(v).to(dev) for k, v in soa.items()}
+        handle.apply_state_device(pol, n, t["state"].data_ptr(), t["flags"].data_ptr(), t["pod_rev"].data_ptr(),
+                                  t["ds_idx"].data_ptr(), len(soa["ds_rev"]), t["ds_rev"].data_ptr(), nxt.data_ptr(),
+                                  act.data_ptr(), counters=cnt.data_ptr())
+        handle.sync()
+        ref = helpers.oracle_apply(pol, soa, variant=1)
+        assert np.array_equal(nxt.cpu().numpy(), ref[1]), f"rep={rep}"
+        assert np.array_equal(act.cpu().numpy().view(np.uint16), ref[2]), f"rep={rep}"
+        c = abi.Counters.from_buffer_copy(cnt.cpu().numpy().tobytes())
+        assert c.as_dict() == ref[4], f"rep={rep}"
