@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--maxpar", type=int, default=None, help="tuning: override MaxParallelUpgrades")
     ap.add_argument("--maxunav", default=None, help="tuning: override MaxUnavailable ('nil', int or 'NN%%')")
     ap.add_argument("--quick", action="store_true", help="tuning: device-resident timing only (no e2e / cpu baseline)")
+    ap.add_argument("--pods", action="store_true", help="tuning (with --quick): the C4 workload - CSR pod lists, pod deletion and drain enabled")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,8 +192,18 @@ def main():
         if isinstance(mu, str) and mu.isdigit():
             mu = int(mu)
         pol = abi.make_policy(max_parallel_upgrades=args.maxpar if args.maxpar is not None else 100, max_unavailable=mu)
+    if args.pods:
+        if not args.quick:
+            raise SystemExit("--pods is a tuning option: use it with --quick")
+        cfg = synth.CONFIGS["C4"]
+        pol = synth.config_policy("C4")
     soa = synth.make_nodes(n, cfg["seed"], start=rank * n)
     n_ds = int(soa["ds_rev"].shape[0])
+    pods_dev = pods_struct = None
+    if args.pods:
+        pods = synth.make_pods_blocked(n, cfg["seed"], start=rank * n)
+        pods_dev = {k: torch.from_numpy(v).to(dev) for k, v in pods.items()}
+        pods_struct = abi.Pods(pods_dev["pod_off"].data_ptr(), pods_dev["pod_flags"].data_ptr(), int(pods["pod_flags"].shape[0]))
 
     h = ustlib.Handle(local_rank)
     if world > 1:
@@ -222,6 +233,7 @@ def main():
         d = {k: torch.from_numpy(v).to(dev) for k, v in soa.items()}
         d["next"] = torch.empty(n, dtype=torch.uint8, device=dev)
         d["actions"] = torch.empty(n, dtype=torch.int16, device=dev)
+        d["outcome"] = torch.empty(n, dtype=torch.uint8, device=dev) if args.pods else None
         bufs.append(d)
     counters = torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)
     # a dedicated stream: torch's default stream has handle 0, which the C ABI reads as "use the handle's own
@@ -240,8 +252,9 @@ def main():
     for b in bufs:
         bound.append((h._h, pol_p, C.c_int64(n), C.c_void_p(b["state"].data_ptr()), C.c_void_p(b["flags"].data_ptr()),
                       C.c_void_p(b["pod_rev"].data_ptr()), C.c_void_p(b["ds_idx"].data_ptr()), C.c_int32(n_ds),
-                      C.c_void_p(b["ds_rev"].data_ptr()), None, C.c_void_p(b["next"].data_ptr()),
-                      C.c_void_p(b["actions"].data_ptr()), None, cnt_p, st_p))
+                      C.c_void_p(b["ds_rev"].data_ptr()), C.byref(pods_struct) if pods_struct is not None else None,
+                      C.c_void_p(b["next"].data_ptr()), C.c_void_p(b["actions"].data_ptr()),
+                      C.c_void_p(b["outcome"].data_ptr()) if b["outcome"] is not None else None, cnt_p, st_p))
 
     def step(i):
         rc = fn(*bound[i % SETS])

@@ -185,7 +185,9 @@ typedef struct ust_counters {
   int64_t reserved[7];
 } ust_counters;
 
-/* Optional per-node workload pod lists (CSR). pod_off has n_nodes+1 entries. */
+/* Optional per-node workload pod lists (CSR). pod_off has n_nodes+1 entries; for device-resident calls
+ * pod_flags must be 16-byte aligned like every other array (the list reader uses 16-byte loads, never past
+ * pod_flags + n_pods). */
 typedef struct ust_pods {
   const int32_t* pod_off;
   const uint16_t* pod_flags;

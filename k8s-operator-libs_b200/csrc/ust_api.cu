@@ -106,6 +106,7 @@ struct ust_handle {
   DevBuf<uint32_t> s_flags;
   DevBuf<int32_t> s_rev, s_ds, s_dsrev, s_podoff, s_dsdesired;
   DevBuf<uint16_t> s_actions, s_podflags;
+  DevBuf<uint8_t> s_podsum;  // per-node pod-list summaries (ust_pod_summary_kernel -> streaming pass)
 
   // multi-GPU
   int rank = 0, world = 1, comm_mode = 0;
@@ -235,7 +236,6 @@ static void fill_params(ust_handle* h, const ust_policy* policy, int64_t n, cons
     for (long long v : parts) { sig ^= (unsigned long long)v; sig *= 1099511628211ull; }
     P.spec_sig = sig ? sig : 1;
   }
-  if (P.eval_pods) chunks = grid;  // pod-list evaluation keeps one static chunk per CTA
   P.grid_chunks = chunks;
   P.chunk_begin = 0;
   P.chunk_end = chunks;
@@ -247,8 +247,8 @@ static void fill_params(ust_handle* h, const ust_policy* policy, int64_t n, cons
 // core: everything device-resident, enqueue on `st`
 static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
                         const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
-                        const int32_t* pod_off, const uint16_t* pod_flags, uint8_t* next_state, uint16_t* actions,
-                        uint8_t* outcome, ust_counters* out_dev, cudaStream_t st) {
+                        const int32_t* pod_off, const uint16_t* pod_flags, int64_t n_pods, uint8_t* next_state,
+                        uint16_t* actions, uint8_t* outcome, ust_counters* out_dev, cudaStream_t st) {
   if (n < 0) return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
   if (n > 0 && (!state || !flags || !pod_rev || !ds_idx || !next_state || !actions))
     return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
@@ -258,6 +258,7 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
   const char* names[] = {"state", "flags", "pod_rev", "ds_idx", "next_state", "actions", "actuator_outcome"};
   for (int i = 0; i < 7; i++)
     if (ptrs[i]) { int rc = check_aligned(h, ptrs[i], names[i]); if (rc) return rc; }
+  if (pod_off && pod_flags) { int rc = check_aligned(h, pod_flags, "pod_flags"); if (rc) return rc; }
   UST_CUDA(h, cudaSetDevice(h->device));
   if (h->ws_dirty) {
     UST_CUDA(h, cudaMemsetAsync(h->ws, 0, sizeof(UstWorkspace), st));
@@ -272,6 +273,15 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
               out_dev, &P, &grid);
 
   h->ws_dirty = true;  // cleared again once every launch of this call has been enqueued successfully
+  if (P.eval_pods) {
+    // pod lists: one byte per node first (only the nodes whose actuator looks at its pods are read),
+    // then the ordinary streaming pass with that byte as a fifth input stream
+    UST_CUDA(h, h->s_podsum.reserve((size_t)n + 16));
+    P.podsum = h->s_podsum.p;
+    int e = ust_launch_pod_summary(n, P.active, P.hot, P.pod_off, P.pod_flags, n_pods, P.podlut, P.podsum, h->num_sms * 6, st);
+    if (e) return h->fail(UST_ERR_CUDA, "pod-summary kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->launches += 1;
+  }
   if (h->world == 1 || P.fused_exchange) {
     if (P.fused_exchange) P.epoch = ++h->epoch;  // collective call number: identical on every rank
     int e = ust_launch_fused(P, grid, st);
@@ -482,7 +492,7 @@ void ust_destroy(ust_handle* h) {
   if (h->ds_count_dev) cudaFree(h->ds_count_dev);
   h->s_hot.release(); h->s_next.release(); h->s_outcome.release(); h->s_flags.release();
   h->s_rev.release(); h->s_ds.release(); h->s_dsrev.release(); h->s_podoff.release(); h->s_dsdesired.release();
-  h->s_actions.release(); h->s_podflags.release();
+  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release();
   for (auto& ev : h->seg_done) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->seg_up) if (ev) cudaEventDestroy(ev);
   if (h->stream_h2d) cudaStreamDestroy(h->stream_h2d);
@@ -515,8 +525,11 @@ int ust_apply_state_device(ust_handle* h, const ust_policy* policy, int64_t n_no
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  if (pods && (!pods->pod_off || pods->n_pods < 0 || (pods->n_pods > 0 && !pods->pod_flags)))
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "bad pod lists");
   return apply_device(h, policy, n_nodes, state, flags, pod_rev, ds_idx, n_ds, ds_rev, pods ? pods->pod_off : nullptr,
-                      pods ? pods->pod_flags : nullptr, next_state, actions, actuator_outcome, out_device, st);
+                      pods ? pods->pod_flags : nullptr, pods ? pods->n_pods : 0, next_state, actions, actuator_outcome,
+                      out_device, st);
 }
 
 int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
@@ -559,8 +572,8 @@ int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const ui
     if (pods->n_pods) UST_CUDA(h, cudaMemcpyAsync(h->s_podflags.p, pods->pod_flags, (size_t)pods->n_pods * 2, cudaMemcpyHostToDevice, st));
   }
   int rc = apply_device(h, policy, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, n_ds, h->s_dsrev.p,
-                        pods ? h->s_podoff.p : nullptr, pods ? h->s_podflags.p : nullptr, h->s_next.p, h->s_actions.p,
-                        actuator_outcome ? h->s_outcome.p : nullptr, nullptr, st);
+                        pods ? h->s_podoff.p : nullptr, pods ? h->s_podflags.p : nullptr, pods ? pods->n_pods : 0, h->s_next.p,
+                        h->s_actions.p, actuator_outcome ? h->s_outcome.p : nullptr, nullptr, st);
   if (rc) return rc;
   if (N) {
     UST_CUDA(h, cudaMemcpyAsync(next_state, h->s_next.p, N, cudaMemcpyDeviceToHost, st));

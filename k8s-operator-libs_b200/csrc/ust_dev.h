@@ -68,6 +68,7 @@ struct UstParams {
   uint8_t* outcome;  // nullable
   const uint32_t* lut;    // UST_LUT_ENTRIES words, then 16 uint2 {shift-2, state*2048}
   const uint8_t* podlut;  // UST_PODLUT_ENTRIES bytes
+  uint8_t* podsum;        // per-node pod-list summary (written by the pod-summary kernel, read by the streaming pass); null = no pod lists
   UstWorkspace* ws;
   long long* xchg;        // UST_V_LEN lanes (split mode: phase 1 writes, phase 2 reads the reduced copy)
   ust_counters* out;      // device
@@ -99,6 +100,8 @@ struct UstParams {
 int ust_launch_fused(const UstParams& p, int grid, void* stream);
 int ust_launch_phase1(const UstParams& p, int grid, void* stream);
 int ust_launch_phase2(const UstParams& p, int grid, void* stream);
+int ust_launch_pod_summary(long long n, int active, const uint8_t* hot, const int32_t* pod_off, const uint16_t* pod_flags,
+                           long long n_pods, const uint8_t* podlut, uint8_t* podsum, int grid, void* stream);
 int ust_launch_build_state(long long n, const uint8_t* hot, const int32_t* ds_idx, int n_ds, const int32_t* ds_desired,
                            unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream);
 int ust_max_coresident_ctas(int device, int* ctas_per_sm, int* num_sms);

@@ -40,8 +40,6 @@ constexpr int kStep = kThreads * 4;   // nodes per CTA step in phase 2 (4 per th
 #endif
 constexpr int kUnroll = UST_UNROLL;            // steps in flight per thread in the fast path
 constexpr int kTile = kStep * kUnroll;
-constexpr int kPrefetchTiles = 2;     // L2 prefetch distance of the phase-2 stream, in tiles
-constexpr int kP1Unroll = 4;          // 16-byte hot loads in flight per thread in phase 1
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kScanSlots = 512;       // prefix table of the per-chunk candidate counts: one entry per chunk up to 512 chunks
 constexpr int kMaxExactSteps = 256;   // steps per block of the exact (ordered) path: 256 x 1024 nodes
@@ -150,23 +148,14 @@ __device__ __forceinline__ void stage_tables_wait(Shared& S) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase 1: counts over the hot bytes of [b0, b1)
+// counting (part of the streaming pass)
 //
 // Byte-sliced SIMD-in-register counting. A 256-entry shared-memory table maps a hot byte to sixteen
 // 4-bit one-hot increments packed in 64 bits (fields 0-13: state code, 14: unavailable, 15: upgrade
-// candidate); a thread sums the entries of 8 nodes (no field can exceed 8), widens the nibbles to byte
-// lanes, and keeps going. Per node: one 8-byte LDS, two shifts/masks for the address, one add. No
-// atomics until the end of the chunk: one REDUX per counter per warp, 16 global atomics per CTA.
+// candidate) next to the node's table window; a thread sums the entries of 8 nodes (no field can exceed 8),
+// widens the nibbles to byte lanes, and keeps going. No atomics until the end of the chunk loop: one REDUX
+// per counter per warp, 16 global atomics per CTA.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void p1_error_byte(const UstParams& P, Shared& S, unsigned b, long long i) {
-  const unsigned code = b & 15u;
-  if (!(b & UST_HOT_REVISION_HASH_ERROR) || !P.active) return;
-  if (!(code == UST_STATE_UNKNOWN || code == UST_STATE_DONE || code == UST_STATE_POD_RESTART_REQUIRED || code == UST_STATE_FAILED)) return;
-  if (__ldg(P.flags + i) & UST_F_POD_ORPHANED) return;  // orphaned pods never reach the hash lookup (common_manager.go:301-303)
-  const unsigned long long key = UST_KEY(pass_of_state(code), (unsigned long long)i + 1ull);
-  atomicMax(&S.errinv, ~key);
-}
-
 // window shift (minus 2) of every state code, 8 bits each — compile-time copy of ust_window_shift[]
 constexpr unsigned long long pack_shifts(int from) {
   unsigned long long v = 0;
@@ -192,74 +181,6 @@ __device__ void p1_build_table(Shared& S) {
 // byte lanes: B[0] = fields 0,2,4,6  B[1] = fields 1,3,5,7  B[2] = fields 8,10,12,14  B[3] = fields 9,11,13,15
 __device__ __forceinline__ unsigned p1_field(const uint32_t (&B)[4], int f) {
   return (B[(f >> 3) * 2 + (f & 1)] >> (8 * ((f & 7) >> 1))) & 0xFFu;
-}
-
-__device__ __forceinline__ void p1_words(const Shared& S, uint32_t x, uint32_t y, uint32_t (&B)[4]) {
-  uint32_t lo = 0, hi = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const uint2 a = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(S.hotent) + (((x >> (8 * k)) & 0xFFu) << 4) + 8);
-    const uint2 c = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(S.hotent) + (((y >> (8 * k)) & 0xFFu) << 4) + 8);
-    lo += a.x + c.x;
-    hi += a.y + c.y;
-  }
-  B[0] += lo & 0x0F0F0F0Fu;
-  B[1] += (lo >> 4) & 0x0F0F0F0Fu;
-  B[2] += hi & 0x0F0F0F0Fu;
-  B[3] += (hi >> 4) & 0x0F0F0F0Fu;
-}
-
-__device__ void phase1_count(const UstParams& P, Shared& S, long long b0, long long b1) {
-  const int t = threadIdx.x;
-  uint32_t B[4] = {0, 0, 0, 0};
-  int pending = 0;
-  constexpr uint32_t kFill = 0x0E0E0E0Eu;  // "excluded": contributes to no counter
-  for (long long base = b0; base < b1; base += 16LL * kThreads * kP1Unroll) {
-    uint4 h[kP1Unroll];
-#pragma unroll
-    for (int u = 0; u < kP1Unroll; u++) {
-      const long long i = base + (long long)u * 16 * kThreads + 16LL * t;
-      if (i + 16 <= b1) {
-        h[u] = __ldg(reinterpret_cast<const uint4*>(P.hot + i));
-      } else {
-        uint32_t w[4] = {kFill, kFill, kFill, kFill};
-        for (long long j = i; j < b1; j++) {  // ragged end of the array (at most 15 bytes, one lane)
-          const int q = (int)(j - i);
-          w[q >> 2] = (w[q >> 2] & ~(0xFFu << (8 * (q & 3)))) | ((uint32_t)P.hot[j] << (8 * (q & 3)));
-        }
-        h[u] = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kP1Unroll; u++) {
-      if ((h[u].x | h[u].y | h[u].z | h[u].w) & 0x80808080u) {  // rare: a revision-hash error bit among these 16 nodes
-        const uint32_t w[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
-        const long long i = base + (long long)u * 16 * kThreads + 16LL * t;
-        for (int q = 0; q < 16; q++) {
-          const unsigned b = (w[q >> 2] >> (8 * (q & 3))) & 0xFFu;
-          if ((b & 15u) < UST_STATE_EXCLUDED) p1_error_byte(P, S, b, i + q);
-        }
-      }
-      p1_words(S, h[u].x, h[u].y, B);
-      p1_words(S, h[u].z, h[u].w, B);
-    }
-    pending += 16 * kP1Unroll;
-    if (pending > 255 - 16 * kP1Unroll) {  // byte lanes hold at most 255: spill (thread-serial, rare)
-#pragma unroll
-      for (int f = 0; f < 16; f++) {
-        const unsigned v = p1_field(B, f);
-        if (v) atomicAdd(&S.cnt[f], v);
-      }
-      B[0] = B[1] = B[2] = B[3] = 0;
-      pending = 0;
-    }
-  }
-  // all threads converged: one REDUX per counter per warp, one shared atomic per warp
-#pragma unroll
-  for (int f = 0; f < 16; f++) {
-    const unsigned v = __reduce_add_sync(kFull, p1_field(B, f));
-    if ((t & 31) == 0 && v) atomicAdd(&S.cnt[f], v);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -360,27 +281,6 @@ __device__ __forceinline__ uint32_t node_entry(const UstParams& P, const Shared&
 
 __device__ __forceinline__ uint32_t noop_entry(uint32_t hb) { return ((hb & 15u) << 16) | 0xFF000000u; }
 
-// pod-list summary for one node (thread-serial; only nodes whose actuator would run are evaluated)
-__device__ __forceinline__ uint32_t pod_summary(const UstParams& P, uint32_t hb, long long i, uint32_t& clear_mask) {
-  const unsigned s = hb & 15u;
-  clear_mask = 0;
-  if (s < UST_STATE_WAIT_FOR_JOBS_REQUIRED || s > UST_STATE_DRAIN_REQUIRED) return 0;
-  unsigned r = 0;
-  const int p0 = __ldg(P.pod_off + i), p1 = __ldg(P.pod_off + i + 1);
-  for (int p = p0; p < p1; p++) r |= __ldg(P.podlut + (__ldg(P.pod_flags + p) & (UST_PODLUT_ENTRIES - 1)));
-  uint32_t extra = 0;
-  if (s == UST_STATE_WAIT_FOR_JOBS_REQUIRED) {
-    clear_mask = UST_F_WAIT_PODS_RUNNING;  // the pod list, when given, overrides the pre-evaluated bit
-    if (r & UST_PODSUM_WAIT_RUNNING) extra |= UST_F_WAIT_PODS_RUNNING;
-  } else if (s == UST_STATE_POD_DELETION_REQUIRED) {
-    if (r & UST_PODSUM_TO_DELETE) extra |= UST_W_PD_HAS;
-    if (r & UST_PODSUM_CANNOT_DELETE) extra |= UST_W_PD_MISMATCH;
-  } else {
-    if (r & UST_PODSUM_DRAIN_ERROR) extra |= UST_W_DRAIN_ERROR;
-  }
-  return extra;
-}
-
 // abort semantics: nodes the sequential passes had not reached when the reference returned its error
 // stay untouched; the aborting node carries UST_A_ERROR; an abort inside ProcessPodRestartNodes also
 // drops the restarts collected so far, SchedulePodsRestart is only called after the loop
@@ -411,6 +311,7 @@ __device__ __forceinline__ void pack4(const uint32_t e[4], uint32_t& next4, uint
 // multiple of 128 (or the tile is full), so validity is uniform per warp and per j.
 struct Tile {
   uint32_t h[kUnroll];
+  uint32_t ps[kUnroll];  // pod-list summaries (one byte per node), PODS variants only
   uint4 f[kUnroll], r[kUnroll], d[kUnroll];
 };
 
@@ -418,6 +319,7 @@ struct Tile {
 // with a 32-bit group index q (thread t of the CTA owns groups done/4 + j*kStepQ + t of a tile).
 struct Cursor {
   const uint32_t* h;
+  const uint32_t* ps;  // null when the call has no pod lists
   const uint4* f;
   const uint4* r;
   const uint4* d;
@@ -432,6 +334,7 @@ constexpr int kTileQ = kTile / 4;
 __device__ __forceinline__ Cursor cursor_at(const UstParams& P, long long base) {
   Cursor c;
   c.h = reinterpret_cast<const uint32_t*>(P.hot + base);
+  c.ps = P.podsum ? reinterpret_cast<const uint32_t*>(P.podsum + base) : nullptr;
   c.f = reinterpret_cast<const uint4*>(P.flags + base);
   c.r = reinterpret_cast<const uint4*>(P.pod_rev + base);
   c.d = reinterpret_cast<const uint4*>(P.ds_idx + base);
@@ -445,7 +348,8 @@ __device__ __forceinline__ void cursor_advance(Cursor& c) { c.q += kTileQ; }
 
 // `room` = nodes left in the chunk from this thread's first node of the tile; chunk ends are multiples of
 // 128 nodes, so for a partial tile validity is uniform per warp and per step.
-template <bool FULL>
+// PODS: 0 = the call has no pod lists, 1 = it has, 2 = decided at run time (out-of-line variants)
+template <bool FULL, int PODS>
 __device__ __forceinline__ void tile_load(const Cursor& c, int room, Tile& T) {
 #pragma unroll
   for (int j = 0; j < kUnroll; j++) {
@@ -453,22 +357,10 @@ __device__ __forceinline__ void tile_load(const Cursor& c, int room, Tile& T) {
     const bool valid = FULL || j * kStep + 4 <= room;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     T.h[j] = valid ? __ldg(c.h + c.q + j * kStepQ) : 0x0E0E0E0Eu;
+    T.ps[j] = (valid && (PODS == 1 || (PODS == 2 && c.ps != nullptr))) ? __ldcs(c.ps + c.q + j * kStepQ) : 0u;
     T.f[j] = valid ? __ldcs(c.f + c.q + j * kStepQ) : zero;
     T.r[j] = valid ? __ldcs(c.r + c.q + j * kStepQ) : zero;
     T.d[j] = valid ? __ldcs(c.d + c.q + j * kStepQ) : zero;
-  }
-}
-
-// pull the int32 arrays of the tile `ahead` tiles further on into L2 (one request per 128-byte line)
-__device__ __forceinline__ void tile_prefetch_l2(const Cursor& c, int ahead, int room) {
-  if ((threadIdx.x & 7) != 0) return;
-#pragma unroll
-  for (int j = 0; j < kUnroll; j++) {
-    if (ahead * kTile + j * kStep + 4 <= room) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(c.f + c.q + ahead * kTileQ + j * kStepQ));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(c.r + c.q + ahead * kTileQ + j * kStepQ));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(c.d + c.q + ahead * kTileQ + j * kStepQ));
-    }
   }
 }
 
@@ -509,6 +401,16 @@ __device__ __forceinline__ void spill_thread(Shared& S, Acc& A) {
 
 // One node of the streaming pass. `xs` = the node's hot byte moved to bits 4..11 of a word (so it indexes
 // the 16-byte hotent table directly), `ws` = its SKIP / UNSCHEDULABLE bits already at w positions 2, 3.
+// pod-list summary byte -> the w bits it stands for (ust_pod_summary_kernel): bit 0 = a wait-selector pod is
+// running, bits 1..3 = UST_W_PD_HAS / UST_W_PD_MISMATCH / UST_W_DRAIN_ERROR, bit 4 = the list overrides the
+// pre-evaluated UST_F_WAIT_PODS_RUNNING of the flags word
+__device__ __forceinline__ uint32_t pods_apply(uint32_t fl, uint32_t ps) {
+  return (fl & ~((ps & 0x10u) << 12)) | ((ps & 1u) << 16) | ((ps & 0xEu) << 21);
+}
+static_assert(UST_F_WAIT_PODS_RUNNING == (1u << 16) && UST_W_PD_HAS == (UST_PODSUM_TO_DELETE << 21) &&
+              UST_W_PD_MISMATCH == (UST_PODSUM_CANNOT_DELETE << 21) && UST_W_DRAIN_ERROR == (UST_PODSUM_DRAIN_ERROR << 21) &&
+              UST_PODSUM_WAIT_RUNNING == 1u, "pod summary byte layout");
+
 template <bool DS_SMEM>
 __device__ __forceinline__ uint32_t stream_node(const UstParams& P, const Shared& S, uint32_t tab_off, uint32_t wbits,
                                                 uint32_t fl, int rev, uint32_t di, uint32_t grant, uint32_t& lo,
@@ -516,7 +418,7 @@ __device__ __forceinline__ uint32_t stream_node(const UstParams& P, const Shared
   const uint4 m = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(S.hotent) + tab_off);
   lo += m.z;
   hi += m.w;
-  uint32_t w = (fl & UST_F_INPUT_MASK) | wbits | grant;
+  uint32_t w = fl | wbits | grant;  // fl: input bits of the flags word (+ pod-list bits), masked by the caller
   if (pod_synced<DS_SMEM>(P, S, rev, di)) w |= UST_W_SYNCED;
   const uint32_t off = (__funnelshift_r(w, 0u, m.x) & 0x7FCu) | m.y;
   return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(S.lut) + off);
@@ -537,7 +439,7 @@ struct ExactCtx {
 // COUNT adds the byte-sliced counting, EXACT replaces the chunk-uniform slot grant by the ordered one: a
 // candidate's rank in slice order = candidates before its step (S.step_base) + before its warp within the step
 // (S.wtot) + a warp-shuffle exclusive scan — no block barrier in the loop (upgrade_inplace.go:71-109).
-template <bool FULL, bool DS_SMEM, bool OUTCOME, bool COUNT, bool EXACT>
+template <bool FULL, bool DS_SMEM, bool OUTCOME, bool COUNT, bool EXACT, int PODS>
 __device__ __forceinline__ void spec_tile(const UstParams& P, Shared& S, const Cursor& c, int room, long long i0,
                                           const Tile& T, uint32_t grant, uint32_t (&B)[4], ExactCtx ex) {
   uint32_t lo = 0, hi = 0;
@@ -577,10 +479,20 @@ __device__ __forceinline__ void spec_tile(const UstParams& P, Shared& S, const C
       constexpr uint32_t kW = UST_W_SKIP | UST_W_UNSCHEDULABLE;
       uint32_t e[4];
       uint32_t dlo = 0, dhi = 0;
-      e[0] = stream_node<DS_SMEM>(P, S, (x << 4) & 0xFF0u, (x >> 3) & kW, T.f[j].x, (int)T.r[j].x, T.d[j].x, g[0], dlo, dhi);
-      e[1] = stream_node<DS_SMEM>(P, S, (x >> 4) & 0xFF0u, (x >> 11) & kW, T.f[j].y, (int)T.r[j].y, T.d[j].y, g[1], dlo, dhi);
-      e[2] = stream_node<DS_SMEM>(P, S, (x >> 12) & 0xFF0u, (x >> 19) & kW, T.f[j].z, (int)T.r[j].z, T.d[j].z, g[2], dlo, dhi);
-      e[3] = stream_node<DS_SMEM>(P, S, (x >> 20) & 0xFF0u, (x >> 27) & kW, T.f[j].w, (int)T.r[j].w, T.d[j].w, g[3], dlo, dhi);
+      // without pod lists the derived pod bits of w are never set: mask them out of the flags word
+      constexpr uint32_t kIn = UST_F_INPUT_MASK;
+      uint32_t fl[4] = {T.f[j].x & kIn, T.f[j].y & kIn, T.f[j].z & kIn, T.f[j].w & kIn};
+      if (PODS) {
+        const uint32_t ps = T.ps[j];
+        fl[0] = pods_apply(fl[0], ps & 0xFFu);
+        fl[1] = pods_apply(fl[1], (ps >> 8) & 0xFFu);
+        fl[2] = pods_apply(fl[2], (ps >> 16) & 0xFFu);
+        fl[3] = pods_apply(fl[3], ps >> 24);
+      }
+      e[0] = stream_node<DS_SMEM>(P, S, (x << 4) & 0xFF0u, (x >> 3) & kW, fl[0], (int)T.r[j].x, T.d[j].x, g[0], dlo, dhi);
+      e[1] = stream_node<DS_SMEM>(P, S, (x >> 4) & 0xFF0u, (x >> 11) & kW, fl[1], (int)T.r[j].y, T.d[j].y, g[1], dlo, dhi);
+      e[2] = stream_node<DS_SMEM>(P, S, (x >> 12) & 0xFF0u, (x >> 19) & kW, fl[2], (int)T.r[j].z, T.d[j].z, g[2], dlo, dhi);
+      e[3] = stream_node<DS_SMEM>(P, S, (x >> 20) & 0xFF0u, (x >> 27) & kW, fl[3], (int)T.r[j].w, T.d[j].w, g[3], dlo, dhi);
       if (COUNT) { lo += dlo; hi += dhi; }
       uint32_t next4, out4;
       uint2 act4;
@@ -660,7 +572,7 @@ __device__ unsigned exact_prepass(const UstParams& P, Shared& S, long long blk0,
 // Evaluate the block [blk0, blk1) of a chunk through the 4-deep tile pipeline. ORDERED: `limit` slots are left
 // for the candidates from node `count_from` (<= blk0) on, in slice order (pre-pass + per-node ranks); otherwise
 // the slot grant is uniform (`grant`). Returns the candidates in [count_from, blk1) (ORDERED only).
-template <bool DS_SMEM, bool OUTCOME, bool COUNT, bool ORDERED>
+template <bool DS_SMEM, bool OUTCOME, bool COUNT, bool ORDERED, int PODS>
 __device__ __forceinline__ long long spec_block(const UstParams& P, Shared& S, long long blk0, long long blk1, uint32_t grant,
                                                 long long limit, long long count_from, Acc& A, bool wait_for_table) {
   const long long span = blk1 - blk0;  // CTA-uniform, a multiple of 128 (or <= 0 for an empty chunk)
@@ -675,7 +587,7 @@ __device__ __forceinline__ long long spec_block(const UstParams& P, Shared& S, l
   long long i0 = blk0 + t4;
   Tile T;
   auto load = [&](long long done) {  // loads of the tile starting `done` nodes into the block; c.q points at it
-    if (kFullVariant && span - done >= kTile) tile_load<true>(c, 0, T); else tile_load<false>(c, room_at(done), T);
+    if (kFullVariant && span - done >= kTile) tile_load<true, PODS>(c, 0, T); else tile_load<false, PODS>(c, room_at(done), T);
   };
   if (span > 0) load(0);  // the first tile's loads go out before anything waits (table copy, pre-pass)
   if (wait_for_table) {
@@ -697,8 +609,8 @@ __device__ __forceinline__ long long spec_block(const UstParams& P, Shared& S, l
     if (done) load(done);
     const int room = room_at(done);
     if (ORDERED) ex.s0 = (int)(done / kStep);
-    if (kFullVariant && span - done >= kTile) spec_tile<true, DS_SMEM, OUTCOME, COUNT, ORDERED>(P, S, c, room, i0, T, grant, A.B, ex);
-    else spec_tile<false, DS_SMEM, OUTCOME, COUNT, ORDERED>(P, S, c, room, i0, T, grant, A.B, ex);
+    if (kFullVariant && span - done >= kTile) spec_tile<true, DS_SMEM, OUTCOME, COUNT, ORDERED, PODS>(P, S, c, room, i0, T, grant, A.B, ex);
+    else spec_tile<false, DS_SMEM, OUTCOME, COUNT, ORDERED, PODS>(P, S, c, room, i0, T, grant, A.B, ex);
     cursor_advance(c);
     i0 += kTile;
     if (COUNT && ++A.tiles >= 14) spill_thread(S, A);  // byte lanes: at most 16 per tile, 255 max
@@ -707,10 +619,10 @@ __device__ __forceinline__ long long spec_block(const UstParams& P, Shared& S, l
 }
 
 // The streaming fast path: uniform grant, counting, inlined into the chunk loop.
-template <bool DS_SMEM, bool OUTCOME>
+template <bool DS_SMEM, bool OUTCOME, bool PODS>
 __device__ __forceinline__ void spec_chunk(const UstParams& P, Shared& S, long long b0, long long lim, uint32_t grant, Acc& A,
                                            bool wait_for_table) {
-  spec_block<DS_SMEM, OUTCOME, true, false>(P, S, b0, lim, grant, 0, b0, A, wait_for_table);
+  spec_block<DS_SMEM, OUTCOME, true, false, PODS ? 1 : 0>(P, S, b0, lim, grant, 0, b0, A, wait_for_table);
 }
 
 // The ordered variant lives out of line so that it cannot cost the fast path registers: blocks of
@@ -728,7 +640,7 @@ __device__ __forceinline__ long long ordered_range(const UstParams& P, Shared& S
   long long blk0 = b0;
   do {
     const long long blk1 = blk0 + kBlk < lim ? blk0 + kBlk : lim;
-    seen += spec_block<DS_SMEM, OUTCOME, COUNT, true>(P, S, blk0, blk1, 0u, slots - seen, blk0 == b0 ? count_from : blk0, A,
+    seen += spec_block<DS_SMEM, OUTCOME, COUNT, true, 2>(P, S, blk0, blk1, 0u, slots - seen, blk0 == b0 ? count_from : blk0, A,
                                                       wait_for_table);
     wait_for_table = false;
     __syncthreads();  // step_base / wtot are rewritten by the next block's pre-pass
@@ -745,7 +657,7 @@ __device__ __forceinline__ void uniform_range(const UstParams& P, Shared& S, lon
   A.B[0] = A.B[1] = A.B[2] = A.B[3] = 0;
   A.tiles = 0;
   A.cand_spilled = 0;
-  spec_block<DS_SMEM, OUTCOME, false, false>(P, S, b0, lim, grant, 0, b0, A, false);
+  spec_block<DS_SMEM, OUTCOME, false, false, 2>(P, S, b0, lim, grant, 0, b0, A, false);
 }
 
 // general path: one step of kStep nodes, bounds-checked; optional exact ordered slot allocation,
@@ -821,10 +733,10 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     uint32_t extra = gbits[k], f = fl[k];
-    if (P.eval_pods && k < nvalid) {
-      uint32_t clear_mask;
-      extra |= pod_summary(P, hb[k], i0 + k, clear_mask);
-      f &= ~clear_mask;
+    if (P.podsum && k < nvalid) {  // pod-list summary of the node (ust_pod_summary_kernel), see pods_apply()
+      const uint32_t ps = P.podsum[i0 + k];
+      f &= ~((ps & 0x10u) << 12);
+      extra |= ((ps & 1u) << 16) | ((ps & 0xEu) << 21);
     }
     e[k] = ds_smem ? node_entry<true>(P, S, hb[k], f, rev[k], di[k], extra) : node_entry<false>(P, S, hb[k], f, rev[k], di[k], extra);
     if (aborting) e[k] = apply_abort(S, e[k], hb[k], S.node_offset + i0 + k);
@@ -873,7 +785,7 @@ __device__ void general_chunk(const UstParams& P, Shared& S, long long b0, long 
 // claimed with an atomic ticket, so CTAs that HBM serves faster take more of them and all CTAs reach the
 // grid barrier together. Per chunk: counts + speculative outputs; the chunk's candidate count is published
 // for the ordered slot allocation. Returns the number of nodes this CTA streamed.
-template <bool DS_SMEM, bool OUTCOME>
+template <bool DS_SMEM, bool OUTCOME, bool PODS>
 __device__ long long stream_loop(const UstParams& P, Shared& S) {
   const int t = threadIdx.x;
   const int n_chunks = P.grid_chunks;
@@ -892,7 +804,7 @@ __device__ long long stream_loop(const UstParams& P, Shared& S) {
     const long long lim = b1 & ~127LL;  // == b1 except for the ragged end of the whole array
     const uint32_t grant = spec_grant(P, S, chunk);
     const unsigned cand0 = A.cand_spilled + p1_field(A.B, 15);
-    spec_chunk<DS_SMEM, OUTCOME>(P, S, b0, lim, grant, A, first);
+    spec_chunk<DS_SMEM, OUTCOME, PODS>(P, S, b0, lim, grant, A, first);
     first = false;
     if (lim < b1) {  // ragged end (< 128 nodes, last chunk only)
       long long running = 0;
@@ -934,20 +846,16 @@ __device__ void stream_phase(const UstParams& P, Shared& S) {
   const int n_chunks = P.grid_chunks;
   UstWorkspace* ws = P.ws;
   long long nodes_seen = 0;
-  if (P.eval_pods) {
-    // pod lists are evaluated by the exact path after the barrier: count only, one static chunk per CTA
-    const int chunk = P.chunk_begin + blockIdx.x;
-    if (chunk < P.chunk_end) {
-      const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
-      phase1_count(P, S, b0, b1);
-      nodes_seen = b1 - b0;
-      __syncthreads();
-      if (t == 0) ws->cand_cta[chunk] = S.cnt[15];
-    }
-  } else if (P.n_ds <= UST_DS_SMEM_MAX) {
-    nodes_seen = P.outcome ? stream_loop<true, true>(P, S) : stream_loop<true, false>(P, S);
-  } else {
-    nodes_seen = P.outcome ? stream_loop<false, true>(P, S) : stream_loop<false, false>(P, S);
+  const int variant = (P.n_ds <= UST_DS_SMEM_MAX ? 4 : 0) | (P.outcome ? 2 : 0) | (P.podsum ? 1 : 0);
+  switch (variant) {
+    case 7: nodes_seen = stream_loop<true, true, true>(P, S); break;
+    case 6: nodes_seen = stream_loop<true, true, false>(P, S); break;
+    case 5: nodes_seen = stream_loop<true, false, true>(P, S); break;
+    case 4: nodes_seen = stream_loop<true, false, false>(P, S); break;
+    case 3: nodes_seen = stream_loop<false, true, true>(P, S); break;
+    case 2: nodes_seen = stream_loop<false, true, false>(P, S); break;
+    case 1: nodes_seen = stream_loop<false, false, true>(P, S); break;
+    default: nodes_seen = stream_loop<false, false, false>(P, S); break;
   }
   __syncthreads();
   // 16 global atomics per CTA
@@ -1092,7 +1000,7 @@ __device__ void finish(const UstParams& P, Shared& S, bool reset_ws) {
 // slot" the speculation only fails if there is a budget at all, with "everybody gets one" only if the
 // budget is smaller than the number of candidates.
 __device__ __forceinline__ bool verification_needed(const UstParams& P, const Shared& S) {
-  if (P.eval_pods || S.abort_key != ~0ull) return true;
+  if (S.abort_key != ~0ull) return true;
   if (!(P.active && !P.requestor)) return false;
   const long long cands = S.V[UST_V_CANDIDATES];
   if (cands == 0) return false;
@@ -1271,7 +1179,7 @@ __device__ void verify_phase(const UstParams& P, Shared& S, const ChunkCands& he
   const int n_chunks = P.grid_chunks;
   const long long rank_base = S.cand_prefix;  // candidates on lower ranks
   scan_chunks(P, S, rank_base, held);
-  if (!(P.eval_pods || S.abort_key != ~0ull)) {
+  if (S.abort_key == ~0ull) {
     redo_wrong_chunks(P, S, rank_base);
     return;
   }
@@ -1325,7 +1233,6 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_fused_kernel(const
   if (threadIdx.x == 0) derive_scalars(P, S);
   __syncthreads();
   if (verification_needed(P, S)) {
-    if (P.eval_pods) { stage_tables_wait(S); __syncthreads(); }
     verify_phase(P, S, held);
   }
   finish(P, S, true);
@@ -1356,7 +1263,6 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase1_kernel(cons
     }
     if (threadIdx.x == 0) { P.ws->depart = 0; P.ws->ticket = 0; }
   }
-  if (P.eval_pods) stage_tables_wait(S);  // never leave a bulk copy in flight at CTA exit
 }
 
 // ... and verification: redo, exactly, the chunks whose speculation did not hold
@@ -1372,6 +1278,132 @@ __global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase2_kernel(cons
   __syncthreads();
   if (verification_needed(P, S)) verify_phase(P, S, held);
   finish(P, S, false);
+}
+
+// Pod-list summaries (rows 12-14 of the scope table: pod_manager.go:256-391, :122-229, drain_manager.go:58-139).
+// Only nodes whose actuator would look at its pods have their list read: wait-for-jobs, pod-deletion and
+// drain-required nodes - everything else costs the hot byte. A CTA takes blocks of kPodBlock consecutive nodes:
+// it compacts the nodes that need their list (in node order) into shared memory, then every thread walks the list
+// of one such node with aligned 16-byte loads (8 pods each, all loads of a pass in flight together), mapping each
+// pod through the per-policy pod table (shared memory) and OR-ing. All lanes of a warp do useful work on every
+// instruction, which is what makes this an HBM-bound kernel instead of an issue-bound one (round-1 measurement:
+// the warp-per-node formulation executed 15x the instructions). Neighbouring threads own neighbouring lists, so
+// their loads share sectors. Output: one byte per node for the streaming pass (layout: pods_apply()), written
+// coalesced per block.
+constexpr int kPodBlock = 4096;            // nodes per block = 16 per thread
+constexpr int kPodChunks = 6;              // 16-byte loads in flight per thread and pass (48 pods: a typical list in one pass)
+
+__global__ void __launch_bounds__(kThreads, 6) ust_pod_summary_kernel(long long n, int active, const uint8_t* __restrict__ hot,
+                                                                      const int32_t* __restrict__ pod_off,
+                                                                      const uint16_t* __restrict__ pod_flags, long long n_pods,
+                                                                      const uint8_t* __restrict__ podlut, uint8_t* __restrict__ podsum) {
+  __shared__ __align__(16) uint8_t lut[UST_PODLUT_ENTRIES];
+  __shared__ __align__(16) uint8_t res[kPodBlock];   // summary byte per node of the block (bits 6-7: state - 3 while in work)
+  __shared__ unsigned short list[kPodBlock];         // block-local indices of the nodes whose list is read
+  __shared__ int cnt;
+  const int t = threadIdx.x, lane = t & 31;
+  for (int i = t; i < (int)(UST_PODLUT_ENTRIES / 4); i += kThreads)
+    reinterpret_cast<uint32_t*>(lut)[i] = __ldg(reinterpret_cast<const uint32_t*>(podlut) + i);
+  const unsigned char* bytes = reinterpret_cast<const unsigned char*>(pod_flags);
+  const long long total_bytes = 2 * n_pods;
+  // hot bytes of this thread's 16 nodes of a block ("excluded" past the end of the array)
+  auto load_hot = [&](long long base) -> uint4 {
+    const long long i0 = base + 16 * t;
+    uint32_t w[4] = {0x0E0E0E0Eu, 0x0E0E0E0Eu, 0x0E0E0E0Eu, 0x0E0E0E0Eu};
+    if (i0 + 16 <= n) return __ldg(reinterpret_cast<const uint4*>(hot + i0));  // base, 16t: multiples of 16
+    for (int k = 0; k < 16; k++)
+      if (i0 + k < n) w[k >> 2] = (w[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | ((uint32_t)hot[i0 + k] << (8 * (k & 3)));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  };
+  for (long long base = (long long)blockIdx.x * kPodBlock; base < n; base += (long long)gridDim.x * kPodBlock) {
+    if (t == 0) cnt = 0;
+    __syncthreads();
+    // ---- scan the block's hot bytes, compact the nodes that need their pods
+    const long long i0 = base + 16 * t;
+    const uint4 hv = load_hot(base);
+    const uint32_t w[4] = {hv.x, hv.y, hv.z, hv.w};
+    unsigned needbits = 0;
+    uint32_t init[4];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const unsigned s = (w[k >> 2] >> (8 * (k & 3))) & 15u;
+      const bool need = active && s >= UST_STATE_WAIT_FOR_JOBS_REQUIRED && s <= UST_STATE_DRAIN_REQUIRED;
+      // wait-for-jobs: the list overrides the pre-evaluated bit (0x10) even when it is empty
+      const uint32_t b = need ? (((s - UST_STATE_WAIT_FOR_JOBS_REQUIRED) << 6) | (s == UST_STATE_WAIT_FOR_JOBS_REQUIRED ? 0x10u : 0u)) : 0u;
+      if ((k & 3) == 0) init[k >> 2] = 0;
+      init[k >> 2] |= b << (8 * (k & 3));
+      needbits |= (need ? 1u : 0u) << k;
+    }
+    *reinterpret_cast<uint4*>(res + 16 * t) = make_uint4(init[0], init[1], init[2], init[3]);
+    const int mine_cnt = __popc(needbits);
+    int incl = mine_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int wbase = 0;
+    if (lane == 31) wbase = atomicAdd(&cnt, incl);   // warps land in arrival order: the list is node-ordered within a warp
+    wbase = __shfl_sync(kFull, wbase, 31);
+    int slot = wbase + incl - mine_cnt;
+    while (needbits) {
+      const int k = __ffs(needbits) - 1;
+      needbits &= needbits - 1;
+      list[slot++] = (unsigned short)(16 * t + k);
+    }
+    __syncthreads();
+    // ---- one thread per listed node
+    const int total = cnt;
+    for (int q = t; q < total; q += kThreads) {
+      const int li = list[q];
+      const long long i = base + li;
+      const int p0 = __ldg(pod_off + i), p1 = __ldg(pod_off + i + 1);
+      const int len = p1 - p0;
+      unsigned r = 0;
+      // 16-byte chunks covering the list; the last one may reach past the list but, when `safe`, not past the array
+      const long long c0 = (2LL * p0) & ~15LL;
+      const int nchunks = len > 0 ? (int)((2LL * p1 - c0 + 15) >> 4) : 0;
+      const bool safe = c0 + 16LL * nchunks <= total_bytes;
+      if (safe) {
+        const uint4* src = reinterpret_cast<const uint4*>(bytes + c0);
+        int rel = (int)((c0 >> 1) - p0);  // pod index of the chunk's element 0, relative to the list (<= 0 for chunk 0)
+        for (int cb = 0; cb < nchunks; cb += kPodChunks) {
+          uint4 x[kPodChunks];
+#pragma unroll
+          for (int u = 0; u < kPodChunks; u++) x[u] = cb + u < nchunks ? __ldcs(src + cb + u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int u = 0; u < kPodChunks; u++) {
+            if (cb + u < nchunks) {
+              const uint32_t wv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+              for (int e = 0; e < 8; e++) {
+                const uint32_t f = (e & 1) ? (wv[e >> 1] >> 16) & (UST_PODLUT_ENTRIES - 1) : wv[e >> 1] & (UST_PODLUT_ENTRIES - 1);
+                if ((unsigned)(rel + e) < (unsigned)len) r |= lut[f];
+              }
+            }
+            rel += 8;
+          }
+        }
+      } else {  // the list ends within the last 16 bytes of the whole array: plain 2-byte loads
+        for (int p = p0; p < p1; p++) r |= lut[__ldg(pod_flags + p) & (UST_PODLUT_ENTRIES - 1)];
+      }
+      const unsigned tag = res[li];
+      const unsigned s = UST_STATE_WAIT_FOR_JOBS_REQUIRED + (tag >> 6);
+      unsigned ps;
+      if (s == UST_STATE_WAIT_FOR_JOBS_REQUIRED) ps = 0x10u | (r & UST_PODSUM_WAIT_RUNNING);
+      else if (s == UST_STATE_POD_DELETION_REQUIRED) ps = r & (UST_PODSUM_TO_DELETE | UST_PODSUM_CANNOT_DELETE);
+      else ps = r & UST_PODSUM_DRAIN_ERROR;
+      res[li] = (uint8_t)ps;
+    }
+    __syncthreads();
+    // ---- coalesced write of the block's bytes
+    if (i0 + 16 <= n) {
+      *reinterpret_cast<uint4*>(podsum + i0) = *reinterpret_cast<const uint4*>(res + 16 * t);
+    } else {
+      for (int k = 0; k < 16; k++)
+        if (i0 + k < n) podsum[i0 + k] = res[16 * t + k];
+    }
+  }
 }
 
 // BuildState's device part (upgrade_state.go:126-133, :158-160): owned pods per DaemonSet and bucket sizes
@@ -1434,6 +1466,14 @@ int ust_launch_phase1(const UstParams& p, int grid, void* stream) {
 }
 int ust_launch_phase2(const UstParams& p, int grid, void* stream) {
   ust_phase2_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+int ust_launch_pod_summary(long long n, int active, const uint8_t* hot, const int32_t* pod_off, const uint16_t* pod_flags,
+                           long long n_pods, const uint8_t* podlut, uint8_t* podsum, int grid, void* stream) {
+  if (n <= 0) return 0;
+  const long long blocks = (n + kPodBlock - 1) / kPodBlock;
+  if (grid > blocks) grid = (int)blocks;
+  ust_pod_summary_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, active, hot, pod_off, pod_flags, n_pods, podlut, podsum);
   return (int)cudaGetLastError();
 }
 int ust_launch_build_state(long long n, const uint8_t* hot, const int32_t* ds_idx, int n_ds, const int32_t* ds_desired,

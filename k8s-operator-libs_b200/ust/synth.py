@@ -120,6 +120,22 @@ def make_pods(n, seed, start=0, lo=20, hi=40):
     return {"pod_off": off.astype(np.int32), "pod_flags": pf.astype(np.uint16)}
 
 
+def make_pods_blocked(n, seed, start=0, block=500_000):
+    """make_pods() for large n in bounded memory (pods are a pure function of the node index, so blocks agree
+    with the one-shot generator bit for bit)."""
+    offs = [np.zeros(1, dtype=np.int64)]
+    flags = []
+    base = 0
+    for b0 in range(0, n, block):
+        part = make_pods(min(block, n - b0), seed, start=start + b0)
+        offs.append(part["pod_off"][1:].astype(np.int64) + base)
+        base += int(part["pod_off"][-1])
+        flags.append(part["pod_flags"])
+    off = np.concatenate(offs)
+    assert off[-1] < 2 ** 31, "pod_off is int32"
+    return {"pod_off": off.astype(np.int32), "pod_flags": np.concatenate(flags) if flags else np.zeros(0, np.uint16)}
+
+
 # BASELINE.json configs as concrete inputs (BASELINE.md §3)
 CONFIGS = {
     "C1": dict(n=100, seed=0x5EED0001, policy=dict(max_parallel_upgrades=1)),

@@ -212,6 +212,30 @@ def test_c4_pod_lists_sample(handle):
     helpers.assert_same(gpu_apply(handle, pol, soa, pods), helpers.oracle_apply(pol, soa, pods, variant=0), "C4 sample")
 
 
+def test_c4_full_size(handle):
+    """C4 at BASELINE.json's size: 10 M nodes with ~300 M workload pods in CSR lists (pod deletion and drain
+    enabled). Bit-exact against the SoA oracle; the SoA oracle itself is checked against the reference-shaped
+    one (an independent restatement of rows 12-14) on a 200 k-node slice of the same input."""
+    cfg = synth.CONFIGS["C4"]
+    n = cfg["n"]
+    soa = synth.make_nodes(n, cfg["seed"])
+    pods = synth.make_pods_blocked(n, cfg["seed"])
+    pol = synth.config_policy("C4")
+    got = gpu_apply(handle, pol, soa, pods)
+    ref = helpers.oracle_apply(pol, soa, pods, variant=1)
+    helpers.assert_same(got, ref, "C4 full size")
+    rc, nxt, act, oc, cnt = got
+    code = soa["state"] & 15
+    assert rc == 0 and cnt["total_managed"] == int(np.isin(code, [0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12]).sum())
+    # reference-shaped oracle on the first 200 k nodes (independent restatement of rows 12-14)
+    m = 200_000
+    sub = {k: (v[:m] if k != "ds_rev" else v) for k, v in soa.items()}
+    psub = {"pod_off": pods["pod_off"][:m + 1].copy(), "pod_flags": pods["pod_flags"][:int(pods["pod_off"][m])]}
+    a = helpers.oracle_apply(pol, sub, psub, variant=0)
+    b = helpers.oracle_apply(pol, sub, psub, variant=1)
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[1], b[1])
+
+
 def test_device_resident_entry_point(handle):
     """ust_apply_state_device on torch-owned device buffers (plumbing only) == host entry point."""
     import torch
