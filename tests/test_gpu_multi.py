@@ -29,9 +29,11 @@ def _worker(rank, world, port, cases, q, mode):
     h.comm_set_mode(mode)  # 0 = NCCL all-reduce between two kernels, 1 = fused NVLink mailbox exchange
     results = []
     for (n, seed, p_err, pol_kwargs) in cases:
+        with_pods = pol_kwargs.get("evaluate_actuators", False)
         pol = abi.make_policy(**pol_kwargs)
         soa = synth.make_nodes(n, seed, start=rank * n, error_pct=p_err)
-        rc, nxt, act, oc, cnt = h.apply_state(pol, soa)
+        pods = synth.make_pods(n, seed, start=rank * n) if with_pods else None   # CSR split at the shard boundary
+        rc, nxt, act, oc, cnt = h.apply_state(pol, soa, pods)
         results.append((rc, nxt, act, oc, cnt))
     gathered = [None] * world
     dist.all_gather_object(gathered, results)
@@ -48,6 +50,7 @@ CASES = [
     (300_000, 0x5EED0005, 0.0, dict(max_parallel_upgrades=250_000)),                          # cut on rank 1
     (150_001, 0x5EED0007, 0.001, dict(max_parallel_upgrades=5, max_unavailable=7)),           # aborts
     (100_000, 0x5EED0008, 0.0, dict(max_parallel_upgrades=3, use_maintenance_operator=True)), # requestor mode
+    (120_000, 0x5EED0004, 0.0, dict(synth.CONFIGS["C4"]["policy"])),                          # C4: pod lists per shard
 ]
 
 
@@ -71,7 +74,8 @@ def test_two_ranks_match_unsharded_oracle(mode):
     for ci, (n, seed, p_err, pol_kwargs) in enumerate(CASES):
         whole = synth.make_nodes(world * n, seed, error_pct=p_err)
         pol = abi.make_policy(**pol_kwargs)
-        ref = helpers.oracle_apply(pol, whole, variant=1)
+        pods = synth.make_pods(world * n, seed) if pol_kwargs.get("evaluate_actuators", False) else None
+        ref = helpers.oracle_apply(pol, whole, pods, variant=1)
         rcs = [gathered[r][ci][0] for r in range(world)]
         nxt = np.concatenate([gathered[r][ci][1] for r in range(world)])
         act = np.concatenate([gathered[r][ci][2] for r in range(world)])
