@@ -251,6 +251,17 @@ int ust_sync(ust_handle* h);
 int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const int32_t* ds_idx,
                     int32_t n_ds, const int32_t* ds_desired, ust_counters* out);
 
+/* The same with the owner join done on the device (upgrade_state.go:126-147, common_manager.go:168-227):
+ * owner_uid holds, per driver pod, the 128-bit UID of OwnerReferences[0] as two uint64 (both 0 = the pod has no
+ * owner reference: IsOrphanedPod, common_manager.go:225-227); ds_uid holds the UIDs of the driver DaemonSets
+ * (the keys of GetDriverDaemonSets' map, so they must be distinct - UST_ERR_INVALID_ARGUMENT otherwise).
+ * ds_idx_out[i] receives the index of the owning DaemonSet, -1 for an orphaned pod, -2 for a pod owned by
+ * something else: GetPodsOwnedbyDs skips it and GetOrphanedPods does not take it, so it is not part of the
+ * snapshot and not counted in any bucket. Everything else as ust_build_state. owner_uid must be 16-byte aligned. */
+int ust_build_state_uids(ust_handle* h, int64_t n_pods, const uint8_t* state, const uint64_t* owner_uid,
+                         int32_t n_ds, const uint64_t* ds_uid, const int32_t* ds_desired, int32_t* ds_idx_out,
+                         ust_counters* out);
+
 /* ---- introspection ----------------------------------------------------------------------------- */
 
 /* The kernel evaluates a node by one lookup in a per-policy table indexed by (state code, 9-bit window

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -106,7 +107,9 @@ struct ust_handle {
   DevBuf<uint32_t> s_flags;
   DevBuf<int32_t> s_rev, s_ds, s_dsrev, s_podoff, s_dsdesired;
   DevBuf<uint16_t> s_actions, s_podflags;
-  DevBuf<uint8_t> s_podsum;  // per-node pod-list summaries (ust_pod_summary_kernel -> streaming pass)
+  DevBuf<uint8_t> s_podsum;
+  DevBuf<uint64_t> s_uid, s_dsuid;   // BuildState owner join: pod owner UIDs, DaemonSet UID hash table (+ s_dsorder: slot -> index)
+  DevBuf<int32_t> s_dsorder;  // per-node pod-list summaries (ust_pod_summary_kernel -> streaming pass)
 
   // multi-GPU
   int rank = 0, world = 1, comm_mode = 0;
@@ -492,7 +495,7 @@ void ust_destroy(ust_handle* h) {
   if (h->ds_count_dev) cudaFree(h->ds_count_dev);
   h->s_hot.release(); h->s_next.release(); h->s_outcome.release(); h->s_flags.release();
   h->s_rev.release(); h->s_ds.release(); h->s_dsrev.release(); h->s_podoff.release(); h->s_dsdesired.release();
-  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release();
+  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release();
   for (auto& ev : h->seg_done) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->seg_up) if (ev) cudaEventDestroy(ev);
   if (h->stream_h2d) cudaStreamDestroy(h->stream_h2d);
@@ -616,6 +619,64 @@ int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const i
   h->ws_dirty = false;
   h->launches += 2;
   return finish_with_counters(h, st, out);
+}
+
+int ust_build_state_uids(ust_handle* h, int64_t n_pods, const uint8_t* state, const uint64_t* owner_uid, int32_t n_ds,
+                         const uint64_t* ds_uid, const int32_t* ds_desired, int32_t* ds_idx_out, ust_counters* out) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  if (n_pods < 0 || (n_pods > 0 && (!state || !owner_uid || !ds_idx_out)) || n_ds < 0 || (n_ds > 0 && (!ds_uid || !ds_desired)))
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
+  // the DaemonSet map is keyed by UID (common_manager.go:181-185): an open-addressing table at load factor <= 1/4
+  size_t slots = 8;
+  while (slots < 4 * (size_t)n_ds) slots <<= 1;
+  std::vector<uint64_t> tab(2 * slots, 0);
+  std::vector<int32_t> tab_idx(slots, -2);
+  for (int32_t d = 0; d < n_ds; d++) {
+    const uint64_t x = ds_uid[2 * (size_t)d], y = ds_uid[2 * (size_t)d + 1];
+    if ((x | y) == 0) return h->fail(UST_ERR_INVALID_ARGUMENT, "DaemonSet %d has an empty UID", (int)d);
+    size_t s = ust_uid_hash(x, y) & (slots - 1);
+    while ((tab[2 * s] | tab[2 * s + 1]) != 0) {
+      if (tab[2 * s] == x && tab[2 * s + 1] == y)
+        return h->fail(UST_ERR_INVALID_ARGUMENT, "DaemonSets %d and %d share a UID", (int)tab_idx[s], (int)d);
+      s = (s + 1) & (slots - 1);
+    }
+    tab[2 * s] = x; tab[2 * s + 1] = y; tab_idx[s] = d;
+  }
+  UST_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t N = (size_t)n_pods;
+  UST_CUDA(h, h->s_hot.reserve(N + 16));
+  UST_CUDA(h, h->s_ds.reserve(N + 4));
+  UST_CUDA(h, h->s_uid.reserve(2 * N + 2));
+  UST_CUDA(h, h->s_dsuid.reserve(2 * slots));
+  UST_CUDA(h, h->s_dsorder.reserve(slots));
+  UST_CUDA(h, h->s_dsdesired.reserve((size_t)n_ds + 1));
+  if ((size_t)n_ds + 1 > h->ds_count_cap) {
+    if (h->ds_count_dev) cudaFree(h->ds_count_dev);
+    h->ds_count_cap = (size_t)n_ds + 64;
+    UST_CUDA(h, cudaMalloc(&h->ds_count_dev, h->ds_count_cap * sizeof(unsigned long long)));
+    UST_CUDA(h, cudaMemsetAsync(h->ds_count_dev, 0, h->ds_count_cap * sizeof(unsigned long long), st));
+  }
+  if (h->ws_dirty) { UST_CUDA(h, cudaMemsetAsync(h->ws, 0, sizeof(UstWorkspace), st)); h->ws_dirty = false; }
+  if (N) {
+    UST_CUDA(h, cudaMemcpyAsync(h->s_hot.p, state, N, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->s_uid.p, owner_uid, N * 16, cudaMemcpyHostToDevice, st));
+  }
+  UST_CUDA(h, cudaMemcpyAsync(h->s_dsuid.p, tab.data(), slots * 16, cudaMemcpyHostToDevice, st));
+  UST_CUDA(h, cudaMemcpyAsync(h->s_dsorder.p, tab_idx.data(), slots * 4, cudaMemcpyHostToDevice, st));
+  if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsdesired.p, ds_desired, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
+  int64_t grid = (n_pods + 1023) / 1024;  // 256 threads x 4 pods per iteration
+  if (grid < 1) grid = 1;
+  if (grid > 8 * h->num_sms) grid = 8 * h->num_sms;
+  h->ws_dirty = true;
+  int e = ust_launch_build_state_uids(n_pods, h->s_hot.p, h->s_uid.p, n_ds, h->s_dsuid.p, h->s_dsorder.p, (int)slots,
+                                      h->s_dsdesired.p, h->s_ds.p, h->ds_count_dev, h->ws, h->counters_dev, (int)grid, st);
+  if (e) return h->fail(UST_ERR_CUDA, "build-state kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  h->ws_dirty = false;
+  h->launches += 2;
+  if (N) UST_CUDA(h, cudaMemcpyAsync(ds_idx_out, h->s_ds.p, N * 4, cudaMemcpyDeviceToHost, st));
+  return finish_with_counters(h, st, out);  // synchronises the stream: `tab` / `tab_idx` outlive their copies
 }
 
 uint32_t ust_table_entry(const ust_policy* policy, unsigned state_code, uint32_t w) {

@@ -104,4 +104,15 @@ int ust_launch_pod_summary(long long n, int active, const uint8_t* hot, const in
                            long long n_pods, const uint8_t* podlut, uint8_t* podsum, int grid, void* stream);
 int ust_launch_build_state(long long n, const uint8_t* hot, const int32_t* ds_idx, int n_ds, const int32_t* ds_desired,
                            unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream);
+// slot of a 128-bit UID in the DaemonSet hash table (before masking to the table size); host build and device lookup
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline unsigned ust_uid_hash(unsigned long long x, unsigned long long y) {
+  unsigned h = (unsigned)x * 0x9E3779B9u + (unsigned)(x >> 32) * 0x85EBCA6Bu + (unsigned)y * 0xC2B2AE35u + (unsigned)(y >> 32) * 0x27D4EB2Fu;
+  return h ^ (h >> 15);
+}
+int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* owner_uid, int n_ds, const void* ds_tab,
+                                const int32_t* ds_tab_idx, int tab_slots, const int32_t* ds_desired, int32_t* ds_idx_out,
+                                unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream);
 int ust_max_coresident_ctas(int device, int* ctas_per_sm, int* num_sms);

@@ -1428,6 +1428,141 @@ __global__ void __launch_bounds__(kThreads) ust_build_state_kernel(long long n, 
   if (threadIdx.x < 18 && cnt[threadIdx.x]) atomicAdd(&ws->acc[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
 }
 
+// BuildState at wire level: the owner join itself. One entry per driver pod with the 128-bit UID of
+// OwnerReferences[0] ((0, 0) = no owner reference: an orphaned pod, common_manager.go:225-227); the driver
+// DaemonSets' UIDs arrive sorted with their original indices. A pod whose owner is none of them is dropped
+// (GetPodsOwnedbyDs skips it, GetOrphanedPods does not take it: common_manager.go:190-222) - it gets ds_idx -2 and
+// counts as "not in snapshot". 17 B read + 4 B written per pod. The DaemonSet map (common_manager.go:181-185, keyed
+// by UID) is an open-addressing hash table built by the host at load factor <= 1/4 (ust_uid_hash, linear probing,
+// (0, 0) = empty slot) and copied to shared memory: one 16-byte lookup per pod in the common case. Counting is
+// byte-sliced as in the streaming pass; per-DaemonSet counts are packed byte counters (<= 8 DaemonSets) or
+// warp-aggregated atomics.
+constexpr int kUidTabSmem = 2048;  // hash slots held in shared memory (DaemonSets <= 512); larger tables stay in global memory
+
+__global__ void __launch_bounds__(kThreads) ust_build_state_uid_kernel(long long n, const uint8_t* __restrict__ hot,
+                                                                       const ulonglong2* __restrict__ owner, int n_ds,
+                                                                       const ulonglong2* __restrict__ ds_tab,
+                                                                       const int32_t* __restrict__ ds_tab_idx, int tab_slots,
+                                                                       int32_t* __restrict__ ds_idx_out,
+                                                                       unsigned long long* ds_count, UstWorkspace* ws) {
+  __shared__ ulonglong2 tab[kUidTabSmem];
+  __shared__ int ord[kUidTabSmem];
+  __shared__ unsigned int cnt_ds[kUidTabSmem / 4];
+  __shared__ unsigned long long inc[256];  // hot byte -> sixteen 4-bit one-hot increments (fields as in the streaming pass)
+  __shared__ unsigned int cnt[16];
+  const int t = threadIdx.x;
+  const bool in_smem = tab_slots <= kUidTabSmem;  // then n_ds <= kUidTabSmem / 4
+  if (in_smem) {
+    for (int i = t; i < tab_slots; i += kThreads) { tab[i] = ds_tab[i]; ord[i] = ds_tab_idx[i]; }
+    for (int i = t; i < n_ds; i += kThreads) cnt_ds[i] = 0;
+  }
+  {
+    const unsigned b = t, code = b & 15u;
+    unsigned long long v = 0;
+    if (code < 14) {
+      v = 1ull << (4 * code);
+      if (b & (UST_HOT_UNSCHEDULABLE | UST_HOT_NOT_READY)) v |= 1ull << 56;
+      if (code == UST_STATE_UPGRADE_REQUIRED && !(b & UST_HOT_SKIP)) v |= 1ull << 60;
+    }
+    inc[b] = v;
+  }
+  if (t < 16) cnt[t] = 0;
+  __syncthreads();
+  const ulonglong2* table = in_smem ? tab : ds_tab;
+  const int* order = in_smem ? ord : ds_tab_idx;
+  const unsigned slot_mask = (unsigned)tab_slots - 1u;  // tab_slots is a power of two
+  uint32_t B[4] = {0, 0, 0, 0}, lo = 0, hi = 0;
+  int pending = 0;
+  long long excluded = 0;
+  unsigned long long dsl = 0;  // n_ds <= 8: this thread's owned-pod count per DaemonSet, one byte each
+  auto spill = [&]() {
+    widen(lo, hi, B);
+#pragma unroll
+    for (int f = 0; f < 16; f++) {
+      const unsigned v = p1_field(B, f);
+      if (v) atomicAdd(&cnt[f], v);
+    }
+    if (dsl) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const unsigned v = (unsigned)(dsl >> (8 * q)) & 0xFFu;
+        if (v) atomicAdd(&cnt_ds[q], v);
+      }
+      dsl = 0;
+    }
+    B[0] = B[1] = B[2] = B[3] = 0;
+    pending = 0;
+  };
+  constexpr int kU = 4;  // pods per thread and iteration: four 16-byte loads in flight
+  const long long stride = (long long)gridDim.x * kThreads * kU;
+  for (long long i0 = (long long)blockIdx.x * kThreads * kU; i0 < n; i0 += stride) {  // warp-uniform trip count
+    ulonglong2 u[kU];
+    unsigned hb[kU];
+#pragma unroll
+    for (int k = 0; k < kU; k++) {
+      const long long i = i0 + (long long)k * kThreads + t;
+      u[k] = make_ulonglong2(0ull, 0ull);
+      hb[k] = UST_STATE_EXCLUDED;
+      if (i < n) { u[k] = __ldcs(owner + i); hb[k] = __ldg(hot + i); }
+    }
+#pragma unroll
+    for (int k = 0; k < kU; k++) {
+      const long long i = i0 + (long long)k * kThreads + t;
+      const bool valid = i < n;
+      int d = -2;
+      if (valid) {
+        if ((u[k].x | u[k].y) == 0ull) {
+          d = -1;  // IsOrphanedPod
+        } else {
+          unsigned slot = ust_uid_hash(u[k].x, u[k].y) & slot_mask;
+          for (;;) {  // linear probing; the table is at most a quarter full
+            const ulonglong2 e = table[slot];
+            if (e.x == u[k].x && e.y == u[k].y) { d = order[slot]; break; }
+            if ((e.x | e.y) == 0ull) break;  // empty slot: not a driver DaemonSet's pod
+            slot = (slot + 1u) & slot_mask;
+          }
+        }
+        __stcs(ds_idx_out + i, d);
+        if (d != -2 && (hb[k] & 15u) < 14u) {  // in the snapshot (the host marks a pending-unscheduled pod with code 14)
+          const unsigned long long v = inc[hb[k]];
+          lo += (uint32_t)v;
+          hi += (uint32_t)(v >> 32);
+        } else {
+          excluded++;
+        }
+        if ((++pending & 7) == 0) widen(lo, hi, B);
+      }
+      // per-DaemonSet owned-pod counts (before the pending-skip, upgrade_state.go:128). A handful of DaemonSets
+      // (the usual case): eight byte counters packed in a register, flushed with the other counters; otherwise
+      // one atomic per distinct DaemonSet per warp
+      if (n_ds <= 8) {
+        if (d >= 0) dsl += 1ull << (8 * d);
+      } else {
+        const unsigned act = __ballot_sync(kFull, d >= 0);
+        if (d >= 0) {
+          const unsigned peers = __match_any_sync(act, d);
+          if ((t & 31) == __ffs(peers) - 1) {
+            if (in_smem) atomicAdd(&cnt_ds[d], (unsigned)__popc(peers));
+            else atomicAdd(&ds_count[d], (unsigned long long)__popc(peers));
+          }
+        }
+      }
+    }
+    if (pending >= 240) spill();
+  }
+  spill();
+  __syncthreads();
+  // fields 0..13 per state code, 14 unavailable, 15 candidates -> ws->acc[0..13], [16], [17]
+  for (int o = 16; o > 0; o >>= 1) excluded += __shfl_xor_sync(kFull, excluded, o);
+  if ((t & 31) == 0 && excluded) atomicAdd(&ws->acc[UST_STATE_EXCLUDED], (unsigned long long)excluded);
+  if (t < 14) { if (cnt[t]) atomicAdd(&ws->acc[t], (unsigned long long)cnt[t]); }
+  else if (t == 14) { if (cnt[14]) atomicAdd(&ws->acc[16], (unsigned long long)cnt[14]); }
+  else if (t == 15) { if (cnt[15]) atomicAdd(&ws->acc[17], (unsigned long long)cnt[15]); }
+  if (in_smem)
+    for (int i = t; i < n_ds; i += kThreads)
+      if (cnt_ds[i]) atomicAdd(&ds_count[i], (unsigned long long)cnt_ds[i]);
+}
+
 __global__ void ust_build_state_finish_kernel(int n_ds, const int32_t* ds_desired, unsigned long long* ds_count,
                                               UstWorkspace* ws, ust_counters* out) {
   ust_counters c;
@@ -1479,6 +1614,15 @@ int ust_launch_pod_summary(long long n, int active, const uint8_t* hot, const in
 int ust_launch_build_state(long long n, const uint8_t* hot, const int32_t* ds_idx, int n_ds, const int32_t* ds_desired,
                            unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream) {
   ust_build_state_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, hot, ds_idx, n_ds, ds_count, ws);
+  ust_build_state_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_ds, ds_desired, ds_count, ws, out);
+  return (int)cudaGetLastError();
+}
+int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* owner_uid, int n_ds, const void* ds_tab,
+                                const int32_t* ds_tab_idx, int tab_slots, const int32_t* ds_desired, int32_t* ds_idx_out,
+                                unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream) {
+  ust_build_state_uid_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+      n, hot, reinterpret_cast<const ulonglong2*>(owner_uid), n_ds, reinterpret_cast<const ulonglong2*>(ds_tab), ds_tab_idx,
+      tab_slots, ds_idx_out, ds_count, ws);
   ust_build_state_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_ds, ds_desired, ds_count, ws, out);
   return (int)cudaGetLastError();
 }

@@ -43,6 +43,8 @@ def load():
         lib.ust_apply_state.argtypes = apply_args
         lib.ust_apply_state_device.argtypes = apply_args + [C.c_void_p]
         lib.ust_build_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.ust_build_state_uids.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]
         lib.ust_get_unique_id.argtypes = [C.c_void_p]
         lib.ust_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.ust_comm_set_mode.argtypes = [C.c_void_p, C.c_int]
@@ -55,7 +57,7 @@ def load():
 
 EXPORTS = ["ust_abi_version", "ust_create", "ust_destroy", "ust_last_error", "ust_create_error", "ust_launch_count",
            "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_sync",
-           "ust_build_state", "ust_get_unique_id", "ust_comm_init", "ust_comm_set_mode", "ust_table_entry",
+           "ust_build_state", "ust_build_state_uids", "ust_get_unique_id", "ust_comm_init", "ust_comm_set_mode", "ust_table_entry",
            "ust_table_window_shift"]
 
 
@@ -166,6 +168,19 @@ class Handle:
         rc = self._lib.ust_build_state(self._h, int(state.shape[0]), _p(state), _p(ds_idx), int(ds_desired.shape[0]),
                                        _p(ds_desired), C.addressof(cnt))
         return rc, cnt.as_dict()
+
+    def build_state_uids(self, state, owner_uid, ds_uid, ds_desired):
+        """BuildState with the owner join on the device: owner_uid (n, 2) uint64, ds_uid (n_ds, 2) uint64.
+        Returns (rc, ds_idx per pod, counters-dict)."""
+        n = int(state.shape[0])
+        owner_uid = np.ascontiguousarray(owner_uid, dtype=np.uint64).reshape(n, 2)
+        ds_uid = np.ascontiguousarray(ds_uid, dtype=np.uint64).reshape(-1, 2)
+        ds_desired = np.ascontiguousarray(ds_desired, dtype=np.int32)
+        ds_idx = np.full(n, -3, np.int32)
+        cnt = abi.Counters()
+        rc = self._lib.ust_build_state_uids(self._h, n, _p(state), _p(owner_uid), int(ds_uid.shape[0]), _p(ds_uid),
+                                            _p(ds_desired), _p(ds_idx), C.addressof(cnt))
+        return rc, ds_idx, cnt.as_dict()
 
     def comm_init(self, rank, world, unique_id_bytes):
         buf = (C.c_char * abi.UST_UNIQUE_ID_BYTES).from_buffer_copy(unique_id_bytes) if unique_id_bytes else None

@@ -27,6 +27,7 @@
 #include <memory>
 #include <string>
 #include <unordered_map>
+#include <map>
 #include <vector>
 
 #include "../include/ust.h"
@@ -1219,6 +1220,55 @@ int ust_oracle_build_state(int64_t n_pods, const uint8_t* state, const int32_t* 
     if (d >= 0 && d < n_ds) owned[(size_t)d]++;  // GetPodsOwnedbyDs  common_manager.go:190-208
     unsigned code = state[i] & 15u;
     if (code == 15) code = 14;
+    c.hist[code]++;
+    if (code < 14 && (state[i] & (UST_HOT_UNSCHEDULABLE | UST_HOT_NOT_READY))) c.unavailable++;
+    if (code == 1 && !(state[i] & UST_HOT_SKIP)) c.candidates++;
+  }
+  c.total_managed = c.hist[0] + c.hist[1] + c.hist[2] + c.hist[3] + c.hist[4] + c.hist[5] + c.hist[8] + c.hist[9] +
+                    c.hist[10] + c.hist[11] + c.hist[12];
+  c.in_progress = c.total_managed - c.hist[0] - c.hist[11] - c.hist[1];
+  int rc = UST_OK;
+  for (int32_t d = 0; d < n_ds; d++)
+    if ((int64_t)ds_desired[d] != owned[(size_t)d]) { rc = UST_ERR_DS_UNSCHEDULED; c.error_code = rc; c.error_index = d; break; }
+  if (out) *out = c;
+  return rc;
+}
+
+// BuildState with the owner join restated at UID level (upgrade_state.go:99-164, common_manager.go:168-227):
+//   daemonSets := map[UID]*DaemonSet                      GetDriverDaemonSets        common_manager.go:168-187
+//   for each DaemonSet: dsPods = pods whose OwnerReferences[0].UID == ds.UID (orphans skipped)   :190-208
+//       len(dsPods) != DesiredNumberScheduled -> error                                upgrade_state.go:128-131
+//   + GetOrphanedPods: pods with no owner reference                                   common_manager.go:211-222
+//   a pod owned by anything else is in neither list: not part of the snapshot.
+// owner_uid: two uint64 per pod, (0, 0) = no owner reference. ds_idx_out: owning DaemonSet, -1 orphan, -2 dropped.
+// Go's map iteration order is random; the error is the same whichever DaemonSet trips it - error_index reports the
+// lowest index, like the device path.
+int ust_oracle_build_state_uids(int64_t n_pods, const uint8_t* state, const uint64_t* owner_uid, int32_t n_ds,
+                                const uint64_t* ds_uid, const int32_t* ds_desired, int32_t* ds_idx_out, ust_counters* out) {
+  typedef std::pair<uint64_t, uint64_t> UID;
+  std::map<UID, int32_t> daemonSets;
+  for (int32_t d = 0; d < n_ds; d++) {
+    const UID u(ds_uid[2 * d], ds_uid[2 * d + 1]);
+    if ((u.first | u.second) == 0 || daemonSets.count(u)) return UST_ERR_INVALID_ARGUMENT;
+    daemonSets[u] = d;
+  }
+  std::vector<int64_t> owned((size_t)std::max(n_ds, 0), 0);
+  ust_counters c;
+  std::memset(&c, 0, sizeof(c));
+  c.error_index = -1;
+  c.error_pass = -1;
+  for (int64_t i = 0; i < n_pods; i++) {
+    const UID u(owner_uid[2 * i], owner_uid[2 * i + 1]);
+    int32_t d;
+    if ((u.first | u.second) == 0) d = -1;                    // IsOrphanedPod
+    else {
+      std::map<UID, int32_t>::const_iterator it = daemonSets.find(u);
+      d = it == daemonSets.end() ? -2 : it->second;           // not owned by a driver DaemonSet: dropped
+    }
+    if (ds_idx_out) ds_idx_out[i] = d;
+    if (d >= 0) owned[(size_t)d]++;
+    unsigned code = state[i] & 15u;
+    if (code == 15 || d == -2) code = 14;
     c.hist[code]++;
     if (code < 14 && (state[i] & (UST_HOT_UNSCHEDULABLE | UST_HOT_NOT_READY))) c.unavailable++;
     if (code == 1 && !(state[i] & UST_HOT_SKIP)) c.candidates++;

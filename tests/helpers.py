@@ -31,6 +31,7 @@ def oracle():
         lib.ust_oracle_time_apply_state.restype = C.c_double
         lib.ust_oracle_scaled_value.restype = C.c_int
         lib.ust_oracle_build_state.restype = C.c_int
+        lib.ust_oracle_build_state_uids.restype = C.c_int
         _oracle = lib
     return _oracle
 
@@ -337,3 +338,36 @@ def random_policy(rng, force_auto=True):
         use_maintenance_operator=rng.random() < 0.3,
         evaluate_actuators=rng.random() < 0.7,
     )
+
+
+def oracle_build_state_uids(state, owner_uid, ds_uid, ds_desired):
+    """Reference-shaped BuildState with the owner join at UID level. Returns (rc, ds_idx, counters-dict)."""
+    n = int(state.shape[0])
+    owner_uid = np.ascontiguousarray(owner_uid, dtype=np.uint64).reshape(n, 2)
+    ds_uid = np.ascontiguousarray(ds_uid, dtype=np.uint64).reshape(-1, 2)
+    ds_desired = np.ascontiguousarray(ds_desired, dtype=np.int32)
+    ds_idx = np.full(n, -3, np.int32)
+    cnt = abi.Counters()
+    rc = oracle().ust_oracle_build_state_uids(
+        C.c_int64(n), _ptr(state), _ptr(owner_uid), C.c_int32(int(ds_uid.shape[0])), _ptr(ds_uid), _ptr(ds_desired),
+        _ptr(ds_idx), C.byref(cnt))
+    return rc, ds_idx, cnt.as_dict()
+
+
+def uid_inputs_from_vector(b, rng):
+    """BuildState golden vector -> UID-level inputs: every DaemonSet gets a random 128-bit UID, a pod carries its
+    owner's UID ((0, 0) when the vector says it has no owner reference)."""
+    pods = b["pods"]
+    n = len(pods)
+    ds_uid = rng.integers(1, 2 ** 63, size=(len(b["daemonsets"]), 2), dtype=np.uint64)
+    state = np.zeros(n, np.uint8)
+    owner = np.zeros((n, 2), np.uint64)
+    for i, p in enumerate(pods):
+        code = abi.STATE_CODE.get(p["node_state"], abi.UST_STATE_OTHER)
+        if p["node_name"] == "" and p["phase"] == "Pending":  # upgrade_state.go:149-152
+            code = abi.UST_STATE_EXCLUDED
+        state[i] = code
+        if p["ds"] is not None:
+            owner[i] = ds_uid[p["ds"]]
+    desired = np.array([d["desired"] for d in b["daemonsets"]], np.int32)
+    return state, owner, ds_uid, desired

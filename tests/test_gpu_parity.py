@@ -79,6 +79,49 @@ def test_build_state_vector(handle, b):
     assert cnt == ocnt.as_dict()
 
 
+@pytest.mark.parametrize("b", G["build_state"], ids=lambda b: b["name"][:40])
+def test_build_state_vector_uid_join(handle, b):
+    """The same specs with the owner join done on the device from 128-bit owner UIDs."""
+    state, owner, ds_uid, desired = helpers.uid_inputs_from_vector(b, np.random.default_rng(11))
+    rc, ds_idx, cnt = handle.build_state_uids(state, owner, ds_uid, desired)
+    orc, ods, ocnt = helpers.oracle_build_state_uids(state, owner, ds_uid, desired)
+    assert rc == orc and cnt == ocnt and np.array_equal(ds_idx, ods)
+    if b["expect_error"]:
+        assert rc == abi.K["UST_ERR_" + b["expect_error"]]
+    else:
+        assert rc == 0
+        assert {abi.STATE_NAMES[c]: cnt["hist"][c] for c in range(13) if cnt["hist"][c]} == b["expect_buckets"]
+
+
+@pytest.mark.parametrize("n,n_ds", [(1, 1), (257, 2), (70_001, 7), (1_000_003, 4), (300_000, 1024), (200_000, 3000)])
+def test_build_state_uid_join_random(handle, n, n_ds):
+    """Owned / orphaned / foreign-owned driver pods in random order, few and many DaemonSets (shared-memory table and
+    the global-memory fallback), with and without a DaemonSet that misses pods (upgrade_state.go:128-131)."""
+    rng = np.random.default_rng(n + n_ds)
+    ds_uid = rng.integers(1, 2 ** 63, size=(n_ds, 2), dtype=np.uint64)
+    kind = rng.random(n)
+    truth = np.where(kind < 0.05, -1, np.where(kind < 0.12, -2, rng.integers(0, n_ds, n))).astype(np.int32)
+    owner = np.zeros((n, 2), np.uint64)
+    owner[truth >= 0] = ds_uid[truth[truth >= 0]]
+    foreign = truth == -2
+    owner[foreign] = rng.integers(2 ** 63, 2 ** 64 - 1, size=(int(foreign.sum()), 2), dtype=np.uint64)
+    # near misses: same first half as a real DaemonSet, different second half
+    nm = np.flatnonzero(foreign)[::3]
+    owner[nm, 0] = ds_uid[rng.integers(0, n_ds, nm.shape[0]), 0]
+    state = (rng.integers(0, 16, n).astype(np.uint8) | (rng.integers(0, 16, n).astype(np.uint8) << 4)).astype(np.uint8)
+    for miss in (False, True):
+        desired = np.bincount(truth[truth >= 0], minlength=n_ds).astype(np.int32)
+        if miss:
+            desired[n_ds // 2] += 1
+        rc, ds_idx, cnt = handle.build_state_uids(state, owner, ds_uid, desired)
+        orc, ods, ocnt = helpers.oracle_build_state_uids(state, owner, ds_uid, desired)
+        assert rc == orc == (abi.K["UST_ERR_DS_UNSCHEDULED"] if miss else 0)
+        assert np.array_equal(ds_idx, ods) and np.array_equal(ds_idx, truth)
+        assert cnt == ocnt
+    dup = np.concatenate([ds_uid[:1], ds_uid[:1]])
+    assert handle.build_state_uids(state[:1], owner[:1], dup, np.zeros(2, np.int32))[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]
+
+
 # ---- random snapshots: every flag bit, abort paths, requestor mode, pod lists ------------------------
 
 SIZES = [0, 1, 3, 4, 5, 127, 128, 129, 1023, 1024, 1025, 4095, 4096, 4097, 8191, 8192, 20_000, 70_001, 300_000]
