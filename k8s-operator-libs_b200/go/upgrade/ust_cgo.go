@@ -20,6 +20,7 @@ import (
 	"fmt"
 	"unsafe"
 
+	appsv1 "k8s.io/api/apps/v1"
 	corev1 "k8s.io/api/core/v1"
 
 	"github.com/NVIDIA/k8s-operator-libs/api/upgrade/v1alpha1"
@@ -240,3 +241,81 @@ func (m *ClusterUpgradeStateManagerImpl) ApplyStateAccelerated(ctx context.Conte
 }
 
 func encodeIntOrPercent(interface{}) (C.int32_t, C.int64_t) { return C.UST_MAXUNAVAIL_NIL, 0 }
+
+// uid128 parses a Kubernetes UID (a UUID string, "xxxxxxxx-xxxx-xxxx-xxxx-xxxxxxxxxxxx") into the two uint64 the
+// ABI joins on; anything that is not 32 hex digits is hashed (FNV-1a) into the same space. (0, 0) is reserved for
+// "no owner reference".
+func uid128(uid string) (hi, lo uint64) {
+	n := 0
+	for i := 0; i < len(uid); i++ {
+		c := uid[i]
+		var v uint64
+		switch {
+		case c >= '0' && c <= '9':
+			v = uint64(c - '0')
+		case c >= 'a' && c <= 'f':
+			v = uint64(c-'a') + 10
+		case c >= 'A' && c <= 'F':
+			v = uint64(c-'A') + 10
+		case c == '-':
+			continue
+		default:
+			n = -1
+		}
+		if n < 0 || n >= 32 {
+			n = -1
+			break
+		}
+		if n < 16 {
+			hi = hi<<4 | v
+		} else {
+			lo = lo<<4 | v
+		}
+		n++
+	}
+	if n != 32 {
+		hi, lo = 14695981039346656037, 1099511628211
+		for i := 0; i < len(uid); i++ {
+			hi = (hi ^ uint64(uid[i])) * 1099511628211
+			lo = (lo ^ hi) * 14029467366897019727
+		}
+	}
+	if hi|lo == 0 {
+		lo = 1
+	}
+	return hi, lo
+}
+
+// BuildStateAccelerated is the device half of BuildState (upgrade_state.go:99-164): it takes the two API lists
+// BuildState already fetched (driver DaemonSets, driver pods) and returns, per pod, the index of the owning
+// DaemonSet (-1 orphaned, -2 not a driver pod: dropped), after checking every DaemonSet's pod count against
+// DesiredNumberScheduled (upgrade_state.go:128-131). buildNodeUpgradeState (the per-node API Get, :354-378) stays
+// in Go and runs for the pods with index >= -1 that are not pending-unscheduled (:149-152).
+func (m *ClusterUpgradeStateManagerImpl) BuildStateAccelerated(acc *Accelerator, daemonSets []*appsv1.DaemonSet,
+	pods []corev1.Pod, stateCode func(*corev1.Pod) C.uint8_t) ([]int32, C.ust_counters, error) {
+	n := len(pods)
+	state := make([]C.uint8_t, n+1)
+	owner := make([]C.uint64_t, 2*n+2)
+	for i := range pods {
+		state[i] = stateCode(&pods[i]) // node's upgrade-state label; UST_STATE_EXCLUDED for NodeName=="" && Pending
+		if len(pods[i].OwnerReferences) > 0 { // IsOrphanedPod, common_manager.go:225-227
+			hi, lo := uid128(string(pods[i].OwnerReferences[0].UID))
+			owner[2*i], owner[2*i+1] = C.uint64_t(hi), C.uint64_t(lo)
+		}
+	}
+	dsUID := make([]C.uint64_t, 2*len(daemonSets)+2)
+	desired := make([]C.int32_t, len(daemonSets)+1)
+	for d, ds := range daemonSets {
+		hi, lo := uid128(string(ds.UID))
+		dsUID[2*d], dsUID[2*d+1] = C.uint64_t(hi), C.uint64_t(lo)
+		desired[d] = C.int32_t(ds.Status.DesiredNumberScheduled)
+	}
+	idx := make([]int32, n+1)
+	var cnt C.ust_counters
+	rc := C.ust_build_state_uids(acc.h, C.int64_t(n), &state[0], &owner[0], C.int32_t(len(daemonSets)), &dsUID[0],
+		&desired[0], (*C.int32_t)(unsafe.Pointer(&idx[0])), &cnt)
+	if rc != C.UST_OK {
+		return nil, cnt, fmt.Errorf("%s", C.GoString(C.ust_last_error(acc.h))) // "driver DaemonSet should not have Unscheduled pods"
+	}
+	return idx[:n], cnt, nil
+}
