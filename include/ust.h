@@ -257,7 +257,8 @@ int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const i
  * (the keys of GetDriverDaemonSets' map, so they must be distinct - UST_ERR_INVALID_ARGUMENT otherwise).
  * ds_idx_out[i] receives the index of the owning DaemonSet, -1 for an orphaned pod, -2 for a pod owned by
  * something else: GetPodsOwnedbyDs skips it and GetOrphanedPods does not take it, so it is not part of the
- * snapshot and not counted in any bucket. Everything else as ust_build_state. owner_uid must be 16-byte aligned. */
+ * snapshot and not counted in any bucket (it shows up in hist[14], "not in snapshot"). Everything else as
+ * ust_build_state; host arrays, no alignment requirement. */
 int ust_build_state_uids(ust_handle* h, int64_t n_pods, const uint8_t* state, const uint64_t* owner_uid,
                          int32_t n_ds, const uint64_t* ds_uid, const int32_t* ds_desired, int32_t* ds_idx_out,
                          ust_counters* out);
