@@ -193,6 +193,34 @@ def test_pipelined_host_path(handle, seed):
     helpers.assert_same(got, ref, f"pipelined seed={seed}")
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_long_and_empty_pod_lists(handle, seed):
+    """Pod lists of every shape the list walker distinguishes: empty, shorter than one 16-byte chunk, unaligned
+    starts, more than one pass (> 48 pods), and the last list ending exactly at the end of the array."""
+    rng = np.random.default_rng(900 + seed)
+    n = (4096 * 3 + 17, 60_001, 4096)[seed]
+    soa, _ = helpers.random_soa(rng, n, with_pods=False, wild=bool(seed))
+    shape = rng.random(n)
+    cnt = np.where(shape < 0.3, 0, np.where(shape < 0.7, rng.integers(1, 9, n), np.where(shape < 0.95, rng.integers(9, 49, n),
+                                                                                         rng.integers(49, 300, n))))
+    if seed == 2:
+        cnt[-1] = 0   # ... and an empty list at the very end
+    off = np.zeros(n + 1, np.int32)
+    np.cumsum(cnt, out=off[1:])
+    total = int(off[-1])
+    pf = rng.integers(0, 6, size=total).astype(np.uint16)
+    for k, v in abi.K.items():
+        if k.startswith("UST_POD_") and k != "UST_POD_PHASE_MASK":
+            pf |= np.where(rng.random(total) < 0.08, np.uint16(v), np.uint16(0))   # sparse: long lists are not all-ones
+    pods = {"pod_off": off, "pod_flags": pf}
+    for rep in range(3):
+        pol = helpers.random_policy(rng)
+        pol.evaluate_actuators = 1
+        got = gpu_apply(handle, pol, soa, pods)
+        ref = helpers.oracle_apply(pol, soa, pods, variant=0)
+        helpers.assert_same(got, ref, f"seed={seed} rep={rep}")
+
+
 def test_many_daemonsets_use_the_global_table(handle):
     rng = np.random.default_rng(99)
     n, n_ds = 50_000, 3000  # > UST_DS_SMEM_MAX
