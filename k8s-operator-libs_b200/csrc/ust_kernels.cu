@@ -843,7 +843,6 @@ __device__ long long stream_loop(const UstParams& P, Shared& S) {
 // Streaming phase of one CTA.
 __device__ void stream_phase(const UstParams& P, Shared& S) {
   const int t = threadIdx.x;
-  const int n_chunks = P.grid_chunks;
   UstWorkspace* ws = P.ws;
   long long nodes_seen = 0;
   const int variant = (P.n_ds <= UST_DS_SMEM_MAX ? 4 : 0) | (P.outcome ? 2 : 0) | (P.podsum ? 1 : 0);
