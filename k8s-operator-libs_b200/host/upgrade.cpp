@@ -147,6 +147,27 @@ int ClusterUpgradeStateManagerImpl::GetUpgradesAvailable(const ClusterUpgradeSta
   return available;
 }
 
+// A Kubernetes UID (UUID string) as the two uint64 the ABI joins on: 32 hex digits are taken literally, anything else
+// is hashed (FNV-1a) into the same space; (0, 0) is reserved for "no owner reference". Same rule as the Go shim.
+struct Uid128 { uint64_t hi, lo; };
+static Uid128 uid128(const std::string& uid) {
+  Uid128 u{0, 0};
+  int n = 0;
+  for (char ch : uid) {
+    if (ch == '-') continue;
+    int v = (ch >= '0' && ch <= '9') ? ch - '0' : (ch >= 'a' && ch <= 'f') ? ch - 'a' + 10 : (ch >= 'A' && ch <= 'F') ? ch - 'A' + 10 : -1;
+    if (v < 0 || n >= 32) { n = -1; break; }
+    if (n < 16) u.hi = (u.hi << 4) | (uint64_t)v; else u.lo = (u.lo << 4) | (uint64_t)v;
+    n++;
+  }
+  if (n != 32) {
+    u.hi = 14695981039346656037ull; u.lo = 1099511628211ull;
+    for (unsigned char ch : uid) { u.hi = (u.hi ^ ch) * 1099511628211ull; u.lo = (u.lo ^ u.hi) * 14029467366897019727ull; }
+  }
+  if ((u.hi | u.lo) == 0) u.lo = 1;
+  return u;
+}
+
 // ---- BuildState (upgrade_state.go:99-164) --------------------------------------------------------------------
 Error ClusterUpgradeStateManagerImpl::BuildState(const std::string& ns, const StringMap& driverLabels,
                                                  std::unique_ptr<ClusterUpgradeState>* out) {
@@ -158,30 +179,49 @@ Error ClusterUpgradeStateManagerImpl::BuildState(const std::string& ns, const St
   std::vector<Pod*> podList;
   if (Error e = K8sClient->ListPods(ns, driverLabels, &podList)) return e;
 
-  // owner join on the host (string UIDs); the per-DaemonSet count check and the bucket sizes run on the GPU
-  std::map<std::string, int> dsIndex;
+  // The owner join runs on the GPU (ust_build_state_uids): every listed pod goes in with the 128-bit form of its
+  // OwnerReferences[0].UID, the DaemonSets with theirs; back comes, per pod, the owning DaemonSet's index, -1 for an
+  // orphaned pod, -2 for a pod owned by something else (dropped: GetPodsOwnedbyDs skips it, GetOrphanedPods does
+  // not take it - common_manager.go:190-222), after the per-DaemonSet count check of upgrade_state.go:128-131.
+  std::vector<DaemonSet*> dsByIndex;
+  std::vector<uint64_t> dsUid;
   std::vector<int32_t> desired;
-  for (const auto& kv : daemonSets) { dsIndex[kv.first] = (int)desired.size(); desired.push_back(kv.second->DesiredNumberScheduled); }
-  std::vector<Pod*> filtered;
-  for (const auto& kv : daemonSets)  // GetPodsOwnedbyDs  common_manager.go:190-208
-    for (Pod* p : podList)
-      if (!IsOrphanedPod(*p) && p->OwnerReferences[0].UID == kv.first) filtered.push_back(p);
-  for (Pod* p : podList)
-    if (IsOrphanedPod(*p)) filtered.push_back(p);  // GetOrphanedPods  common_manager.go:211-221
-
-  std::vector<Node*> nodes(filtered.size(), nullptr);
-  std::vector<uint8_t> state(filtered.size() + 1);
-  std::vector<int32_t> ds_idx(filtered.size() + 1);
-  for (size_t i = 0; i < filtered.size(); i++) {
-    Pod* pod = filtered[i];
-    ds_idx[i] = IsOrphanedPod(*pod) ? -1 : dsIndex[pod->OwnerReferences[0].UID];
-    if (pod->NodeName.empty() && pod->Phase == "Pending") { state[i] = UST_STATE_EXCLUDED; continue; }  // upgrade_state.go:149-152
-    state[i] = UST_STATE_OTHER;  // label resolved below; the count check does not depend on it
+  for (const auto& kv : daemonSets) {
+    const Uid128 u = uid128(kv.first);
+    dsByIndex.push_back(kv.second);
+    dsUid.push_back(u.hi); dsUid.push_back(u.lo);
+    desired.push_back(kv.second->DesiredNumberScheduled);
   }
+  const size_t np = podList.size();
+  std::vector<uint8_t> podState(np + 1);
+  std::vector<uint64_t> owner(2 * np + 2, 0);
+  std::vector<int32_t> owner_idx(np + 1, -2);
+  for (size_t i = 0; i < np; i++) {
+    Pod* pod = podList[i];
+    // upgrade_state.go:149-152: a pod not yet scheduled to a node is skipped - after the count check
+    podState[i] = (pod->NodeName.empty() && pod->Phase == "Pending") ? UST_STATE_EXCLUDED : UST_STATE_OTHER;
+    if (!IsOrphanedPod(*pod)) {
+      const Uid128 u = uid128(pod->OwnerReferences[0].UID);
+      owner[2 * i] = u.hi; owner[2 * i + 1] = u.lo;
+    }
+  }
+  dsUid.resize(dsUid.size() + 2); desired.push_back(0);  // never pass empty vectors' data()
   ust_counters c;
-  int rc = ust_build_state(handle_, (int64_t)filtered.size(), state.data(), ds_idx.data(), (int32_t)desired.size(), desired.data(), &c);
+  int rc = ust_build_state_uids(handle_, (int64_t)np, podState.data(), owner.data(), (int32_t)dsByIndex.size(), dsUid.data(),
+                                desired.data(), owner_idx.data(), &c);
   if (rc == UST_ERR_DS_UNSCHEDULED) return Errorf("driver DaemonSet should not have Unscheduled pods");  // upgrade_state.go:128-131
   if (rc != UST_OK) return Errorf(ust_last_error(handle_));
+
+  // filteredPodList in the reference's order: DaemonSet by DaemonSet (map order), then the orphans (:126-136)
+  std::vector<Pod*> filtered;
+  std::vector<uint8_t> state;
+  std::vector<std::vector<size_t>> byOwner(dsByIndex.size() + 1);  // last bucket: orphans
+  for (size_t i = 0; i < np; i++) {
+    if (owner_idx[i] >= 0) byOwner[(size_t)owner_idx[i]].push_back(i);
+    else if (owner_idx[i] == -1) byOwner.back().push_back(i);
+  }
+  for (const auto& bucket : byOwner)
+    for (size_t i : bucket) { filtered.push_back(podList[i]); state.push_back(podState[i]); }
 
   auto st = std::make_unique<ClusterUpgradeState>();
   const std::string labelKey = GetUpgradeStateLabelKey();

@@ -36,8 +36,11 @@ int main() {
     Pod a; a.Name = "a"; a.NodeName = "node1"; a.Phase = "Running"; a.OwnerReferences = {{"DaemonSet", "ds", "uid-1"}};
     Pod b; b.Name = "b"; b.NodeName = ""; b.Phase = "Pending"; b.OwnerReferences = {{"DaemonSet", "ds", "uid-1"}};
     Pod c; c.Name = "c"; c.NodeName = "node2"; c.Phase = "Running";  // orphan
+    // a pod with the driver labels but owned by something that is not a driver DaemonSet: neither GetPodsOwnedbyDs nor
+    // GetOrphanedPods keeps it (common_manager.go:190-222)
+    Pod d; d.Name = "d"; d.NodeName = "node1"; d.Phase = "Running"; d.OwnerReferences = {{"ReplicaSet", "rs", "3f0e7c1a-9a57-4c55-8f2b-0d6c3f5b7e11"}};
     k8s.daemonSets = {&ds};
-    k8s.pods = {&a, &b, &c};
+    k8s.pods = {&a, &b, &c, &d};
     std::unique_ptr<ClusterUpgradeState> st;
     EXPECT(R, !e.m->BuildState("ns", {}, &st).has_value());
     EXPECT(R, st && st->NodeStates[""].size() == 1 && st->NodeStates[UpgradeStateDone].size() == 1);
