@@ -309,11 +309,20 @@ __device__ __forceinline__ void pack4(const uint32_t e[4], uint32_t& next4, uint
 
 // One tile = kUnroll steps of kStep nodes; thread t owns nodes base + j*kStep + 4t .. +3. `lim` is a
 // multiple of 128 (or the tile is full), so validity is uniform per warp and per j.
-struct Tile {
-  uint32_t h[kUnroll];
-  uint32_t ps[kUnroll];  // pod-list summaries (one byte per node), PODS variants only
-  uint4 f[kUnroll], r[kUnroll], d[kUnroll];
+template <int U>
+struct TileT {
+  uint32_t h[U];
+  uint32_t ps[U];  // pod-list summaries (one byte per node), PODS variants only
+  uint4 f[U], r[U], d[U];
 };
+// The streaming fast path keeps kUnroll steps in flight per thread; the redo variants after the barrier keep
+// kColdUnroll: with a four-step tile the compiler parks their tile on the stack (STL/LDL in the tile loop, seen with
+// nvdisasm), with a smaller one most of it stays in registers. Measured (profiles/README.md): 1 / 2 / 4 steps ->
+// hinted redo 49.0 / 49.7 / 51.5 us, unhinted 81 / 77 / 78 us.
+#ifndef UST_COLD_UNROLL
+#define UST_COLD_UNROLL 2
+#endif
+constexpr int kColdUnroll = UST_COLD_UNROLL;
 
 // Chunk-relative addressing: the chunk's base pointers are CTA-uniform; a thread addresses 4-node groups
 // with a 32-bit group index q (thread t of the CTA owns groups done/4 + j*kStepQ + t of a tile).
@@ -344,15 +353,16 @@ __device__ __forceinline__ Cursor cursor_at(const UstParams& P, long long base) 
   c.q = threadIdx.x;
   return c;
 }
-__device__ __forceinline__ void cursor_advance(Cursor& c) { c.q += kTileQ; }
+template <int U>
+__device__ __forceinline__ void cursor_advance(Cursor& c) { c.q += U * kStepQ; }
 
 // `room` = nodes left in the chunk from this thread's first node of the tile; chunk ends are multiples of
 // 128 nodes, so for a partial tile validity is uniform per warp and per step.
 // PODS: 0 = the call has no pod lists, 1 = it has, 2 = decided at run time (out-of-line variants)
-template <bool FULL, int PODS>
-__device__ __forceinline__ void tile_load(const Cursor& c, int room, Tile& T) {
+template <bool FULL, int PODS, int U>
+__device__ __forceinline__ void tile_load(const Cursor& c, int room, TileT<U>& T) {
 #pragma unroll
-  for (int j = 0; j < kUnroll; j++) {
+  for (int j = 0; j < U; j++) {
     // every element is assigned on every path, so that the tile stays in registers (no stack copy)
     const bool valid = FULL || j * kStep + 4 <= room;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -439,12 +449,12 @@ struct ExactCtx {
 // COUNT adds the byte-sliced counting, EXACT replaces the chunk-uniform slot grant by the ordered one: a
 // candidate's rank in slice order = candidates before its step (S.step_base) + before its warp within the step
 // (S.wtot) + a warp-shuffle exclusive scan — no block barrier in the loop (upgrade_inplace.go:71-109).
-template <bool FULL, bool DS_SMEM, bool OUTCOME, bool COUNT, bool EXACT, int PODS>
+template <bool FULL, bool DS_SMEM, bool OUTCOME, bool COUNT, bool EXACT, int PODS, int U>
 __device__ __forceinline__ void spec_tile(const UstParams& P, Shared& S, const Cursor& c, int room, long long i0,
-                                          const Tile& T, uint32_t grant, uint32_t (&B)[4], ExactCtx ex) {
+                                          const TileT<U>& T, uint32_t grant, uint32_t (&B)[4], ExactCtx ex) {
   uint32_t lo = 0, hi = 0;
 #pragma unroll
-  for (int j = 0; j < kUnroll; j++) {
+  for (int j = 0; j < U; j++) {
     if (FULL || j * kStep + 4 <= room) {
       const uint32_t x = T.h[j];
       if (COUNT && (x & 0x80808080u)) {  // rare
@@ -503,7 +513,7 @@ __device__ __forceinline__ void spec_tile(const UstParams& P, Shared& S, const C
     }
     if (COUNT && (j & 1)) widen(lo, hi, B);  // at most 8 per nibble so far
   }
-  if (COUNT && (kUnroll & 1)) widen(lo, hi, B);
+  if (COUNT && (U & 1)) widen(lo, hi, B);
 }
 
 // Pre-pass of the ordered path over one block of steps [blk0, blk1): hot bytes only (they are L2-resident or
@@ -572,12 +582,13 @@ __device__ unsigned exact_prepass(const UstParams& P, Shared& S, long long blk0,
 // Evaluate the block [blk0, blk1) of a chunk through the 4-deep tile pipeline. ORDERED: `limit` slots are left
 // for the candidates from node `count_from` (<= blk0) on, in slice order (pre-pass + per-node ranks); otherwise
 // the slot grant is uniform (`grant`). Returns the candidates in [count_from, blk1) (ORDERED only).
-template <bool DS_SMEM, bool OUTCOME, bool COUNT, bool ORDERED, int PODS>
+template <bool DS_SMEM, bool OUTCOME, bool COUNT, bool ORDERED, int PODS, int U>
 __device__ __forceinline__ long long spec_block(const UstParams& P, Shared& S, long long blk0, long long blk1, uint32_t grant,
                                                 long long limit, long long count_from, Acc& A, bool wait_for_table) {
   const long long span = blk1 - blk0;  // CTA-uniform, a multiple of 128 (or <= 0 for an empty chunk)
   // the streaming fast path has a specialised body for full tiles; the out-of-line variants keep one (predicated) body
   constexpr bool kFullVariant = COUNT && !ORDERED;
+  constexpr int kTileU = U * kStep;  // nodes per tile
   const int t4 = 4 * threadIdx.x;
   auto room_at = [&](long long done) -> int {  // nodes from this thread's first node of the tile to the block end
     const long long r = span - done - t4;
@@ -585,9 +596,9 @@ __device__ __forceinline__ long long spec_block(const UstParams& P, Shared& S, l
   };
   Cursor c = cursor_at(P, blk0);
   long long i0 = blk0 + t4;
-  Tile T;
+  TileT<U> T;
   auto load = [&](long long done) {  // loads of the tile starting `done` nodes into the block; c.q points at it
-    if (kFullVariant && span - done >= kTile) tile_load<true, PODS>(c, 0, T); else tile_load<false, PODS>(c, room_at(done), T);
+    if (kFullVariant && span - done >= kTileU) tile_load<true, PODS, U>(c, 0, T); else tile_load<false, PODS, U>(c, room_at(done), T);
   };
   if (span > 0) load(0);  // the first tile's loads go out before anything waits (table copy, pre-pass)
   if (wait_for_table) {
@@ -605,15 +616,15 @@ __device__ __forceinline__ long long spec_block(const UstParams& P, Shared& S, l
     ex.limit = limit <= 0 ? 0u : (limit > 0x7FFFFFFFLL ? 0x7FFFFFFFu : (unsigned)limit);
   }
 #pragma unroll 1
-  for (long long done = 0; done < span; done += kTile) {
+  for (long long done = 0; done < span; done += kTileU) {
     if (done) load(done);
     const int room = room_at(done);
     if (ORDERED) ex.s0 = (int)(done / kStep);
-    if (kFullVariant && span - done >= kTile) spec_tile<true, DS_SMEM, OUTCOME, COUNT, ORDERED, PODS>(P, S, c, room, i0, T, grant, A.B, ex);
-    else spec_tile<false, DS_SMEM, OUTCOME, COUNT, ORDERED, PODS>(P, S, c, room, i0, T, grant, A.B, ex);
-    cursor_advance(c);
-    i0 += kTile;
-    if (COUNT && ++A.tiles >= 14) spill_thread(S, A);  // byte lanes: at most 16 per tile, 255 max
+    if (kFullVariant && span - done >= kTileU) spec_tile<true, DS_SMEM, OUTCOME, COUNT, ORDERED, PODS, U>(P, S, c, room, i0, T, grant, A.B, ex);
+    else spec_tile<false, DS_SMEM, OUTCOME, COUNT, ORDERED, PODS, U>(P, S, c, room, i0, T, grant, A.B, ex);
+    cursor_advance<U>(c);
+    i0 += kTileU;
+    if (COUNT && ++A.tiles >= 224 / (4 * U)) spill_thread(S, A);  // byte lanes: at most 4U per tile, 255 max
   }
   return blk_cand;
 }
@@ -622,7 +633,7 @@ __device__ __forceinline__ long long spec_block(const UstParams& P, Shared& S, l
 template <bool DS_SMEM, bool OUTCOME, bool PODS>
 __device__ __forceinline__ void spec_chunk(const UstParams& P, Shared& S, long long b0, long long lim, uint32_t grant, Acc& A,
                                            bool wait_for_table) {
-  spec_block<DS_SMEM, OUTCOME, true, false, PODS ? 1 : 0>(P, S, b0, lim, grant, 0, b0, A, wait_for_table);
+  spec_block<DS_SMEM, OUTCOME, true, false, PODS ? 1 : 0, kUnroll>(P, S, b0, lim, grant, 0, b0, A, wait_for_table);
 }
 
 // The ordered variant lives out of line so that it cannot cost the fast path registers: blocks of
@@ -640,7 +651,7 @@ __device__ __forceinline__ long long ordered_range(const UstParams& P, Shared& S
   long long blk0 = b0;
   do {
     const long long blk1 = blk0 + kBlk < lim ? blk0 + kBlk : lim;
-    seen += spec_block<DS_SMEM, OUTCOME, COUNT, true, 2>(P, S, blk0, blk1, 0u, slots - seen, blk0 == b0 ? count_from : blk0, A,
+    seen += spec_block<DS_SMEM, OUTCOME, COUNT, true, 2, kColdUnroll>(P, S, blk0, blk1, 0u, slots - seen, blk0 == b0 ? count_from : blk0, A,
                                                       wait_for_table);
     wait_for_table = false;
     __syncthreads();  // step_base / wtot are rewritten by the next block's pre-pass
@@ -657,7 +668,7 @@ __device__ __forceinline__ void uniform_range(const UstParams& P, Shared& S, lon
   A.B[0] = A.B[1] = A.B[2] = A.B[3] = 0;
   A.tiles = 0;
   A.cand_spilled = 0;
-  spec_block<DS_SMEM, OUTCOME, false, false, 2>(P, S, b0, lim, grant, 0, b0, A, false);
+  spec_block<DS_SMEM, OUTCOME, false, false, 2, kColdUnroll>(P, S, b0, lim, grant, 0, b0, A, false);
 }
 
 // general path: one step of kStep nodes, bounds-checked; optional exact ordered slot allocation,
