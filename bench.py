@@ -387,7 +387,33 @@ def main():
     e2e_value = world * n * args.e2e_steps / float(te.item())
     assert np.array_equal(out[0], nxt), "e2e result differs from the device-resident result"
 
+    # ---- the same through the delta entry point: the snapshot stays resident, 1 % of the nodes are re-encoded and
+    # re-uploaded per step (a reconcile that watches resourceVersions), the whole snapshot is evaluated, all outputs
+    # come back. Informative only - `e2e` above (full upload every step) is the headline.
+    delta = None
+    if world == 1:
+        rng = np.random.default_rng(7)
+        m = max(1, n // 100)
+        steps_d = max(3, args.e2e_steps)
+        deltas = []
+        for _ in range(steps_d + 1):
+            idx = rng.choice(n, size=m, replace=False).astype(np.int64)
+            src = rng.integers(0, n, size=m)
+            deltas.append((idx, {k: np.ascontiguousarray(soa[k][src]) for k in ("state", "flags", "pod_rev", "ds_idx")}))
+        h.apply_state_delta(pol, n, deltas[0][0], deltas[0][1], soa["ds_rev"], want_outcome=False, out=out)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for idx, ch in deltas[1:]:
+            rc = h.apply_state_delta(pol, n, idx, ch, soa["ds_rev"], want_outcome=False, out=out)[0]
+            assert rc == 0, h.last_error()
+        torch.cuda.synchronize()
+        d_s = time.time() - t0
+        delta = {"value": n * steps_d / d_s, "unit": "nodes/s", "ms_per_step": d_s / steps_d * 1e3, "changed_nodes_per_step": m,
+                 "h2d_bytes_per_step": 21 * m + 4 * n_ds, "d2h_bytes_per_step": 3 * n + C.sizeof(abi.Counters), "steps": steps_d}
+
     if rank == 0:
+        if delta is not None:
+            line["e2e_delta"] = delta
         line["e2e"] = {"value": e2e_value, "unit": "nodes/s", "h2d_bytes_per_step": 13 * n + 4 * n_ds,
                        "d2h_bytes_per_step": 3 * n + C.sizeof(abi.Counters), "steps": args.e2e_steps,
                        "ms_per_step": float(te.item()) / args.e2e_steps * 1e3}

@@ -242,6 +242,18 @@ int ust_apply_state_device(ust_handle* h, const ust_policy* policy, int64_t n_no
                            ust_counters* out_device, void* stream);
 int ust_sync(ust_handle* h);
 
+/* Delta form: a successful ust_apply_state without pod lists leaves the uploaded snapshot resident on
+ * the device. ust_apply_state_delta overwrites the n_changed nodes named by idx (distinct indices into that
+ * snapshot) with freshly encoded values - what a reconcile that watches resourceVersions re-encodes - and evaluates
+ * the whole snapshot again: same outputs and counters as ust_apply_state on the updated arrays, without
+ * re-uploading the unchanged nodes. The DaemonSet table is passed in full (it is small). Returns
+ * UST_ERR_INVALID_ARGUMENT when there is no resident snapshot (first call, a call with pod lists, or
+ * ust_build_state* since, which share the staging memory). */
+int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_changed, const int64_t* idx,
+                          const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx,
+                          int32_t n_ds, const int32_t* ds_rev, uint8_t* next_state, uint16_t* actions,
+                          uint8_t* actuator_outcome, ust_counters* out);
+
 /* ---- BuildState -------------------------------------------------------------------------------- */
 
 /* The device part of BuildState (upgrade_state.go:99-164): per-DaemonSet count of owned driver pods

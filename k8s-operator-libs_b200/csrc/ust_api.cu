@@ -87,6 +87,7 @@ struct ust_handle {
   int64_t launches = 0;
   int ctas_per_sm = 0, num_sms = 0;
   bool ws_dirty = false;
+  int64_t resident_n = -1;  // nodes of the snapshot the last ust_apply_state left in the staging arrays (-1 = none)
   bool no_hint = false;  // UST_NO_HINT=1 (tuning): every call speculates from the policy default, never from the previous call
 
   UstWorkspace* ws = nullptr;
@@ -109,7 +110,11 @@ struct ust_handle {
   DevBuf<uint16_t> s_actions, s_podflags;
   DevBuf<uint8_t> s_podsum;
   DevBuf<uint64_t> s_uid, s_dsuid;   // BuildState owner join: pod owner UIDs, DaemonSet UID hash table (+ s_dsorder: slot -> index)
-  DevBuf<int32_t> s_dsorder;  // per-node pod-list summaries (ust_pod_summary_kernel -> streaming pass)
+  DevBuf<int32_t> s_dsorder;
+  DevBuf<long long> d_idx;           // delta updates: indices and values of the changed nodes
+  DevBuf<uint8_t> d_state;
+  DevBuf<uint32_t> d_flags;
+  DevBuf<int32_t> d_rev, d_ds;  // per-node pod-list summaries (ust_pod_summary_kernel -> streaming pass)
 
   // multi-GPU
   int rank = 0, world = 1, comm_mode = 0;
@@ -495,7 +500,7 @@ void ust_destroy(ust_handle* h) {
   if (h->ds_count_dev) cudaFree(h->ds_count_dev);
   h->s_hot.release(); h->s_next.release(); h->s_outcome.release(); h->s_flags.release();
   h->s_rev.release(); h->s_ds.release(); h->s_dsrev.release(); h->s_podoff.release(); h->s_dsdesired.release();
-  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release();
+  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release(); h->d_idx.release(); h->d_state.release(); h->d_flags.release(); h->d_rev.release(); h->d_ds.release();
   for (auto& ev : h->seg_done) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->seg_up) if (ev) cudaEventDestroy(ev);
   if (h->stream_h2d) cudaStreamDestroy(h->stream_h2d);
@@ -562,8 +567,13 @@ int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const ui
     UST_CUDA(h, h->s_podflags.reserve((size_t)pods->n_pods + 8));
   }
   if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsrev.p, ds_rev, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
+  h->resident_n = -1;
+  auto keep = [&](int rc) {  // the uploaded snapshot stays usable unless the call itself failed (not the policy / the data)
+    if (rc != UST_ERR_CUDA && rc != UST_ERR_INVALID_ARGUMENT && rc != UST_ERR_COMM && rc != UST_ERR_NIL_STATE && !pods) h->resident_n = n;
+    return rc;
+  };
   if (!pods && h->world == 1 && n >= (1 << 19))
-    return apply_pipelined(h, policy, n, state, flags, pod_rev, ds_idx, n_ds, next_state, actions, actuator_outcome, out);
+    return keep(apply_pipelined(h, policy, n, state, flags, pod_rev, ds_idx, n_ds, next_state, actions, actuator_outcome, out));
   if (N) {
     UST_CUDA(h, cudaMemcpyAsync(h->s_hot.p, state, N, cudaMemcpyHostToDevice, st));
     UST_CUDA(h, cudaMemcpyAsync(h->s_flags.p, flags, N * 4, cudaMemcpyHostToDevice, st));
@@ -583,7 +593,54 @@ int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const ui
     UST_CUDA(h, cudaMemcpyAsync(actions, h->s_actions.p, N * 2, cudaMemcpyDeviceToHost, st));
     if (actuator_outcome) UST_CUDA(h, cudaMemcpyAsync(actuator_outcome, h->s_outcome.p, N, cudaMemcpyDeviceToHost, st));
   }
-  return finish_with_counters(h, st, out);
+  return keep(finish_with_counters(h, st, out));
+}
+
+int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_changed, const int64_t* idx, const uint8_t* state,
+                          const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds,
+                          const int32_t* ds_rev, uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome,
+                          ust_counters* out) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  const int64_t n = h->resident_n;
+  if (n < 0) return h->fail(UST_ERR_INVALID_ARGUMENT, "no resident snapshot: call ust_apply_state (without pod lists) first");
+  if (n_changed < 0 || (n_changed > 0 && (!idx || !state || !flags || !pod_rev || !ds_idx)) || (n > 0 && (!next_state || !actions)))
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (n_ds < 0 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table");
+  for (int64_t k = 0; k < n_changed; k++)
+    if (idx[k] < 0 || idx[k] >= n) return h->fail(UST_ERR_INVALID_ARGUMENT, "changed node %lld has index %lld outside the snapshot of %lld nodes", (long long)k, (long long)idx[k], (long long)n);
+  UST_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t N = (size_t)n, M = (size_t)n_changed;
+  UST_CUDA(h, h->s_dsrev.reserve((size_t)n_ds + 1));
+  if (actuator_outcome) UST_CUDA(h, h->s_outcome.reserve(N + 16));
+  UST_CUDA(h, h->d_idx.reserve(M + 1)); UST_CUDA(h, h->d_state.reserve(M + 16)); UST_CUDA(h, h->d_flags.reserve(M + 4));
+  UST_CUDA(h, h->d_rev.reserve(M + 4)); UST_CUDA(h, h->d_ds.reserve(M + 4));
+  h->resident_n = -1;  // until the patched snapshot has been evaluated
+  if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsrev.p, ds_rev, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
+  if (M) {
+    static_assert(sizeof(long long) == sizeof(int64_t), "index width");
+    UST_CUDA(h, cudaMemcpyAsync(h->d_idx.p, idx, M * 8, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->d_state.p, state, M, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->d_flags.p, flags, M * 4, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->d_rev.p, pod_rev, M * 4, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->d_ds.p, ds_idx, M * 4, cudaMemcpyHostToDevice, st));
+    int e = ust_launch_patch((long long)n_changed, h->d_idx.p, h->d_state.p, h->d_flags.p, h->d_rev.p, h->d_ds.p, h->s_hot.p,
+                             h->s_flags.p, h->s_rev.p, h->s_ds.p, st);
+    if (e) return h->fail(UST_ERR_CUDA, "patch kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->launches += 1;
+  }
+  int rc = apply_device(h, policy, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, n_ds, h->s_dsrev.p, nullptr, nullptr, 0,
+                        h->s_next.p, h->s_actions.p, actuator_outcome ? h->s_outcome.p : nullptr, nullptr, st);
+  if (rc) return rc;
+  if (N) {
+    UST_CUDA(h, cudaMemcpyAsync(next_state, h->s_next.p, N, cudaMemcpyDeviceToHost, st));
+    UST_CUDA(h, cudaMemcpyAsync(actions, h->s_actions.p, N * 2, cudaMemcpyDeviceToHost, st));
+    if (actuator_outcome) UST_CUDA(h, cudaMemcpyAsync(actuator_outcome, h->s_outcome.p, N, cudaMemcpyDeviceToHost, st));
+  }
+  rc = finish_with_counters(h, st, out);
+  if (rc != UST_ERR_CUDA && rc != UST_ERR_COMM) h->resident_n = n;
+  return rc;
 }
 
 int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const int32_t* ds_idx, int32_t n_ds,
@@ -592,6 +649,7 @@ int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const i
   std::lock_guard<std::mutex> g(h->mu);
   if (n_pods < 0 || (n_pods > 0 && (!state || !ds_idx)) || n_ds < 0 || (n_ds > 0 && !ds_desired))
     return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
+  h->resident_n = -1;  // shares the staging arrays
   UST_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const size_t N = (size_t)n_pods;
@@ -643,6 +701,7 @@ int ust_build_state_uids(ust_handle* h, int64_t n_pods, const uint8_t* state, co
     }
     tab[2 * s] = x; tab[2 * s + 1] = y; tab_idx[s] = d;
   }
+  h->resident_n = -1;  // shares the staging arrays
   UST_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const size_t N = (size_t)n_pods;

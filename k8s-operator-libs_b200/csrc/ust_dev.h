@@ -115,4 +115,6 @@ static inline unsigned ust_uid_hash(unsigned long long x, unsigned long long y) 
 int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* owner_uid, int n_ds, const void* ds_tab,
                                 const int32_t* ds_tab_idx, int tab_slots, const int32_t* ds_desired, int32_t* ds_idx_out,
                                 unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream);
+int ust_launch_patch(long long m, const long long* idx, const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev,
+                     const int32_t* ds_idx, uint8_t* hot_out, uint32_t* flags_out, int32_t* rev_out, int32_t* ds_out, void* stream);
 int ust_max_coresident_ctas(int device, int* ctas_per_sm, int* num_sms);

@@ -1599,6 +1599,21 @@ __global__ void ust_build_state_finish_kernel(int n_ds, const int32_t* ds_desire
   for (int d = 0; d < n_ds; d++) ds_count[d] = 0;
 }
 
+// Delta update of the resident snapshot: scatter the re-encoded nodes into the SoA arrays.
+__global__ void __launch_bounds__(kThreads) ust_patch_kernel(long long m, const long long* __restrict__ idx,
+                                                             const uint8_t* __restrict__ state, const uint32_t* __restrict__ flags,
+                                                             const int32_t* __restrict__ pod_rev, const int32_t* __restrict__ ds_idx,
+                                                             uint8_t* hot_out, uint32_t* flags_out, int32_t* rev_out, int32_t* ds_out) {
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long k = (long long)blockIdx.x * kThreads + threadIdx.x; k < m; k += stride) {
+    const long long i = __ldg(idx + k);
+    hot_out[i] = __ldg(state + k);
+    flags_out[i] = __ldg(flags + k);
+    rev_out[i] = __ldg(pod_rev + k);
+    ds_out[i] = __ldg(ds_idx + k);
+  }
+}
+
 }  // namespace
 
 int ust_launch_fused(const UstParams& p, int grid, void* stream) {
@@ -1625,6 +1640,14 @@ int ust_launch_build_state(long long n, const uint8_t* hot, const int32_t* ds_id
                            unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream) {
   ust_build_state_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, hot, ds_idx, n_ds, ds_count, ws);
   ust_build_state_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_ds, ds_desired, ds_count, ws, out);
+  return (int)cudaGetLastError();
+}
+int ust_launch_patch(long long m, const long long* idx, const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev,
+                     const int32_t* ds_idx, uint8_t* hot_out, uint32_t* flags_out, int32_t* rev_out, int32_t* ds_out, void* stream) {
+  if (m <= 0) return 0;
+  const long long grid = (m + kThreads - 1) / kThreads;
+  ust_patch_kernel<<<(unsigned)(grid > 65535 * 16 ? 65535 * 16 : grid), kThreads, 0, (cudaStream_t)stream>>>(
+      m, idx, state, flags, pod_rev, ds_idx, hot_out, flags_out, rev_out, ds_out);
   return (int)cudaGetLastError();
 }
 int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* owner_uid, int n_ds, const void* ds_tab,

@@ -42,6 +42,8 @@ def load():
                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ust_apply_state.argtypes = apply_args
         lib.ust_apply_state_device.argtypes = apply_args + [C.c_void_p]
+        lib.ust_apply_state_delta.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ust_build_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.ust_build_state_uids.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p]
@@ -56,7 +58,7 @@ def load():
 
 
 EXPORTS = ["ust_abi_version", "ust_create", "ust_destroy", "ust_last_error", "ust_create_error", "ust_launch_count",
-           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_sync",
+           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_apply_state_delta", "ust_sync",
            "ust_build_state", "ust_build_state_uids", "ust_get_unique_id", "ust_comm_init", "ust_comm_set_mode", "ust_table_entry",
            "ust_table_window_shift"]
 
@@ -148,6 +150,28 @@ class Handle:
             C.addressof(ps) if ps is not None else None, _p(nxt), _p(act), _p(oc), C.addressof(cnt))
         if check and rc:
             raise UstError(rc, self.last_error())
+        return rc, nxt, act, oc, cnt.as_dict()
+
+    def apply_state_delta(self, policy, n, idx, changed, ds_rev, want_outcome=True, out=None):
+        """ust_apply_state_delta: overwrite nodes `idx` of the resident snapshot (n nodes) with `changed`
+        (dict of state / flags / pod_rev / ds_idx arrays of len(idx)) and evaluate it again."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        ch = {"state": np.ascontiguousarray(changed["state"], dtype=np.uint8),
+              "flags": np.ascontiguousarray(changed["flags"], dtype=np.uint32),
+              "pod_rev": np.ascontiguousarray(changed["pod_rev"], dtype=np.int32),
+              "ds_idx": np.ascontiguousarray(changed["ds_idx"], dtype=np.int32)}
+        ds_rev = np.ascontiguousarray(ds_rev, dtype=np.int32)
+        if out is None:
+            nxt = np.zeros(n, np.uint8)
+            act = np.zeros(n, np.uint16)
+            oc = np.full(n, 0xFF, np.uint8) if want_outcome else None
+        else:
+            nxt, act, oc = out
+        cnt = abi.Counters()
+        rc = self._lib.ust_apply_state_delta(
+            self._h, C.addressof(policy) if policy is not None else None, int(idx.shape[0]), _p(idx), _p(ch["state"]),
+            _p(ch["flags"]), _p(ch["pod_rev"]), _p(ch["ds_idx"]), int(ds_rev.shape[0]), _p(ds_rev), _p(nxt), _p(act), _p(oc),
+            C.addressof(cnt))
         return rc, nxt, act, oc, cnt.as_dict()
 
     def apply_state_device(self, policy, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, next_state, actions,

@@ -221,6 +221,34 @@ def test_long_and_empty_pod_lists(handle, seed):
         helpers.assert_same(got, ref, f"seed={seed} rep={rep}")
 
 
+@pytest.mark.parametrize("n", [5000, 700_001])
+def test_delta_updates_of_the_resident_snapshot(handle, n):
+    """ust_apply_state_delta: re-encode a few nodes, evaluate the resident snapshot again - identical to a full call
+    on the updated arrays (direct and pipelined upload paths leave the same resident arrays), any policy, repeated."""
+    rng = np.random.default_rng(n)
+    soa, _ = helpers.random_soa(rng, n, wild=True)
+    pol = helpers.random_policy(rng)
+    helpers.assert_same(gpu_apply(handle, pol, soa), helpers.oracle_apply(pol, soa, variant=1), "full call")
+    for rep, frac in enumerate((0.0, 0.0005, 0.02, 0.3)):
+        m = int(n * frac)
+        idx = rng.choice(n, size=m, replace=False).astype(np.int64)
+        fresh, _ = helpers.random_soa(rng, m, wild=True, p_err=1e-4 if rep == 3 else 0.0)
+        for k in ("state", "flags", "pod_rev", "ds_idx"):
+            soa[k][idx] = fresh[k]
+        if rep == 2:
+            soa["ds_rev"] = (soa["ds_rev"] + 1).astype(np.int32)   # a DaemonSet rolled to a new revision
+        pol = helpers.random_policy(rng)
+        got = handle.apply_state_delta(pol, n, idx, {k: fresh[k] for k in ("state", "flags", "pod_rev", "ds_idx")}, soa["ds_rev"])
+        ref = helpers.oracle_apply(pol, soa, variant=1)
+        helpers.assert_same(got, ref, f"delta rep={rep} m={m}")
+    # contract errors
+    bad = handle.apply_state_delta(pol, n, np.array([n], np.int64), {k: soa[k][:1] for k in ("state", "flags", "pod_rev", "ds_idx")}, soa["ds_rev"])
+    assert bad[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]
+    handle.build_state(soa["state"][:10], np.zeros(10, np.int32), np.array([10], np.int32))   # shares the staging arrays
+    gone = handle.apply_state_delta(pol, n, np.zeros(0, np.int64), {k: soa[k][:0] for k in ("state", "flags", "pod_rev", "ds_idx")}, soa["ds_rev"])
+    assert gone[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]
+
+
 def test_many_daemonsets_use_the_global_table(handle):
     rng = np.random.default_rng(99)
     n, n_ds = 50_000, 3000  # > UST_DS_SMEM_MAX
