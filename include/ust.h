@@ -254,6 +254,20 @@ int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_cha
                           int32_t n_ds, const int32_t* ds_rev, uint8_t* next_state, uint16_t* actions,
                           uint8_t* actuator_outcome, ust_counters* out);
 
+/* Rollout simulation on the resident snapshot (see ust_apply_state_delta): `steps` reconciles in a row,
+ * entirely on the device. After each ApplyState the decisions are fed back into the snapshot under "ideal
+ * actuators": every provider call takes effect (state label, annotations, cordon / uncordon), every scheduled
+ * asynchronous actuator succeeds with the state in actuator_outcome (evaluate_actuators is forced on), a restarted
+ * driver pod comes back at its DaemonSet's current revision and ready (an orphaned one is gone: the node leaves the
+ * snapshot), and what a node is still waiting for (jobs, pod readiness, validation) has happened by the next
+ * reconcile - so the only thing that paces the rollout is the MaxParallelUpgrades / MaxUnavailable budget, which is
+ * the planning question. history[k] (nullable, `steps` entries) receives the counters of reconcile k; final_*
+ * (nullable) the snapshot afterwards; *steps_done the number of reconciles fed back. A reconcile that returns a
+ * reference-level error stops the feedback: its code is returned, the state before it is kept. In-place mode, one
+ * GPU, no pod lists. */
+int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps, ust_counters* history,
+                         uint8_t* final_state, uint32_t* final_flags, int32_t* final_pod_rev, int32_t* steps_done);
+
 /* ---- BuildState -------------------------------------------------------------------------------- */
 
 /* The device part of BuildState (upgrade_state.go:99-164): per-DaemonSet count of owned driver pods

@@ -88,6 +88,9 @@ struct ust_handle {
   int ctas_per_sm = 0, num_sms = 0;
   bool ws_dirty = false;
   int64_t resident_n = -1;  // nodes of the snapshot the last ust_apply_state left in the staging arrays (-1 = none)
+  int32_t resident_n_ds = 0;  // ... and the size of its DaemonSet table
+  ust_counters* hist_dev = nullptr;  // rollout simulation: one ust_counters per simulated reconcile
+  size_t hist_cap = 0;
   bool no_hint = false;  // UST_NO_HINT=1 (tuning): every call speculates from the policy default, never from the previous call
 
   UstWorkspace* ws = nullptr;
@@ -492,6 +495,7 @@ void ust_destroy(ust_handle* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->lut_dev) cudaFree(h->lut_dev);
   if (h->podlut_dev) cudaFree(h->podlut_dev);
+  if (h->hist_dev) cudaFree(h->hist_dev);
   if (h->lut_host) cudaFreeHost(h->lut_host);
   if (h->podlut_host) cudaFreeHost(h->podlut_host);
   if (h->counters_dev) cudaFree(h->counters_dev);
@@ -569,7 +573,7 @@ int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const ui
   if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsrev.p, ds_rev, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
   h->resident_n = -1;
   auto keep = [&](int rc) {  // the uploaded snapshot stays usable unless the call itself failed (not the policy / the data)
-    if (rc != UST_ERR_CUDA && rc != UST_ERR_INVALID_ARGUMENT && rc != UST_ERR_COMM && rc != UST_ERR_NIL_STATE && !pods) h->resident_n = n;
+    if (rc != UST_ERR_CUDA && rc != UST_ERR_INVALID_ARGUMENT && rc != UST_ERR_COMM && rc != UST_ERR_NIL_STATE && !pods) { h->resident_n = n; h->resident_n_ds = n_ds; }
     return rc;
   };
   if (!pods && h->world == 1 && n >= (1 << 19))
@@ -639,8 +643,58 @@ int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_cha
     if (actuator_outcome) UST_CUDA(h, cudaMemcpyAsync(actuator_outcome, h->s_outcome.p, N, cudaMemcpyDeviceToHost, st));
   }
   rc = finish_with_counters(h, st, out);
-  if (rc != UST_ERR_CUDA && rc != UST_ERR_COMM) h->resident_n = n;
+  if (rc != UST_ERR_CUDA && rc != UST_ERR_COMM) { h->resident_n = n; h->resident_n_ds = n_ds; }
   return rc;
+}
+
+int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps, ust_counters* history, uint8_t* final_state,
+                         uint32_t* final_flags, int32_t* final_pod_rev, int32_t* steps_done) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  const int64_t n = h->resident_n;
+  if (n < 0) return h->fail(UST_ERR_INVALID_ARGUMENT, "no resident snapshot: call ust_apply_state (without pod lists) first");
+  if (steps < 0 || steps > (1 << 20)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad step count");
+  if (h->world > 1) return h->fail(UST_ERR_INVALID_ARGUMENT, "rollout simulation runs on one GPU");
+  if (policy && policy->use_maintenance_operator)
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "rollout simulation models the in-place mode only");
+  ust_policy pol;
+  if (policy) { pol = *policy; pol.evaluate_actuators = 1; }  // the asynchronous actuators' results are what is fed back
+  UST_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t N = (size_t)n;
+  UST_CUDA(h, h->s_outcome.reserve(N + 16));
+  if ((size_t)steps + 1 > h->hist_cap) {
+    if (h->hist_dev) cudaFree(h->hist_dev);
+    h->hist_cap = (size_t)steps + 64;
+    UST_CUDA(h, cudaMalloc(&h->hist_dev, h->hist_cap * sizeof(ust_counters)));
+  }
+  h->resident_n = -1;
+  int grid = 8 * h->num_sms;
+  for (int32_t k = 0; k < steps; k++) {
+    int rc = apply_device(h, policy ? &pol : nullptr, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, h->resident_n_ds,
+                          h->s_dsrev.p, nullptr, nullptr, 0, h->s_next.p, h->s_actions.p, h->s_outcome.p, h->hist_dev + k, st);
+    if (rc) return rc;
+    int e = ust_launch_feedback(n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, h->resident_n_ds, h->s_dsrev.p, h->s_next.p,
+                                h->s_actions.p, h->s_outcome.p, h->hist_dev + k, grid, st);
+    if (e) return h->fail(UST_ERR_CUDA, "feedback kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->launches += 1;
+  }
+  std::vector<ust_counters> hist((size_t)steps);
+  if (steps) UST_CUDA(h, cudaMemcpyAsync(hist.data(), h->hist_dev, (size_t)steps * sizeof(ust_counters), cudaMemcpyDeviceToHost, st));
+  if (N && final_state) UST_CUDA(h, cudaMemcpyAsync(final_state, h->s_hot.p, N, cudaMemcpyDeviceToHost, st));
+  if (N && final_flags) UST_CUDA(h, cudaMemcpyAsync(final_flags, h->s_flags.p, N * 4, cudaMemcpyDeviceToHost, st));
+  if (N && final_pod_rev) UST_CUDA(h, cudaMemcpyAsync(final_pod_rev, h->s_rev.p, N * 4, cudaMemcpyDeviceToHost, st));
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) { h->ws_dirty = true; return h->fail(UST_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(ce)); }
+  h->resident_n = n;  // the snapshot now holds the simulated state
+  int32_t done = steps;
+  int rc = UST_OK;
+  for (int32_t k = 0; k < steps; k++)
+    if (hist[(size_t)k].error_code != UST_OK) { done = k; rc = (int)hist[(size_t)k].error_code; break; }
+  if (history) memcpy(history, hist.data(), (size_t)steps * sizeof(ust_counters));
+  if (steps_done) *steps_done = done;
+  if (rc) return h->fail(rc, "the simulated reconcile %d returned an error (code %d); the state before it is kept", (int)done, rc);
+  return UST_OK;
 }
 
 int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const int32_t* ds_idx, int32_t n_ds,

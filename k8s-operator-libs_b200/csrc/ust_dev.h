@@ -117,4 +117,7 @@ int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* own
                                 unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream);
 int ust_launch_patch(long long m, const long long* idx, const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev,
                      const int32_t* ds_idx, uint8_t* hot_out, uint32_t* flags_out, int32_t* rev_out, int32_t* ds_out, void* stream);
+int ust_launch_feedback(long long n, uint8_t* hot, uint32_t* flags, int32_t* pod_rev, const int32_t* ds_idx, int n_ds,
+                        const int32_t* ds_rev, const uint8_t* next, const uint16_t* actions, const uint8_t* outcome,
+                        const ust_counters* step, int grid, void* stream);
 int ust_max_coresident_ctas(int device, int* ctas_per_sm, int* num_sms);

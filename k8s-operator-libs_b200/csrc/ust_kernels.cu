@@ -1614,6 +1614,64 @@ __global__ void __launch_bounds__(kThreads) ust_patch_kernel(long long m, const 
   }
 }
 
+// Rollout simulation: the state feedback between two reconciles under "ideal actuators" - every call
+// the reference makes through its providers takes effect, every asynchronous actuator succeeds, and whatever a node
+// is waiting for (jobs, pod readiness, validation) has happened by the next reconcile. One streaming pass, in place:
+// 13 B read + up to 9 B written per node.
+//   state   <- actuator_outcome when the pass scheduled an asynchronous actuator (pod_manager.go:393-403,
+//              drain_manager.go:111-139), else next_state (NodeUpgradeStateProvider.ChangeNodeUpgradeState)
+//   annotations per action bit (ChangeNodeUpgradeAnnotation, upgrade_suit_test.go:121-130)
+//   CORDON / UNCORDON -> Spec.Unschedulable (cordon_manager.go:40-47)
+//   RESTART_DRIVER_POD -> the DaemonSet controller recreates the pod at the current revision and it becomes ready;
+//              an orphaned pod is not recreated: the node leaves the snapshot (no driver pod to list)
+//   still waiting after the pass: wait-for-jobs with running pods -> the jobs finish; pod-restart with a synced pod
+//              that is not ready -> it becomes ready; validation-required -> the validation pod becomes ready
+__global__ void __launch_bounds__(kThreads) ust_feedback_kernel(long long n, uint8_t* hot, uint32_t* flags, int32_t* pod_rev,
+                                                                const int32_t* __restrict__ ds_idx, int n_ds,
+                                                                const int32_t* __restrict__ ds_rev,
+                                                                const uint8_t* __restrict__ next, const uint16_t* __restrict__ actions,
+                                                                const uint8_t* __restrict__ outcome, const ust_counters* step) {
+  if (step->error_code != UST_OK) return;  // the reconcile returned an error: nothing it decided is fed back
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    unsigned b = hot[i];
+    const unsigned s = b & 15u;
+    if (s >= UST_STATE_OTHER) continue;  // other label values / not in the snapshot: never processed
+    uint32_t f = flags[i];
+    const unsigned a = actions[i];
+    const unsigned oc = outcome[i];
+    unsigned ns = next[i];
+    if ((a & (UST_A_SCHEDULE_WAIT_CHECK | UST_A_SCHEDULE_POD_EVICTION | UST_A_SCHEDULE_DRAIN)) && oc != UST_OUTCOME_NONE) ns = oc;
+    if (a & UST_A_CLEAR_UPGRADE_REQUESTED) f &= ~UST_F_UPGRADE_REQUESTED;
+    if (a & UST_A_SET_INITIAL_STATE_ANNO) f |= UST_F_INITIAL_STATE_ANNO;
+    if (a & UST_A_CLEAR_INITIAL_STATE_ANNO) f &= ~UST_F_INITIAL_STATE_ANNO;
+    if (a & UST_A_CORDON) b |= UST_HOT_UNSCHEDULABLE;
+    if (a & UST_A_UNCORDON) b &= ~UST_HOT_UNSCHEDULABLE;
+    if (a & UST_A_UNBLOCK_SAFE_LOAD) f &= ~UST_F_SAFE_LOAD;
+    if (a & UST_A_SET_WAIT_START) f |= UST_F_WAIT_START_ANNO;
+    if (a & UST_A_CLEAR_WAIT_START) f &= ~(UST_F_WAIT_START_ANNO | UST_F_WAIT_TIMED_OUT | UST_F_WAIT_START_INVALID);
+    int rev = pod_rev[i];
+    if (a & UST_A_RESTART_DRIVER_POD) {
+      const int d = ds_idx[i];
+      if ((f & UST_F_POD_ORPHANED) || d < 0 || d >= n_ds) {
+        ns = UST_STATE_EXCLUDED;
+      } else {
+        rev = ds_rev[d];
+        f = (f | UST_F_POD_READY) & ~(UST_F_POD_FAILING | UST_F_POD_TERMINATING);
+      }
+    }
+    if (ns == UST_STATE_WAIT_FOR_JOBS_REQUIRED) f &= ~UST_F_WAIT_PODS_RUNNING;
+    if (ns == UST_STATE_POD_RESTART_REQUIRED) {
+      f &= ~UST_F_POD_TERMINATING;
+      if (!(f & UST_F_POD_FAILING)) f |= UST_F_POD_READY;
+    }
+    if (ns == UST_STATE_VALIDATION_REQUIRED) f |= UST_F_VALIDATION_DONE;
+    hot[i] = (uint8_t)((b & 0xF0u) | (ns & 15u));
+    flags[i] = f;
+    pod_rev[i] = rev;
+  }
+}
+
 }  // namespace
 
 int ust_launch_fused(const UstParams& p, int grid, void* stream) {
@@ -1648,6 +1706,13 @@ int ust_launch_patch(long long m, const long long* idx, const uint8_t* state, co
   const long long grid = (m + kThreads - 1) / kThreads;
   ust_patch_kernel<<<(unsigned)(grid > 65535 * 16 ? 65535 * 16 : grid), kThreads, 0, (cudaStream_t)stream>>>(
       m, idx, state, flags, pod_rev, ds_idx, hot_out, flags_out, rev_out, ds_out);
+  return (int)cudaGetLastError();
+}
+int ust_launch_feedback(long long n, uint8_t* hot, uint32_t* flags, int32_t* pod_rev, const int32_t* ds_idx, int n_ds,
+                        const int32_t* ds_rev, const uint8_t* next, const uint16_t* actions, const uint8_t* outcome,
+                        const ust_counters* step, int grid, void* stream) {
+  if (n <= 0) return 0;
+  ust_feedback_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, hot, flags, pod_rev, ds_idx, n_ds, ds_rev, next, actions, outcome, step);
   return (int)cudaGetLastError();
 }
 int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* owner_uid, int n_ds, const void* ds_tab,

@@ -44,6 +44,7 @@ def load():
         lib.ust_apply_state_device.argtypes = apply_args + [C.c_void_p]
         lib.ust_apply_state_delta.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ust_simulate_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ust_build_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.ust_build_state_uids.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p]
@@ -58,7 +59,7 @@ def load():
 
 
 EXPORTS = ["ust_abi_version", "ust_create", "ust_destroy", "ust_last_error", "ust_create_error", "ust_launch_count",
-           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_apply_state_delta", "ust_sync",
+           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_apply_state_delta", "ust_simulate_rollout", "ust_sync",
            "ust_build_state", "ust_build_state_uids", "ust_get_unique_id", "ust_comm_init", "ust_comm_set_mode", "ust_table_entry",
            "ust_table_window_shift"]
 
@@ -173,6 +174,17 @@ class Handle:
             _p(ch["flags"]), _p(ch["pod_rev"]), _p(ch["ds_idx"]), int(ds_rev.shape[0]), _p(ds_rev), _p(nxt), _p(act), _p(oc),
             C.addressof(cnt))
         return rc, nxt, act, oc, cnt.as_dict()
+
+    def simulate_rollout(self, policy, n, steps, want_final=True):
+        """ust_simulate_rollout on the resident snapshot. Returns (rc, steps_done, [counters-dict per step], final dict)."""
+        hist = (abi.Counters * max(steps, 1))()
+        fin = {"state": np.zeros(n, np.uint8), "flags": np.zeros(n, np.uint32), "pod_rev": np.zeros(n, np.int32)} if want_final else None
+        done = C.c_int32(0)
+        rc = self._lib.ust_simulate_rollout(
+            self._h, C.addressof(policy) if policy is not None else None, int(steps), C.addressof(hist),
+            _p(fin["state"]) if fin else None, _p(fin["flags"]) if fin else None, _p(fin["pod_rev"]) if fin else None,
+            C.addressof(done))
+        return rc, int(done.value), [hist[k].as_dict() for k in range(steps)], fin
 
     def apply_state_device(self, policy, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, next_state, actions,
                            outcome=None, pods=None, counters=None, stream=None):

@@ -1283,4 +1283,81 @@ int ust_oracle_build_state_uids(int64_t n_pods, const uint8_t* state, const uint
   return rc;
 }
 
+// Rollout simulation (not in the reference: SURVEY 8f.3 "what-if planning"). The reconcile itself is the oracle's
+// ApplyState; between two reconciles the decisions are applied the way the reference's providers and actuators
+// would, all of them succeeding before the next reconcile:
+//   ChangeNodeUpgradeState / ChangeNodeUpgradeAnnotation        upgrade_suit_test.go:114-130 (what the mocks do)
+//   Cordon / Uncordon set Spec.Unschedulable                   cordon_manager.go:40-47
+//   eviction / drain / completion check end in the state       pod_manager.go:393-403, drain_manager.go:111-139,
+//       the oracle reports as actuator_outcome                 pod_manager.go:256-317
+//   a deleted driver pod is recreated by its DaemonSet at the current revision and becomes ready; an orphaned pod
+//       (common_manager.go:225-227) has no controller: the node has no driver pod any more and leaves the snapshot
+//   whatever the node still waits for - wait-for-jobs pods, pod readiness, validation - has happened by then.
+int ust_oracle_simulate(int variant, const ust_policy* policy, int64_t n, uint8_t* state, uint32_t* flags, int32_t* pod_rev,
+                        const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev, int32_t steps, ust_counters* history,
+                        int32_t* steps_done) {
+  ust_policy pol;
+  if (policy) {
+    if (policy->use_maintenance_operator) return UST_ERR_INVALID_ARGUMENT;
+    pol = *policy;
+    pol.evaluate_actuators = 1;
+  }
+  std::vector<uint8_t> next((size_t)n + 1), outcome((size_t)n + 1);
+  std::vector<uint16_t> actions((size_t)n + 1);
+  int32_t done = 0;
+  int rc = UST_OK;
+  for (int32_t k = 0; k < steps; k++) {
+    ust_counters c;
+    rc = ust_oracle_apply_state(variant, policy ? &pol : nullptr, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, nullptr,
+                                next.data(), actions.data(), outcome.data(), &c);
+    if (history) history[k] = c;
+    if (rc != UST_OK) {  // the reconcile failed: nothing is fed back, later reconciles would fail the same way
+      if (history) for (int32_t j = k + 1; j < steps; j++) history[j] = c;
+      break;
+    }
+    done = k + 1;
+    for (int64_t i = 0; i < n; i++) {
+      const unsigned code = state[i] & UST_HOT_STATE_MASK;
+      if (code >= UST_STATE_OTHER) continue;
+      const unsigned a = actions[i];
+      unsigned ns = next[i];
+      const bool scheduled = (a & UST_A_SCHEDULE_WAIT_CHECK) || (a & UST_A_SCHEDULE_POD_EVICTION) || (a & UST_A_SCHEDULE_DRAIN);
+      if (scheduled && outcome[i] != UST_OUTCOME_NONE) ns = outcome[i];
+      uint32_t f = flags[i];
+      uint8_t hb = state[i];
+      if (a & UST_A_CLEAR_UPGRADE_REQUESTED) f &= ~UST_F_UPGRADE_REQUESTED;
+      if (a & UST_A_SET_INITIAL_STATE_ANNO) f |= UST_F_INITIAL_STATE_ANNO;
+      if (a & UST_A_CLEAR_INITIAL_STATE_ANNO) f &= ~UST_F_INITIAL_STATE_ANNO;
+      if (a & UST_A_CORDON) hb |= UST_HOT_UNSCHEDULABLE;
+      if (a & UST_A_UNCORDON) hb = (uint8_t)(hb & ~UST_HOT_UNSCHEDULABLE);
+      if (a & UST_A_UNBLOCK_SAFE_LOAD) f &= ~UST_F_SAFE_LOAD;
+      if (a & UST_A_SET_WAIT_START) f |= UST_F_WAIT_START_ANNO;
+      if (a & UST_A_CLEAR_WAIT_START) f &= ~(UST_F_WAIT_START_ANNO | UST_F_WAIT_TIMED_OUT | UST_F_WAIT_START_INVALID);
+      if (a & UST_A_RESTART_DRIVER_POD) {
+        const bool has_owner = !(f & UST_F_POD_ORPHANED) && ds_idx[i] >= 0 && ds_idx[i] < n_ds;
+        if (!has_owner) {
+          ns = UST_STATE_EXCLUDED;
+        } else {
+          pod_rev[i] = ds_rev[ds_idx[i]];
+          f |= UST_F_POD_READY;
+          f &= ~(UST_F_POD_FAILING | UST_F_POD_TERMINATING);
+        }
+      }
+      switch (ns) {
+        case UST_STATE_WAIT_FOR_JOBS_REQUIRED: f &= ~UST_F_WAIT_PODS_RUNNING; break;
+        case UST_STATE_POD_RESTART_REQUIRED:
+          f &= ~UST_F_POD_TERMINATING;
+          if (!(f & UST_F_POD_FAILING)) f |= UST_F_POD_READY;
+          break;
+        case UST_STATE_VALIDATION_REQUIRED: f |= UST_F_VALIDATION_DONE; break;
+        default: break;
+      }
+      state[i] = (uint8_t)((hb & 0xF0u) | (ns & UST_HOT_STATE_MASK));
+      flags[i] = f;
+    }
+  }
+  if (steps_done) *steps_done = done;
+  return rc;
+}
+
 }  // extern "C"

@@ -32,6 +32,7 @@ def oracle():
         lib.ust_oracle_scaled_value.restype = C.c_int
         lib.ust_oracle_build_state.restype = C.c_int
         lib.ust_oracle_build_state_uids.restype = C.c_int
+        lib.ust_oracle_simulate.restype = C.c_int
         _oracle = lib
     return _oracle
 
@@ -371,3 +372,16 @@ def uid_inputs_from_vector(b, rng):
             owner[i] = ds_uid[p["ds"]]
     desired = np.array([d["desired"] for d in b["daemonsets"]], np.int32)
     return state, owner, ds_uid, desired
+
+
+def oracle_simulate(policy, soa, steps, variant=1):
+    """CPU rollout simulation (oracle ApplyState + the feedback restatement). Returns (rc, steps_done, history, final)."""
+    n = int(soa["state"].shape[0])
+    fin = {"state": soa["state"].copy(), "flags": soa["flags"].copy(), "pod_rev": soa["pod_rev"].copy()}
+    hist = (abi.Counters * max(steps, 1))()
+    done = C.c_int32(0)
+    rc = oracle().ust_oracle_simulate(
+        C.c_int(variant), C.byref(policy) if policy is not None else None, C.c_int64(n), _ptr(fin["state"]), _ptr(fin["flags"]),
+        _ptr(fin["pod_rev"]), _ptr(soa["ds_idx"]), C.c_int32(int(soa["ds_rev"].shape[0])), _ptr(soa["ds_rev"]), C.c_int32(steps),
+        hist, C.byref(done))
+    return rc, int(done.value), [hist[k].as_dict() for k in range(steps)], fin

@@ -249,6 +249,39 @@ def test_delta_updates_of_the_resident_snapshot(handle, n):
     assert gone[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]
 
 
+@pytest.mark.parametrize("n,steps", [(3000, 25), (120_000, 30), (700_001, 8)])
+def test_simulated_rollout_matches_the_cpu_simulation(handle, n, steps):
+    """ust_simulate_rollout (ApplyState + feedback kernel, `steps` times on the device) against the oracle's
+    simulation: every reconcile's counters and the final snapshot, bit for bit; then the error paths."""
+    rng = np.random.default_rng(n + steps)
+    soa = synth.make_nodes(n, 0xABC + n)
+    soa["flags"] = (soa["flags"] | np.where(rng.random(n) < 0.2, np.uint32(abi.UST_F_WAIT_PODS_RUNNING), np.uint32(0))).astype(np.uint32)
+    for pol in (abi.make_policy(max_parallel_upgrades=0, max_unavailable="10%"),
+                abi.make_policy(max_parallel_upgrades=max(1, n // 50), max_unavailable=None, pod_deletion_enabled=True,
+                                validation_enabled=True, pod_deletion={"force": True}, drain={"enable": True},
+                                wait_for_completion={"podSelector": "app=job", "timeoutSeconds": 60})):
+        assert gpu_apply(handle, pol, soa)[0] == 0          # makes the snapshot resident
+        rc, done, hist, fin = handle.simulate_rollout(pol, n, steps)
+        orc, odone, ohist, ofin = helpers.oracle_simulate(pol, soa, steps, variant=1)
+        assert rc == orc == 0 and done == odone == steps
+        for k in range(steps):
+            assert hist[k] == ohist[k], f"counters of reconcile {k}"
+        for key in ("state", "flags", "pod_rev"):
+            assert np.array_equal(fin[key], ofin[key]), key
+        # the snapshot stays resident: a delta call with nothing changed evaluates the simulated state
+        got = handle.apply_state_delta(pol, n, np.zeros(0, np.int64), {k: soa[k][:0] for k in ("state", "flags", "pod_rev", "ds_idx")}, soa["ds_rev"])
+        after = dict(soa); after.update(ofin)
+        helpers.assert_same(got, helpers.oracle_apply(pol, after, variant=1), "ApplyState on the simulated snapshot")
+    # a reconcile that fails (maxUnavailable does not parse) feeds nothing back
+    bad = abi.make_policy(max_parallel_upgrades=1, max_unavailable="a-few")
+    gpu_apply(handle, bad, soa)
+    rc, done, hist, fin = handle.simulate_rollout(bad, n, 3)
+    orc, odone, ohist, ofin = helpers.oracle_simulate(bad, soa, 3, variant=1)
+    assert rc == orc == abi.K["UST_ERR_MAX_UNAVAILABLE"] and done == odone == 0
+    assert all(np.array_equal(fin[k], soa[k]) for k in ("state", "flags", "pod_rev"))
+    assert handle.simulate_rollout(abi.make_policy(use_maintenance_operator=True), n, 1)[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]
+
+
 def test_many_daemonsets_use_the_global_table(handle):
     rng = np.random.default_rng(99)
     n, n_ds = 50_000, 3000  # > UST_DS_SMEM_MAX

@@ -5,6 +5,7 @@ import pytest
 from hypothesis import given, settings, strategies as st
 
 import helpers
+from helpers import abi
 
 
 @pytest.mark.parametrize("seed", range(40))
@@ -49,3 +50,58 @@ def test_disabled_policy_is_noop():
         assert rc == 0 and not act.any() and (nxt == (soa["state"] & 15)).all()
         rc2, nxt2, act2, _, _ = helpers.oracle_apply(pol, soa, variant=variant, nil_policy=True)
         assert rc2 == 0 and not act2.any() and (nxt2 == nxt).all()
+
+
+# ---- rollout simulation: the CPU side ---------------------------------------------------
+
+def test_simulated_rollout_reference_shaped_equals_soa():
+    """Both oracle variants drive the same feedback: identical histories and final snapshots; step 0 is a plain
+    ApplyState; zero steps change nothing."""
+    from ust import synth
+    rng = np.random.default_rng(21)
+    for n, steps in ((0, 3), (1, 3), (700, 12), (3000, 6)):
+        soa, _ = helpers.random_soa(rng, n, wild=False, all_states=True)
+        soa["flags"] &= ~np.uint32(abi.UST_F_REQUESTOR_MODE)
+        pol = abi.make_policy(max_parallel_upgrades=int(rng.integers(0, 50)), max_unavailable=["25%", None, 40][int(rng.integers(0, 3))],
+                              pod_deletion_enabled=bool(rng.integers(0, 2)), validation_enabled=bool(rng.integers(0, 2)),
+                              pod_deletion={"force": False}, drain={"enable": True},
+                              wait_for_completion={"podSelector": "app=job", "timeoutSeconds": 30})
+        a = helpers.oracle_simulate(pol, soa, steps, variant=0)
+        b = helpers.oracle_simulate(pol, soa, steps, variant=1)
+        assert a[0] == b[0] == 0 and a[1] == b[1] == steps and a[2] == b[2]
+        for k in ("state", "flags", "pod_rev"):
+            assert np.array_equal(a[3][k], b[3][k]), k
+        if steps:
+            one = helpers.oracle_apply(_with_actuators(pol), soa, variant=1)
+            assert a[2][0] == one[4]
+        z = helpers.oracle_simulate(pol, soa, 0, variant=1)
+        assert z[1] == 0 and all(np.array_equal(z[3][k], soa[k]) for k in ("state", "flags", "pod_rev"))
+
+
+def _with_actuators(pol):
+    import copy
+    p = copy.copy(pol)
+    p.evaluate_actuators = 1
+    return p
+
+
+def test_simulated_rollout_converges_and_respects_the_budget():
+    """With ideal actuators the budget is the only brake: every reconcile moves at most max(upgradesAvailable, 0)
+    nodes out of upgrade-required (plus the already cordoned ones, upgrade_inplace.go:87-101), the unavailable count
+    never exceeds what it started with or maxUnavailable allows, and the rollout ends with every node done, failed or
+    deliberately skipped."""
+    from ust import synth
+    soa = synth.make_nodes(20_000, 5)
+    pol = abi.make_policy(max_parallel_upgrades=0, max_unavailable="10%")
+    rc, done, hist, fin = helpers.oracle_simulate(pol, soa, 120)
+    assert rc == 0 and done == 120
+    code = fin["state"] & 15
+    skip = (fin["state"] & abi.UST_HOT_SKIP) != 0
+    left = np.isin(code, [1]) & ~skip
+    assert not left.any(), "an unskipped node is still waiting for a slot after 120 reconciles"
+    assert set(np.unique(code)) <= {1, 11, 12, 13, 14, 15}
+    for k in range(1, 120):
+        moved = hist[k - 1]["hist"][1] - hist[k]["hist"][1]
+        assert moved <= max(hist[k - 1]["upgrades_available"], 0) + hist[k - 1]["unavailable"], k
+        if hist[k]["max_unavailable"] < hist[k]["total_managed"] and k > 8:
+            assert hist[k]["unavailable"] <= max(hist[0]["unavailable"], hist[k]["max_unavailable"]), k
