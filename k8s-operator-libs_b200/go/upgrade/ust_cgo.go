@@ -319,3 +319,39 @@ func (m *ClusterUpgradeStateManagerImpl) BuildStateAccelerated(acc *Accelerator,
 	}
 	return idx[:n], cnt, nil
 }
+
+// ApplyStateDelta: for a reconcile loop that tracks resourceVersions. `changed` are the positions (in the order of
+// the last full ApplyStateAccelerated call) of the nodes whose Node / Pod / DaemonSet objects changed; only those
+// are re-encoded and uploaded, the resident snapshot is evaluated again (ust_apply_state_delta). The replay half is
+// the one of ApplyStateAccelerated.
+func (a *Accelerator) ApplyStateDelta(pol *C.ust_policy, changed []int64, state []C.uint8_t, flags []C.uint32_t,
+	rev, ds []C.int32_t, dsRev []C.int32_t, next []C.uint8_t, actions []C.uint16_t) (C.ust_counters, error) {
+	var cnt C.ust_counters
+	var idxp *C.int64_t
+	var sp *C.uint8_t
+	var fp *C.uint32_t
+	var rp, dp *C.int32_t
+	if len(changed) > 0 {
+		idxp, sp, fp = (*C.int64_t)(unsafe.Pointer(&changed[0])), &state[0], &flags[0]
+		rp, dp = &rev[0], &ds[0]
+	}
+	rc := C.ust_apply_state_delta(a.h, pol, C.int64_t(len(changed)), idxp, sp, fp, rp, dp, C.int32_t(len(dsRev)), &dsRev[0],
+		&next[0], &actions[0], nil, &cnt)
+	if rc != C.UST_OK {
+		return cnt, fmt.Errorf("%s", C.GoString(C.ust_last_error(a.h)))
+	}
+	return cnt, nil
+}
+
+// SimulateRollout answers the planning question "how many reconciles does this rollout take under this policy":
+// `steps` reconciles on the resident snapshot with ideal actuators (ust_simulate_rollout); history[k] holds the
+// counters the k-th reconcile would have reported (GetUpgradesDone / InProgress / Available ...).
+func (a *Accelerator) SimulateRollout(pol *C.ust_policy, steps int) ([]C.ust_counters, int, error) {
+	history := make([]C.ust_counters, steps+1)
+	var done C.int32_t
+	rc := C.ust_simulate_rollout(a.h, pol, C.int32_t(steps), &history[0], nil, nil, nil, &done)
+	if rc != C.UST_OK {
+		return history[:done], int(done), fmt.Errorf("%s", C.GoString(C.ust_last_error(a.h)))
+	}
+	return history[:steps], int(done), nil
+}
