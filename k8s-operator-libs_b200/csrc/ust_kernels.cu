@@ -6,20 +6,24 @@
 // the cluster counters of common_manager.go:715-788.
 //
 // Shape of the kernel (HBM-bound byte/integer streaming, no tensor-core work):
-//   * persistent, cooperative grid of (#SM x resident CTAs); CTA c owns one contiguous chunk of nodes, so
-//     slice order of the upgrade-required bucket (upgrade_inplace.go:71) is chunk order;
-//   * phase 1 streams ONLY the 1-byte hot array (state code + 4 constraint predicates): 14-bin state
-//     histogram, unavailable count, upgrade candidates per chunk, earliest abort point — byte-sliced
-//     SIMD-in-register counters fed from a 256-entry shared-memory table, one REDUX per counter per warp,
-//     16 global atomics per CTA;
+//   * cooperative grid of (#SM x 2 resident CTAs); CTA c owns one contiguous chunk of nodes, so slice order of the
+//     upgrade-required bucket (upgrade_inplace.go:71) is chunk order;
+//   * the per-policy transition table (32 KiB, built by the host: ust_lut.h) is staged into shared memory with one
+//     TMA bulk copy that completes on an mbarrier; the first tile's loads are in flight before anything waits on it;
+//   * ONE streaming pass over state(1 B) + flags(4) + pod_rev(4) + ds_idx(4) with 128-bit coalesced loads, four
+//     steps (16 nodes) per thread in flight: every node is evaluated by one shared-memory lookup indexed by its hot
+//     byte and one lookup in the transition table, and counted (14-bin state histogram, unavailable, upgrade
+//     candidates) in byte-sliced SIMD-in-register counters; next_state(1) + actions(2) leave with full-width
+//     coalesced stores: 16 algorithmic bytes per node, each touched once. The upgrade-slot grant - the only
+//     cluster-wide dependency - is SPECULATED per chunk (from the policy, or from where the previous call's budget cut);
 //   * one grid-wide barrier (single global atomic counter); every CTA then derives the slot budget
-//     (GetUpgradesAvailable, common_manager.go:748-776) and its exclusive candidate prefix;
-//   * phase 2 streams state(1 B, L2-resident by now) + flags(4) + pod_rev(4) + ds_idx(4) with 128-bit
-//     coalesced loads, evaluates each node by ONE shared-memory table lookup (policy staged in shared
-//     memory as a per-state transition table, see ust_lut.h) and writes next_state(1) + actions(2) with
-//     full-width coalesced stores: 16 algorithmic bytes per node, each touched once;
-//   * only the single chunk that straddles the slot budget runs the exact ordered path (warp-shuffle +
-//     shared-memory exclusive scan of candidate bits); all other chunks are on one side of the cut.
+//     (GetUpgradesAvailable, common_manager.go:748-776) and checks the speculation in O(1); only when it cannot hold
+//     do the CTAs scan the per-chunk candidate counts and re-evaluate the wrong interval, in pieces spread over the
+//     whole grid (ordered path: hot-byte pre-pass + warp-scan ranks; uniform path elsewhere);
+//   * last CTA out writes the counters and restores the workspace.
+// Around it: ust_phase1/2_kernel (the same device code split at the barrier, for the NCCL mode and the pipelined
+// host path), ust_pod_summary_kernel (pod lists -> one byte per node), ust_build_state*_kernel (BuildState),
+// ust_patch_kernel / ust_feedback_kernel (delta updates, rollout simulation).
 #include <cuda_runtime.h>
 
 #include "ust_dev.h"
@@ -28,12 +32,9 @@ namespace {
 
 constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kStep = kThreads * 4;   // nodes per CTA step in phase 2 (4 per thread)
+constexpr int kStep = kThreads * 4;   // nodes per CTA step (4 per thread)
 #ifndef UST_UNROLL
 #define UST_UNROLL 4
-#endif
-#ifndef UST_DOUBLE_BUFFER
-#define UST_DOUBLE_BUFFER 0
 #endif
 #ifndef UST_MIN_CTAS
 #define UST_MIN_CTAS 2
@@ -100,7 +101,7 @@ __device__ __forceinline__ long long chunk_bound(long long n, int c, int chunks)
 // ------------------------------------------------------------------------------------------------
 // table staging: the per-policy transition table (DriverUpgradePolicySpec + manager options, compiled
 // to 32 KiB by ust_lut.h) goes global -> shared with one TMA bulk copy that completes on an mbarrier;
-// nothing waits for it until phase 2 starts.
+// nothing waits for it until the first tile's loads are in flight.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void stamp(const UstParams& P, int k) {
   if (threadIdx.x == 0 && k < 8) {
@@ -259,7 +260,7 @@ __device__ void write_counters(const UstParams& P, const Shared& S) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase 2: per-node transition
+// per-node transition
 // ------------------------------------------------------------------------------------------------
 template <bool DS_SMEM>
 __device__ __forceinline__ bool pod_synced(const UstParams& P, const Shared& S, int rev, uint32_t di) {
