@@ -53,8 +53,9 @@ enum {
 
 /* ------------------------------------------------------------------------------------------------
  * state[i] (uint8): the "hot" byte. Low nibble = state code above. High nibble = the four node
- * predicates the cluster-wide constraint logic needs, so that the counting phase of the kernel
- * streams 1 byte per node and everything else is read exactly once.
+ * predicates the cluster-wide constraint logic needs: one shared-memory lookup indexed by this byte
+ * gives the kernel a node's counter increments and its transition-table window, and the passes that
+ * only count or rank (ordered slot allocation, pod-list selection, BuildState) read nothing else.
  * ---------------------------------------------------------------------------------------------- */
 #define UST_HOT_STATE_MASK 0x0Fu
 #define UST_HOT_NOT_READY 0x10u   /* some NodeReady condition has Status != True   common_manager.go:656-663 */
