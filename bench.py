@@ -9,6 +9,8 @@ per step.
   value      device-resident inputs, CUDA-event time of K steps, max over ranks, whole-job nodes/s
   e2e        the same step through the host-pointer C ABI (ust_apply_state): pinned host arrays in,
              H2D + kernel + D2H inside the timed region
+  e2e_delta  (N=1, informative) ust_apply_state_delta: the snapshot stays resident, 1 % of the nodes are
+             re-encoded and uploaded per step, everything is evaluated, all outputs come back
   roofline   dominant kernel (ust_fused_kernel): 16 algorithmic bytes per node / its CUDA-event duration,
              against the measured HBM copy bandwidth of MEASURED_PEAKS.json
   cpu_baseline / --impl reference   the oracle's reference-shaped restatement of the Go loop (1 thread —
