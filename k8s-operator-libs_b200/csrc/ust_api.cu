@@ -722,9 +722,9 @@ int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const i
     UST_CUDA(h, cudaMemcpyAsync(h->s_ds.p, ds_idx, N * 4, cudaMemcpyHostToDevice, st));
   }
   if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsdesired.p, ds_desired, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
-  int64_t grid = (n_pods + 4095) / 4096;
+  int64_t grid = (n_pods + 1023) / 1024;  // 256 threads x 4 pods per iteration
   if (grid < 1) grid = 1;
-  if (grid > 4 * h->num_sms) grid = 4 * h->num_sms;
+  if (grid > 8 * h->num_sms) grid = 8 * h->num_sms;
   h->ws_dirty = true;
   int e = ust_launch_build_state(n_pods, h->s_hot.p, h->s_ds.p, n_ds, h->s_dsdesired.p, h->ds_count_dev, h->ws, h->counters_dev, (int)grid, st);
   if (e) return h->fail(UST_ERR_CUDA, "build-state kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));

@@ -1417,28 +1417,6 @@ __global__ void __launch_bounds__(kThreads, 6) ust_pod_summary_kernel(long long 
   }
 }
 
-// BuildState's device part (upgrade_state.go:126-133, :158-160): owned pods per DaemonSet and bucket sizes
-__global__ void __launch_bounds__(kThreads) ust_build_state_kernel(long long n, const uint8_t* hot, const int32_t* ds_idx,
-                                                                   int n_ds, unsigned long long* ds_count,
-                                                                   UstWorkspace* ws) {
-  __shared__ unsigned int cnt[18];
-  if (threadIdx.x < 18) cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const unsigned b = hot[i];
-    unsigned code = b & 15u;
-    if (code == 15) code = 14;
-    atomicAdd(&cnt[code], 1u);
-    if (code < 14 && (b & (UST_HOT_UNSCHEDULABLE | UST_HOT_NOT_READY))) atomicAdd(&cnt[16], 1u);
-    if (code == UST_STATE_UPGRADE_REQUIRED && !(b & UST_HOT_SKIP)) atomicAdd(&cnt[17], 1u);
-    const int d = ds_idx[i];
-    if (d >= 0 && d < n_ds) atomicAdd(&ds_count[d], 1ull);
-  }
-  __syncthreads();
-  if (threadIdx.x < 18 && cnt[threadIdx.x]) atomicAdd(&ws->acc[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
-}
-
 // BuildState at wire level: the owner join itself. One entry per driver pod with the 128-bit UID of
 // OwnerReferences[0] ((0, 0) = no owner reference: an orphaned pod, common_manager.go:225-227); the driver
 // DaemonSets' UIDs arrive sorted with their original indices. A pod whose owner is none of them is dropped
@@ -1450,8 +1428,12 @@ __global__ void __launch_bounds__(kThreads) ust_build_state_kernel(long long n, 
 // warp-aggregated atomics.
 constexpr int kUidTabSmem = 2048;  // hash slots held in shared memory (DaemonSets <= 512); larger tables stay in global memory
 
+// UID = false is the index form (ust_build_state: the host has already resolved the owner, ds_idx_in holds it; an index
+// outside [0, n_ds) counts for no DaemonSet): same counting machinery, no join, nothing dropped.
+template <bool UID>
 __global__ void __launch_bounds__(kThreads) ust_build_state_uid_kernel(long long n, const uint8_t* __restrict__ hot,
-                                                                       const ulonglong2* __restrict__ owner, int n_ds,
+                                                                       const ulonglong2* __restrict__ owner,
+                                                                       const int32_t* __restrict__ ds_idx_in, int n_ds,
                                                                        const ulonglong2* __restrict__ ds_tab,
                                                                        const int32_t* __restrict__ ds_tab_idx, int tab_slots,
                                                                        int32_t* __restrict__ ds_idx_out,
@@ -1462,9 +1444,10 @@ __global__ void __launch_bounds__(kThreads) ust_build_state_uid_kernel(long long
   __shared__ unsigned long long inc[256];  // hot byte -> sixteen 4-bit one-hot increments (fields as in the streaming pass)
   __shared__ unsigned int cnt[16];
   const int t = threadIdx.x;
-  const bool in_smem = tab_slots <= kUidTabSmem;  // then n_ds <= kUidTabSmem / 4
+  const bool in_smem = UID ? tab_slots <= kUidTabSmem : n_ds <= kUidTabSmem / 4;  // UID: then n_ds <= kUidTabSmem / 4 too
   if (in_smem) {
-    for (int i = t; i < tab_slots; i += kThreads) { tab[i] = ds_tab[i]; ord[i] = ds_tab_idx[i]; }
+    if (UID)
+      for (int i = t; i < tab_slots; i += kThreads) { tab[i] = ds_tab[i]; ord[i] = ds_tab_idx[i]; }
     for (int i = t; i < n_ds; i += kThreads) cnt_ds[i] = 0;
   }
   {
@@ -1508,13 +1491,18 @@ __global__ void __launch_bounds__(kThreads) ust_build_state_uid_kernel(long long
   const long long stride = (long long)gridDim.x * kThreads * kU;
   for (long long i0 = (long long)blockIdx.x * kThreads * kU; i0 < n; i0 += stride) {  // warp-uniform trip count
     ulonglong2 u[kU];
+    int dk[kU];
     unsigned hb[kU];
 #pragma unroll
     for (int k = 0; k < kU; k++) {
       const long long i = i0 + (long long)k * kThreads + t;
       u[k] = make_ulonglong2(0ull, 0ull);
+      dk[k] = -1;
       hb[k] = UST_STATE_EXCLUDED;
-      if (i < n) { u[k] = __ldcs(owner + i); hb[k] = __ldg(hot + i); }
+      if (i < n) {
+        if (UID) u[k] = __ldcs(owner + i); else dk[k] = __ldcs(ds_idx_in + i);
+        hb[k] = __ldg(hot + i);
+      }
     }
 #pragma unroll
     for (int k = 0; k < kU; k++) {
@@ -1522,7 +1510,9 @@ __global__ void __launch_bounds__(kThreads) ust_build_state_uid_kernel(long long
       const bool valid = i < n;
       int d = -2;
       if (valid) {
-        if ((u[k].x | u[k].y) == 0ull) {
+        if (!UID) {
+          d = (dk[k] >= 0 && dk[k] < n_ds) ? dk[k] : -1;
+        } else if ((u[k].x | u[k].y) == 0ull) {
           d = -1;  // IsOrphanedPod
         } else {
           unsigned slot = ust_uid_hash(u[k].x, u[k].y) & slot_mask;
@@ -1533,7 +1523,7 @@ __global__ void __launch_bounds__(kThreads) ust_build_state_uid_kernel(long long
             slot = (slot + 1u) & slot_mask;
           }
         }
-        __stcs(ds_idx_out + i, d);
+        if (UID) __stcs(ds_idx_out + i, d);
         if (d != -2 && (hb[k] & 15u) < 14u) {  // in the snapshot (the host marks a pending-unscheduled pod with code 14)
           const unsigned long long v = inc[hb[k]];
           lo += (uint32_t)v;
@@ -1697,7 +1687,8 @@ int ust_launch_pod_summary(long long n, int active, const uint8_t* hot, const in
 }
 int ust_launch_build_state(long long n, const uint8_t* hot, const int32_t* ds_idx, int n_ds, const int32_t* ds_desired,
                            unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream) {
-  ust_build_state_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, hot, ds_idx, n_ds, ds_count, ws);
+  ust_build_state_uid_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, hot, nullptr, ds_idx, n_ds, nullptr, nullptr, 8,
+                                                                                 nullptr, ds_count, ws);
   ust_build_state_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_ds, ds_desired, ds_count, ws, out);
   return (int)cudaGetLastError();
 }
@@ -1719,8 +1710,8 @@ int ust_launch_feedback(long long n, uint8_t* hot, uint32_t* flags, int32_t* pod
 int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* owner_uid, int n_ds, const void* ds_tab,
                                 const int32_t* ds_tab_idx, int tab_slots, const int32_t* ds_desired, int32_t* ds_idx_out,
                                 unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream) {
-  ust_build_state_uid_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-      n, hot, reinterpret_cast<const ulonglong2*>(owner_uid), n_ds, reinterpret_cast<const ulonglong2*>(ds_tab), ds_tab_idx,
+  ust_build_state_uid_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+      n, hot, reinterpret_cast<const ulonglong2*>(owner_uid), nullptr, n_ds, reinterpret_cast<const ulonglong2*>(ds_tab), ds_tab_idx,
       tab_slots, ds_idx_out, ds_count, ws);
   ust_build_state_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_ds, ds_desired, ds_count, ws, out);
   return (int)cudaGetLastError();
