@@ -17,7 +17,10 @@
 //   * k8s.io/apimachinery v0.35.1 pkg/util/intstr.GetScaledValueFromIntOrPercent (go.mod:13)
 //   * k8s.io/kubectl v0.35.1 pkg/drain filter chain (go.mod:15)
 // The daemonset / mirror / finished-pod branches of the drain filter chain are NOT exercised by any
-// reference test: parity unpinned for those branches (stated in DESIGN.md).
+// reference test: parity unpinned for those branches (stated in DESIGN.md). Likewise unpinned: the skip of a pod
+// owned by something other than a driver DaemonSet in ust_oracle_build_state_uids (common_manager.go:199-203).
+// ust_oracle_simulate's feedback between reconciles is not reference behaviour at all (the reference has only
+// mocks): it is an independent second implementation of this repo's documented model.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
