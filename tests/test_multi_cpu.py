@@ -98,3 +98,27 @@ def test_exchange_vector_protocol_world2(p_err):
         assert abort is not None and (abort >> 56) == cnt["error_pass"] and (abort & ((1 << 56) - 1)) - 1 == cnt["error_index"]
     else:
         assert abort is None
+
+
+def test_pod_lists_shard_at_node_boundaries():
+    """Sharded generation (what each rank of tests/test_gpu_multi.py and bench.py feeds its GPU) is the unsharded
+    snapshot cut at node boundaries: per-rank CSR offsets start at 0 and the concatenated lists are the whole."""
+    import numpy as np
+    from ust import synth
+    n, world, seed = 3000, 3, 0x5EED0004
+    whole_nodes = synth.make_nodes(world * n, seed)
+    whole_pods = synth.make_pods(world * n, seed)
+    flags, total = [], 0
+    for r in range(world):
+        part = synth.make_nodes(n, seed, start=r * n)
+        for k in ("state", "flags", "pod_rev", "ds_idx"):
+            assert np.array_equal(part[k], whole_nodes[k][r * n:(r + 1) * n]), k
+        pods = synth.make_pods(n, seed, start=r * n)
+        assert pods["pod_off"][0] == 0
+        lo, hi = int(whole_pods["pod_off"][r * n]), int(whole_pods["pod_off"][(r + 1) * n])
+        assert np.array_equal(pods["pod_off"], whole_pods["pod_off"][r * n:(r + 1) * n + 1] - lo)
+        assert np.array_equal(pods["pod_flags"], whole_pods["pod_flags"][lo:hi])
+        total += hi - lo
+    assert total == whole_pods["pod_flags"].shape[0]
+    blocked = synth.make_pods_blocked(world * n, seed, block=777)
+    assert np.array_equal(blocked["pod_off"], whole_pods["pod_off"]) and np.array_equal(blocked["pod_flags"], whole_pods["pod_flags"])
