@@ -7,8 +7,9 @@ shard of an N x 10 M-node cluster (config C5 at N=8): weak scaling, one exchange
 per step.
 
   value      device-resident inputs, CUDA-event time of K steps, max over ranks, whole-job nodes/s
-  e2e        the same step through the host-pointer C ABI (ust_apply_state): pinned host arrays in,
-             H2D + kernel + D2H inside the timed region
+  e2e        the same step through the host-pointer C ABI, pinned host arrays in, H2D + kernel + D2H inside the
+             timed region. N=1: ust_apply_state_packed (uint16 revisions / int8 DaemonSet indices on the host side,
+             8 B/node up; --e2e-format wide = ust_apply_state, 13 B/node up); N>1: ust_apply_state
   e2e_delta  (N=1, informative) ust_apply_state_delta: the snapshot stays resident, 1 % of the nodes are
              re-encoded and uploaded per step, everything is evaluated, all outputs come back
   roofline   dominant kernel (ust_fused_kernel): 16 algorithmic bytes per node / its CUDA-event duration,
@@ -163,6 +164,9 @@ def main():
     ap.add_argument("--maxpar", type=int, default=None, help="tuning: override MaxParallelUpgrades")
     ap.add_argument("--maxunav", default=None, help="tuning: override MaxUnavailable ('nil', int or 'NN%%')")
     ap.add_argument("--quick", action="store_true", help="tuning: device-resident timing only (no e2e / cpu baseline)")
+    ap.add_argument("--e2e-format", default="packed", choices=["wide", "packed"],
+                    help="host format of the e2e leg: wide = ust_apply_state (int32 pod_rev / ds_idx), packed = "
+                         "ust_apply_state_packed (uint16 / int8: 8 instead of 13 bytes per node over PCIe)")
     ap.add_argument("--pods", action="store_true", help="tuning (with --quick): the C4 workload - CSR pod lists, pod deletion and drain enabled")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -375,12 +379,25 @@ def main():
     for k in soa:
         host[k][...] = soa[k]
     out = (ustlib.pinned_array(n, np.uint8), ustlib.pinned_array(n, np.uint16), None)
+    packed = args.e2e_format == "packed" and world == 1   # N > 1 keeps the int32 host format
+    if packed:
+        assert soa["pod_rev"].min() >= 0 and soa["pod_rev"].max() < 65536 and soa["ds_idx"].min() >= -128 and n_ds <= 127
+        pk = (ustlib.pinned_array(n, np.uint16), ustlib.pinned_array(n, np.int8))
+        pk[0][...] = soa["pod_rev"]
+        pk[1][...] = soa["ds_idx"]
+
+    def e2e_step():
+        if packed:
+            h.apply_state_packed(pol, host, want_outcome=False, out=out, check=True, packed=pk)
+        else:
+            h.apply_state(pol, host, want_outcome=False, out=out, check=True)
+
     for _ in range(2):
-        h.apply_state(pol, host, want_outcome=False, out=out, check=True)
+        e2e_step()
     barrier()
     t0 = time.time()
     for _ in range(args.e2e_steps):
-        h.apply_state(pol, host, want_outcome=False, out=out, check=True)
+        e2e_step()
     barrier()
     e2e_s = time.time() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -416,7 +433,8 @@ def main():
     if rank == 0:
         if delta is not None:
             line["e2e_delta"] = delta
-        line["e2e"] = {"value": e2e_value, "unit": "nodes/s", "h2d_bytes_per_step": 13 * n + 4 * n_ds,
+        line["e2e"] = {"value": e2e_value, "unit": "nodes/s", "h2d_bytes_per_step": (8 if packed else 13) * n + 4 * n_ds,
+                       "entry_point": "ust_apply_state_packed" if packed else "ust_apply_state",
                        "d2h_bytes_per_step": 3 * n + C.sizeof(abi.Counters), "steps": args.e2e_steps,
                        "ms_per_step": float(te.item()) / args.e2e_steps * 1e3}
         # ---- CPU baseline beside it: bounded sample, 1 thread (the reference loop is sequential) ----

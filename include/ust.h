@@ -243,6 +243,16 @@ int ust_apply_state_device(ust_handle* h, const ust_policy* policy, int64_t n_no
                            ust_counters* out_device, void* stream);
 int ust_sync(ust_handle* h);
 
+/* Packed host format: ust_apply_state with the two interned columns at the width they need - pod_rev16[i] is the
+ * interned driver-pod revision hash (0 = none) as uint16, ds_idx8[i] the DaemonSet index as int8 (< 0 = orphaned),
+ * so 8 instead of 13 bytes per node cross PCIe; the device widens them. For encoders that intern at most 65535
+ * revision hashes and 127 DaemonSets (the reference's driver DaemonSets per cluster are a handful); anything else
+ * uses ust_apply_state. No pod lists. Same outputs, counters, errors and resident snapshot as ust_apply_state. */
+int ust_apply_state_packed(ust_handle* h, const ust_policy* policy, int64_t n_nodes, const uint8_t* state,
+                           const uint32_t* flags, const uint16_t* pod_rev16, const int8_t* ds_idx8, int32_t n_ds,
+                           const int32_t* ds_rev, uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome,
+                           ust_counters* out);
+
 /* Delta form: a successful ust_apply_state without pod lists leaves the uploaded snapshot resident on
  * the device. ust_apply_state_delta overwrites the n_changed nodes named by idx (distinct indices into that
  * snapshot) with freshly encoded values - what a reconcile that watches resourceVersions re-encodes - and evaluates

@@ -110,6 +110,8 @@ struct ust_handle {
   DevBuf<uint8_t> s_hot, s_next, s_outcome;
   DevBuf<uint32_t> s_flags;
   DevBuf<int32_t> s_rev, s_ds, s_dsrev, s_podoff, s_dsdesired;
+  DevBuf<uint16_t> s_rev16;          // packed host format: interned pod revisions / DaemonSet indices as uploaded
+  DevBuf<int8_t> s_ds8;
   DevBuf<uint16_t> s_actions, s_podflags;
   DevBuf<uint8_t> s_podsum;
   DevBuf<uint64_t> s_uid, s_dsuid;   // BuildState owner join: pod owner UIDs, DaemonSet UID hash table (+ s_dsorder: slot -> index)
@@ -347,7 +349,8 @@ static int64_t host_chunk_bound(int64_t n, int c, int chunks) {
 // then (rare) the outputs are downloaded again.
 static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
                            const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, uint8_t* next_state,
-                           uint16_t* actions, uint8_t* outcome, ust_counters* out) {
+                           uint16_t* actions, uint8_t* outcome, ust_counters* out, const uint16_t* rev16 = nullptr,
+                           const int8_t* ds8 = nullptr) {
   cudaStream_t up = h->stream, down = h->stream_d2h, h2d = h->stream_h2d;  // up = compute stream of the call
   if (h->ws_dirty) {
     UST_CUDA(h, cudaMemsetAsync(h->ws, 0, sizeof(UstWorkspace), up));
@@ -377,11 +380,21 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
     if (len) {
       UST_CUDA(h, cudaMemcpyAsync(h->s_hot.p + n0, state + n0, len, cudaMemcpyHostToDevice, h2d));
       UST_CUDA(h, cudaMemcpyAsync(h->s_flags.p + n0, flags + n0, len * 4, cudaMemcpyHostToDevice, h2d));
-      UST_CUDA(h, cudaMemcpyAsync(h->s_rev.p + n0, pod_rev + n0, len * 4, cudaMemcpyHostToDevice, h2d));
-      UST_CUDA(h, cudaMemcpyAsync(h->s_ds.p + n0, ds_idx + n0, len * 4, cudaMemcpyHostToDevice, h2d));
+      if (rev16) {  // packed host format: 3 instead of 8 bytes per node over PCIe, widened on the device
+        UST_CUDA(h, cudaMemcpyAsync(h->s_rev16.p + n0, rev16 + n0, len * 2, cudaMemcpyHostToDevice, h2d));
+        UST_CUDA(h, cudaMemcpyAsync(h->s_ds8.p + n0, ds8 + n0, len, cudaMemcpyHostToDevice, h2d));
+      } else {
+        UST_CUDA(h, cudaMemcpyAsync(h->s_rev.p + n0, pod_rev + n0, len * 4, cudaMemcpyHostToDevice, h2d));
+        UST_CUDA(h, cudaMemcpyAsync(h->s_ds.p + n0, ds_idx + n0, len * 4, cudaMemcpyHostToDevice, h2d));
+      }
     }
     UST_CUDA(h, cudaEventRecord(h->seg_up[seg], h2d));
     UST_CUDA(h, cudaStreamWaitEvent(up, h->seg_up[seg], 0));
+    if (rev16 && len) {
+      int we = ust_launch_widen((long long)len, h->s_rev16.p + n0, h->s_ds8.p + n0, h->s_rev.p + n0, h->s_ds.p + n0, 4 * h->num_sms, up);
+      if (we) return h->fail(UST_ERR_CUDA, "widen kernel launch failed: %s", cudaGetErrorString((cudaError_t)we));
+      h->launches += 1;
+    }
     UstParams Ps = P;
     Ps.chunk_begin = c0;
     Ps.chunk_end = c1;
@@ -504,7 +517,7 @@ void ust_destroy(ust_handle* h) {
   if (h->ds_count_dev) cudaFree(h->ds_count_dev);
   h->s_hot.release(); h->s_next.release(); h->s_outcome.release(); h->s_flags.release();
   h->s_rev.release(); h->s_ds.release(); h->s_dsrev.release(); h->s_podoff.release(); h->s_dsdesired.release();
-  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release(); h->d_idx.release(); h->d_state.release(); h->d_flags.release(); h->d_rev.release(); h->d_ds.release();
+  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release(); h->s_rev16.release(); h->s_ds8.release(); h->d_idx.release(); h->d_state.release(); h->d_flags.release(); h->d_rev.release(); h->d_ds.release();
   for (auto& ev : h->seg_done) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->seg_up) if (ev) cudaEventDestroy(ev);
   if (h->stream_h2d) cudaStreamDestroy(h->stream_h2d);
@@ -645,6 +658,56 @@ int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_cha
   rc = finish_with_counters(h, st, out);
   if (rc != UST_ERR_CUDA && rc != UST_ERR_COMM) { h->resident_n = n; h->resident_n_ds = n_ds; }
   return rc;
+}
+
+int ust_apply_state_packed(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
+                           const uint16_t* pod_rev16, const int8_t* ds_idx8, int32_t n_ds, const int32_t* ds_rev,
+                           uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome, ust_counters* out) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  if (n < 0 || (n > 0 && (!state || !flags || !pod_rev16 || !ds_idx8 || !next_state || !actions)))
+    return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
+  if (n_ds < 0 || n_ds > 127 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table (the packed format holds at most 127 DaemonSets)");
+  UST_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t N = (size_t)n;
+  UST_CUDA(h, h->s_hot.reserve(N + 16));
+  UST_CUDA(h, h->s_flags.reserve(N + 4));
+  UST_CUDA(h, h->s_rev.reserve(N + 4));
+  UST_CUDA(h, h->s_ds.reserve(N + 4));
+  UST_CUDA(h, h->s_rev16.reserve(N + 8));
+  UST_CUDA(h, h->s_ds8.reserve(N + 16));
+  UST_CUDA(h, h->s_next.reserve(N + 16));
+  UST_CUDA(h, h->s_actions.reserve(N + 8));
+  UST_CUDA(h, h->s_dsrev.reserve((size_t)n_ds + 1));
+  if (actuator_outcome) UST_CUDA(h, h->s_outcome.reserve(N + 16));
+  if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsrev.p, ds_rev, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
+  h->resident_n = -1;
+  auto keep = [&](int rc) {
+    if (rc != UST_ERR_CUDA && rc != UST_ERR_INVALID_ARGUMENT && rc != UST_ERR_COMM && rc != UST_ERR_NIL_STATE) { h->resident_n = n; h->resident_n_ds = n_ds; }
+    return rc;
+  };
+  if (h->world == 1 && n >= (1 << 19))
+    return keep(apply_pipelined(h, policy, n, state, flags, nullptr, nullptr, n_ds, next_state, actions, actuator_outcome, out,
+                                pod_rev16, ds_idx8));
+  if (N) {
+    UST_CUDA(h, cudaMemcpyAsync(h->s_hot.p, state, N, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->s_flags.p, flags, N * 4, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->s_rev16.p, pod_rev16, N * 2, cudaMemcpyHostToDevice, st));
+    UST_CUDA(h, cudaMemcpyAsync(h->s_ds8.p, ds_idx8, N, cudaMemcpyHostToDevice, st));
+    int we = ust_launch_widen((long long)n, h->s_rev16.p, h->s_ds8.p, h->s_rev.p, h->s_ds.p, 4 * h->num_sms, st);
+    if (we) return h->fail(UST_ERR_CUDA, "widen kernel launch failed: %s", cudaGetErrorString((cudaError_t)we));
+    h->launches += 1;
+  }
+  int rc = apply_device(h, policy, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, n_ds, h->s_dsrev.p, nullptr, nullptr, 0,
+                        h->s_next.p, h->s_actions.p, actuator_outcome ? h->s_outcome.p : nullptr, nullptr, st);
+  if (rc) return rc;
+  if (N) {
+    UST_CUDA(h, cudaMemcpyAsync(next_state, h->s_next.p, N, cudaMemcpyDeviceToHost, st));
+    UST_CUDA(h, cudaMemcpyAsync(actions, h->s_actions.p, N * 2, cudaMemcpyDeviceToHost, st));
+    if (actuator_outcome) UST_CUDA(h, cudaMemcpyAsync(actuator_outcome, h->s_outcome.p, N, cudaMemcpyDeviceToHost, st));
+  }
+  return keep(finish_with_counters(h, st, out));
 }
 
 int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps, ust_counters* history, uint8_t* final_state,

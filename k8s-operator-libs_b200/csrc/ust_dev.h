@@ -120,4 +120,6 @@ int ust_launch_patch(long long m, const long long* idx, const uint8_t* state, co
 int ust_launch_feedback(long long n, uint8_t* hot, uint32_t* flags, int32_t* pod_rev, const int32_t* ds_idx, int n_ds,
                         const int32_t* ds_rev, const uint8_t* next, const uint16_t* actions, const uint8_t* outcome,
                         const ust_counters* step, int grid, void* stream);
+int ust_launch_widen(long long n, const uint16_t* rev16, const int8_t* ds8, int32_t* rev_out, int32_t* ds_out, int grid,
+                     void* stream);
 int ust_max_coresident_ctas(int device, int* ctas_per_sm, int* num_sms);

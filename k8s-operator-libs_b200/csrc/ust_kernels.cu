@@ -1663,6 +1663,19 @@ __global__ void __launch_bounds__(kThreads) ust_feedback_kernel(long long n, uin
   }
 }
 
+// Packed host format (ust_apply_state_packed): the interned pod revision travels as uint16 and the DaemonSet index
+// as int8 over PCIe; this widens a range of them into the int32 arrays the streaming pass reads. 3 B read + 8 B
+// written per node, once per upload segment.
+__global__ void __launch_bounds__(kThreads) ust_widen_kernel(long long n, const uint16_t* __restrict__ rev16,
+                                                             const int8_t* __restrict__ ds8, int32_t* __restrict__ rev_out,
+                                                             int32_t* __restrict__ ds_out) {
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    rev_out[i] = (int32_t)__ldcs(rev16 + i);
+    ds_out[i] = (int32_t)__ldcs(ds8 + i);
+  }
+}
+
 }  // namespace
 
 int ust_launch_fused(const UstParams& p, int grid, void* stream) {
@@ -1690,6 +1703,13 @@ int ust_launch_build_state(long long n, const uint8_t* hot, const int32_t* ds_id
   ust_build_state_uid_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, hot, nullptr, ds_idx, n_ds, nullptr, nullptr, 8,
                                                                                  nullptr, ds_count, ws);
   ust_build_state_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_ds, ds_desired, ds_count, ws, out);
+  return (int)cudaGetLastError();
+}
+int ust_launch_widen(long long n, const uint16_t* rev16, const int8_t* ds8, int32_t* rev_out, int32_t* ds_out, int grid,
+                     void* stream) {
+  if (n <= 0) return 0;
+  const long long want = (n + kThreads - 1) / kThreads;
+  ust_widen_kernel<<<(unsigned)(want < grid ? want : grid), kThreads, 0, (cudaStream_t)stream>>>(n, rev16, ds8, rev_out, ds_out);
   return (int)cudaGetLastError();
 }
 int ust_launch_patch(long long m, const long long* idx, const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev,

@@ -42,6 +42,8 @@ def load():
                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ust_apply_state.argtypes = apply_args
         lib.ust_apply_state_device.argtypes = apply_args + [C.c_void_p]
+        lib.ust_apply_state_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ust_apply_state_delta.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ust_simulate_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -59,7 +61,7 @@ def load():
 
 
 EXPORTS = ["ust_abi_version", "ust_create", "ust_destroy", "ust_last_error", "ust_create_error", "ust_launch_count",
-           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_apply_state_delta", "ust_simulate_rollout", "ust_sync",
+           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_apply_state_packed", "ust_apply_state_delta", "ust_simulate_rollout", "ust_sync",
            "ust_build_state", "ust_build_state_uids", "ust_get_unique_id", "ust_comm_init", "ust_comm_set_mode", "ust_table_entry",
            "ust_table_window_shift"]
 
@@ -149,6 +151,27 @@ class Handle:
             self._h, C.addressof(policy) if policy is not None else None, n, _p(soa["state"]), _p(soa["flags"]),
             _p(soa["pod_rev"]), _p(soa["ds_idx"]), int(soa["ds_rev"].shape[0]), _p(soa["ds_rev"]),
             C.addressof(ps) if ps is not None else None, _p(nxt), _p(act), _p(oc), C.addressof(cnt))
+        if check and rc:
+            raise UstError(rc, self.last_error())
+        return rc, nxt, act, oc, cnt.as_dict()
+
+    def apply_state_packed(self, policy, soa, want_outcome=True, out=None, check=False, packed=None):
+        """ust_apply_state_packed: the same snapshot with pod_rev as uint16 and ds_idx as int8 on the host side.
+        `packed` = (pod_rev16, ds_idx8) arrays to reuse (e.g. pinned); by default they are made from soa."""
+        n = int(soa["state"].shape[0])
+        if packed is None:
+            assert n == 0 or (soa["pod_rev"].min() >= 0 and soa["pod_rev"].max() < 65536 and soa["ds_idx"].min() >= -128 and soa["ds_idx"].max() < 128)
+            packed = (np.ascontiguousarray(soa["pod_rev"], dtype=np.uint16), np.ascontiguousarray(soa["ds_idx"], dtype=np.int8))
+        if out is None:
+            nxt = np.zeros(n, np.uint8)
+            act = np.zeros(n, np.uint16)
+            oc = np.full(n, 0xFF, np.uint8) if want_outcome else None
+        else:
+            nxt, act, oc = out
+        cnt = abi.Counters()
+        rc = self._lib.ust_apply_state_packed(
+            self._h, C.addressof(policy) if policy is not None else None, n, _p(soa["state"]), _p(soa["flags"]), _p(packed[0]),
+            _p(packed[1]), int(soa["ds_rev"].shape[0]), _p(soa["ds_rev"]), _p(nxt), _p(act), _p(oc), C.addressof(cnt))
         if check and rc:
             raise UstError(rc, self.last_error())
         return rc, nxt, act, oc, cnt.as_dict()

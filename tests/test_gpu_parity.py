@@ -282,6 +282,34 @@ def test_simulated_rollout_matches_the_cpu_simulation(handle, n, steps):
     assert handle.simulate_rollout(abi.make_policy(use_maintenance_operator=True), n, 1)[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]
 
 
+@pytest.mark.parametrize("n", [0, 1, 5000, 700_001])
+def test_packed_host_format(handle, n):
+    """ust_apply_state_packed (uint16 revisions, int8 DaemonSet indices over PCIe, widened on the device) ==
+    ust_apply_state == the oracle, on the direct and the pipelined upload path; the snapshot it leaves resident
+    takes delta updates."""
+    rng = np.random.default_rng(77 + n)
+    soa, _ = helpers.random_soa(rng, n, wild=True, p_err=1e-4 if n == 5000 else 0.0)
+    soa["pod_rev"] = rng.integers(0, 65536, n).astype(np.int32)      # the whole uint16 range
+    soa["ds_rev"] = rng.integers(0, 65536, 3).astype(np.int32)
+    soa["pod_rev"][::3] = soa["ds_rev"][rng.integers(0, 3, soa["pod_rev"][::3].shape[0])]
+    for rep in range(2):
+        pol = helpers.random_policy(rng)
+        got = handle.apply_state_packed(pol, soa)
+        ref = helpers.oracle_apply(pol, soa, variant=1)
+        helpers.assert_same(got, ref, f"packed n={n} rep={rep}")
+        helpers.assert_same(gpu_apply(handle, pol, soa), ref, f"wide n={n} rep={rep}")
+    if n >= 5000:
+        handle.apply_state_packed(pol, soa)
+        idx = rng.choice(n, size=n // 50, replace=False).astype(np.int64)
+        fresh, _ = helpers.random_soa(rng, idx.shape[0], wild=True)
+        for k in ("state", "flags", "pod_rev", "ds_idx"):
+            soa[k][idx] = fresh[k]
+        got = handle.apply_state_delta(pol, n, idx, {k: fresh[k] for k in ("state", "flags", "pod_rev", "ds_idx")}, soa["ds_rev"])
+        helpers.assert_same(got, helpers.oracle_apply(pol, soa, variant=1), "delta after a packed call")
+    too_many = dict(soa); too_many["ds_rev"] = np.zeros(128, np.int32)
+    assert handle.apply_state_packed(pol, too_many)[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]
+
+
 def test_many_daemonsets_use_the_global_table(handle):
     rng = np.random.default_rng(99)
     n, n_ds = 50_000, 3000  # > UST_DS_SMEM_MAX
