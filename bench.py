@@ -342,7 +342,7 @@ def main():
                        "exchange": "none" if world == 1 else exchange},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic() if (world == 1 and n == SHARD_NODES) else None, "peak_source": peak_src,
-                         "kernel": "ust_fused_kernel" if (world == 1 or "fused" in exchange) else "ust_phase1_kernel",
+                         "kernel": "ust_stream_kernel",
                          "kernel_ms": kern_ms, "kernel_ms_event_pairs_median": float(np.median(per_step_ms)),
                          "frac_of_8TBs": achieved / 8000.0},
             "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
@@ -351,22 +351,17 @@ def main():
 
     if args.quick:
         if rank == 0 and os.environ.get("UST_STAMPS"):
-            g = int(os.environ["UST_STAMPS"])
-            st = (C.c_uint64 * (8 * g))()
+            g = min(int(os.environ["UST_STAMPS"]), 148)
+            st = (C.c_uint64 * (4 * g))()
             ustlib.load().ust_debug_stamps(h._h, st, g)
-            a = np.array(st, dtype=np.int64).reshape(g, 8)
+            a = np.array(st, dtype=np.int64).reshape(g, 4)
             t0 = a[:, 0].min()
-            a = a - t0
-            print("stamps us: entry[min,max]=%.1f,%.1f stream_end[min,med,max]=%.1f,%.1f,%.1f barrier_release[min,max]=%.1f,%.1f "
-                  "exit[min,max]=%.1f,%.1f stream_dur[min,med,max]=%.1f,%.1f,%.1f" % (
-                      a[:, 0].min() / 1e3, a[:, 0].max() / 1e3, a[:, 1].min() / 1e3, np.median(a[:, 1]) / 1e3, a[:, 1].max() / 1e3,
-                      a[:, 2].min() / 1e3, a[:, 2].max() / 1e3, a[:, 3].min() / 1e3, a[:, 3].max() / 1e3,
-                      (a[:, 1] - a[:, 0]).min() / 1e3, np.median(a[:, 1] - a[:, 0]) / 1e3, (a[:, 1] - a[:, 0]).max() / 1e3), flush=True)
-            tail = (a[:, 3] - a[:, 2]) / 1e3
-            w = int(tail.argmax())
-            print("after-barrier us: median %.1f max %.1f (CTA %d)" % (np.median(tail), tail.max(), w), flush=True)
-            print("slowest CTA stamps us (entry, stream end, barrier, exit, piece begin, rank known, pre-pass done, piece end):",
-                  [round(float(v) / 1e3, 1) for v in a[w]], flush=True)
+            rel = (a - t0) / 1e3
+            last = int(a[:, 3].argmax())
+            print("stamps us: entry[min,max]=%.1f,%.1f first_tile[min,med,max]=%.1f,%.1f,%.1f stream_end[min,med,max]=%.1f,%.1f,%.1f "
+                  "deciding CTA %d: stream end %.1f exit %.1f" % (
+                      rel[:, 0].min(), rel[:, 0].max(), rel[:, 1].min(), np.median(rel[:, 1]), rel[:, 1].max(),
+                      rel[:, 2].min(), np.median(rel[:, 2]), rel[:, 2].max(), last, rel[last, 2], rel[last, 3]), flush=True)
         if rank == 0:
             print(json.dumps({k: line[k] for k in ("value", "ms_per_step", "roofline", "clocks")}), flush=True)
         h.close()

@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libust.so")
-SOURCES = ["ust_kernels.cu", "ust_api.cu"]
-DEPS = SOURCES + ["ust_dev.h", "ust_lut.h", os.path.join("..", "..", "include", "ust.h")]
+SOURCES = ["ust_stream.cu", "ust_kernels.cu", "ust_api.cu"]
+DEPS = SOURCES + ["ust_dev.h", "ust_common.cuh", "ust_lut.h", os.path.join("..", "..", "include", "ust.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-ffp-contract=off", "--fmad=false",

@@ -85,8 +85,13 @@ struct ust_handle {
   std::mutex mu;
   std::string err;
   int64_t launches = 0;
-  int ctas_per_sm = 0, num_sms = 0;
+  int num_sms = 0;
+  size_t stream_smem = 0;   // dynamic shared memory of the streaming kernel (largest variant)
   bool ws_dirty = false;
+  bool pdl = true;          // launch the kernels of a call with programmatic dependent launch (UST_PDL=0 turns it off: tuning)
+  bool stamps = false;      // UST_STAMPS: per-CTA %globaltimer stamps (diagnostics)
+  int static_pct = 75;      // share of a launch's tile rounds taken in stride order before the ticket (UST_STATIC_PCT: tuning)
+  cudaStream_t last_stream = nullptr;  // stream of the previous device-resident call (calls on another stream are ordered behind it)
   int64_t resident_n = -1;  // nodes of the snapshot the last ust_apply_state left in the staging arrays (-1 = none)
   int32_t resident_n_ds = 0;  // ... and the size of its DaemonSet table
   ust_counters* hist_dev = nullptr;  // rollout simulation: one ust_counters per simulated reconcile
@@ -114,6 +119,7 @@ struct ust_handle {
   DevBuf<int8_t> s_ds8;
   DevBuf<uint16_t> s_actions, s_podflags;
   DevBuf<uint8_t> s_podsum;
+  DevBuf<unsigned int> s_candtile;   // upgrade candidates per tile of the current call
   DevBuf<uint64_t> s_uid, s_dsuid;   // BuildState owner join: pod owner UIDs, DaemonSet UID hash table (+ s_dsorder: slot -> index)
   DevBuf<int32_t> s_dsorder;
   DevBuf<long long> d_idx;           // delta updates: indices and values of the changed nodes
@@ -184,20 +190,23 @@ static int ensure_tables(ust_handle* h, const ust_policy* p, cudaStream_t st) {
   return UST_OK;
 }
 
-// The shard is cut into contiguous chunks that CTAs claim with an atomic ticket. Measured on B200 (round 1,
-// profiles/README.md): one chunk per co-resident CTA beats finer dynamic chunks, because every chunk start
-// exposes one full HBM latency before its first tile arrives — so chunks == grid unless the snapshot is small.
-static int pick_chunks(const ust_handle* h, int64_t n) {
-  const int64_t max_grid = (int64_t)h->ctas_per_sm * h->num_sms;
-  int64_t c = n / 8192;
-  if (c < 1) c = 1;
-  if (c > max_grid) c = max_grid;
-  if (c > UST_MAX_CTAS) c = UST_MAX_CTAS;
-  return (int)c;
+// Tiling of a shard: tiles of UST_TILE_NODES nodes; smaller (power-of-two) tiles when the snapshot is so small that
+// full-size tiles would leave SMs without work. One persistent CTA per SM, never more CTAs than tiles.
+static int pick_tile_nodes(const ust_handle* h, int64_t n) {
+  int tn = UST_TILE_NODES;
+  while (tn > 128 && n / tn < 2LL * h->num_sms) tn >>= 1;
+  return tn;
 }
-static int pick_grid(const ust_handle* h, int chunks) {
-  const int64_t max_grid = (int64_t)h->ctas_per_sm * h->num_sms;
-  return (int)(chunks < max_grid ? chunks : max_grid);
+static int pick_grid(const ust_handle* h, int tiles) {
+  const int g = tiles < h->num_sms ? tiles : h->num_sms;
+  return g < 1 ? 1 : g;
+}
+// rounds of a launch's tile range that a CTA takes in stride order before it starts claiming tiles by ticket
+static int pick_static_rounds(const ust_handle* h, int tiles, int grid) {
+  const int rounds = tiles / grid;
+  int r = (int)((int64_t)rounds * h->static_pct / 100);
+  if (rounds - r < 2) r = rounds - 2;
+  return r < 0 ? 0 : r;
 }
 
 static int check_aligned(ust_handle* h, const void* p, const char* what) {
@@ -205,10 +214,10 @@ static int check_aligned(ust_handle* h, const void* p, const char* what) {
   return UST_OK;
 }
 
-static void fill_params(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
-                        const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
-                        const int32_t* pod_off, const uint16_t* pod_flags, uint8_t* next_state, uint16_t* actions,
-                        uint8_t* outcome, ust_counters* out_dev, UstParams* out, int* grid_out) {
+static int fill_params(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
+                       const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                       const int32_t* pod_off, const uint16_t* pod_flags, uint8_t* next_state, uint16_t* actions,
+                       uint8_t* outcome, ust_counters* out_dev, UstParams* out, int* grid_out) {
   const bool active = policy_active(policy);
   UstParams P;
   memset(&P, 0, sizeof(P));
@@ -228,7 +237,8 @@ static void fill_params(ust_handle* h, const ust_policy* policy, int64_t n, cons
     P.requestor = policy->use_maintenance_operator != 0;
     P.pd_enabled = policy->pod_deletion_enabled != 0;
     P.pd_spec_present = policy->pod_deletion_spec_present != 0;
-    P.eval_pods = (policy->evaluate_actuators != 0 && pod_off && pod_flags) ? 1 : 0;
+    // pod lists given (even empty ones: "no pods" is an answer, not "unknown") and actuator evaluation asked for
+    P.eval_pods = (policy->evaluate_actuators != 0 && pod_off) ? 1 : 0;
   }
   P.rank = h->rank;
   P.world = h->world;
@@ -236,25 +246,57 @@ static void fill_params(ust_handle* h, const ust_policy* policy, int64_t n, cons
     P.fused_exchange = 1;
     for (int r = 0; r < h->world; r++) P.mbox[r] = h->mbox[r];
   }
-  // Speculative slot grant (verified in-kernel after the grid barrier, so only speed depends on it):
+  P.split = (h->world > 1 && !P.fused_exchange) ? 1 : 0;
+  // Speculative slot grant (verified by the call's last CTA, so only speed depends on it):
   // with no MaxParallelUpgrades / MaxUnavailable limit every candidate gets a slot (upgrade_inplace.go:49-62);
   // with limits the budget is normally tiny next to the number of candidates.
-  P.spec_cut_chunk = (active && policy->max_parallel_upgrades == 0 && policy->max_unavailable_kind == UST_MAXUNAVAIL_NIL) ? 0x7FFFFFFF : 0;
-  int chunks = pick_chunks(h, n);
-  int grid = pick_grid(h, chunks);
+  P.spec_cut_tile = (active && policy->max_parallel_upgrades == 0 && policy->max_unavailable_kind == UST_MAXUNAVAIL_NIL) ? 0x7FFFFFFF : 0;
+  const int tn = pick_tile_nodes(h, n);
+  const int64_t tiles64 = (n + tn - 1) / tn;
+  const int tiles = (int)tiles64;
+  const int grid = pick_grid(h, tiles);
   if (active && !P.requestor && !h->no_hint) {
     // signature of everything the cut position depends on besides the data itself (FNV-1a)
     unsigned long long sig = 1469598103934665603ull;
-    const long long parts[6] = {n, chunks, policy->max_parallel_upgrades, policy->max_unavailable_kind, policy->max_unavailable_value, h->world * 64 + h->rank};
+    const long long parts[6] = {n, tn, policy->max_parallel_upgrades, policy->max_unavailable_kind, policy->max_unavailable_value, h->world * 64 + h->rank};
     for (long long v : parts) { sig ^= (unsigned long long)v; sig *= 1099511628211ull; }
     P.spec_sig = sig ? sig : 1;
   }
-  P.grid_chunks = chunks;
-  P.chunk_begin = 0;
-  P.chunk_end = chunks;
+  P.tile_nodes = tn;
+  P.n_tiles = tiles;
+  P.tile_begin = 0;
+  P.tile_end = tiles;
+  P.static_rounds = pick_static_rounds(h, tiles, grid);
   P.publish = 1;
+  P.stamps = (h->stamps && grid <= UST_MAX_CTAS) ? 1 : 0;
+  cudaError_t ce = h->s_candtile.reserve((size_t)tiles + 1);
+  if (ce != cudaSuccess) return h->fail(UST_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(ce));
+  P.cand_tile = h->s_candtile.p;
   *out = P;
   *grid_out = grid;
+  return UST_OK;
+}
+
+// the verification kernel behind the streaming launches of a call (+ the collective, split mode)
+static int launch_verify(ust_handle* h, UstParams& P, cudaStream_t st, bool pdl) {
+  if (P.split) {
+    ncclResult_t r = g_nccl.AllReduce(h->xchg_dev, h->xchg_dev, UST_V_LEN, ncclInt64, ncclSum, h->comm, st);
+    if (r != ncclSuccess) return h->fail(UST_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  }
+  int e = ust_launch_verify(P, h->num_sms * 2, st, (pdl && !P.split) ? 1 : 0);
+  if (e) return h->fail(UST_ERR_CUDA, "verification kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  h->launches += 1;
+  return UST_OK;
+}
+
+// The pod CSR must be well-formed before a kernel walks it: pod_off[0] == 0, non-decreasing, pod_off[n] == n_pods.
+static int check_pod_offsets_host(ust_handle* h, int64_t n, const int32_t* pod_off, int64_t n_pods) {
+  if (n == 0) return UST_OK;
+  if (pod_off[0] != 0) return h->fail(UST_ERR_INVALID_ARGUMENT, "pod_off[0] must be 0");
+  for (int64_t i = 0; i < n; i++)
+    if (pod_off[i + 1] < pod_off[i]) return h->fail(UST_ERR_INVALID_ARGUMENT, "pod_off must not decrease (node %lld)", (long long)i);
+  if ((int64_t)pod_off[n] != n_pods) return h->fail(UST_ERR_INVALID_ARGUMENT, "pod_off[n_nodes] must equal n_pods");
+  return UST_OK;
 }
 
 // core: everything device-resident, enqueue on `st`
@@ -266,13 +308,17 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
   if (n > 0 && (!state || !flags || !pod_rev || !ds_idx || !next_state || !actions))
     return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
   if (n_ds < 0 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table");
-  if (n >= (1LL << 48)) return h->fail(UST_ERR_INVALID_ARGUMENT, "too many nodes");
+  if (n >= (1LL << 40)) return h->fail(UST_ERR_INVALID_ARGUMENT, "too many nodes");
   const void* ptrs[] = {state, flags, pod_rev, ds_idx, next_state, actions, outcome};
   const char* names[] = {"state", "flags", "pod_rev", "ds_idx", "next_state", "actions", "actuator_outcome"};
   for (int i = 0; i < 7; i++)
     if (ptrs[i]) { int rc = check_aligned(h, ptrs[i], names[i]); if (rc) return rc; }
   if (pod_off && pod_flags) { int rc = check_aligned(h, pod_flags, "pod_flags"); if (rc) return rc; }
   UST_CUDA(h, cudaSetDevice(h->device));
+  // a handle's workspace, tables and counters serve one call at a time: a call on another stream than the previous
+  // one is ordered behind it (calls on the same stream are ordered by the stream)
+  if (h->last_stream && h->last_stream != st) UST_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  h->last_stream = st;
   if (h->ws_dirty) {
     UST_CUDA(h, cudaMemsetAsync(h->ws, 0, sizeof(UstWorkspace), st));
     h->ws_dirty = false;
@@ -282,8 +328,9 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
 
   UstParams P;
   int grid = 0;
-  fill_params(h, policy, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, pod_off, pod_flags, next_state, actions, outcome,
-              out_dev, &P, &grid);
+  rc = fill_params(h, policy, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, pod_off, pod_flags, next_state, actions, outcome,
+                   out_dev, &P, &grid);
+  if (rc) return rc;
 
   h->ws_dirty = true;  // cleared again once every launch of this call has been enqueued successfully
   if (P.eval_pods) {
@@ -295,20 +342,12 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
     if (e) return h->fail(UST_ERR_CUDA, "pod-summary kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
     h->launches += 1;
   }
-  if (h->world == 1 || P.fused_exchange) {
-    if (P.fused_exchange) P.epoch = ++h->epoch;  // collective call number: identical on every rank
-    int e = ust_launch_fused(P, grid, st);
-    if (e) return h->fail(UST_ERR_CUDA, "fused kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
-    h->launches += 1;
-  } else {
-    int e = ust_launch_phase1(P, grid, st);
-    if (e) return h->fail(UST_ERR_CUDA, "phase-1 kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
-    ncclResult_t r = g_nccl.AllReduce(h->xchg_dev, h->xchg_dev, UST_V_LEN, ncclInt64, ncclSum, h->comm, st);
-    if (r != ncclSuccess) return h->fail(UST_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
-    e = ust_launch_phase2(P, grid, st);
-    if (e) return h->fail(UST_ERR_CUDA, "phase-2 kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
-    h->launches += 2;
-  }
+  if (P.fused_exchange) P.epoch = ++h->epoch;  // collective call number: identical on every rank
+  int e = ust_launch_stream(P, grid, st, h->pdl ? 1 : 0);
+  if (e) return h->fail(UST_ERR_CUDA, "streaming kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  h->launches += 1;
+  rc = launch_verify(h, P, st, h->pdl);
+  if (rc) return rc;
   h->ws_dirty = false;
   return UST_OK;
 }
@@ -330,28 +369,40 @@ static int finish_with_counters(ust_handle* h, cudaStream_t st, ust_counters* ou
       case UST_ERR_MAX_UNAVAILABLE: return h->fail(code, "failed to compute maxUnavailable from the current total nodes");
       case UST_ERR_POD_DELETION_SPEC: return h->fail(code, "pod deletion spec should not be empty");
       case UST_ERR_DS_UNSCHEDULED: return h->fail(code, "driver DaemonSet should not have Unscheduled pods");
+      case UST_ERR_COMM: return h->fail(code, "multi-GPU exchange timed out: a peer rank did not take part in the call");
       default: return h->fail(code, "ApplyState aborted with code %d", code);
     }
   }
   return UST_OK;
 }
 
-#pragma GCC visibility push(default)
-// host mirror of chunk_bound() in ust_kernels.cu
-static int64_t host_chunk_bound(int64_t n, int c, int chunks) {
-  if (c >= chunks) return n;
-  return ((n * (int64_t)c) / chunks) & ~(int64_t)127;
-}
+// Host-pointer entry points hand caller-owned buffers to asynchronous copies: whatever way such a call ends, nothing
+// of it may still be in flight when it returns (the caller may free or reuse the buffers).
+struct StreamDrain {
+  ust_handle* h;
+  bool armed = true;
+  explicit StreamDrain(ust_handle* hh) : h(hh) {}
+  ~StreamDrain() {
+    if (!armed) return;
+    if (h->stream_h2d) cudaStreamSynchronize(h->stream_h2d);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream_d2h) cudaStreamSynchronize(h->stream_d2h);
+  }
+};
 
-// Pipelined host path: the snapshot is cut into segments of whole chunks; segment s+1 uploads while segment
+#pragma GCC visibility push(default)
+
+// Pipelined host path: the snapshot is cut into segments of whole tiles; segment s+1 uploads while segment
 // s streams through the kernel and segment s-1's results download (PCIe is full duplex). The streaming pass
-// is speculative, so a segment's outputs are final unless the end-of-call verification had to redo chunks —
+// is speculative, so a segment's outputs are final unless the end-of-call verification had to redo tiles —
 // then (rare) the outputs are downloaded again.
 static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
                            const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, uint8_t* next_state,
                            uint16_t* actions, uint8_t* outcome, ust_counters* out, const uint16_t* rev16 = nullptr,
                            const int8_t* ds8 = nullptr) {
   cudaStream_t up = h->stream, down = h->stream_d2h, h2d = h->stream_h2d;  // up = compute stream of the call
+  if (h->last_stream && h->last_stream != up) UST_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  h->last_stream = up;
   if (h->ws_dirty) {
     UST_CUDA(h, cudaMemsetAsync(h->ws, 0, sizeof(UstWorkspace), up));
     h->ws_dirty = false;
@@ -360,11 +411,13 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
   if (rc) return rc;
   UstParams P;
   int grid = 0;
-  fill_params(h, policy, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, n_ds, h->s_dsrev.p, nullptr, nullptr,
-              h->s_next.p, h->s_actions.p, outcome ? h->s_outcome.p : nullptr, nullptr, &P, &grid);
-  const int chunks = P.grid_chunks;
+  rc = fill_params(h, policy, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, n_ds, h->s_dsrev.p, nullptr, nullptr,
+                   h->s_next.p, h->s_actions.p, outcome ? h->s_outcome.p : nullptr, nullptr, &P, &grid);
+  if (rc) return rc;
+  if (P.fused_exchange) P.epoch = ++h->epoch;
+  const int tiles = P.n_tiles;
   const int kSegments = 8;
-  const int per = (chunks + kSegments - 1) / kSegments;
+  const int per = (tiles + kSegments - 1) / kSegments;
   h->ws_dirty = true;
   const bool dbg = getenv("UST_DEBUG_PIPE") != nullptr;
   cudaEvent_t ev[4];
@@ -373,9 +426,9 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
   UST_CUDA(h, cudaEventRecord(h->d2h_done, up));
   UST_CUDA(h, cudaStreamWaitEvent(h2d, h->d2h_done, 0));
   int seg = 0;
-  for (int c0 = 0; c0 < chunks; c0 += per, seg++) {
-    const int c1 = c0 + per < chunks ? c0 + per : chunks;
-    const int64_t n0 = host_chunk_bound(n, c0, chunks), n1 = host_chunk_bound(n, c1, chunks);
+  for (int c0 = 0; c0 < tiles; c0 += per, seg++) {
+    const int c1 = c0 + per < tiles ? c0 + per : tiles;
+    const int64_t n0 = (int64_t)c0 * P.tile_nodes, n1 = c1 == tiles ? n : (int64_t)c1 * P.tile_nodes;
     const size_t len = (size_t)(n1 - n0);
     if (len) {
       UST_CUDA(h, cudaMemcpyAsync(h->s_hot.p + n0, state + n0, len, cudaMemcpyHostToDevice, h2d));
@@ -396,10 +449,13 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
       h->launches += 1;
     }
     UstParams Ps = P;
-    Ps.chunk_begin = c0;
-    Ps.chunk_end = c1;
-    Ps.publish = c1 == chunks;
-    int e = ust_launch_phase1(Ps, c1 - c0, up);
+    Ps.tile_begin = c0;
+    Ps.tile_end = c1;
+    Ps.publish = c1 == tiles;
+    const int g = pick_grid(h, c1 - c0);
+    Ps.static_rounds = pick_static_rounds(h, c1 - c0, g);
+    Ps.stamps = 0;
+    int e = ust_launch_stream(Ps, g, up, 0);
     if (e) return h->fail(UST_ERR_CUDA, "streaming kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
     h->launches += 1;
     UST_CUDA(h, cudaEventRecord(h->seg_done[seg], up));
@@ -411,9 +467,8 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
     }
   }
   if (dbg) { cudaEventRecord(ev[1], up); }
-  int e = ust_launch_phase2(P, grid, up);
-  if (e) return h->fail(UST_ERR_CUDA, "verification kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
-  h->launches += 1;
+  rc = launch_verify(h, P, up, false);
+  if (rc) return rc;
   h->ws_dirty = false;
   UST_CUDA(h, cudaMemcpyAsync(h->counters_host, h->counters_dev, sizeof(ust_counters), cudaMemcpyDeviceToHost, up));
   if (dbg) { cudaEventRecord(ev[2], up); cudaEventRecord(ev[3], down); }
@@ -429,7 +484,7 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
     h->ws_dirty = true;
     return h->fail(UST_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(ce));
   }
-  if (h->counters_host->reserved[0] != 0) {  // the verification redid chunks: fetch the final outputs
+  if (h->counters_host->reserved[0] != 0) {  // the verification redid tiles: fetch the final outputs
     UST_CUDA(h, cudaMemcpyAsync(next_state, h->s_next.p, (size_t)n, cudaMemcpyDeviceToHost, up));
     UST_CUDA(h, cudaMemcpyAsync(actions, h->s_actions.p, (size_t)n * 2, cudaMemcpyDeviceToHost, up));
     if (outcome) UST_CUDA(h, cudaMemcpyAsync(outcome, h->s_outcome.p, (size_t)n, cudaMemcpyDeviceToHost, up));
@@ -487,8 +542,11 @@ int ust_create(ust_handle** out, int device) {
   if ((e = cudaMallocHost(&h->counters_host, sizeof(ust_counters))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMalloc(&h->xchg_dev, UST_V_LEN * sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(h->xchg_dev, 0, UST_V_LEN * sizeof(long long))) != cudaSuccess) return bail("cudaMemset", e);
-  int rc = ust_max_coresident_ctas(device, &h->ctas_per_sm, &h->num_sms);
-  if (rc != 0 || h->ctas_per_sm < 1) {
+  if (const char* v = getenv("UST_PDL")) h->pdl = atoi(v) != 0;
+  if (const char* v = getenv("UST_STATIC_PCT")) { h->static_pct = atoi(v); if (h->static_pct < 0) h->static_pct = 0; if (h->static_pct > 100) h->static_pct = 100; }
+  h->stamps = getenv("UST_STAMPS") != nullptr;
+  int rc = ust_stream_config(device, &h->num_sms, &h->stream_smem);
+  if (rc != 0 || h->num_sms < 1) {
     g_create_error = std::string("no sm_100a kernel image usable on this device: ") + cudaGetErrorString((cudaError_t)rc);
     ust_destroy(h);
     return UST_ERR_CUDA;
@@ -500,7 +558,10 @@ int ust_create(ust_handle** out, int device) {
 void ust_destroy(ust_handle* h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
+  if (h->stream_h2d) cudaStreamSynchronize(h->stream_h2d);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream_d2h) cudaStreamSynchronize(h->stream_d2h);
+  if (h->last_stream) cudaStreamSynchronize(h->last_stream);
   for (int r = 0; r < UST_MAX_WORLD; r++)
     if (h->mbox[r] && h->mbox[r] != h->mbox_own) cudaIpcCloseMemHandle(h->mbox[r]);
   if (h->mbox_own) cudaFree(h->mbox_own);
@@ -517,7 +578,7 @@ void ust_destroy(ust_handle* h) {
   if (h->ds_count_dev) cudaFree(h->ds_count_dev);
   h->s_hot.release(); h->s_next.release(); h->s_outcome.release(); h->s_flags.release();
   h->s_rev.release(); h->s_ds.release(); h->s_dsrev.release(); h->s_podoff.release(); h->s_dsdesired.release();
-  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release(); h->s_rev16.release(); h->s_ds8.release(); h->d_idx.release(); h->d_state.release(); h->d_flags.release(); h->d_rev.release(); h->d_ds.release();
+  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_candtile.release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release(); h->s_rev16.release(); h->s_ds8.release(); h->d_idx.release(); h->d_state.release(); h->d_flags.release(); h->d_rev.release(); h->d_ds.release();
   for (auto& ev : h->seg_done) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->seg_up) if (ev) cudaEventDestroy(ev);
   if (h->stream_h2d) cudaStreamDestroy(h->stream_h2d);
@@ -539,6 +600,7 @@ int ust_sync(ust_handle* h) {
   std::lock_guard<std::mutex> g(h->mu);
   UST_CUDA(h, cudaSetDevice(h->device));
   cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess && h->last_stream && h->last_stream != h->stream) e = cudaStreamSynchronize(h->last_stream);
   if (e != cudaSuccess) { h->ws_dirty = true; return h->fail(UST_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e)); }
   return UST_OK;
 }
@@ -568,7 +630,9 @@ int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const ui
   if (n_ds < 0 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table");
   if (pods && (!pods->pod_off || pods->n_pods < 0 || (pods->n_pods > 0 && !pods->pod_flags)))
     return h->fail(UST_ERR_INVALID_ARGUMENT, "bad pod lists");
+  if (pods) { int prc = check_pod_offsets_host(h, n, pods->pod_off, pods->n_pods); if (prc) return prc; }
   UST_CUDA(h, cudaSetDevice(h->device));
+  StreamDrain drain(h);
   cudaStream_t st = h->stream;
   const size_t N = (size_t)n;
   UST_CUDA(h, h->s_hot.reserve(N + 16));
@@ -589,7 +653,7 @@ int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const ui
     if (rc != UST_ERR_CUDA && rc != UST_ERR_INVALID_ARGUMENT && rc != UST_ERR_COMM && rc != UST_ERR_NIL_STATE && !pods) { h->resident_n = n; h->resident_n_ds = n_ds; }
     return rc;
   };
-  if (!pods && h->world == 1 && n >= (1 << 19))
+  if (!pods && n >= (1 << 19))
     return keep(apply_pipelined(h, policy, n, state, flags, pod_rev, ds_idx, n_ds, next_state, actions, actuator_outcome, out));
   if (N) {
     UST_CUDA(h, cudaMemcpyAsync(h->s_hot.p, state, N, cudaMemcpyHostToDevice, st));
@@ -627,6 +691,7 @@ int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_cha
   for (int64_t k = 0; k < n_changed; k++)
     if (idx[k] < 0 || idx[k] >= n) return h->fail(UST_ERR_INVALID_ARGUMENT, "changed node %lld has index %lld outside the snapshot of %lld nodes", (long long)k, (long long)idx[k], (long long)n);
   UST_CUDA(h, cudaSetDevice(h->device));
+  StreamDrain drain(h);
   cudaStream_t st = h->stream;
   const size_t N = (size_t)n, M = (size_t)n_changed;
   UST_CUDA(h, h->s_dsrev.reserve((size_t)n_ds + 1));
@@ -669,6 +734,7 @@ int ust_apply_state_packed(ust_handle* h, const ust_policy* policy, int64_t n, c
     return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
   if (n_ds < 0 || n_ds > 127 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table (the packed format holds at most 127 DaemonSets)");
   UST_CUDA(h, cudaSetDevice(h->device));
+  StreamDrain drain(h);
   cudaStream_t st = h->stream;
   const size_t N = (size_t)n;
   UST_CUDA(h, h->s_hot.reserve(N + 16));
@@ -687,7 +753,7 @@ int ust_apply_state_packed(ust_handle* h, const ust_policy* policy, int64_t n, c
     if (rc != UST_ERR_CUDA && rc != UST_ERR_INVALID_ARGUMENT && rc != UST_ERR_COMM && rc != UST_ERR_NIL_STATE) { h->resident_n = n; h->resident_n_ds = n_ds; }
     return rc;
   };
-  if (h->world == 1 && n >= (1 << 19))
+  if (n >= (1 << 19))
     return keep(apply_pipelined(h, policy, n, state, flags, nullptr, nullptr, n_ds, next_state, actions, actuator_outcome, out,
                                 pod_rev16, ds_idx8));
   if (N) {
@@ -723,6 +789,7 @@ int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps,
   ust_policy pol;
   if (policy) { pol = *policy; pol.evaluate_actuators = 1; }  // the asynchronous actuators' results are what is fed back
   UST_CUDA(h, cudaSetDevice(h->device));
+  StreamDrain drain(h);
   cudaStream_t st = h->stream;
   const size_t N = (size_t)n;
   UST_CUDA(h, h->s_outcome.reserve(N + 16));
@@ -768,6 +835,7 @@ int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const i
     return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
   h->resident_n = -1;  // shares the staging arrays
   UST_CUDA(h, cudaSetDevice(h->device));
+  StreamDrain drain(h);
   cudaStream_t st = h->stream;
   const size_t N = (size_t)n_pods;
   UST_CUDA(h, h->s_hot.reserve(N + 16));
@@ -820,6 +888,7 @@ int ust_build_state_uids(ust_handle* h, int64_t n_pods, const uint8_t* state, co
   }
   h->resident_n = -1;  // shares the staging arrays
   UST_CUDA(h, cudaSetDevice(h->device));
+  StreamDrain drain(h);
   cudaStream_t st = h->stream;
   const size_t N = (size_t)n_pods;
   UST_CUDA(h, h->s_hot.reserve(N + 16));
@@ -871,7 +940,7 @@ int ust_debug_stamps(ust_handle* h, unsigned long long* out, int n_ctas) {
   std::lock_guard<std::mutex> g(h->mu);
   UST_CUDA(h, cudaSetDevice(h->device));
   UST_CUDA(h, cudaDeviceSynchronize());
-  UST_CUDA(h, cudaMemcpy(out, h->ws->dbg, (size_t)n_ctas * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  UST_CUDA(h, cudaMemcpy(out, h->ws->dbg, (size_t)n_ctas * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return UST_OK;
 }
 

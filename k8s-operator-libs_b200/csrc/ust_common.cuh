@@ -1,0 +1,333 @@
+// ust_common.cuh — device code shared by the streaming kernel (ust_stream.cu) and the verification kernel
+// (ust_kernels.cu): PTX wrappers (mbarrier, TMA bulk copy, programmatic dependent launch, system-scope accesses),
+// the cluster-wide arithmetic between the two (GetUpgradesAvailable and friends), and the decision a call's last
+// CTA makes about the slot speculation.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ust_dev.h"
+
+namespace ustd {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+// one 1-D TMA bulk copy global -> shared, completing `bytes` on the mbarrier (bytes: multiple of 16, both ends
+// 16-byte aligned); streamed data carries an evict-first L2 policy
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, uint32_t bytes, unsigned long long* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// programmatic dependent launch: let the next kernel of the stream start its prologue / wait for the previous one
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_relaxed_sys(long long* p, long long v) { asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) { asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long ld_relaxed_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr unsigned long long kCommTimeoutNs = 4000000000ull;  // give up on a missing peer after 4 s
+
+// (pass + 1) of each state code, one nibble per code: position of its Process* pass in ApplyState
+// (upgrade_state.go:205-274), 0 = never processed. Same content as ust_pass_of_state[] in ust_lut.h.
+__device__ __forceinline__ int pass_of_state(unsigned code) {
+  constexpr unsigned long long kPassPlus1 =
+      (1ull << 0) | (3ull << 4) | (4ull << 8) | (5ull << 12) | (6ull << 16) | (7ull << 20) | (8ull << 24) | (0ull << 28) |
+      (9ull << 32) | (11ull << 36) | (12ull << 40) | (2ull << 44) | (10ull << 48);
+  return (int)((kPassPlus1 >> (4 * code)) & 15ull) - 1;
+}
+
+// candidate bytes of a hot word: bit 7 of byte k set iff node k is upgrade-required and not marked skip
+// (upgrade_inplace.go:82)
+__device__ __forceinline__ uint32_t cand_mask4(uint32_t x) {
+  const uint32_t y = (x & 0x2F2F2F2Fu) ^ 0x01010101u;  // zero byte <=> code == 1 && !SKIP
+  return ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u;
+}
+
+// four table entries (actions | next << 16 | outcome << 24) -> the three output words of a 4-node group
+__device__ __forceinline__ void pack4(const uint32_t e[4], uint32_t& next4, uint2& act4, uint32_t& out4) {
+  act4.x = __byte_perm(e[0], e[1], 0x5410);
+  act4.y = __byte_perm(e[2], e[3], 0x5410);
+  const uint32_t hi01 = __byte_perm(e[0], e[1], 0x7632);  // [e0.b2 e0.b3 e1.b2 e1.b3]
+  const uint32_t hi23 = __byte_perm(e[2], e[3], 0x7632);
+  next4 = __byte_perm(hi01, hi23, 0x6420);
+  out4 = __byte_perm(hi01, hi23, 0x7531);
+}
+
+// pod-list summary byte -> the w bits it stands for (ust_pod_summary_kernel): bit 0 = a wait-selector pod is
+// running, bits 1..3 = UST_W_PD_HAS / UST_W_PD_MISMATCH / UST_W_DRAIN_ERROR, bit 4 = the list overrides the
+// pre-evaluated UST_F_WAIT_PODS_RUNNING of the flags word
+__device__ __forceinline__ uint32_t pods_apply(uint32_t fl, uint32_t ps) {
+  return (fl & ~((ps & 0x10u) << 12)) | ((ps & 1u) << 16) | ((ps & 0xEu) << 21);
+}
+static_assert(UST_F_WAIT_PODS_RUNNING == (1u << 16) && UST_W_PD_HAS == (UST_PODSUM_TO_DELETE << 21) &&
+              UST_W_PD_MISMATCH == (UST_PODSUM_CANNOT_DELETE << 21) && UST_W_DRAIN_ERROR == (UST_PODSUM_DRAIN_ERROR << 21) &&
+              UST_PODSUM_WAIT_RUNNING == 1u, "pod summary byte layout");
+
+// ---- the decision between streaming and verification ------------------------------------------------------------
+struct DecideShared {
+  long long V[UST_V_LEN];        // cluster-wide exchange vector
+  unsigned long long abort_key;  // ~0 = none
+  long long budget;              // max(upgradesAvailable, 0)
+  long long avail;
+  long long max_unav;
+  long long node_offset;         // global index of this shard's node 0
+  long long cand_before;         // upgrade candidates on lower ranks
+  long long slots_left;
+  long long part[32];
+  int spec_cut;                  // effective speculative cut of this call (hint or policy default), in tiles
+  int redo, cut, lo, hi;
+};
+
+// this shard's lanes of the exchange vector from the workspace accumulators
+__device__ __forceinline__ void load_local_vector(const UstParams& P, DecideShared& D) {
+  const int t = threadIdx.x;
+  if (t < UST_V_LEN) {
+    long long v = 0;
+    if (t < 14 || t == UST_V_UNAVAILABLE || t == UST_V_CANDIDATES) v = (long long)__ldcg(&P.ws->acc[t]);
+    else if (t == UST_STATE_EXCLUDED) {  // everything that is in no bucket: "not in snapshot" (upgrade_state.go:149-152) and code 15
+      long long in = 0;
+      for (int f = 0; f < 14; f++) in += (long long)__ldcg(&P.ws->acc[f]);
+      v = P.n - in;
+    }
+    else if (t == UST_V_RANK_CAND + P.rank) v = (long long)__ldcg(&P.ws->acc[UST_V_CANDIDATES]);
+    else if (t == UST_V_RANK_NODES + P.rank) v = P.n;
+    else if (t == UST_V_RANK_ERRINV + P.rank) v = (long long)__ldcg(&P.ws->errinv);
+    D.V[t] = v;
+  }
+}
+
+// cluster-wide scalars from the exchange vector (one thread)
+__device__ inline void derive_scalars(const UstParams& P, DecideShared& D) {
+  const long long* V = D.V;
+  const long long h0 = V[0], h1 = V[1], h2 = V[2], h4 = V[4], h11 = V[11];
+  // GetTotalManagedNodes (common_manager.go:715-730): 11 buckets — not 6, 7, other
+  const long long total = h0 + h1 + h2 + V[3] + h4 + V[5] + V[8] + V[9] + V[10] + h11 + V[12];
+  const long long in_progress = total - h0 - h11 - h1;  // GetUpgradesInProgress (:733-739)
+  unsigned long long abort_key = ~0ull;
+  long long off = 0, my_off = 0, cand_before = 0;
+  for (int r = 0; r < P.world; r++) {
+    if (r == P.rank) my_off = off;
+    if (r < P.rank) cand_before += V[UST_V_RANK_CAND + r];
+    const unsigned long long e = (unsigned long long)V[UST_V_RANK_ERRINV + r];
+    if (e) {
+      const unsigned long long k = ~e;
+      const unsigned long long gk = (k & 0xFF00000000000000ull) | ((k & 0x00FFFFFFFFFFFFFFull) + (unsigned long long)off);
+      if (gk < abort_key) abort_key = gk;
+    }
+    off += V[UST_V_RANK_NODES + r];
+  }
+  long long max_unav = 0, avail = 0;
+  const bool slots = P.active && !P.requestor;
+  if (slots) {
+    // upgrade_inplace.go:49-62 + intstr.GetScaledValueFromIntOrPercent(v, total, roundUp=true)
+    if (P.max_unav_kind == UST_MAXUNAVAIL_INVALID && UST_KEY(2, 0) < abort_key) abort_key = UST_KEY(2, 0);
+    max_unav = total;
+    if (P.max_unav_kind == UST_MAXUNAVAIL_INT) max_unav = P.max_unav_value;
+    else if (P.max_unav_kind == UST_MAXUNAVAIL_PERCENT)
+      max_unav = (long long)ceil(__ddiv_rn(__dmul_rn((double)P.max_unav_value, (double)total), 100.0));
+    // GetUpgradesAvailable (common_manager.go:748-776)
+    avail = (P.max_parallel == 0) ? h1 : P.max_parallel - in_progress;
+    const long long cur_unav = V[UST_V_UNAVAILABLE] + h2;
+    if (avail > max_unav) avail = max_unav;
+    if (cur_unav >= max_unav) avail = 0;
+    else if (max_unav < total && cur_unav + avail > max_unav) avail = max_unav - cur_unav;
+  }
+  // SchedulePodEviction with a nil DeletionSpec (pod_manager.go:125-134)
+  if (P.active && P.pd_enabled && !P.pd_spec_present && h4 > 0 && UST_KEY(5, 0) < abort_key) abort_key = UST_KEY(5, 0);
+  D.abort_key = abort_key;
+  D.avail = avail;
+  D.max_unav = max_unav;
+  D.budget = avail > 0 ? avail : 0;
+  D.node_offset = my_off;
+  D.cand_before = cand_before;
+}
+
+__device__ inline void write_counters(const UstParams& P, const DecideShared& D, long long redone_tiles) {
+  ust_counters c;
+  const long long* V = D.V;
+  for (int i = 0; i < 16; i++) c.hist[i] = V[i];
+  c.unavailable = V[UST_V_UNAVAILABLE];
+  c.candidates = V[UST_V_CANDIDATES];
+  c.total_managed = V[0] + V[1] + V[2] + V[3] + V[4] + V[5] + V[8] + V[9] + V[10] + V[11] + V[12];
+  c.in_progress = c.total_managed - V[0] - V[11] - V[1];
+  c.error_code = UST_OK;
+  c.error_index = -1;
+  c.error_pass = -1;
+  if (D.abort_key != ~0ull) {
+    const int pass = (int)(D.abort_key >> 56);
+    const long long idx1 = (long long)(D.abort_key & 0x00FFFFFFFFFFFFFFull);
+    c.error_pass = pass;
+    c.error_index = idx1 - 1;
+    c.error_code = idx1 ? UST_ERR_REVISION_HASH : (pass == 2 ? UST_ERR_MAX_UNAVAILABLE : UST_ERR_POD_DELETION_SPEC);
+  }
+  const bool slots = P.active && !P.requestor && !(c.error_code && c.error_pass < 2) && c.error_code != UST_ERR_MAX_UNAVAILABLE;
+  c.max_unavailable = slots ? D.max_unav : 0;
+  c.upgrades_available = slots ? D.avail : 0;
+  for (int i = 0; i < 7; i++) c.reserved[i] = 0;
+  if (__ldcg(&P.ws->comm_timeout)) { c.error_code = UST_ERR_COMM; c.error_index = -1; c.error_pass = -1; }
+  c.reserved[0] = redone_tiles;  // tiles the verification kernel re-evaluates (diagnostic; the pipelined host path re-downloads when != 0)
+  *P.out = c;
+}
+
+// The decision, made by every thread of ONE CTA once the cluster-wide vector is in D.V: derive the slot budget, check
+// the speculation in O(1) (rank-local: "nobody gets a slot" only fails if this shard has a budget, "everybody" only if
+// the budget is smaller than its candidates), and only when that cannot tell - or the call aborts - scan the per-tile
+// candidate counts for the tile where the budget cuts. Tiles before the cut are fully granted, tiles behind it get
+// nothing, the cut tile hands out `slots_left` in slice order (upgrade_inplace.go:71-109). `write_global`: this CTA
+// also publishes the verdict, the counters and the next call's speculation hint.
+__device__ inline void decide(const UstParams& P, DecideShared& D, bool write_global) {
+  const int t = threadIdx.x, nt = blockDim.x, nT = P.n_tiles;
+  if (t == 0) derive_scalars(P, D);
+  __syncthreads();
+  const bool slotted = P.active && !P.requestor;
+  const bool aborting = D.abort_key != ~0ull;
+  const long long lc = D.V[UST_V_RANK_CAND + P.rank];   // this shard's candidates
+  const long long lb = D.budget - D.cand_before;         // slots left when slice order reaches this shard
+  const int sc = D.spec_cut < 0 ? 0 : (D.spec_cut > nT ? nT : D.spec_cut);
+  bool need = false;
+  if (slotted && lc > 0) need = sc <= 0 ? lb > 0 : (sc >= nT ? lb < lc : true);
+  if (t == 0) { D.cut = nT; D.slots_left = 0; }
+  __syncthreads();
+  if (slotted && lc > 0 && (need || aborting)) {
+    if (lb <= 0) {
+      if (t == 0) D.cut = 0;
+    } else if (lb < lc) {
+      // thread t owns tiles [c0, c1): sum, block-wide exclusive scan, then the one thread whose run contains the
+      // crossing walks it
+      const int per = (nT + nt - 1) / nt;
+      const int c0 = t * per < nT ? t * per : nT, c1 = c0 + per < nT ? c0 + per : nT;
+      long long mine = 0;
+#pragma unroll 8
+      for (int c = c0; c < c1; c++) mine += __ldcg(&P.cand_tile[c]);
+      long long incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long v = __shfl_up_sync(kFull, incl, o);
+        if ((t & 31) >= o) incl += v;
+      }
+      if ((t & 31) == 31) D.part[t >> 5] = incl;
+      __syncthreads();
+      long long before = incl - mine;
+      for (int w = 0; w < (t >> 5); w++) before += D.part[w];
+      if (before <= lb && lb < before + mine) {
+        long long local = before;
+        for (int c = c0; c < c1; c++) {
+          const long long cand = __ldcg(&P.cand_tile[c]);
+          if (local + cand > lb) { D.cut = c; D.slots_left = lb - local; break; }
+          local += cand;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    const int cut = D.cut;
+    int lo = 1, hi = 0;
+    if (!aborting && need) {
+      if (sc <= cut) { lo = sc; hi = (cut < nT && D.slots_left > 0) ? cut : cut - 1; }
+      else { lo = cut; hi = sc - 1; }
+    }
+    int redo = aborting ? 2 : (lo <= hi ? 1 : 0);
+    if (__ldcg(&P.ws->comm_timeout)) redo = 0;  // a peer never showed up: the call fails, nothing more is written
+    D.redo = redo; D.lo = lo; D.hi = hi;
+    if (write_global) {
+      UstVerdict v;
+      v.redo = redo; v.cut = cut; v.lo = lo; v.hi = hi; v.slots_left = D.slots_left;
+      v.abort_key = D.abort_key; v.node_offset = D.node_offset;
+      P.ws->verdict = v;
+      write_counters(P, D, redo == 2 ? (long long)nT : (redo == 1 ? (long long)(hi - lo + 1) : 0));
+      if (P.spec_sig != 0 && slotted && !aborting) {
+        // where the budget really cut this time = next call's speculation (else: the all-or-nothing guess that held)
+        P.ws->hint_cut = need ? cut : D.spec_cut;
+        P.ws->hint_sig = P.spec_sig;
+      }
+      P.ws->comm_timeout = 0;
+    }
+  }
+  __syncthreads();
+}
+
+// Cluster-wide vector for world > 1 without leaving the kernel, run by the ONE CTA of a rank that finishes streaming
+// last: push this shard's lanes into every rank's mailbox over NVLink (all lanes of all peers in parallel), release a
+// flag per peer, wait for every rank's flag in the own mailbox, sum. One-hot per-rank lanes make the sum an
+// all-gather. Nothing else on the GPU spins: the other CTAs of the rank have already exited.
+__device__ inline void exchange_vector(const UstParams& P, DecideShared& D) {
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int par = (int)(P.epoch & 1);
+  for (int i = t; i < P.world * UST_V_LEN; i += nt) {
+    const int r = i / UST_V_LEN, l = i - r * UST_V_LEN;
+    st_relaxed_sys(&P.mbox[r]->slot[par][P.rank][l], D.V[l]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < P.world) {
+    st_release_sys(&P.mbox[t]->slot[par][P.rank][UST_MBOX_FLAG], P.epoch);
+    const unsigned long long t0 = now_ns();
+    while (ld_acquire_sys(&P.mbox[P.rank]->slot[par][t][UST_MBOX_FLAG]) != P.epoch) {
+      if (now_ns() - t0 > kCommTimeoutNs) { P.ws->comm_timeout = 1; break; }
+      __nanosleep(40);
+    }
+  }
+  __syncthreads();
+  if (t < UST_V_LEN) {
+    long long v[UST_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < UST_MAX_WORLD; r++) v[r] = r < P.world ? ld_relaxed_sys(&P.mbox[P.rank]->slot[par][r][t]) : 0;
+    long long sum = 0;
+#pragma unroll
+    for (int r = 0; r < UST_MAX_WORLD; r++) sum += v[r];
+    D.V[t] = sum;
+  }
+  __threadfence();
+  __syncthreads();
+}
+
+}  // namespace ustd

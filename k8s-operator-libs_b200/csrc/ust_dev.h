@@ -5,10 +5,24 @@
 #include "../../include/ust.h"
 #include "ust_lut.h"
 
-#define UST_THREADS 256
-#define UST_MAX_CTAS 4096
+#define UST_THREADS 256          /* verification / auxiliary kernels */
+#define UST_MAX_CTAS 1024        /* per-CTA diagnostic stamps */
 #define UST_MAX_WORLD 8
 #define UST_DS_SMEM_MAX 1024
+
+// Streaming kernel geometry (ust_stream.cu): a tile is the unit a CTA claims, the TMA engine copies into one ring
+// stage, and the slot speculation is made for. Tiles of fewer nodes (a power of two >= 128) are used for small
+// snapshots so that every SM gets work; the ring stages are sized for the largest.
+#ifndef UST_TILE_NODES
+#define UST_TILE_NODES 2048
+#endif
+#ifndef UST_STAGES
+#define UST_STAGES 5
+#endif
+#ifndef UST_CONSUMER_WARPS
+#define UST_CONSUMER_WARPS 8
+#endif
+#define UST_STREAM_THREADS (32 * (1 + UST_CONSUMER_WARPS))
 
 // Exchange vector (int64 lanes): what one shard contributes to / learns from the cluster-wide
 // constraint arithmetic (upgrade_inplace.go:49-62). Summed across shards; per-rank slots are one-hot,
@@ -29,25 +43,32 @@ struct UstMailbox {
   long long slot[2][UST_MAX_WORLD][UST_MBOX_LANES];
 };
 
-// Device workspace owned by a handle. Invariant: acc / errinv / arrive / depart are zero between launches.
+// What the deciding CTA of a call (the last one to finish streaming) leaves for the verification kernel.
+struct UstVerdict {
+  int redo;               // 0 = every speculative output stands; 1 = the slot speculation was wrong for the tiles
+                          // [lo, hi]; 2 = the call aborts: every tile is re-evaluated with abort masking
+  int cut;                // first tile whose upgrade candidates do not all get a slot (n_tiles = there is none)
+  int lo, hi;
+  long long slots_left;   // slots left for the candidates of tile `cut`, handed out in slice order
+  unsigned long long abort_key;  // ~0 = none
+  long long node_offset;  // global index of this shard's node 0
+};
+
+// Device workspace owned by a handle. Invariant: acc / errinv / arrive / depart / ticket are zero between calls.
 struct UstWorkspace {
-  unsigned long long acc[18];   // hist[0..15], unavailable, candidates (this shard)
-  unsigned long long errinv;    // ~min abort key seen by phase 1, 0 = none
-  unsigned int arrive;
-  unsigned int depart;
-  unsigned int ticket;   // dynamic chunk claiming
-  unsigned int fixups;   // chunks redone by the verification phase of the current call
-  unsigned long long go; // fused exchange: epoch whose cluster-wide vector CTA 0 has published in gv[]
-  long long gv[UST_V_LEN];
-  unsigned int comm_timeout;  // set when a peer did not show up (kernel gives up instead of hanging)
-  unsigned int pad0_;
-  // Speculation hint carried from call to call (results never depend on it, only how many chunks are redone):
-  // the previous call's cut chunk, valid for calls with the same signature (size, chunking, slot policy).
+  unsigned long long acc[18];   // hist[0..13], -, -, unavailable, candidates (this shard)
+  unsigned long long errinv;    // ~min abort key seen while streaming, 0 = none
+  unsigned int arrive;          // CTAs of the current streaming launch that have finished
+  unsigned int depart;          // verification kernel in deciding mode: CTAs that have finished
+  unsigned int ticket;          // dynamic tile claiming
+  unsigned int comm_timeout;    // set when a peer did not show up (kernel gives up instead of hanging)
+  UstVerdict verdict;
+  // Speculation hint carried from call to call (results never depend on it, only how many tiles are redone):
+  // the previous call's cut tile, valid for calls with the same signature (size, tiling, slot policy).
   unsigned long long hint_sig;
   int hint_cut;
-  int pad_;
-  unsigned int cand_cta[UST_MAX_CTAS];  // candidates per CTA chunk (written by phase 1, read by phase 2)
-  unsigned long long dbg[UST_MAX_CTAS][8];  // %globaltimer stamps per CTA: entry, stream end, barrier release, exit; 4..7 = redo path (diagnostics)
+  int spec_cut_used;  // split mode: the speculative cut the streaming kernel ran with (read by the deciding verification kernel)
+  unsigned long long dbg[UST_MAX_CTAS][4];  // %globaltimer stamps per streaming CTA: entry, first tile landed, stream end, exit
 };
 
 // abort key: (pass << 56) | (global node index + 1); policy-level aborts use index part 0
@@ -70,7 +91,8 @@ struct UstParams {
   const uint8_t* podlut;  // UST_PODLUT_ENTRIES bytes
   uint8_t* podsum;        // per-node pod-list summary (written by the pod-summary kernel, read by the streaming pass); null = no pod lists
   UstWorkspace* ws;
-  long long* xchg;        // UST_V_LEN lanes (split mode: phase 1 writes, phase 2 reads the reduced copy)
+  unsigned int* cand_tile;  // upgrade candidates per tile (streaming pass writes, the decision reads)
+  long long* xchg;        // UST_V_LEN lanes (split mode: the streaming kernel writes, the verification kernel reads the reduced copy)
   ust_counters* out;      // device
   // policy (flattened; see include/ust.h)
   long long max_parallel;
@@ -81,25 +103,30 @@ struct UstParams {
   int pd_enabled;
   int pd_spec_present;
   int eval_pods;          // pod lists present and evaluate_actuators
-  int spec_cut_chunk;     // speculation: chunks before this index assume every upgrade candidate gets a slot
+  int spec_cut_tile;      // speculation: tiles before this index assume every upgrade candidate gets a slot
   unsigned long long spec_sig;  // signature under which a device-resident hint from the previous call applies (0 = none)
   // sharding
   int rank;
   int world;
-  int grid_chunks;        // number of chunks the shard is cut into (>= grid size; claimed dynamically)
-  int chunk_begin;        // streaming sub-range launches (pipelined uploads): chunks [chunk_begin, chunk_end)
-  int chunk_end;
-  int publish;            // split mode: this streaming launch is the last one of the call (publish + reset)
+  // tiling
+  int tile_nodes;         // nodes per tile (power of two, 128 .. UST_TILE_NODES)
+  int n_tiles;            // tiles of the shard
+  int tile_begin;         // streaming sub-range launches (pipelined uploads): tiles [tile_begin, tile_end)
+  int tile_end;
+  int static_rounds;      // rounds of the range a CTA takes in stride order before it claims tiles by ticket
+  int publish;            // this streaming launch is the last one of the call: its last CTA decides (or publishes, split mode)
+  int split;              // split mode: the decision is made by the verification kernel from P.xchg (reduced by a host-launched collective)
+  int stamps;             // diagnostics: write %globaltimer stamps
   // fused multi-GPU exchange (world > 1): mailboxes of all ranks as mapped into this process, call number
   int fused_exchange;
   long long epoch;
   UstMailbox* mbox[UST_MAX_WORLD];
 };
 
-// kernel launchers (ust_kernels.cu); all return cudaError_t as int
-int ust_launch_fused(const UstParams& p, int grid, void* stream);
-int ust_launch_phase1(const UstParams& p, int grid, void* stream);
-int ust_launch_phase2(const UstParams& p, int grid, void* stream);
+// kernel launchers; all return cudaError_t as int. `pdl` = launch with programmatic stream serialization.
+int ust_launch_stream(const UstParams& p, int grid, void* stream, int pdl);   // ust_stream.cu
+int ust_launch_verify(const UstParams& p, int grid, void* stream, int pdl);   // ust_kernels.cu
+int ust_stream_config(int device, int* num_sms, size_t* smem_bytes);          // also raises the dynamic shared-memory limit
 int ust_launch_pod_summary(long long n, int active, const uint8_t* hot, const int32_t* pod_off, const uint16_t* pod_flags,
                            long long n_pods, const uint8_t* podlut, uint8_t* podsum, int grid, void* stream);
 int ust_launch_build_state(long long n, const uint8_t* hot, const int32_t* ds_idx, int n_ds, const int32_t* ds_desired,
@@ -122,4 +149,3 @@ int ust_launch_feedback(long long n, uint8_t* hot, uint32_t* flags, int32_t* pod
                         const ust_counters* step, int grid, void* stream);
 int ust_launch_widen(long long n, const uint16_t* rev16, const int8_t* ds8, int32_t* rev_out, int32_t* ds_out, int grid,
                      void* stream);
-int ust_max_coresident_ctas(int device, int* ctas_per_sm, int* num_sms);

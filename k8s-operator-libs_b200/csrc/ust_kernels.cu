@@ -1,280 +1,65 @@
-// ust_kernels.cu — the ApplyState kernels for sm_100a (B200).
+// ust_kernels.cu — the verification kernel of ApplyState and the auxiliary kernels of libust.so (sm_100a).
 //
-// What replaces what: one launch of ust_fused_kernel computes, for every node of the snapshot, what the
-// reference's ClusterUpgradeStateManagerImpl.ApplyState (pkg/upgrade/upgrade_state.go:171-281) computes
-// with its twelve sequential Process* loops: next state label and actuator-call bitmask per node, plus
-// the cluster counters of common_manager.go:715-788.
-//
-// Shape of the kernel (HBM-bound byte/integer streaming, no tensor-core work):
-//   * cooperative grid of (#SM x 2 resident CTAs); CTA c owns one contiguous chunk of nodes, so slice order of the
-//     upgrade-required bucket (upgrade_inplace.go:71) is chunk order;
-//   * the per-policy transition table (32 KiB, built by the host: ust_lut.h) is staged into shared memory with one
-//     TMA bulk copy that completes on an mbarrier; the first tile's loads are in flight before anything waits on it;
-//   * ONE streaming pass over state(1 B) + flags(4) + pod_rev(4) + ds_idx(4) with 128-bit coalesced loads, four
-//     steps (16 nodes) per thread in flight: every node is evaluated by one shared-memory lookup indexed by its hot
-//     byte and one lookup in the transition table, and counted (14-bin state histogram, unavailable, upgrade
-//     candidates) in byte-sliced SIMD-in-register counters; next_state(1) + actions(2) leave with full-width
-//     coalesced stores: 16 algorithmic bytes per node, each touched once. The upgrade-slot grant - the only
-//     cluster-wide dependency - is SPECULATED per chunk (from the policy, or from where the previous call's budget cut);
-//   * one grid-wide barrier (single global atomic counter); every CTA then derives the slot budget
-//     (GetUpgradesAvailable, common_manager.go:748-776) and checks the speculation in O(1); only when it cannot hold
-//     do the CTAs scan the per-chunk candidate counts and re-evaluate the wrong interval, in pieces spread over the
-//     whole grid (ordered path: hot-byte pre-pass + warp-scan ranks; uniform path elsewhere);
-//   * last CTA out writes the counters and restores the workspace.
-// Around it: ust_phase1/2_kernel (the same device code split at the barrier, for the NCCL mode and the pipelined
-// host path), ust_pod_summary_kernel (pod lists -> one byte per node), ust_build_state*_kernel (BuildState),
-// ust_patch_kernel / ust_feedback_kernel (delta updates, rollout simulation).
-#include <cuda_runtime.h>
+// ust_verify_kernel runs behind ust_stream_kernel (ust_stream.cu) on the same stream, launched with programmatic
+// dependent launch: its CTAs are resident (and asleep in griddepcontrol.wait) while the streaming kernel runs, read
+// the verdict its last CTA left, and return at once in the common case - the slot speculation held, every output
+// is final. Otherwise they re-evaluate, exactly, the tiles the verdict names: tiles before the cut with every
+// upgrade candidate granted, tiles behind it with none, the cut tile with the ordered allocation of
+// upgrade_inplace.go:71-109 (candidate rank in slice order < slots left: warp-shuffle scan + per-step totals), and -
+// when the call aborts - every tile with the reference's abort semantics (nodes the sequential passes had not
+// reached stay untouched, common_manager.go:462-523). In split mode (a host-launched NCCL all-reduce between the two
+// kernels) it also makes the decision itself, from the reduced exchange vector.
+// Around it: ust_pod_summary_kernel (pod lists -> one byte per node), ust_build_state*_kernel (BuildState),
+// ust_patch_kernel / ust_feedback_kernel (delta updates, rollout simulation), ust_widen_kernel (packed host format).
+#include "ust_common.cuh"
 
-#include "ust_dev.h"
+using namespace ustd;
 
 namespace {
 
 constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStep = kThreads * 4;   // nodes per CTA step (4 per thread)
-#ifndef UST_UNROLL
-#define UST_UNROLL 4
-#endif
-#ifndef UST_MIN_CTAS
-#define UST_MIN_CTAS 2
-#endif
-constexpr int kUnroll = UST_UNROLL;            // steps in flight per thread in the fast path
-constexpr int kTile = kStep * kUnroll;
-constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kScanSlots = 512;       // prefix table of the per-chunk candidate counts: one entry per chunk up to 512 chunks
-constexpr int kMaxExactSteps = 256;   // steps per block of the exact (ordered) path: 256 x 1024 nodes
 constexpr uint32_t kLutBytes = (UST_LUT_ENTRIES + 32) * sizeof(uint32_t);  // table + 16 {shift, base} pairs
 
 struct __align__(128) Shared {
   uint32_t lut[UST_LUT_ENTRIES];  // + meta directly behind it: filled by ONE bulk (TMA) copy
   uint2 meta[16];
-  uint4 hotent[256];             // per hot byte: {window shift - 2, table base, sixteen 4-bit one-hot count increments}
   int dsrev[UST_DS_SMEM_MAX + 1];
-  unsigned int cnt[16];
-  unsigned long long errinv;
-  unsigned long long mbar;       // mbarrier the bulk copy completes on
-  long long V[UST_V_LEN];
-  // derived, CTA-uniform
-  unsigned long long abort_key;  // ~0 = none
-  long long budget;              // max(upgradesAvailable, 0)
-  long long avail;
-  long long max_unav;
-  long long node_offset;         // global index of this shard's node 0
-  long long cand_prefix;         // candidates before this chunk (global order)
-  long long part[kWarps];
-  int spec_cut;                  // effective speculative cut of this call (hint or default)
-  int cut;                       // where the budget really cut: first chunk that is not fully granted (INT_MAX = none)
-  int wrong_lo, wrong_hi;        // chunks whose speculation did not hold all lie in [wrong_lo, wrong_hi]
-  long long tbase[kScanSlots];   // candidates before chunk slot * ceil(chunks / kScanSlots), shard-local
-  unsigned int step_base[kMaxExactSteps];     // exact path: candidates before each step of the block
-  unsigned char wtot[kMaxExactSteps][kWarps];  // ... and per warp within the step
-  unsigned int chunk_cand;       // candidates of the chunk being streamed
-  int next_chunk;                // next claimed chunk
+  unsigned long long mbar;        // mbarrier the bulk copy completes on
   unsigned int warp_tot[kWarps];
-  int last;
+  // the verdict, CTA-uniform
+  unsigned long long abort_key;   // ~0 = none
+  long long node_offset;          // global index of this shard's node 0
+  long long slots;                // ordered path: slots left at the start of the tile being evaluated
+  int redo, cut, lo, hi;
+  DecideShared D;                 // split mode: the decision is made here
 };
-
-__device__ __forceinline__ uint4 ld_stream_u4(const void* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ uint32_t ld_keep_u32(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// (pass + 1) of each state code, one nibble per code: position of its Process* pass in ApplyState
-// (upgrade_state.go:205-274), 0 = never processed. Same content as ust_pass_of_state[] in ust_lut.h.
-__device__ __forceinline__ int pass_of_state(unsigned code) {
-  constexpr unsigned long long kPassPlus1 =
-      (1ull << 0) | (3ull << 4) | (4ull << 8) | (5ull << 12) | (6ull << 16) | (7ull << 20) | (8ull << 24) | (0ull << 28) |
-      (9ull << 32) | (11ull << 36) | (12ull << 40) | (2ull << 44) | (10ull << 48);
-  return (int)((kPassPlus1 >> (4 * code)) & 15ull) - 1;
-}
-
-__device__ __forceinline__ long long chunk_bound(long long n, int c, int chunks) {
-  if (c >= chunks) return n;
-  long long b = (n * (long long)c) / chunks;
-  return b & ~127LL;  // chunks start on 128-node boundaries: a warp's 128-node span never straddles two chunks
-}
-
-// ------------------------------------------------------------------------------------------------
-// table staging: the per-policy transition table (DriverUpgradePolicySpec + manager options, compiled
-// to 32 KiB by ust_lut.h) goes global -> shared with one TMA bulk copy that completes on an mbarrier;
-// nothing waits for it until the first tile's loads are in flight.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stamp(const UstParams& P, int k) {
-  if (threadIdx.x == 0 && k < 8) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    P.ws->dbg[blockIdx.x][k] = t;
-  }
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ void p1_build_table(Shared& S);
-
-__device__ void stage_tables_begin(const UstParams& P, Shared& S) {
-  const int t = threadIdx.x;
-  if (t == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.mbar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&S.mbar)), "r"(kLutBytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(S.lut)), "l"(P.lut), "r"(kLutBytes), "r"(smem_u32(&S.mbar)) : "memory");
-  }
-  if (P.n_ds <= UST_DS_SMEM_MAX)
-    for (int i = t; i <= P.n_ds; i += kThreads) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
-  p1_build_table(S);
-  if (t < 16) S.cnt[t] = 0;
-  if (t == 32) {
-    S.errinv = 0; S.abort_key = ~0ull; S.chunk_cand = 0;
-    // speculative cut: the previous call's, when it was made under the same signature; else the policy default
-    const bool hinted = P.spec_sig != 0 && __ldcg(&P.ws->hint_sig) == P.spec_sig;
-    S.spec_cut = hinted ? __ldcg(&P.ws->hint_cut) : P.spec_cut_chunk;
-  }
-}
-
-__device__ __forceinline__ void stage_tables_wait(Shared& S) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(smem_u32(&S.mbar)) : "memory");
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// counting (part of the streaming pass)
-//
-// Byte-sliced SIMD-in-register counting. A 256-entry shared-memory table maps a hot byte to sixteen
-// 4-bit one-hot increments packed in 64 bits (fields 0-13: state code, 14: unavailable, 15: upgrade
-// candidate) next to the node's table window; a thread sums the entries of 8 nodes (no field can exceed 8),
-// widens the nibbles to byte lanes, and keeps going. No atomics until the end of the chunk loop: one REDUX
-// per counter per warp, 16 global atomics per CTA.
-// ------------------------------------------------------------------------------------------------
-// window shift (minus 2) of every state code, 8 bits each — compile-time copy of ust_window_shift[]
-constexpr unsigned long long pack_shifts(int from) {
-  unsigned long long v = 0;
-  for (int i = 0; i < 8; i++) v |= (unsigned long long)(ust_window_shift[from + i] - 2) << (8 * i);
-  return v;
-}
-constexpr unsigned long long kShiftLo = pack_shifts(0), kShiftHi = pack_shifts(8);
-
-__device__ void p1_build_table(Shared& S) {
-  // GetCurrentUnavailableNodes (common_manager.go:146-165) counts every snapshot entry that is cordoned or
-  // not ready; an upgrade candidate is upgrade-required and not marked skip (upgrade_inplace.go:82)
-  const unsigned b = threadIdx.x, code = b & 15u;
-  unsigned long long v = 0;
-  if (code < 14) {
-    v = 1ull << (4 * code);
-    if (b & (UST_HOT_UNSCHEDULABLE | UST_HOT_NOT_READY)) v |= 1ull << 56;
-    if (code == UST_STATE_UPGRADE_REQUIRED && !(b & UST_HOT_SKIP)) v |= 1ull << 60;
-  }
-  const unsigned shift = (unsigned)(((code < 8 ? kShiftLo : kShiftHi) >> (8 * (code & 7))) & 0xFFull);
-  S.hotent[b] = make_uint4(shift, code * (UST_LUT_WINDOW * 4u), (uint32_t)v, (uint32_t)(v >> 32));
-}
 
 // byte lanes: B[0] = fields 0,2,4,6  B[1] = fields 1,3,5,7  B[2] = fields 8,10,12,14  B[3] = fields 9,11,13,15
 __device__ __forceinline__ unsigned p1_field(const uint32_t (&B)[4], int f) {
   return (B[(f >> 3) * 2 + (f & 1)] >> (8 * ((f & 7) >> 1))) & 0xFFu;
 }
-
-// ------------------------------------------------------------------------------------------------
-// between the phases: cluster-wide scalars from the exchange vector (every CTA, redundantly)
-// ------------------------------------------------------------------------------------------------
-__device__ void derive_scalars(const UstParams& P, Shared& S) {
-  const long long* V = S.V;
-  const long long h0 = V[0], h1 = V[1], h2 = V[2], h4 = V[4], h11 = V[11];
-  // GetTotalManagedNodes (common_manager.go:715-730): 11 buckets — not 6, 7, other
-  const long long total = h0 + h1 + h2 + V[3] + h4 + V[5] + V[8] + V[9] + V[10] + h11 + V[12];
-  const long long in_progress = total - h0 - h11 - h1;  // GetUpgradesInProgress (:733-739)
-  unsigned long long abort_key = ~0ull;
-  long long off = 0, my_off = 0, cand_before = 0;
-  for (int r = 0; r < P.world; r++) {
-    if (r == P.rank) my_off = off;
-    if (r < P.rank) cand_before += V[UST_V_RANK_CAND + r];
-    const unsigned long long e = (unsigned long long)V[UST_V_RANK_ERRINV + r];
-    if (e) {
-      const unsigned long long k = ~e;
-      const unsigned long long gk = (k & 0xFF00000000000000ull) | ((k & 0x00FFFFFFFFFFFFFFull) + (unsigned long long)off);
-      if (gk < abort_key) abort_key = gk;
-    }
-    off += V[UST_V_RANK_NODES + r];
-  }
-  long long max_unav = 0, avail = 0;
-  const bool slots = P.active && !P.requestor;
-  if (slots) {
-    // upgrade_inplace.go:49-62 + intstr.GetScaledValueFromIntOrPercent(v, total, roundUp=true)
-    if (P.max_unav_kind == UST_MAXUNAVAIL_INVALID && UST_KEY(2, 0) < abort_key) abort_key = UST_KEY(2, 0);
-    max_unav = total;
-    if (P.max_unav_kind == UST_MAXUNAVAIL_INT) max_unav = P.max_unav_value;
-    else if (P.max_unav_kind == UST_MAXUNAVAIL_PERCENT)
-      max_unav = (long long)ceil(__ddiv_rn(__dmul_rn((double)P.max_unav_value, (double)total), 100.0));
-    // GetUpgradesAvailable (common_manager.go:748-776)
-    avail = (P.max_parallel == 0) ? h1 : P.max_parallel - in_progress;
-    const long long cur_unav = V[UST_V_UNAVAILABLE] + h2;
-    if (avail > max_unav) avail = max_unav;
-    if (cur_unav >= max_unav) avail = 0;
-    else if (max_unav < total && cur_unav + avail > max_unav) avail = max_unav - cur_unav;
-  }
-  // SchedulePodEviction with a nil DeletionSpec (pod_manager.go:125-134)
-  if (P.active && P.pd_enabled && !P.pd_spec_present && h4 > 0 && UST_KEY(5, 0) < abort_key) abort_key = UST_KEY(5, 0);
-  S.abort_key = abort_key;
-  S.avail = avail;
-  S.max_unav = max_unav;
-  S.budget = avail > 0 ? avail : 0;
-  S.node_offset = my_off;
-  S.cand_prefix = cand_before;  // completed with the chunk prefix by the caller
-}
-
-__device__ void write_counters(const UstParams& P, const Shared& S) {
-  ust_counters c;
-  const long long* V = S.V;
-  for (int i = 0; i < 16; i++) c.hist[i] = V[i];
-  c.unavailable = V[UST_V_UNAVAILABLE];
-  c.candidates = V[UST_V_CANDIDATES];
-  c.total_managed = V[0] + V[1] + V[2] + V[3] + V[4] + V[5] + V[8] + V[9] + V[10] + V[11] + V[12];
-  c.in_progress = c.total_managed - V[0] - V[11] - V[1];
-  c.error_code = UST_OK;
-  c.error_index = -1;
-  c.error_pass = -1;
-  if (S.abort_key != ~0ull) {
-    const int pass = (int)(S.abort_key >> 56);
-    const long long idx1 = (long long)(S.abort_key & 0x00FFFFFFFFFFFFFFull);
-    c.error_pass = pass;
-    c.error_index = idx1 - 1;
-    c.error_code = idx1 ? UST_ERR_REVISION_HASH : (pass == 2 ? UST_ERR_MAX_UNAVAILABLE : UST_ERR_POD_DELETION_SPEC);
-  }
-  const bool slots = P.active && !P.requestor && !(c.error_code && c.error_pass < 2) && c.error_code != UST_ERR_MAX_UNAVAILABLE;
-  c.max_unavailable = slots ? S.max_unav : 0;
-  c.upgrades_available = slots ? S.avail : 0;
-  for (int i = 0; i < 7; i++) c.reserved[i] = 0;
-  if (__ldcg(&P.ws->comm_timeout)) { c.error_code = UST_ERR_COMM; c.error_index = -1; c.error_pass = -1; }
-  c.reserved[0] = (long long)__ldcg(&P.ws->fixups);  // chunks the verification phase had to redo (diagnostic)
-  *P.out = c;
+__device__ __forceinline__ void widen(uint32_t& lo, uint32_t& hi, uint32_t (&B)[4]) {
+  B[0] += lo & 0x0F0F0F0Fu;
+  B[1] += (lo >> 4) & 0x0F0F0F0Fu;
+  B[2] += hi & 0x0F0F0F0Fu;
+  B[3] += (hi >> 4) & 0x0F0F0F0Fu;
+  lo = hi = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // per-node transition
 // ------------------------------------------------------------------------------------------------
-template <bool DS_SMEM>
-__device__ __forceinline__ bool pod_synced(const UstParams& P, const Shared& S, int rev, uint32_t di) {
-  // podRevisionHash == daemonsetRevisionHash (common_manager.go:318); a missing DaemonSet never matches
-  if (DS_SMEM) return (di < (uint32_t)P.n_ds) && (rev == S.dsrev[min(di, (uint32_t)P.n_ds)]);
-  return di < (uint32_t)P.n_ds && rev == __ldg(P.ds_rev + di);
-}
-
 // table entry for one node. hb = hot byte, extra = derived bits (slot grant, pod-list summaries)
-template <bool DS_SMEM>
-__device__ __forceinline__ uint32_t node_entry(const UstParams& P, const Shared& S, uint32_t hb, uint32_t fl, int rev,
+__device__ __forceinline__ uint32_t node_entry(const UstParams& P, const Shared& S, bool ds_smem, uint32_t hb, uint32_t fl, int rev,
                                                uint32_t di, uint32_t extra) {
   uint32_t w = (fl & UST_F_INPUT_MASK) | ((hb >> 3) & (UST_W_SKIP | UST_W_UNSCHEDULABLE)) | extra;
-  if (pod_synced<DS_SMEM>(P, S, rev, di)) w |= UST_W_SYNCED;
+  // podRevisionHash == daemonsetRevisionHash (common_manager.go:318); a missing DaemonSet never matches
+  bool synced;
+  if (ds_smem) synced = (di < (uint32_t)P.n_ds) && (rev == S.dsrev[min(di, (uint32_t)P.n_ds)]);
+  else synced = di < (uint32_t)P.n_ds && rev == __ldg(P.ds_rev + di);
+  if (synced) w |= UST_W_SYNCED;
   const uint2 m = S.meta[hb & 15u];
   const uint32_t off = (__funnelshift_r(w, 0u, m.x) & 0x7FCu) | m.y;
   return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(S.lut) + off);
@@ -299,384 +84,13 @@ __device__ __forceinline__ uint32_t apply_abort(const Shared& S, uint32_t ent, u
   return ent;
 }
 
-__device__ __forceinline__ void pack4(const uint32_t e[4], uint32_t& next4, uint2& act4, uint32_t& out4) {
-  act4.x = __byte_perm(e[0], e[1], 0x5410);
-  act4.y = __byte_perm(e[2], e[3], 0x5410);
-  const uint32_t hi01 = __byte_perm(e[0], e[1], 0x7632);  // [e0.b2 e0.b3 e1.b2 e1.b3]
-  const uint32_t hi23 = __byte_perm(e[2], e[3], 0x7632);
-  next4 = __byte_perm(hi01, hi23, 0x6420);
-  out4 = __byte_perm(hi01, hi23, 0x7531);
-}
-
-// One tile = kUnroll steps of kStep nodes; thread t owns nodes base + j*kStep + 4t .. +3. `lim` is a
-// multiple of 128 (or the tile is full), so validity is uniform per warp and per j.
-template <int U>
-struct TileT {
-  uint32_t h[U];
-  uint32_t ps[U];  // pod-list summaries (one byte per node), PODS variants only
-  uint4 f[U], r[U], d[U];
-};
-// The streaming fast path keeps kUnroll steps in flight per thread; the redo variants after the barrier keep
-// kColdUnroll: with a four-step tile the compiler parks their tile on the stack (STL/LDL in the tile loop, seen with
-// nvdisasm), with a smaller one most of it stays in registers. Measured (profiles/README.md): 1 / 2 / 4 steps ->
-// hinted redo 49.0 / 49.7 / 51.5 us, unhinted 81 / 77 / 78 us.
-#ifndef UST_COLD_UNROLL
-#define UST_COLD_UNROLL 2
-#endif
-constexpr int kColdUnroll = UST_COLD_UNROLL;
-
-// Chunk-relative addressing: the chunk's base pointers are CTA-uniform; a thread addresses 4-node groups
-// with a 32-bit group index q (thread t of the CTA owns groups done/4 + j*kStepQ + t of a tile).
-struct Cursor {
-  const uint32_t* h;
-  const uint32_t* ps;  // null when the call has no pod lists
-  const uint4* f;
-  const uint4* r;
-  const uint4* d;
-  uint32_t* nx;
-  uint2* ac;
-  uint32_t* oc;
-  int q;
-};
-constexpr int kStepQ = kStep / 4;  // a step in units of 4-node groups
-constexpr int kTileQ = kTile / 4;
-
-__device__ __forceinline__ Cursor cursor_at(const UstParams& P, long long base) {
-  Cursor c;
-  c.h = reinterpret_cast<const uint32_t*>(P.hot + base);
-  c.ps = P.podsum ? reinterpret_cast<const uint32_t*>(P.podsum + base) : nullptr;
-  c.f = reinterpret_cast<const uint4*>(P.flags + base);
-  c.r = reinterpret_cast<const uint4*>(P.pod_rev + base);
-  c.d = reinterpret_cast<const uint4*>(P.ds_idx + base);
-  c.nx = reinterpret_cast<uint32_t*>(P.next + base);
-  c.ac = reinterpret_cast<uint2*>(P.actions + base);
-  c.oc = P.outcome ? reinterpret_cast<uint32_t*>(P.outcome + base) : nullptr;
-  c.q = threadIdx.x;
-  return c;
-}
-template <int U>
-__device__ __forceinline__ void cursor_advance(Cursor& c) { c.q += U * kStepQ; }
-
-// `room` = nodes left in the chunk from this thread's first node of the tile; chunk ends are multiples of
-// 128 nodes, so for a partial tile validity is uniform per warp and per step.
-// PODS: 0 = the call has no pod lists, 1 = it has, 2 = decided at run time (out-of-line variants)
-template <bool FULL, int PODS, int U>
-__device__ __forceinline__ void tile_load(const Cursor& c, int room, TileT<U>& T) {
-#pragma unroll
-  for (int j = 0; j < U; j++) {
-    // every element is assigned on every path, so that the tile stays in registers (no stack copy)
-    const bool valid = FULL || j * kStep + 4 <= room;
-    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    T.h[j] = valid ? __ldg(c.h + c.q + j * kStepQ) : 0x0E0E0E0Eu;
-    T.ps[j] = (valid && (PODS == 1 || (PODS == 2 && c.ps != nullptr))) ? __ldcs(c.ps + c.q + j * kStepQ) : 0u;
-    T.f[j] = valid ? __ldcs(c.f + c.q + j * kStepQ) : zero;
-    T.r[j] = valid ? __ldcs(c.r + c.q + j * kStepQ) : zero;
-    T.d[j] = valid ? __ldcs(c.d + c.q + j * kStepQ) : zero;
-  }
-}
-
-// revision-hash error seen while streaming (flags word already in registers)
-__device__ __forceinline__ void spec_error_byte(const UstParams& P, Shared& S, unsigned b, uint32_t fl, long long i) {
-  const unsigned code = b & 15u;
-  if (!(b & UST_HOT_REVISION_HASH_ERROR) || !P.active) return;
-  if (!(code == UST_STATE_UNKNOWN || code == UST_STATE_DONE || code == UST_STATE_POD_RESTART_REQUIRED || code == UST_STATE_FAILED)) return;
-  if (fl & UST_F_POD_ORPHANED) return;
-  atomicMax(&S.errinv, ~UST_KEY(pass_of_state(code), (unsigned long long)i + 1ull));
-}
-
-__device__ __forceinline__ void widen(uint32_t& lo, uint32_t& hi, uint32_t (&B)[4]) {
-  B[0] += lo & 0x0F0F0F0Fu;
-  B[1] += (lo >> 4) & 0x0F0F0F0Fu;
-  B[2] += hi & 0x0F0F0F0Fu;
-  B[3] += (hi >> 4) & 0x0F0F0F0Fu;
-  lo = hi = 0;
-}
-
-// per-thread counting state of the streaming phase (lives across the chunks a CTA claims)
-struct Acc {
-  uint32_t B[4];           // sixteen byte-lane counters
-  int tiles;               // tiles accumulated since the last spill (byte lanes hold 255)
-  unsigned cand_spilled;   // candidates already spilled: cand_spilled + field 15 of B is monotonic per thread
-};
-
-__device__ __forceinline__ void spill_thread(Shared& S, Acc& A) {
-#pragma unroll
-  for (int f = 0; f < 16; f++) {
-    const unsigned v = p1_field(A.B, f);
-    if (v) atomicAdd(&S.cnt[f], v);
-  }
-  A.cand_spilled += p1_field(A.B, 15);
-  A.B[0] = A.B[1] = A.B[2] = A.B[3] = 0;
-  A.tiles = 0;
-}
-
-// One node of the streaming pass. `xs` = the node's hot byte moved to bits 4..11 of a word (so it indexes
-// the 16-byte hotent table directly), `ws` = its SKIP / UNSCHEDULABLE bits already at w positions 2, 3.
-// pod-list summary byte -> the w bits it stands for (ust_pod_summary_kernel): bit 0 = a wait-selector pod is
-// running, bits 1..3 = UST_W_PD_HAS / UST_W_PD_MISMATCH / UST_W_DRAIN_ERROR, bit 4 = the list overrides the
-// pre-evaluated UST_F_WAIT_PODS_RUNNING of the flags word
-__device__ __forceinline__ uint32_t pods_apply(uint32_t fl, uint32_t ps) {
-  return (fl & ~((ps & 0x10u) << 12)) | ((ps & 1u) << 16) | ((ps & 0xEu) << 21);
-}
-static_assert(UST_F_WAIT_PODS_RUNNING == (1u << 16) && UST_W_PD_HAS == (UST_PODSUM_TO_DELETE << 21) &&
-              UST_W_PD_MISMATCH == (UST_PODSUM_CANNOT_DELETE << 21) && UST_W_DRAIN_ERROR == (UST_PODSUM_DRAIN_ERROR << 21) &&
-              UST_PODSUM_WAIT_RUNNING == 1u, "pod summary byte layout");
-
-template <bool DS_SMEM>
-__device__ __forceinline__ uint32_t stream_node(const UstParams& P, const Shared& S, uint32_t tab_off, uint32_t wbits,
-                                                uint32_t fl, int rev, uint32_t di, uint32_t grant, uint32_t& lo,
-                                                uint32_t& hi) {
-  const uint4 m = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(S.hotent) + tab_off);
-  lo += m.z;
-  hi += m.w;
-  uint32_t w = fl | wbits | grant;  // fl: input bits of the flags word (+ pod-list bits), masked by the caller
-  if (pod_synced<DS_SMEM>(P, S, rev, di)) w |= UST_W_SYNCED;
-  const uint32_t off = (__funnelshift_r(w, 0u, m.x) & 0x7FCu) | m.y;
-  return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(S.lut) + off);
-}
-
-// candidate bytes of a hot word: bit 7 of byte k set iff node k is upgrade-required and not marked skip
-__device__ __forceinline__ uint32_t cand_mask4(uint32_t x) {
-  const uint32_t y = (x & 0x2F2F2F2Fu) ^ 0x01010101u;  // zero byte <=> code == 1 && !SKIP
-  return ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u;
-}
-
-struct ExactCtx {
-  int s0;              // step index (within the block) of the tile's first step
-  unsigned int limit;  // candidates of the block that get a slot (rank < limit), block-relative
-};
-
-// One tile of the streaming pass: evaluate every node (one table lookup) and write next_state / actions;
-// COUNT adds the byte-sliced counting, EXACT replaces the chunk-uniform slot grant by the ordered one: a
-// candidate's rank in slice order = candidates before its step (S.step_base) + before its warp within the step
-// (S.wtot) + a warp-shuffle exclusive scan — no block barrier in the loop (upgrade_inplace.go:71-109).
-template <bool FULL, bool DS_SMEM, bool OUTCOME, bool COUNT, bool EXACT, int PODS, int U>
-__device__ __forceinline__ void spec_tile(const UstParams& P, Shared& S, const Cursor& c, int room, long long i0,
-                                          const TileT<U>& T, uint32_t grant, uint32_t (&B)[4], ExactCtx ex) {
-  uint32_t lo = 0, hi = 0;
-#pragma unroll
-  for (int j = 0; j < U; j++) {
-    if (FULL || j * kStep + 4 <= room) {
-      const uint32_t x = T.h[j];
-      if (COUNT && (x & 0x80808080u)) {  // rare
-        const long long i = i0 + j * kStep;
-        spec_error_byte(P, S, x & 0xFFu, T.f[j].x, i);
-        spec_error_byte(P, S, (x >> 8) & 0xFFu, T.f[j].y, i + 1);
-        spec_error_byte(P, S, (x >> 16) & 0xFFu, T.f[j].z, i + 2);
-        spec_error_byte(P, S, x >> 24, T.f[j].w, i + 3);
-      }
-      uint32_t g[4] = {grant, grant, grant, grant};
-      if (EXACT) {
-        const uint32_t cm = cand_mask4(x);
-        const unsigned tc = __popc(cm);
-        unsigned incl = tc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned v = __shfl_up_sync(kFull, incl, o);
-          if ((threadIdx.x & 31) >= o) incl += v;
-        }
-        const int s = ex.s0 + j, warp = threadIdx.x >> 5;
-        unsigned rank = S.step_base[s] + incl - tc;
-#pragma unroll
-        for (int w = 0; w < kWarps; w++)
-          if (w < warp) rank += S.wtot[s][w];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const unsigned isc = (cm >> (8 * k + 7)) & 1u;
-          g[k] = (isc && rank < ex.limit) ? UST_W_GRANTED : 0u;
-          rank += isc;
-        }
-      }
-      constexpr uint32_t kW = UST_W_SKIP | UST_W_UNSCHEDULABLE;
-      uint32_t e[4];
-      uint32_t dlo = 0, dhi = 0;
-      // without pod lists the derived pod bits of w are never set: mask them out of the flags word
-      constexpr uint32_t kIn = UST_F_INPUT_MASK;
-      uint32_t fl[4] = {T.f[j].x & kIn, T.f[j].y & kIn, T.f[j].z & kIn, T.f[j].w & kIn};
-      if (PODS) {
-        const uint32_t ps = T.ps[j];
-        fl[0] = pods_apply(fl[0], ps & 0xFFu);
-        fl[1] = pods_apply(fl[1], (ps >> 8) & 0xFFu);
-        fl[2] = pods_apply(fl[2], (ps >> 16) & 0xFFu);
-        fl[3] = pods_apply(fl[3], ps >> 24);
-      }
-      e[0] = stream_node<DS_SMEM>(P, S, (x << 4) & 0xFF0u, (x >> 3) & kW, fl[0], (int)T.r[j].x, T.d[j].x, g[0], dlo, dhi);
-      e[1] = stream_node<DS_SMEM>(P, S, (x >> 4) & 0xFF0u, (x >> 11) & kW, fl[1], (int)T.r[j].y, T.d[j].y, g[1], dlo, dhi);
-      e[2] = stream_node<DS_SMEM>(P, S, (x >> 12) & 0xFF0u, (x >> 19) & kW, fl[2], (int)T.r[j].z, T.d[j].z, g[2], dlo, dhi);
-      e[3] = stream_node<DS_SMEM>(P, S, (x >> 20) & 0xFF0u, (x >> 27) & kW, fl[3], (int)T.r[j].w, T.d[j].w, g[3], dlo, dhi);
-      if (COUNT) { lo += dlo; hi += dhi; }
-      uint32_t next4, out4;
-      uint2 act4;
-      pack4(e, next4, act4, out4);
-      __stcs(c.nx + c.q + j * kStepQ, next4);
-      __stcs(c.ac + c.q + j * kStepQ, act4);
-      if (OUTCOME) __stcs(c.oc + c.q + j * kStepQ, out4);
-    }
-    if (COUNT && (j & 1)) widen(lo, hi, B);  // at most 8 per nibble so far
-  }
-  if (COUNT && (U & 1)) widen(lo, hi, B);
-}
-
-// Pre-pass of the ordered path over one block of steps [blk0, blk1): hot bytes only (they are L2-resident or
-// about to be), all loads in flight at once; leaves per-step/per-warp candidate totals and the per-step exclusive
-// prefix in shared memory. Returns the block's candidate total; `before` gets the candidates among the nodes
-// [count_from, blk0) (the part of the chunk that precedes the block; same batch of loads, no extra round trip).
-__device__ unsigned exact_prepass(const UstParams& P, Shared& S, long long blk0, long long blk1, long long count_from,
-                                  long long& before) {
-  const int t = threadIdx.x, warp = t >> 5;
-  const int nsteps = (int)((blk1 - blk0 + kStep - 1) / kStep);
-  unsigned pre = 0;
-  for (long long a = count_from; a < blk0; a += 8LL * 16 * kThreads) {  // 16 nodes per load, 8 loads in flight
-    uint4 x[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const long long i = a + (long long)u * 16 * kThreads + 16 * t;     // count_from, blk0: multiples of 128
-      x[u] = i < blk0 ? __ldg(reinterpret_cast<const uint4*>(P.hot + i)) : make_uint4(0x0E0E0E0Eu, 0x0E0E0E0Eu, 0x0E0E0E0Eu, 0x0E0E0E0Eu);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-      pre += __popc(cand_mask4(x[u].x)) + __popc(cand_mask4(x[u].y)) + __popc(cand_mask4(x[u].z)) + __popc(cand_mask4(x[u].w));
-  }
-  for (int s0 = 0; s0 < nsteps; s0 += 8) {
-    uint32_t x[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const long long i = blk0 + (long long)(s0 + u) * kStep + 4 * t;
-      x[u] = (s0 + u < nsteps && i + 4 <= blk1) ? __ldg(reinterpret_cast<const uint32_t*>(P.hot + i)) : 0x0E0E0E0Eu;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const unsigned w = __reduce_add_sync(kFull, (unsigned)__popc(cand_mask4(x[u])));
-      if ((t & 31) == 0 && s0 + u < nsteps) S.wtot[s0 + u][warp] = (unsigned char)w;  // <= 128
-    }
-  }
-  pre = __reduce_add_sync(kFull, pre);
-  if ((t & 31) == 0) S.part[warp] = pre;
-  __syncthreads();
-  // exclusive prefix over the steps of the block (kMaxExactSteps == kThreads: one step per thread)
-  unsigned tot = 0;
-  if (t < nsteps)
-    for (int w = 0; w < kWarps; w++) tot += S.wtot[t][w];
-  unsigned incl = tot;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned v = __shfl_up_sync(kFull, incl, o);
-    if ((t & 31) >= o) incl += v;
-  }
-  if ((t & 31) == 31) S.warp_tot[warp] = incl;
-  __syncthreads();
-  unsigned before_steps = 0, total = 0;
-  long long pre_all = 0;
-#pragma unroll
-  for (int w = 0; w < kWarps; w++) {
-    const unsigned v = S.warp_tot[w];
-    if (w < warp) before_steps += v;
-    total += v;
-    pre_all += S.part[w];
-  }
-  if (t < nsteps) S.step_base[t] = before_steps + incl - tot;
-  __syncthreads();
-  before = pre_all;
-  return total;
-}
-
-// Evaluate the block [blk0, blk1) of a chunk through the 4-deep tile pipeline. ORDERED: `limit` slots are left
-// for the candidates from node `count_from` (<= blk0) on, in slice order (pre-pass + per-node ranks); otherwise
-// the slot grant is uniform (`grant`). Returns the candidates in [count_from, blk1) (ORDERED only).
-template <bool DS_SMEM, bool OUTCOME, bool COUNT, bool ORDERED, int PODS, int U>
-__device__ __forceinline__ long long spec_block(const UstParams& P, Shared& S, long long blk0, long long blk1, uint32_t grant,
-                                                long long limit, long long count_from, Acc& A, bool wait_for_table) {
-  const long long span = blk1 - blk0;  // CTA-uniform, a multiple of 128 (or <= 0 for an empty chunk)
-  // the streaming fast path has a specialised body for full tiles; the out-of-line variants keep one (predicated) body
-  constexpr bool kFullVariant = COUNT && !ORDERED;
-  constexpr int kTileU = U * kStep;  // nodes per tile
-  const int t4 = 4 * threadIdx.x;
-  auto room_at = [&](long long done) -> int {  // nodes from this thread's first node of the tile to the block end
-    const long long r = span - done - t4;
-    return r > (1LL << 30) ? (1 << 30) : (r < 0 ? 0 : (int)r);
-  };
-  Cursor c = cursor_at(P, blk0);
-  long long i0 = blk0 + t4;
-  TileT<U> T;
-  auto load = [&](long long done) {  // loads of the tile starting `done` nodes into the block; c.q points at it
-    if (kFullVariant && span - done >= kTileU) tile_load<true, PODS, U>(c, 0, T); else tile_load<false, PODS, U>(c, room_at(done), T);
-  };
-  if (span > 0) load(0);  // the first tile's loads go out before anything waits (table copy, pre-pass)
-  if (wait_for_table) {
-    stage_tables_wait(S);
-    __syncthreads();
-  }
-  ExactCtx ex{0, 0};
-  long long blk_cand = 0;  // candidates in [count_from, blk1)
-  if (ORDERED && span > 0) {
-    long long before = 0;
-    blk_cand = exact_prepass(P, S, blk0, blk1, count_from, before);
-    stamp(P, 6);
-    limit -= before;  // `limit` slots were left at count_from
-    blk_cand += before;
-    ex.limit = limit <= 0 ? 0u : (limit > 0x7FFFFFFFLL ? 0x7FFFFFFFu : (unsigned)limit);
-  }
-#pragma unroll 1
-  for (long long done = 0; done < span; done += kTileU) {
-    if (done) load(done);
-    const int room = room_at(done);
-    if (ORDERED) ex.s0 = (int)(done / kStep);
-    if (kFullVariant && span - done >= kTileU) spec_tile<true, DS_SMEM, OUTCOME, COUNT, ORDERED, PODS, U>(P, S, c, room, i0, T, grant, A.B, ex);
-    else spec_tile<false, DS_SMEM, OUTCOME, COUNT, ORDERED, PODS, U>(P, S, c, room, i0, T, grant, A.B, ex);
-    cursor_advance<U>(c);
-    i0 += kTileU;
-    if (COUNT && ++A.tiles >= 224 / (4 * U)) spill_thread(S, A);  // byte lanes: at most 4U per tile, 255 max
-  }
-  return blk_cand;
-}
-
-// The streaming fast path: uniform grant, counting, inlined into the chunk loop.
-template <bool DS_SMEM, bool OUTCOME, bool PODS>
-__device__ __forceinline__ void spec_chunk(const UstParams& P, Shared& S, long long b0, long long lim, uint32_t grant, Acc& A,
-                                           bool wait_for_table) {
-  spec_block<DS_SMEM, OUTCOME, true, false, PODS ? 1 : 0, kUnroll>(P, S, b0, lim, grant, 0, b0, A, wait_for_table);
-}
-
-// The ordered variant lives out of line so that it cannot cost the fast path registers: blocks of
-// kMaxExactSteps steps; `slots` slots are left for the candidates from node `count_from` (<= b0, same chunk) on.
-// Counts (COUNT) go straight to the CTA's shared counters; returns the candidates in [count_from, lim).
-template <bool DS_SMEM, bool OUTCOME, bool COUNT>
-__device__ __forceinline__ long long ordered_range(const UstParams& P, Shared& S, long long b0, long long lim, long long slots,
-                                                long long count_from, bool wait_for_table) {
-  Acc A;
-  A.B[0] = A.B[1] = A.B[2] = A.B[3] = 0;
-  A.tiles = 0;
-  A.cand_spilled = 0;
-  constexpr long long kBlk = (long long)kMaxExactSteps * kStep;
-  long long seen = 0;
-  long long blk0 = b0;
-  do {
-    const long long blk1 = blk0 + kBlk < lim ? blk0 + kBlk : lim;
-    seen += spec_block<DS_SMEM, OUTCOME, COUNT, true, 2, kColdUnroll>(P, S, blk0, blk1, 0u, slots - seen, blk0 == b0 ? count_from : blk0, A,
-                                                      wait_for_table);
-    wait_for_table = false;
-    __syncthreads();  // step_base / wtot are rewritten by the next block's pre-pass
-    blk0 = blk1;
-  } while (blk0 < lim);
-  if (COUNT) spill_thread(S, A);
-  return seen;
-}
-
-// ... and so does the uniform-grant variant without counting (redo of chunks whose every candidate, or none, gets a slot)
-template <bool DS_SMEM, bool OUTCOME>
-__device__ __forceinline__ void uniform_range(const UstParams& P, Shared& S, long long b0, long long lim, uint32_t grant) {
-  Acc A;
-  A.B[0] = A.B[1] = A.B[2] = A.B[3] = 0;
-  A.tiles = 0;
-  A.cand_spilled = 0;
-  spec_block<DS_SMEM, OUTCOME, false, false, 2, kColdUnroll>(P, S, b0, lim, grant, 0, b0, A, false);
-}
-
-// general path: one step of kStep nodes, bounds-checked; optional exact ordered slot allocation,
-// abort masking and pod-list evaluation
+// One step of kStep nodes starting at `base`, bounds-checked against b1 (the end of the tile / the shard).
+// EXACT: the ordered slot allocation - candidate = upgrade-required && !skip; rank = exclusive count of candidates in
+// slice order from the start of the tile (`running` carries it from step to step); granted iff rank < S.slots
+// (upgrade_inplace.go:71-109). Otherwise the grant is uniform. Abort masking and pod-list summaries as in the
+// streaming pass.
 template <bool EXACT>
-__device__ void general_step(const UstParams& P, Shared& S, long long base, long long b1, uint32_t grant,
-                             long long& running /* candidates seen in this chunk so far (EXACT) */) {
+__device__ void general_step(const UstParams& P, Shared& S, long long base, long long b1, uint32_t grant, long long& running) {
   const int t = threadIdx.x;
   const long long i0 = base + 4 * t;
   const bool aborting = S.abort_key != ~0ull;
@@ -685,8 +99,9 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
   int nvalid = 0;
   if (i0 + 4 <= b1) {
     nvalid = 4;
-    const uint32_t h = ld_keep_u32(P.hot + i0);
-    const uint4 f = ld_stream_u4(P.flags + i0), r = ld_stream_u4(P.pod_rev + i0), d = ld_stream_u4(P.ds_idx + i0);
+    const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(P.hot + i0));
+    const uint4 f = __ldcs(reinterpret_cast<const uint4*>(P.flags + i0)), r = __ldcs(reinterpret_cast<const uint4*>(P.pod_rev + i0)),
+                d = __ldcs(reinterpret_cast<const uint4*>(P.ds_idx + i0));
     hb[0] = h & 0xFFu; hb[1] = (h >> 8) & 0xFFu; hb[2] = (h >> 16) & 0xFFu; hb[3] = h >> 24;
     fl[0] = f.x; fl[1] = f.y; fl[2] = f.z; fl[3] = f.w;
     rev[0] = (int)r.x; rev[1] = (int)r.y; rev[2] = (int)r.z; rev[3] = (int)r.w;
@@ -706,8 +121,6 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
 
   uint32_t gbits[4] = {grant, grant, grant, grant};
   if (EXACT) {
-    // ordered slot allocation: candidate = upgrade-required && !skip; rank = exclusive count of
-    // candidates in slice order; granted iff rank < max(upgradesAvailable, 0) (upgrade_inplace.go:71-109)
     unsigned c[4], tc = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -730,10 +143,10 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
       step_total += v;
     }
     __syncthreads();
-    long long rank = S.cand_prefix + running + before + (incl - tc);
+    long long rank = running + before + (incl - tc);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      gbits[k] = (c[k] && rank < S.budget) ? UST_W_GRANTED : 0u;
+      gbits[k] = (c[k] && rank < S.slots) ? UST_W_GRANTED : 0u;
       rank += c[k];
     }
     running += step_total;
@@ -750,7 +163,7 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
       f &= ~((ps & 0x10u) << 12);
       extra |= ((ps & 1u) << 16) | ((ps & 0xEu) << 21);
     }
-    e[k] = ds_smem ? node_entry<true>(P, S, hb[k], f, rev[k], di[k], extra) : node_entry<false>(P, S, hb[k], f, rev[k], di[k], extra);
+    e[k] = node_entry(P, S, ds_smem, hb[k], f, rev[k], di[k], extra);
     if (aborting) e[k] = apply_abort(S, e[k], hb[k], S.node_offset + i0 + k);
   }
   uint32_t next4, out4;
@@ -769,526 +182,113 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
   }
 }
 
-// how many candidates of a chunk get a slot, given the cluster-wide budget and the candidates before the chunk
-__device__ __forceinline__ long long required_local(const Shared& S, unsigned chunk_cand) {
-  long long l = S.budget - S.cand_prefix;
-  if (l < 0) l = 0;
-  return l > (long long)chunk_cand ? (long long)chunk_cand : l;
+// A span of full steps with a uniform grant and no abort: two steps (2048 nodes) per iteration, all loads of both
+// steps in flight before the first lookup. b0, b1: multiples of kStep apart (the caller peels the ragged end).
+__device__ void uniform_span(const UstParams& P, Shared& S, long long b0, long long b1, uint32_t grant) {
+  const int t = threadIdx.x;
+  const bool ds_smem = P.n_ds <= UST_DS_SMEM_MAX;
+  constexpr int U = 2;
+  for (long long base = b0; base < b1; base += (long long)U * kStep) {
+    uint32_t h[U], ps[U];
+    uint4 f[U], r[U], d[U];
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+      const long long i = base + (long long)j * kStep + 4 * t;
+      const bool v = i < b1;   // warp-uniform: spans are multiples of kStep
+      h[j] = v ? __ldg(reinterpret_cast<const uint32_t*>(P.hot + i)) : 0x0E0E0E0Eu;
+      ps[j] = (v && P.podsum) ? __ldcs(reinterpret_cast<const uint32_t*>(P.podsum + i)) : 0u;
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      f[j] = v ? __ldcs(reinterpret_cast<const uint4*>(P.flags + i)) : zero;
+      r[j] = v ? __ldcs(reinterpret_cast<const uint4*>(P.pod_rev + i)) : zero;
+      d[j] = v ? __ldcs(reinterpret_cast<const uint4*>(P.ds_idx + i)) : zero;
+    }
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+      const long long i = base + (long long)j * kStep + 4 * t;
+      if (i >= b1) continue;
+      const uint32_t fl[4] = {f[j].x, f[j].y, f[j].z, f[j].w};
+      const uint32_t rv[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
+      const uint32_t dv[4] = {d[j].x, d[j].y, d[j].z, d[j].w};
+      uint32_t e[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t hb = (h[j] >> (8 * k)) & 0xFFu, p = (ps[j] >> (8 * k)) & 0xFFu;
+        const uint32_t fk = fl[k] & ~((p & 0x10u) << 12);
+        e[k] = node_entry(P, S, ds_smem, hb, fk, (int)rv[k], dv[k], grant | ((p & 1u) << 16) | ((p & 0xEu) << 21));
+      }
+      uint32_t next4, out4;
+      uint2 act4;
+      pack4(e, next4, act4, out4);
+      __stcs(reinterpret_cast<uint32_t*>(P.next + i), next4);
+      __stcs(reinterpret_cast<uint2*>(P.actions + i), act4);
+      if (P.outcome) __stcs(reinterpret_cast<uint32_t*>(P.outcome + i), out4);
+    }
+  }
 }
-__device__ __forceinline__ uint32_t spec_grant(const UstParams& P, const Shared& S, int chunk) {
-  return (P.active && !P.requestor && chunk < S.spec_cut) ? UST_W_GRANTED : 0u;
-}
-// Redo one chunk through the bounds-checked step path: aborts (nodes of later passes keep their state) and
-// pod lists (per-node CSR walk) need it; the slot grant is exact here too.
-__device__ void general_chunk(const UstParams& P, Shared& S, long long b0, long long b1, unsigned chunk_cand) {
+
+// Re-evaluate one tile exactly, given where the slot budget cuts.
+__device__ void redo_tile(const UstParams& P, Shared& S, int tile) {
+  const long long b0 = (long long)tile * P.tile_nodes;
+  long long b1 = b0 + P.tile_nodes;
+  if (b1 > P.n) b1 = P.n;
   const bool slotted = P.active && !P.requestor;
-  const long long need = slotted ? required_local(S, chunk_cand) : 0;
-  const bool ordered = slotted && chunk_cand != 0 && need > 0 && need < (long long)chunk_cand;
-  const uint32_t grant = (slotted && chunk_cand != 0 && need == (long long)chunk_cand) ? UST_W_GRANTED : 0u;
+  const bool aborting = S.abort_key != ~0ull;
   long long running = 0;
-  if (!ordered) {
-    for (long long base = b0; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
-  } else {
+  if (slotted && tile == S.cut) {  // the cut tile: S.slots of its candidates get a slot, in slice order
     for (long long base = b0; base < b1; base += kStep) general_step<true>(P, S, base, b1, 0u, running);
-  }
-}
-
-// The chunk loop of the streaming phase: chunks (contiguous node ranges, chunk order == slice order) are
-// claimed with an atomic ticket, so CTAs that HBM serves faster take more of them and all CTAs reach the
-// grid barrier together. Per chunk: counts + speculative outputs; the chunk's candidate count is published
-// for the ordered slot allocation. Returns the number of nodes this CTA streamed.
-template <bool DS_SMEM, bool OUTCOME, bool PODS>
-__device__ long long stream_loop(const UstParams& P, Shared& S) {
-  const int t = threadIdx.x;
-  const int n_chunks = P.grid_chunks;
-  UstWorkspace* ws = P.ws;
-  long long nodes_seen = 0;
-  Acc A;
-  A.B[0] = A.B[1] = A.B[2] = A.B[3] = 0;
-  A.tiles = 0;
-  A.cand_spilled = 0;
-  bool first = true;
-  unsigned cand_published = 0;
-  int chunk = P.chunk_begin + blockIdx.x;
-  while (chunk < P.chunk_end) {
-    if (t == 0) S.next_chunk = P.chunk_begin + (int)(atomicAdd(&ws->ticket, 1u) + gridDim.x);  // claimed early: its latency hides behind the chunk
-    const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
-    const long long lim = b1 & ~127LL;  // == b1 except for the ragged end of the whole array
-    const uint32_t grant = spec_grant(P, S, chunk);
-    const unsigned cand0 = A.cand_spilled + p1_field(A.B, 15);
-    spec_chunk<DS_SMEM, OUTCOME, PODS>(P, S, b0, lim, grant, A, first);
-    first = false;
-    if (lim < b1) {  // ragged end (< 128 nodes, last chunk only)
-      long long running = 0;
-      general_step<false>(P, S, lim, b1, grant, running);
-      for (long long j = lim + t; j < b1; j += kThreads) {
-        const unsigned b = P.hot[j];
-        uint32_t lo = S.hotent[b].z, hi = S.hotent[b].w;
-        widen(lo, hi, A.B);
-        spec_error_byte(P, S, b, P.flags[j], j);
-      }
-    }
-    const unsigned mine = A.cand_spilled + p1_field(A.B, 15) - cand0;
-    const unsigned warp_cand = __reduce_add_sync(kFull, mine);
-    if ((t & 31) == 0 && warp_cand) atomicAdd(&S.chunk_cand, warp_cand);
-    __syncthreads();
-    const int next = S.next_chunk;
-    if (t == 0) {  // S.chunk_cand only ever grows: no shared write between the two barriers
-      const unsigned total = S.chunk_cand;
-      ws->cand_cta[chunk] = total - cand_published;
-      cand_published = total;
-    }
-    __syncthreads();
-    nodes_seen += b1 - b0;
-    chunk = next;
-  }
-  if (first) stage_tables_wait(S);  // no chunk for this CTA: still never exit with the bulk copy in flight
-  // all threads converged: one REDUX per counter per warp, one shared atomic per warp
-#pragma unroll
-  for (int f = 0; f < 16; f++) {
-    const unsigned v = __reduce_add_sync(kFull, p1_field(A.B, f));
-    if ((t & 31) == 0 && v) atomicAdd(&S.cnt[f], v);
-  }
-  return nodes_seen;
-}
-
-// Streaming phase of one CTA.
-__device__ void stream_phase(const UstParams& P, Shared& S) {
-  const int t = threadIdx.x;
-  UstWorkspace* ws = P.ws;
-  long long nodes_seen = 0;
-  const int variant = (P.n_ds <= UST_DS_SMEM_MAX ? 4 : 0) | (P.outcome ? 2 : 0) | (P.podsum ? 1 : 0);
-  switch (variant) {
-    case 7: nodes_seen = stream_loop<true, true, true>(P, S); break;
-    case 6: nodes_seen = stream_loop<true, true, false>(P, S); break;
-    case 5: nodes_seen = stream_loop<true, false, true>(P, S); break;
-    case 4: nodes_seen = stream_loop<true, false, false>(P, S); break;
-    case 3: nodes_seen = stream_loop<false, true, true>(P, S); break;
-    case 2: nodes_seen = stream_loop<false, true, false>(P, S); break;
-    case 1: nodes_seen = stream_loop<false, false, true>(P, S); break;
-    default: nodes_seen = stream_loop<false, false, false>(P, S); break;
-  }
-  __syncthreads();
-  // 16 global atomics per CTA
-  if (t < 14) {
-    if (S.cnt[t]) atomicAdd(&ws->acc[t], (unsigned long long)S.cnt[t]);
-  } else if (t == 14) {
-    unsigned long long in = 0;
-    for (int f = 0; f < 14; f++) in += S.cnt[f];
-    const unsigned long long excluded = (unsigned long long)nodes_seen - in;
-    if (excluded) atomicAdd(&ws->acc[UST_STATE_EXCLUDED], excluded);
-  } else if (t == 15) {
-    if (S.cnt[14]) atomicAdd(&ws->acc[UST_V_UNAVAILABLE], (unsigned long long)S.cnt[14]);
-    if (S.cnt[15]) atomicAdd(&ws->acc[UST_V_CANDIDATES], (unsigned long long)S.cnt[15]);
-  } else if (t == 32) {
-    if (S.errinv) atomicMax(&ws->errinv, S.errinv);
-  }
-}
-
-__device__ void load_local_vector(const UstParams& P, Shared& S) {
-  // world == 1: the exchange vector is just this shard's accumulators
-  const int t = threadIdx.x;
-  if (t < UST_V_LEN) {
-    long long v = 0;
-    if (t < 18) v = (long long)__ldcg(&P.ws->acc[t]);
-    else if (t == UST_V_RANK_CAND + P.rank) v = (long long)__ldcg(&P.ws->acc[UST_V_CANDIDATES]);
-    else if (t == UST_V_RANK_NODES + P.rank) v = P.n;
-    else if (t == UST_V_RANK_ERRINV + P.rank) v = (long long)__ldcg(&P.ws->errinv);
-    S.V[t] = v;
-  }
-}
-
-// ---- system-scope accessors for the NVLink mailbox exchange -------------------------------------------------
-__device__ __forceinline__ void st_relaxed_sys(long long* p, long long v) { asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ void st_release_sys(long long* p, long long v) { asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
-  long long v;
-  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ long long ld_relaxed_sys(const long long* p) {
-  long long v;
-  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long now_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-constexpr unsigned long long kCommTimeoutNs = 4000000000ull;  // give up on a missing peer after 4 s
-
-// Cluster-wide vector for world > 1 without leaving the kernel: CTA 0 waits for the local CTAs, pushes this
-// shard's lanes into every rank's mailbox over NVLink, waits for every rank's lanes in its own mailbox, sums,
-// and publishes the result to the other local CTAs. One-hot per-rank lanes make the sum an all-gather.
-__device__ void fused_exchange(const UstParams& P, Shared& S) {
-  const int t = threadIdx.x;
-  UstWorkspace* ws = P.ws;
-  const int par = (int)(P.epoch & 1);
-  if (blockIdx.x == 0) {
-    if (t == 0) {
-      while (ld_acquire_u32(&ws->arrive) < gridDim.x) __nanosleep(20);
-      __threadfence();
-    }
-    __syncthreads();
-    load_local_vector(P, S);
-    __syncthreads();
-    if (t < UST_V_LEN) {
-      for (int r = 0; r < P.world; r++) st_relaxed_sys(&P.mbox[r]->slot[par][P.rank][t], S.V[t]);
-      __threadfence_system();
-    }
-    __syncthreads();
-    if (t < P.world) st_release_sys(&P.mbox[t]->slot[par][P.rank][UST_MBOX_FLAG], P.epoch);
-    if (t < P.world) {
-      const unsigned long long t0 = now_ns();
-      while (ld_acquire_sys(&P.mbox[P.rank]->slot[par][t][UST_MBOX_FLAG]) != P.epoch) {
-        if (now_ns() - t0 > kCommTimeoutNs) { ws->comm_timeout = 1; break; }
-        __nanosleep(50);
-      }
-    }
-    __syncthreads();
-    if (t < UST_V_LEN) {
-      long long sum = 0;
-      for (int r = 0; r < P.world; r++) sum += ld_relaxed_sys(&P.mbox[P.rank]->slot[par][r][t]);
-      S.V[t] = sum;
-      ws->gv[t] = sum;
-    }
-    __threadfence();
-    __syncthreads();
-    if (t == 0) {
-      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&ws->go), "l"((unsigned long long)P.epoch) : "memory");
-    }
-  } else {
-    if (t == 0) {
-      const unsigned long long t0 = now_ns();
-      while (ld_acquire_u64(&ws->go) != (unsigned long long)P.epoch) {
-        if (now_ns() - t0 > kCommTimeoutNs + 1000000000ull) break;
-        __nanosleep(50);
-      }
-      __threadfence();
-    }
-    __syncthreads();
-    if (t < UST_V_LEN) S.V[t] = __ldcg(&ws->gv[t]);
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ bool verification_needed(const UstParams& P, const Shared& S);
-
-__device__ void finish(const UstParams& P, Shared& S, bool reset_ws) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned prev = atomicAdd(&P.ws->depart, 1u);
-    if (prev == gridDim.x - 1u) {  // last CTA out: publish counters, restore the workspace invariant
-      write_counters(P, S);
-      if (P.spec_sig != 0 && P.active && !P.requestor && S.abort_key == ~0ull) {
-        // where the budget really cut this time = next call's speculation
-        const int cut = verification_needed(P, S) ? S.cut : S.spec_cut;  // else: all-or-nothing guess that held
-        P.ws->hint_cut = cut;
-        P.ws->hint_sig = P.spec_sig;
-      }
-      P.ws->fixups = 0;
-      P.ws->comm_timeout = 0;
-      if (reset_ws) {
-        for (int i = 0; i < 18; i++) P.ws->acc[i] = 0;
-        P.ws->errinv = 0;
-        P.ws->ticket = 0;
-      }
-      P.ws->arrive = 0;
-      P.ws->depart = 0;
-      __threadfence();
-    }
-  }
-}
-
-// Is any chunk's speculation possibly wrong? O(1) from the cluster-wide scalars: with "nobody gets a
-// slot" the speculation only fails if there is a budget at all, with "everybody gets one" only if the
-// budget is smaller than the number of candidates.
-__device__ __forceinline__ bool verification_needed(const UstParams& P, const Shared& S) {
-  if (S.abort_key != ~0ull) return true;
-  if (!(P.active && !P.requestor)) return false;
-  const long long cands = S.V[UST_V_CANDIDATES];
-  if (cands == 0) return false;
-  if (S.spec_cut > 0 && S.spec_cut < P.grid_chunks) return true;  // hint in the middle: check chunk by chunk
-  return S.spec_cut ? (S.budget < cands) : (S.budget > 0);
-}
-
-// Per-chunk candidate counts of the chunks a thread scans: thread t owns the chunks [t * cpt, (t + 1) * cpt),
-// cpt = 2 * ceil(chunks / kScanSlots). Loaded right after the grid barrier, together with the exchange vector.
-constexpr int kScanRegs = 4;
-struct ChunkCands { unsigned int v[kScanRegs]; };
-__device__ __forceinline__ int scan_slot_chunks(const UstParams& P) { return (P.grid_chunks + kScanSlots - 1) / kScanSlots; }
-__device__ __forceinline__ ChunkCands load_chunk_cands(const UstParams& P) {
-  ChunkCands r;
-  const int cpt = 2 * scan_slot_chunks(P), c0 = threadIdx.x * cpt;
-#pragma unroll
-  for (int k = 0; k < kScanRegs; k++) r.v[k] = (k < cpt && c0 + k < P.grid_chunks) ? __ldcg(&P.ws->cand_cta[c0 + k]) : 0u;
-  return r;
-}
-
-// Every CTA scans the per-chunk candidate counts once: where the budget really cuts, and the interval of chunks
-// whose speculation did not hold. Leaves prefix bases in shared memory for chunk_prefix().
-__device__ void scan_chunks(const UstParams& P, Shared& S, long long rank_base, const ChunkCands& held) {
-  const int t = threadIdx.x, n_chunks = P.grid_chunks;
-  const int spt = scan_slot_chunks(P), cpt = 2 * spt;
-  const int c0 = t * cpt < n_chunks ? t * cpt : n_chunks, c1 = c0 + cpt < n_chunks ? c0 + cpt : n_chunks;
-  const bool in_regs = cpt <= kScanRegs;
-  auto cand_of = [&](int c) -> long long { return __ldcg(&P.ws->cand_cta[c]); };
-  if (t == 0) { S.wrong_lo = 0x7FFFFFFF; S.wrong_hi = -1; S.cut = 0x7FFFFFFF; }
-  long long mine = 0;
-  if (in_regs) {
-#pragma unroll
-    for (int k = 0; k < kScanRegs; k++) mine += held.v[k];
-  } else {
-    for (int c = c0; c < c1; c++) mine += cand_of(c);
-  }
-  long long incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const long long v = __shfl_up_sync(kFull, incl, o);
-    if ((t & 31) >= o) incl += v;
-  }
-  if ((t & 31) == 31) S.part[t >> 5] = incl;
-  __syncthreads();
-  long long before = 0;
-#pragma unroll
-  for (int w = 0; w < kWarps; w++)
-    if (w < (t >> 5)) before += S.part[w];
-  const bool slotted = P.active && !P.requestor;
-  int lo = 0x7FFFFFFF, hi = -1, cut = 0x7FFFFFFF;
-  long long local = before + incl - mine;  // shard-local candidates before chunk c
-  auto visit = [&](int c, long long cand) {
-    if ((c - c0) % spt == 0) S.tbase[c / spt] = local;
-    const long long pre = rank_base + local;
-    if (cand != 0 && slotted) {
-      long long req = S.budget - pre;
-      req = req < 0 ? 0 : (req > cand ? cand : req);
-      const long long spec = c < S.spec_cut ? cand : 0;
-      if (req != spec) { lo = lo < c ? lo : c; hi = c; }
-      if (pre + cand > S.budget && c < cut) cut = c;
-    }
-    local += cand;
-  };
-  if (in_regs) {
-#pragma unroll
-    for (int k = 0; k < kScanRegs; k++)
-      if (c0 + k < c1) visit(c0 + k, held.v[k]);
-  } else {
-    for (int c = c0; c < c1; c++) visit(c, cand_of(c));
-  }
-  lo = __reduce_min_sync(kFull, lo);
-  hi = __reduce_max_sync(kFull, hi);
-  cut = __reduce_min_sync(kFull, cut);
-  if ((t & 31) == 0) {
-    if (hi >= 0) { atomicMin(&S.wrong_lo, lo); atomicMax(&S.wrong_hi, hi); }
-    atomicMin(&S.cut, cut);
-  }
-  __syncthreads();
-}
-
-// shard-local candidates before chunk c (after scan_chunks); no loads up to kScanSlots chunks
-__device__ __forceinline__ long long chunk_prefix(const UstParams& P, const Shared& S, int c) {
-  const int spt = scan_slot_chunks(P);
-  const int slot = c / spt;
-  long long v = S.tbase[slot];
-  for (int k = slot * spt; k < c; k++) v += __ldcg(&P.ws->cand_cta[k]);
-  return v;
-}
-
-// pull the first tile of a piece towards L2 while its starting rank is still being worked out
-__device__ __forceinline__ void prefetch_piece(const UstParams& P, long long p0, long long p1) {
-  const long long end = p1 - p0 > kTile ? p0 + kTile : p1;
-  for (long long i = p0 + 32LL * threadIdx.x; i < end; i += 32LL * kThreads) {  // 32 nodes = one 128-byte line of an int32 array
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.flags + i));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pod_rev + i));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.ds_idx + i));
-  }
-}
-
-// The slot speculation was wrong for the chunks in [wrong_lo, wrong_hi] (a contiguous node range): re-evaluate
-// them with the ordered grant (global candidate rank < budget). The range is cut into pieces that are spread
-// over ALL CTAs of the grid - a single CTA would be latency-bound - each piece finding its starting rank from
-// the per-chunk counts plus a hot-byte count of the part of its chunk that precedes it.
-__device__ void redo_wrong_chunks(const UstParams& P, Shared& S, long long rank_base) {
-  const int lo = S.wrong_lo, hi = S.wrong_hi, n_chunks = P.grid_chunks;
-  if (lo > hi) return;
-  const int m = hi - lo + 1;
-  const long long max_len = P.n / n_chunks + 256;                 // no chunk is longer (chunk_bound rounds to 128)
-  const int max_steps = (int)((max_len + kStep - 1) / kStep);
-  int pieces = (int)gridDim.x / m;                                  // at most one piece per CTA when that is possible
-  pieces = pieces < 1 ? 1 : (pieces > max_steps ? max_steps : pieces);
-  const int variant = (P.n_ds <= UST_DS_SMEM_MAX ? 2 : 0) | (P.outcome ? 1 : 0);
-  const long long items = (long long)m * pieces;
-  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const int chunk = lo + (int)(item / pieces), j = (int)(item % pieces);
-    const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
-    const long long lim = b1 & ~127LL;
-    const long long steps = (b1 - b0 + kStep - 1) / kStep, per = (steps + pieces - 1) / pieces;
-    const long long p0 = b0 + (long long)j * per * kStep;
-    long long p1 = p0 + per * kStep;
-    if (p0 >= b1) continue;   // CTA-uniform
-    const bool last = p1 >= b1;
-    if (last) p1 = lim;
-    stamp(P, 4);
-    prefetch_piece(P, p0, p1);
-    const long long slots = S.budget - (rank_base + chunk_prefix(P, S, chunk));  // left at the start of the chunk
-    const long long cand = __ldcg(&P.ws->cand_cta[chunk]);
-    stamp(P, 5);
-    long long seen = 0;  // candidates in [b0, p1)
-    if (slots <= 0 || slots >= cand) {  // nobody / everybody in this chunk gets a slot: no ranks needed
-      const uint32_t grant = (cand != 0 && slots >= cand) ? UST_W_GRANTED : 0u;
-      if (p1 > p0) {
-        switch (variant) {
-          case 3: uniform_range<true, true>(P, S, p0, p1, grant); break;
-          case 2: uniform_range<true, false>(P, S, p0, p1, grant); break;
-          case 1: uniform_range<false, true>(P, S, p0, p1, grant); break;
-          default: uniform_range<false, false>(P, S, p0, p1, grant); break;
-        }
-      }
-      if (last && lim < b1) {
-        long long running = 0;
-        general_step<false>(P, S, lim, b1, grant, running);
-      }
-      continue;
-    }
-    if (p1 > p0) {
-      switch (variant) {
-        case 3: seen = ordered_range<true, true, false>(P, S, p0, p1, slots, b0, false); break;
-        case 2: seen = ordered_range<true, false, false>(P, S, p0, p1, slots, b0, false); break;
-        case 1: seen = ordered_range<false, true, false>(P, S, p0, p1, slots, b0, false); break;
-        default: seen = ordered_range<false, false, false>(P, S, p0, p1, slots, b0, false); break;
-      }
-    }
-    stamp(P, 7);
-    if (last && lim < b1) {  // ragged end of the whole array (< 128 nodes); p1 == lim
-      long long running = 0;
-      if (p1 > p0) {
-        running = seen;
-      } else {  // the piece is nothing but the ragged end: count what precedes it in the chunk
-        long long before = 0;
-        exact_prepass(P, S, p0, p0, b0, before);
-        running = before;
-      }
-      if (threadIdx.x == 0) S.cand_prefix = rank_base + chunk_prefix(P, S, chunk);
-      __syncthreads();
-      general_step<true>(P, S, lim, b1, 0u, running);
-      __syncthreads();
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.ws->fixups, (unsigned)m);
-}
-
-// After the grid barrier: redo what the streaming phase could not know. Aborts and pod lists: every CTA redoes
-// its own chunks through the step path. Otherwise only a wrong slot speculation is left to repair.
-__device__ void verify_phase(const UstParams& P, Shared& S, const ChunkCands& held) {
-  const int n_chunks = P.grid_chunks;
-  const long long rank_base = S.cand_prefix;  // candidates on lower ranks
-  scan_chunks(P, S, rank_base, held);
-  if (S.abort_key == ~0ull) {
-    redo_wrong_chunks(P, S, rank_base);
     return;
   }
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const unsigned chunk_cand = __ldcg(&P.ws->cand_cta[chunk]);
-    const long long before = chunk_prefix(P, S, chunk);
-    __syncthreads();
-    if (threadIdx.x == 0) S.cand_prefix = rank_base + before;
-    __syncthreads();
-    const long long b0 = chunk_bound(P.n, chunk, n_chunks), b1 = chunk_bound(P.n, chunk + 1, n_chunks);
-    general_chunk(P, S, b0, b1, chunk_cand);
-    if (threadIdx.x == 0) atomicAdd(&P.ws->fixups, 1u);
+  const uint32_t grant = (slotted && tile < S.cut) ? UST_W_GRANTED : 0u;
+  long long full_end = b0;
+  if (!aborting) {
+    full_end = b0 + ((b1 - b0) / kStep) * kStep;
+    if (full_end > b0) uniform_span(P, S, b0, full_end, grant);
   }
+  for (long long base = full_end; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_fused_kernel(const __grid_constant__ UstParams P) {
+__global__ void __launch_bounds__(kThreads, 2) ust_verify_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
-  stamp(P, 0);
-  stage_tables_begin(P, S);
-  __syncthreads();
-  stream_phase(P, S);
-  stamp(P, 1);
-  // grid-wide barrier (every CTA is co-resident: cooperative launch). After it the cluster-wide
-  // counters are final and the speculation can be checked.
-  __syncthreads();
-  ChunkCands held;
-  if (P.fused_exchange) {
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(&P.ws->arrive, 1u);
-    }
-    fused_exchange(P, S);
-    stamp(P, 2);
-    held = load_chunk_cands(P);
-  } else {
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(&P.ws->arrive, 1u);
-      while (ld_acquire_u32(&P.ws->arrive) < gridDim.x) __nanosleep(20);
-      __threadfence();
-    }
+  const int t = threadIdx.x;
+  griddep_launch_dependents();  // the next call's streaming kernel may become resident (it waits for this grid itself)
+  griddep_wait();               // the streaming kernel (and, split mode, the collective) has completed
+  if (P.split) {
+    if (t < UST_V_LEN) S.D.V[t] = P.xchg[t];
+    if (t == 0) S.D.spec_cut = __ldcg(&P.ws->spec_cut_used);
     __syncthreads();
-    stamp(P, 2);
-    held = load_chunk_cands(P);  // same round trip as the vector
-    load_local_vector(P, S);
+    decide(P, S.D, blockIdx.x == 0);
+    if (t == 0) {
+      S.redo = S.D.redo; S.cut = S.D.cut; S.lo = S.D.lo; S.hi = S.D.hi; S.slots = S.D.slots_left;
+      S.abort_key = S.D.abort_key; S.node_offset = S.D.node_offset;
+    }
+  } else if (t == 0) {
+    const UstVerdict* v = &P.ws->verdict;
+    S.redo = __ldcg(&v->redo); S.cut = __ldcg(&v->cut); S.lo = __ldcg(&v->lo); S.hi = __ldcg(&v->hi);
+    S.slots = __ldcg(&v->slots_left); S.abort_key = __ldcg(&v->abort_key); S.node_offset = __ldcg(&v->node_offset);
+  }
+  __syncthreads();
+  if (S.redo == 0) return;  // the speculation held: every output of the streaming kernel is final
+  int first = S.lo, last = S.hi;
+  if (S.redo == 2) { first = 0; last = P.n_tiles - 1; }
+  if (first + (int)blockIdx.x > last) return;
+  // tables: the transition table by one TMA bulk copy, the DaemonSet revisions by plain loads
+  if (t == 0) {
+    mbar_init(&S.mbar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&S.mbar, kLutBytes);
+    bulk_g2s(S.lut, P.lut, kLutBytes, &S.mbar);
+  }
+  if (P.n_ds <= UST_DS_SMEM_MAX)
+    for (int i = t; i <= P.n_ds; i += kThreads) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
+  __syncthreads();
+  mbar_wait(&S.mbar, 0);
+  for (int tile = first + (int)blockIdx.x; tile <= last; tile += (int)gridDim.x) {
+    redo_tile(P, S, tile);
     __syncthreads();
   }
-  if (threadIdx.x == 0) derive_scalars(P, S);
-  __syncthreads();
-  if (verification_needed(P, S)) {
-    verify_phase(P, S, held);
-  }
-  finish(P, S, true);
-  stamp(P, 3);
-}
-
-// split mode (multi-GPU with a host-launched collective between the kernels): streaming phase ...
-__global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase1_kernel(const __grid_constant__ UstParams P) {
-  __shared__ Shared S;
-  stage_tables_begin(P, S);
-  __syncthreads();
-  stream_phase(P, S);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    S.last = atomicAdd(&P.ws->depart, 1u) == gridDim.x - 1u;
-  }
-  __syncthreads();
-  if (S.last) {  // last CTA of this launch
-    __threadfence();
-    if (P.publish) {  // ... and last streaming launch of the call: publish this shard's lanes, restore the invariant
-      load_local_vector(P, S);
-      __syncthreads();
-      if (threadIdx.x < UST_V_LEN) P.xchg[threadIdx.x] = S.V[threadIdx.x];
-      __syncthreads();
-      if (threadIdx.x < 18) P.ws->acc[threadIdx.x] = 0;
-      if (threadIdx.x == 0) P.ws->errinv = 0;
-    }
-    if (threadIdx.x == 0) { P.ws->depart = 0; P.ws->ticket = 0; }
-  }
-}
-
-// ... and verification: redo, exactly, the chunks whose speculation did not hold
-__global__ void __launch_bounds__(kThreads, UST_MIN_CTAS) ust_phase2_kernel(const __grid_constant__ UstParams P) {
-  __shared__ Shared S;
-  stage_tables_begin(P, S);
-  if (threadIdx.x < UST_V_LEN) S.V[threadIdx.x] = P.xchg[threadIdx.x];
-  const ChunkCands held = load_chunk_cands(P);
-  __syncthreads();
-  if (threadIdx.x == 0) derive_scalars(P, S);
-  __syncthreads();
-  stage_tables_wait(S);
-  __syncthreads();
-  if (verification_needed(P, S)) verify_phase(P, S, held);
-  finish(P, S, false);
 }
 
 // Pod-list summaries (rows 12-14 of the scope table: pod_manager.go:256-391, :122-229, drain_manager.go:58-139).
@@ -1675,20 +675,20 @@ __global__ void __launch_bounds__(kThreads) ust_widen_kernel(long long n, const 
     ds_out[i] = (int32_t)__ldcs(ds8 + i);
   }
 }
-
 }  // namespace
 
-int ust_launch_fused(const UstParams& p, int grid, void* stream) {
-  void* args[] = {(void*)&p};
-  return (int)cudaLaunchCooperativeKernel((const void*)ust_fused_kernel, dim3(grid), dim3(kThreads), args, 0, (cudaStream_t)stream);
-}
-int ust_launch_phase1(const UstParams& p, int grid, void* stream) {
-  ust_phase1_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(p);
-  return (int)cudaGetLastError();
-}
-int ust_launch_phase2(const UstParams& p, int grid, void* stream) {
-  ust_phase2_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(p);
-  return (int)cudaGetLastError();
+int ust_launch_verify(const UstParams& p, int grid, void* stream, int pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, ust_verify_kernel, p);
 }
 int ust_launch_pod_summary(long long n, int active, const uint8_t* hot, const int32_t* pod_off, const uint16_t* pod_flags,
                            long long n_pods, const uint8_t* podlut, uint8_t* podsum, int grid, void* stream) {
@@ -1735,14 +735,4 @@ int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* own
       tab_slots, ds_idx_out, ds_count, ws);
   ust_build_state_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_ds, ds_desired, ds_count, ws, out);
   return (int)cudaGetLastError();
-}
-int ust_max_coresident_ctas(int device, int* ctas_per_sm, int* num_sms) {
-  int per_sm = 0, sms = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ust_fused_kernel, kThreads, 0);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (e != cudaSuccess) return (int)e;
-  *ctas_per_sm = per_sm;
-  *num_sms = sms;
-  return 0;
 }
