@@ -352,16 +352,19 @@ def main():
     if args.quick:
         if rank == 0 and os.environ.get("UST_STAMPS"):
             g = min(int(os.environ["UST_STAMPS"]), 148)
-            st = (C.c_uint64 * (4 * g))()
+            st = (C.c_uint64 * (4 * g + 4))()
             ustlib.load().ust_debug_stamps(h._h, st, g)
-            a = np.array(st, dtype=np.int64).reshape(g, 4)
+            a = np.array(st, dtype=np.int64)
+            v = a[4 * g:]
+            a = a[:4 * g].reshape(g, 4)
+            a = a[a[:, 0] > a[:, 0].max() - 1_000_000]   # CTAs of the last launch only (a small snapshot uses fewer)
             t0 = a[:, 0].min()
             rel = (a - t0) / 1e3
-            last = int(a[:, 3].argmax())
+            v = (v - t0) / 1e3
             print("stamps us: entry[min,max]=%.1f,%.1f first_tile[min,med,max]=%.1f,%.1f,%.1f stream_end[min,med,max]=%.1f,%.1f,%.1f "
-                  "deciding CTA %d: stream end %.1f exit %.1f" % (
+                  "exit[max]=%.1f | verify kernel CTA 0: woken %.1f vector %.1f decided %.1f redo done %.1f" % (
                       rel[:, 0].min(), rel[:, 0].max(), rel[:, 1].min(), np.median(rel[:, 1]), rel[:, 1].max(),
-                      rel[:, 2].min(), np.median(rel[:, 2]), rel[:, 2].max(), last, rel[last, 2], rel[last, 3]), flush=True)
+                      rel[:, 2].min(), np.median(rel[:, 2]), rel[:, 2].max(), rel[:, 3].max(), v[0], v[1], v[2], v[3]), flush=True)
         if rank == 0:
             print(json.dumps({k: line[k] for k in ("value", "ms_per_step", "roofline", "clocks")}), flush=True)
         h.close()

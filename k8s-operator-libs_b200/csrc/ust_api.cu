@@ -91,6 +91,7 @@ struct ust_handle {
   bool pdl = true;          // launch the kernels of a call with programmatic dependent launch (UST_PDL=0 turns it off: tuning)
   bool stamps = false;      // UST_STAMPS: per-CTA %globaltimer stamps (diagnostics)
   int static_pct = 75;      // share of a launch's tile rounds taken in stride order before the ticket (UST_STATIC_PCT: tuning)
+  unsigned call_seq = 0;    // calls whose kernels were launched: call k uses accumulator set k & 1 of the workspace
   cudaStream_t last_stream = nullptr;  // stream of the previous device-resident call (calls on another stream are ordered behind it)
   int64_t resident_n = -1;  // nodes of the snapshot the last ust_apply_state left in the staging arrays (-1 = none)
   int32_t resident_n_ds = 0;  // ... and the size of its DaemonSet table
@@ -206,6 +207,7 @@ static int pick_static_rounds(const ust_handle* h, int tiles, int grid) {
   const int rounds = tiles / grid;
   int r = (int)((int64_t)rounds * h->static_pct / 100);
   if (rounds - r < 2) r = rounds - 2;
+  if (r < 1 && rounds >= 1) r = 1;  // the first round never waits for a ticket
   return r < 0 ? 0 : r;
 }
 
@@ -283,7 +285,7 @@ static int launch_verify(ust_handle* h, UstParams& P, cudaStream_t st, bool pdl)
     ncclResult_t r = g_nccl.AllReduce(h->xchg_dev, h->xchg_dev, UST_V_LEN, ncclInt64, ncclSum, h->comm, st);
     if (r != ncclSuccess) return h->fail(UST_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   }
-  int e = ust_launch_verify(P, h->num_sms * 2, st, (pdl && !P.split) ? 1 : 0);
+  int e = ust_launch_verify(P, h->num_sms, st, (pdl && !P.split) ? 1 : 0);
   if (e) return h->fail(UST_ERR_CUDA, "verification kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
   h->launches += 1;
   return UST_OK;
@@ -343,6 +345,7 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
     h->launches += 1;
   }
   if (P.fused_exchange) P.epoch = ++h->epoch;  // collective call number: identical on every rank
+  P.parity = (int)(h->call_seq++ & 1u);
   int e = ust_launch_stream(P, grid, st, h->pdl ? 1 : 0);
   if (e) return h->fail(UST_ERR_CUDA, "streaming kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
   h->launches += 1;
@@ -415,8 +418,10 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
                    h->s_next.p, h->s_actions.p, outcome ? h->s_outcome.p : nullptr, nullptr, &P, &grid);
   if (rc) return rc;
   if (P.fused_exchange) P.epoch = ++h->epoch;
+  P.parity = (int)(h->call_seq++ & 1u);
   const int tiles = P.n_tiles;
   const int kSegments = 8;
+  static_assert(kSegments <= UST_MAX_SEGMENTS, "one ticket per streaming launch");
   const int per = (tiles + kSegments - 1) / kSegments;
   h->ws_dirty = true;
   const bool dbg = getenv("UST_DEBUG_PIPE") != nullptr;
@@ -452,6 +457,7 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
     Ps.tile_begin = c0;
     Ps.tile_end = c1;
     Ps.publish = c1 == tiles;
+    Ps.seg = seg;
     const int g = pick_grid(h, c1 - c0);
     Ps.static_rounds = pick_static_rounds(h, c1 - c0, g);
     Ps.stamps = 0;
@@ -941,6 +947,7 @@ int ust_debug_stamps(ust_handle* h, unsigned long long* out, int n_ctas) {
   UST_CUDA(h, cudaSetDevice(h->device));
   UST_CUDA(h, cudaDeviceSynchronize());
   UST_CUDA(h, cudaMemcpy(out, h->ws->dbg, (size_t)n_ctas * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  UST_CUDA(h, cudaMemcpy(out + (size_t)n_ctas * 4, h->ws->dbg2, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));  // verification kernel
   return UST_OK;
 }
 

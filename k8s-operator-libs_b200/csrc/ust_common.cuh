@@ -126,20 +126,22 @@ struct DecideShared {
   int redo, cut, lo, hi;
 };
 
-// this shard's lanes of the exchange vector from the workspace accumulators
+// this shard's lanes of the exchange vector from the workspace accumulators of the call
 __device__ __forceinline__ void load_local_vector(const UstParams& P, DecideShared& D) {
   const int t = threadIdx.x;
+  const unsigned long long* acc = P.ws->acc[P.parity];
   if (t < UST_V_LEN) {
     long long v = 0;
-    if (t < 14 || t == UST_V_UNAVAILABLE || t == UST_V_CANDIDATES) v = (long long)__ldcg(&P.ws->acc[t]);
+    if (t < 14 || t == UST_V_UNAVAILABLE || t == UST_V_CANDIDATES) v = (long long)__ldcg(&acc[t]);
     else if (t == UST_STATE_EXCLUDED) {  // everything that is in no bucket: "not in snapshot" (upgrade_state.go:149-152) and code 15
       long long in = 0;
-      for (int f = 0; f < 14; f++) in += (long long)__ldcg(&P.ws->acc[f]);
+#pragma unroll
+      for (int f = 0; f < 14; f++) in += (long long)__ldcg(&acc[f]);
       v = P.n - in;
     }
-    else if (t == UST_V_RANK_CAND + P.rank) v = (long long)__ldcg(&P.ws->acc[UST_V_CANDIDATES]);
+    else if (t == UST_V_RANK_CAND + P.rank) v = (long long)__ldcg(&acc[UST_V_CANDIDATES]);
     else if (t == UST_V_RANK_NODES + P.rank) v = P.n;
-    else if (t == UST_V_RANK_ERRINV + P.rank) v = (long long)__ldcg(&P.ws->errinv);
+    else if (t == UST_V_RANK_ERRINV + P.rank) v = (long long)__ldcg(&P.ws->errinv[P.parity]);
     D.V[t] = v;
   }
 }
@@ -190,7 +192,7 @@ __device__ inline void derive_scalars(const UstParams& P, DecideShared& D) {
   D.cand_before = cand_before;
 }
 
-__device__ inline void write_counters(const UstParams& P, const DecideShared& D, long long redone_tiles) {
+__device__ inline void write_counters(const UstParams& P, const DecideShared& D, long long redone_tiles, bool comm_failed) {
   ust_counters c;
   const long long* V = D.V;
   for (int i = 0; i < 16; i++) c.hist[i] = V[i];
@@ -212,18 +214,20 @@ __device__ inline void write_counters(const UstParams& P, const DecideShared& D,
   c.max_unavailable = slots ? D.max_unav : 0;
   c.upgrades_available = slots ? D.avail : 0;
   for (int i = 0; i < 7; i++) c.reserved[i] = 0;
-  if (__ldcg(&P.ws->comm_timeout)) { c.error_code = UST_ERR_COMM; c.error_index = -1; c.error_pass = -1; }
+  if (comm_failed) { c.error_code = UST_ERR_COMM; c.error_index = -1; c.error_pass = -1; }
   c.reserved[0] = redone_tiles;  // tiles the verification kernel re-evaluates (diagnostic; the pipelined host path re-downloads when != 0)
   *P.out = c;
 }
 
-// The decision, made by every thread of ONE CTA once the cluster-wide vector is in D.V: derive the slot budget, check
-// the speculation in O(1) (rank-local: "nobody gets a slot" only fails if this shard has a budget, "everybody" only if
+// The decision, made by every thread of a CTA once the cluster-wide vector is in D.V (every CTA of the verification
+// kernel makes it for itself - it is a few hundred instructions on 42 numbers): derive the slot budget, check the
+// speculation in O(1) (rank-local: "nobody gets a slot" only fails if this shard has a budget, "everybody" only if
 // the budget is smaller than its candidates), and only when that cannot tell - or the call aborts - scan the per-tile
 // candidate counts for the tile where the budget cuts. Tiles before the cut are fully granted, tiles behind it get
 // nothing, the cut tile hands out `slots_left` in slice order (upgrade_inplace.go:71-109). `write_global`: this CTA
-// also publishes the verdict, the counters and the next call's speculation hint.
-__device__ inline void decide(const UstParams& P, DecideShared& D, bool write_global) {
+// also publishes the counters and the next call's speculation hint. `comm_failed`: a peer never showed up - the call
+// fails, nothing is re-evaluated.
+__device__ inline void decide(const UstParams& P, DecideShared& D, bool write_global, bool comm_failed) {
   const int t = threadIdx.x, nt = blockDim.x, nT = P.n_tiles;
   if (t == 0) derive_scalars(P, D);
   __syncthreads();
@@ -236,7 +240,7 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
   if (slotted && lc > 0) need = sc <= 0 ? lb > 0 : (sc >= nT ? lb < lc : true);
   if (t == 0) { D.cut = nT; D.slots_left = 0; }
   __syncthreads();
-  if (slotted && lc > 0 && (need || aborting)) {
+  if (slotted && lc > 0 && (need || aborting) && !comm_failed) {
     if (lb <= 0) {
       if (t == 0) D.cut = 0;
     } else if (lb < lc) {
@@ -276,47 +280,46 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
       else { lo = cut; hi = sc - 1; }
     }
     int redo = aborting ? 2 : (lo <= hi ? 1 : 0);
-    if (__ldcg(&P.ws->comm_timeout)) redo = 0;  // a peer never showed up: the call fails, nothing more is written
+    if (comm_failed) redo = 0;
     D.redo = redo; D.lo = lo; D.hi = hi;
     if (write_global) {
-      UstVerdict v;
-      v.redo = redo; v.cut = cut; v.lo = lo; v.hi = hi; v.slots_left = D.slots_left;
-      v.abort_key = D.abort_key; v.node_offset = D.node_offset;
-      P.ws->verdict = v;
-      write_counters(P, D, redo == 2 ? (long long)nT : (redo == 1 ? (long long)(hi - lo + 1) : 0));
-      if (P.spec_sig != 0 && slotted && !aborting) {
+      write_counters(P, D, redo == 2 ? (long long)nT : (redo == 1 ? (long long)(hi - lo + 1) : 0), comm_failed);
+      if (P.spec_sig != 0 && slotted && !aborting && !comm_failed) {
         // where the budget really cut this time = next call's speculation (else: the all-or-nothing guess that held)
         P.ws->hint_cut = need ? cut : D.spec_cut;
         P.ws->hint_sig = P.spec_sig;
       }
-      P.ws->comm_timeout = 0;
     }
   }
   __syncthreads();
 }
 
-// Cluster-wide vector for world > 1 without leaving the kernel, run by the ONE CTA of a rank that finishes streaming
-// last: push this shard's lanes into every rank's mailbox over NVLink (all lanes of all peers in parallel), release a
-// flag per peer, wait for every rank's flag in the own mailbox, sum. One-hot per-rank lanes make the sum an
-// all-gather. Nothing else on the GPU spins: the other CTAs of the rank have already exited.
-__device__ inline void exchange_vector(const UstParams& P, DecideShared& D) {
+// Cluster-wide vector for world > 1 without a host-launched collective (verification kernel, every CTA): CTA 0 pushes
+// this shard's lanes into every rank's mailbox over NVLink (all lanes of all peers in parallel) and releases a flag per
+// peer; every CTA waits for every rank's flag in the OWN mailbox (local memory) and sums for itself - no intra-GPU
+// broadcast, no CTA waits for another CTA of its grid. One-hot per-rank lanes make the sum an all-gather. Returns
+// false when a peer did not show up in time.
+__device__ inline bool exchange_vector(const UstParams& P, DecideShared& D, bool pusher) {
   const int t = threadIdx.x, nt = blockDim.x;
   const int par = (int)(P.epoch & 1);
-  for (int i = t; i < P.world * UST_V_LEN; i += nt) {
-    const int r = i / UST_V_LEN, l = i - r * UST_V_LEN;
-    st_relaxed_sys(&P.mbox[r]->slot[par][P.rank][l], D.V[l]);
+  if (pusher) {
+    for (int i = t; i < P.world * UST_V_LEN; i += nt) {
+      const int r = i / UST_V_LEN, l = i - r * UST_V_LEN;
+      st_relaxed_sys(&P.mbox[r]->slot[par][P.rank][l], D.V[l]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < P.world) st_release_sys(&P.mbox[t]->slot[par][P.rank][UST_MBOX_FLAG], P.epoch);
   }
-  __threadfence_system();
-  __syncthreads();
+  int ok = 1;
   if (t < P.world) {
-    st_release_sys(&P.mbox[t]->slot[par][P.rank][UST_MBOX_FLAG], P.epoch);
     const unsigned long long t0 = now_ns();
     while (ld_acquire_sys(&P.mbox[P.rank]->slot[par][t][UST_MBOX_FLAG]) != P.epoch) {
-      if (now_ns() - t0 > kCommTimeoutNs) { P.ws->comm_timeout = 1; break; }
+      if (now_ns() - t0 > kCommTimeoutNs) { ok = 0; break; }
       __nanosleep(40);
     }
   }
-  __syncthreads();
+  ok = __syncthreads_and(ok);
   if (t < UST_V_LEN) {
     long long v[UST_MAX_WORLD];
 #pragma unroll
@@ -326,8 +329,8 @@ __device__ inline void exchange_vector(const UstParams& P, DecideShared& D) {
     for (int r = 0; r < UST_MAX_WORLD; r++) sum += v[r];
     D.V[t] = sum;
   }
-  __threadfence();
   __syncthreads();
+  return ok != 0;
 }
 
 }  // namespace ustd

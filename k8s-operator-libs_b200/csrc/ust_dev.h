@@ -43,32 +43,25 @@ struct UstMailbox {
   long long slot[2][UST_MAX_WORLD][UST_MBOX_LANES];
 };
 
-// What the deciding CTA of a call (the last one to finish streaming) leaves for the verification kernel.
-struct UstVerdict {
-  int redo;               // 0 = every speculative output stands; 1 = the slot speculation was wrong for the tiles
-                          // [lo, hi]; 2 = the call aborts: every tile is re-evaluated with abort masking
-  int cut;                // first tile whose upgrade candidates do not all get a slot (n_tiles = there is none)
-  int lo, hi;
-  long long slots_left;   // slots left for the candidates of tile `cut`, handed out in slice order
-  unsigned long long abort_key;  // ~0 = none
-  long long node_offset;  // global index of this shard's node 0
-};
-
-// Device workspace owned by a handle. Invariant: acc / errinv / arrive / depart / ticket are zero between calls.
+// Device workspace owned by a handle. The per-call accumulators exist twice: call k uses set (k & 1); the streaming
+// kernel of call k+1 clears the set of call k (the verification kernel of call k, the only reader, has completed by
+// then - stream order), so nobody ever waits for a reset. Invariant between calls: the set of the NEXT call is zero.
+#define UST_MAX_SEGMENTS 16   /* streaming launches per call (pipelined uploads): one ticket each */
 struct UstWorkspace {
-  unsigned long long acc[18];   // hist[0..13], -, -, unavailable, candidates (this shard)
-  unsigned long long errinv;    // ~min abort key seen while streaming, 0 = none
-  unsigned int arrive;          // CTAs of the current streaming launch that have finished
-  unsigned int depart;          // verification kernel in deciding mode: CTAs that have finished
-  unsigned int ticket;          // dynamic tile claiming
-  unsigned int comm_timeout;    // set when a peer did not show up (kernel gives up instead of hanging)
-  UstVerdict verdict;
+  unsigned long long acc[2][18];  // hist[0..13], -, -, unavailable, candidates (this shard)
+  unsigned long long errinv[2];   // ~min abort key seen while streaming, 0 = none
+  unsigned int ticket[2][UST_MAX_SEGMENTS];  // dynamic tile claiming, one counter per streaming launch of the call
+  int spec_used[2];               // the speculative cut the streaming kernel ran with
+  unsigned long long bs_acc[18];  // BuildState kernels (zero between calls: their finish kernel clears it)
+  unsigned int arrive;            // split mode: CTAs of the publishing streaming launch that have finished
+  unsigned int comm_timeout;      // set when a peer did not show up (kernel gives up instead of hanging)
   // Speculation hint carried from call to call (results never depend on it, only how many tiles are redone):
   // the previous call's cut tile, valid for calls with the same signature (size, tiling, slot policy).
   unsigned long long hint_sig;
   int hint_cut;
-  int spec_cut_used;  // split mode: the speculative cut the streaming kernel ran with (read by the deciding verification kernel)
+  int pad_;
   unsigned long long dbg[UST_MAX_CTAS][4];  // %globaltimer stamps per streaming CTA: entry, first tile landed, stream end, exit
+  unsigned long long dbg2[4];               // verification kernel, CTA 0: woken, vector loaded, decided, done
 };
 
 // abort key: (pass << 56) | (global node index + 1); policy-level aborts use index part 0
@@ -114,8 +107,10 @@ struct UstParams {
   int tile_begin;         // streaming sub-range launches (pipelined uploads): tiles [tile_begin, tile_end)
   int tile_end;
   int static_rounds;      // rounds of the range a CTA takes in stride order before it claims tiles by ticket
-  int publish;            // this streaming launch is the last one of the call: its last CTA decides (or publishes, split mode)
-  int split;              // split mode: the decision is made by the verification kernel from P.xchg (reduced by a host-launched collective)
+  int parity;             // which accumulator set of the workspace this call uses (call number & 1)
+  int seg;                // index of this streaming launch within the call (its ticket counter)
+  int publish;            // split mode: this streaming launch is the last one of the call, its last CTA publishes P.xchg
+  int split;              // split mode: a host-launched collective reduces P.xchg between the two kernels
   int stamps;             // diagnostics: write %globaltimer stamps
   // fused multi-GPU exchange (world > 1): mailboxes of all ranks as mapped into this process, call number
   int fused_exchange;

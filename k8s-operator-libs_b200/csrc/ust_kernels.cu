@@ -1,14 +1,16 @@
 // ust_kernels.cu — the verification kernel of ApplyState and the auxiliary kernels of libust.so (sm_100a).
 //
 // ust_verify_kernel runs behind ust_stream_kernel (ust_stream.cu) on the same stream, launched with programmatic
-// dependent launch: its CTAs are resident (and asleep in griddepcontrol.wait) while the streaming kernel runs, read
-// the verdict its last CTA left, and return at once in the common case - the slot speculation held, every output
-// is final. Otherwise they re-evaluate, exactly, the tiles the verdict names: tiles before the cut with every
-// upgrade candidate granted, tiles behind it with none, the cut tile with the ordered allocation of
-// upgrade_inplace.go:71-109 (candidate rank in slice order < slots left: warp-shuffle scan + per-step totals), and -
-// when the call aborts - every tile with the reference's abort semantics (nodes the sequential passes had not
-// reached stay untouched, common_manager.go:462-523). In split mode (a host-launched NCCL all-reduce between the two
-// kernels) it also makes the decision itself, from the reduced exchange vector.
+// dependent launch: one small CTA per SM, resident (asleep in griddepcontrol.wait, transition table already staged)
+// while the streaming kernel runs. When that ends every CTA reads the shard's counters - on several GPUs: exchanges
+// them through NVLink mailboxes, or takes the result of a host-launched NCCL all-reduce - derives the slot budget
+// (GetUpgradesAvailable, common_manager.go:748-776) and judges the speculation the streaming kernel made. CTA 0 writes
+// ust_counters. In the common case the speculation held, every output is final, and the kernel returns at once.
+// Otherwise the CTAs re-evaluate, exactly, the tiles that need it: tiles before the cut with every upgrade candidate
+// granted, tiles behind it with none, the cut tile with the ordered allocation of upgrade_inplace.go:71-109
+// (candidate rank in slice order < slots left: warp-shuffle scan + per-step totals), and - when the call aborts -
+// every tile with the reference's abort semantics (nodes the sequential passes had not reached stay untouched,
+// common_manager.go:462-523).
 // Around it: ust_pod_summary_kernel (pod lists -> one byte per node), ust_build_state*_kernel (BuildState),
 // ust_patch_kernel / ust_feedback_kernel (delta updates, rollout simulation), ust_widen_kernel (packed host format).
 #include "ust_common.cuh"
@@ -21,11 +23,12 @@ constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStep = kThreads * 4;   // nodes per CTA step (4 per thread)
 constexpr uint32_t kLutBytes = (UST_LUT_ENTRIES + 32) * sizeof(uint32_t);  // table + 16 {shift, base} pairs
+constexpr int kDsSmem = 64;  // the kernel sits next to the streaming kernel on every SM: keep its shared memory small
 
 struct __align__(128) Shared {
   uint32_t lut[UST_LUT_ENTRIES];  // + meta directly behind it: filled by ONE bulk (TMA) copy
   uint2 meta[16];
-  int dsrev[UST_DS_SMEM_MAX + 1];
+  int dsrev[kDsSmem + 1];         // DaemonSet revisions (larger tables are read from global memory: this is the rare path)
   unsigned long long mbar;        // mbarrier the bulk copy completes on
   unsigned int warp_tot[kWarps];
   // the verdict, CTA-uniform
@@ -153,7 +156,7 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
   }
 
   if (nvalid == 0) return;
-  const bool ds_smem = P.n_ds <= UST_DS_SMEM_MAX;
+  const bool ds_smem = P.n_ds <= kDsSmem;
   uint32_t e[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -186,7 +189,7 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
 // steps in flight before the first lookup. b0, b1: multiples of kStep apart (the caller peels the ragged end).
 __device__ void uniform_span(const UstParams& P, Shared& S, long long b0, long long b1, uint32_t grant) {
   const int t = threadIdx.x;
-  const bool ds_smem = P.n_ds <= UST_DS_SMEM_MAX;
+  const bool ds_smem = P.n_ds <= kDsSmem;
   constexpr int U = 2;
   for (long long base = b0; base < b1; base += (long long)U * kStep) {
     uint32_t h[U], ps[U];
@@ -250,45 +253,54 @@ __device__ void redo_tile(const UstParams& P, Shared& S, int tile) {
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2) ust_verify_kernel(const __grid_constant__ UstParams P) {
+__global__ void __launch_bounds__(kThreads, 1) ust_verify_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
   const int t = threadIdx.x;
-  griddep_launch_dependents();  // the next call's streaming kernel may become resident (it waits for this grid itself)
-  griddep_wait();               // the streaming kernel (and, split mode, the collective) has completed
-  if (P.split) {
-    if (t < UST_V_LEN) S.D.V[t] = P.xchg[t];
-    if (t == 0) S.D.spec_cut = __ldcg(&P.ws->spec_cut_used);
-    __syncthreads();
-    decide(P, S.D, blockIdx.x == 0);
-    if (t == 0) {
-      S.redo = S.D.redo; S.cut = S.D.cut; S.lo = S.D.lo; S.hi = S.D.hi; S.slots = S.D.slots_left;
-      S.abort_key = S.D.abort_key; S.node_offset = S.D.node_offset;
-    }
-  } else if (t == 0) {
-    const UstVerdict* v = &P.ws->verdict;
-    S.redo = __ldcg(&v->redo); S.cut = __ldcg(&v->cut); S.lo = __ldcg(&v->lo); S.hi = __ldcg(&v->hi);
-    S.slots = __ldcg(&v->slots_left); S.abort_key = __ldcg(&v->abort_key); S.node_offset = __ldcg(&v->node_offset);
-  }
-  __syncthreads();
-  if (S.redo == 0) return;  // the speculation held: every output of the streaming kernel is final
-  int first = S.lo, last = S.hi;
-  if (S.redo == 2) { first = 0; last = P.n_tiles - 1; }
-  if (first + (int)blockIdx.x > last) return;
-  // tables: the transition table by one TMA bulk copy, the DaemonSet revisions by plain loads
+  // prologue (overlaps the streaming kernel): the transition table by one TMA bulk copy - uploaded by a copy, not by
+  // a kernel, so it need not wait
   if (t == 0) {
     mbar_init(&S.mbar, 1);
     mbar_fence_init();
     mbar_arrive_expect_tx(&S.mbar, kLutBytes);
     bulk_g2s(S.lut, P.lut, kLutBytes, &S.mbar);
   }
-  if (P.n_ds <= UST_DS_SMEM_MAX)
+  griddep_launch_dependents();  // the next call's streaming kernel may become resident (it waits for this grid itself)
+  griddep_wait();               // the streaming kernel (and, split mode, the collective) has completed
+  const bool lead = blockIdx.x == 0;
+  if (P.stamps && lead && t == 0) P.ws->dbg2[0] = now_ns();
+  bool comm_ok = true;
+  if (P.split) {
+    if (t < UST_V_LEN) S.D.V[t] = P.xchg[t];
+  } else {
+    load_local_vector(P, S.D);
+    if (P.fused_exchange) {
+      __syncthreads();
+      comm_ok = exchange_vector(P, S.D, lead);
+    }
+  }
+  if (t == 0) S.D.spec_cut = __ldcg(&P.ws->spec_used[P.parity]);
+  __syncthreads();
+  if (P.stamps && lead && t == 0) P.ws->dbg2[1] = now_ns();
+  decide(P, S.D, lead, !comm_ok);
+  if (t == 0) {
+    S.redo = S.D.redo; S.cut = S.D.cut; S.lo = S.D.lo; S.hi = S.D.hi; S.slots = S.D.slots_left;
+    S.abort_key = S.D.abort_key; S.node_offset = S.D.node_offset;
+  }
+  __syncthreads();
+  if (P.stamps && lead && t == 0) P.ws->dbg2[2] = now_ns();
+  mbar_wait(&S.mbar, 0);      // never leave with the bulk copy in flight (it landed long ago)
+  if (S.redo == 0) return;    // the speculation held: every output of the streaming kernel is final
+  int first = S.lo, last = S.hi;
+  if (S.redo == 2) { first = 0; last = P.n_tiles - 1; }
+  if (first + (int)blockIdx.x > last) return;
+  if (P.n_ds <= kDsSmem)
     for (int i = t; i <= P.n_ds; i += kThreads) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
   __syncthreads();
-  mbar_wait(&S.mbar, 0);
   for (int tile = first + (int)blockIdx.x; tile <= last; tile += (int)gridDim.x) {
     redo_tile(P, S, tile);
     __syncthreads();
   }
+  if (P.stamps && lead && t == 0) P.ws->dbg2[3] = now_ns();
 }
 
 // Pod-list summaries (rows 12-14 of the scope table: pod_manager.go:256-391, :122-229, drain_manager.go:58-139).
@@ -553,12 +565,12 @@ __global__ void __launch_bounds__(kThreads) ust_build_state_uid_kernel(long long
   }
   spill();
   __syncthreads();
-  // fields 0..13 per state code, 14 unavailable, 15 candidates -> ws->acc[0..13], [16], [17]
+  // fields 0..13 per state code, 14 unavailable, 15 candidates -> ws->bs_acc[0..13], [16], [17]
   for (int o = 16; o > 0; o >>= 1) excluded += __shfl_xor_sync(kFull, excluded, o);
-  if ((t & 31) == 0 && excluded) atomicAdd(&ws->acc[UST_STATE_EXCLUDED], (unsigned long long)excluded);
-  if (t < 14) { if (cnt[t]) atomicAdd(&ws->acc[t], (unsigned long long)cnt[t]); }
-  else if (t == 14) { if (cnt[14]) atomicAdd(&ws->acc[16], (unsigned long long)cnt[14]); }
-  else if (t == 15) { if (cnt[15]) atomicAdd(&ws->acc[17], (unsigned long long)cnt[15]); }
+  if ((t & 31) == 0 && excluded) atomicAdd(&ws->bs_acc[UST_STATE_EXCLUDED], (unsigned long long)excluded);
+  if (t < 14) { if (cnt[t]) atomicAdd(&ws->bs_acc[t], (unsigned long long)cnt[t]); }
+  else if (t == 14) { if (cnt[14]) atomicAdd(&ws->bs_acc[16], (unsigned long long)cnt[14]); }
+  else if (t == 15) { if (cnt[15]) atomicAdd(&ws->bs_acc[17], (unsigned long long)cnt[15]); }
   if (in_smem)
     for (int i = t; i < n_ds; i += kThreads)
       if (cnt_ds[i]) atomicAdd(&ds_count[i], (unsigned long long)cnt_ds[i]);
@@ -567,9 +579,9 @@ __global__ void __launch_bounds__(kThreads) ust_build_state_uid_kernel(long long
 __global__ void ust_build_state_finish_kernel(int n_ds, const int32_t* ds_desired, unsigned long long* ds_count,
                                               UstWorkspace* ws, ust_counters* out) {
   ust_counters c;
-  for (int i = 0; i < 16; i++) c.hist[i] = (long long)ws->acc[i];
-  c.unavailable = (long long)ws->acc[16];
-  c.candidates = (long long)ws->acc[17];
+  for (int i = 0; i < 16; i++) c.hist[i] = (long long)ws->bs_acc[i];
+  c.unavailable = (long long)ws->bs_acc[16];
+  c.candidates = (long long)ws->bs_acc[17];
   c.total_managed = c.hist[0] + c.hist[1] + c.hist[2] + c.hist[3] + c.hist[4] + c.hist[5] + c.hist[8] + c.hist[9] +
                     c.hist[10] + c.hist[11] + c.hist[12];
   c.in_progress = c.total_managed - c.hist[0] - c.hist[11] - c.hist[1];
@@ -586,7 +598,7 @@ __global__ void ust_build_state_finish_kernel(int n_ds, const int32_t* ds_desire
     }
   for (int i = 0; i < 7; i++) c.reserved[i] = 0;
   *out = c;
-  for (int i = 0; i < 18; i++) ws->acc[i] = 0;
+  for (int i = 0; i < 18; i++) ws->bs_acc[i] = 0;
   for (int d = 0; d < n_ds; d++) ds_count[d] = 0;
 }
 

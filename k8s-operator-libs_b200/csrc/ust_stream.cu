@@ -20,11 +20,12 @@
 //     (2 B) with full-width coalesced stores, and arrive on the stage's "empty" mbarrier: 16 algorithmic bytes per
 //     node, each touched once;
 //   * the upgrade-slot grant - the only cluster-wide dependency - is SPECULATED per tile (from the policy, or from
-//     where the previous call's budget cut). No grid barrier: a CTA that runs out of tiles adds its counters to the
-//     workspace and leaves; the CTA that leaves last derives the slot budget (GetUpgradesAvailable,
-//     common_manager.go:748-776), checks the speculation in O(1), writes the counters and a verdict;
-//   * ust_verify_kernel (ust_kernels.cu), launched behind this kernel with programmatic dependent launch,
-//     re-evaluates the tiles of a wrong speculation - and returns at once when there are none.
+//     where the previous call's budget cut). No grid barrier, no fence, nobody waits: a CTA that runs out of tiles
+//     adds its counters to the workspace (fire-and-forget reductions) and leaves;
+//   * ust_verify_kernel (ust_kernels.cu), launched behind this kernel with programmatic dependent launch and already
+//     resident when it ends, derives the slot budget (GetUpgradesAvailable, common_manager.go:748-776), checks the
+//     speculation in O(1), writes the counters, and re-evaluates the tiles of a wrong speculation - in the common
+//     case there are none and it returns at once.
 #include "ust_common.cuh"
 
 using namespace ustd;
@@ -71,7 +72,7 @@ struct __align__(128) SS {
   unsigned long long errinv;
   int spec_cut;
   int last;
-  DecideShared D;
+  long long V[UST_V_LEN];          // split mode: the vector the last CTA publishes
 };
 
 // window shift (minus 2) of every state code, 8 bits each — compile-time copy of ust_window_shift[]
@@ -225,7 +226,7 @@ __device__ void produce(const UstParams& P, SS<PODS>& S) {
   const int t_end = P.tile_end;
   const int dyn_base = P.tile_begin + R * G;
   const uint64_t pol = policy_evict_first();
-  unsigned int* ticket = &P.ws->ticket;
+  unsigned int* ticket = &P.ws->ticket[P.parity][P.seg];
   int pA = 0x7FFFFFFF, pB = 0x7FFFFFFF;
   if (lane == 0) {
     if (R == 0) { pA = dyn_base + (int)atomicAdd(ticket, 1u); pB = dyn_base + (int)atomicAdd(ticket, 1u); }
@@ -374,43 +375,56 @@ __global__ void __launch_bounds__(kThreads, 1) ust_stream_kernel(const __grid_co
       const bool hinted = P.spec_sig != 0 && __ldcg(&ws->hint_sig) == P.spec_sig;
       const int cut = !slotted ? 0 : (hinted ? __ldcg(&ws->hint_cut) : P.spec_cut_tile);
       S.spec_cut = cut;
-      S.D.spec_cut = cut;
+      if (blockIdx.x == 0) ws->spec_used[P.parity] = cut;  // the verification kernel judges the speculation that was made
+    }
+    if (blockIdx.x == 0 && P.seg == 0 && ct >= 32 && ct < 32 + 18 + 1 + UST_MAX_SEGMENTS) {
+      // clear the previous call's accumulator set: its only reader, that call's verification kernel, has completed
+      const int o = ct - 32, q = P.parity ^ 1;
+      if (o < 18) ws->acc[q][o] = 0;
+      else if (o == 18) ws->errinv[q] = 0;
+      else ws->ticket[q][o - 19] = 0;
     }
     __syncthreads();
     mbar_wait(&S.lutbar, 0);
     consume<DS_SMEM, OUTCOME, PODS>(P, S, warp - 1);
   }
   if (P.stamps && t == 32) ws->dbg[blockIdx.x][2] = now_ns();
-  // this CTA has run out of tiles: add its counts to the shard's and leave
-  __threadfence();  // the per-tile candidate counts written by the consumer warps
+  // this CTA has run out of tiles: add its counts to the shard's (reductions, nobody waits for them) and leave
   __syncthreads();
-  if (t < 14) { if (S.cnt[t]) atomicAdd(&ws->acc[t], (unsigned long long)S.cnt[t]); }
-  else if (t == 14) { if (S.cnt[14]) atomicAdd(&ws->acc[UST_V_UNAVAILABLE], (unsigned long long)S.cnt[14]); }
-  else if (t == 15) { if (S.cnt[15]) atomicAdd(&ws->acc[UST_V_CANDIDATES], (unsigned long long)S.cnt[15]); }
-  else if (t == 32) { if (S.errinv) atomicMax(&ws->errinv, S.errinv); }
+  unsigned long long* acc = ws->acc[P.parity];
+  if (t < 14) { if (S.cnt[t]) atomicAdd(&acc[t], (unsigned long long)S.cnt[t]); }
+  else if (t == 14) { if (S.cnt[14]) atomicAdd(&acc[UST_V_UNAVAILABLE], (unsigned long long)S.cnt[14]); }
+  else if (t == 15) { if (S.cnt[15]) atomicAdd(&acc[UST_V_CANDIDATES], (unsigned long long)S.cnt[15]); }
+  else if (t == 32) { if (S.errinv) atomicMax(&ws->errinv[P.parity], S.errinv); }
+  if (P.stamps && t == 0) ws->dbg[blockIdx.x][3] = now_ns();
+  if (!(P.split && P.publish)) return;
+  // ---- split mode (a host-launched collective follows): the last CTA of the call's last streaming launch publishes
+  // this shard's lanes of the exchange vector
   __threadfence();
   __syncthreads();
   if (t == 0) S.last = atomicAdd(&ws->arrive, 1u) == gridDim.x - 1u;
   __syncthreads();
   if (!S.last) return;
-  // ---- the last CTA of the launch -------------------------------------------------------------------------------
   __threadfence();
-  if (t == 0) { ws->arrive = 0; ws->ticket = 0; }
-  if (!P.publish) return;  // more streaming launches of this call follow (pipelined uploads)
-  load_local_vector(P, S.D);
-  __syncthreads();
-  if (P.split) {  // a host-launched collective reduces the vector; the verification kernel decides
-    if (t < UST_V_LEN) P.xchg[t] = S.D.V[t];
-    if (t == 0) ws->spec_cut_used = S.spec_cut;
-  } else {
-    if (P.fused_exchange) exchange_vector(P, S.D);
-    decide(P, S.D, true);
+  if (t == 0) ws->arrive = 0;
+  if (t < UST_V_LEN) {
+    long long v = 0;
+    if (t < 14 || t == UST_V_UNAVAILABLE || t == UST_V_CANDIDATES) v = (long long)__ldcg(&acc[t]);
+    else if (t == UST_V_RANK_CAND + P.rank) v = (long long)__ldcg(&acc[UST_V_CANDIDATES]);
+    else if (t == UST_V_RANK_NODES + P.rank) v = P.n;
+    else if (t == UST_V_RANK_ERRINV + P.rank) v = (long long)__ldcg(&ws->errinv[P.parity]);
+    S.V[t] = v;
   }
-  // restore the workspace invariant (the kernel is a pure function of its inputs, the reference's statelessness
-  // contract upgrade_state.go:166-170)
-  if (t < 18) ws->acc[t] = 0;
-  if (t == 18) ws->errinv = 0;
-  if (P.stamps && t == 0) ws->dbg[blockIdx.x][3] = now_ns();
+  __syncthreads();
+  if (t < UST_V_LEN) {
+    long long v = S.V[t];
+    if (t == UST_STATE_EXCLUDED) {  // everything that is in no bucket
+      long long in = 0;
+      for (int f = 0; f < 14; f++) in += S.V[f];
+      v = P.n - in;
+    }
+    P.xchg[t] = v;
+  }
 }
 
 template <bool DS_SMEM, bool OUTCOME, bool PODS>
