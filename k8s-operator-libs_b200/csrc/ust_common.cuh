@@ -122,33 +122,42 @@ struct DecideShared {
   long long cand_before;         // upgrade candidates on lower ranks
   long long slots_left;
   long long part[32];
+  long long run_before;
+  int run0, run1;                // cut search: the run of tiles that contains the crossing
   int spec_cut;                  // effective speculative cut of this call (hint or policy default), in tiles
-  int redo, cut, lo, hi;
+  int redo, cut, lo, hi, scan;
 };
 
-// this shard's lanes of the exchange vector from the workspace accumulators of the call
+// this shard's lanes of the exchange vector from the workspace accumulators of the call (one load per thread)
 __device__ __forceinline__ void load_local_vector(const UstParams& P, DecideShared& D) {
   const int t = threadIdx.x;
   const unsigned long long* acc = P.ws->acc[P.parity];
   if (t < UST_V_LEN) {
     long long v = 0;
     if (t < 14 || t == UST_V_UNAVAILABLE || t == UST_V_CANDIDATES) v = (long long)__ldcg(&acc[t]);
-    else if (t == UST_STATE_EXCLUDED) {  // everything that is in no bucket: "not in snapshot" (upgrade_state.go:149-152) and code 15
-      long long in = 0;
-#pragma unroll
-      for (int f = 0; f < 14; f++) in += (long long)__ldcg(&acc[f]);
-      v = P.n - in;
-    }
     else if (t == UST_V_RANK_CAND + P.rank) v = (long long)__ldcg(&acc[UST_V_CANDIDATES]);
     else if (t == UST_V_RANK_NODES + P.rank) v = P.n;
     else if (t == UST_V_RANK_ERRINV + P.rank) v = (long long)__ldcg(&P.ws->errinv[P.parity]);
     D.V[t] = v;
   }
 }
+// ... lane 14 of the LOCAL vector: everything that is in no bucket - "not in snapshot" (upgrade_state.go:149-152) and
+// code 15. One thread of warp 0, after a __syncwarp() (lanes 0..13 are written by warp 0), before any exchange.
+__device__ __forceinline__ void fix_excluded_lane(const UstParams& P, DecideShared& D) {
+  long long in = 0;
+#pragma unroll
+  for (int f = 0; f < 14; f++) in += D.V[f];
+  D.V[UST_STATE_EXCLUDED] = P.n - in;
+}
 
-// cluster-wide scalars from the exchange vector (one thread)
-__device__ inline void derive_scalars(const UstParams& P, DecideShared& D) {
-  const long long* V = D.V;
+// Cluster-wide scalars from the exchange vector. Every calling thread computes all of them (same instructions, same
+// values: no broadcast needed afterwards).
+struct Scalars {
+  unsigned long long abort_key;
+  long long total, in_progress, budget, avail, max_unav, node_offset, cand_before;
+};
+__device__ inline Scalars derive_scalars(const UstParams& P, const long long* V) {
+  Scalars s;
   const long long h0 = V[0], h1 = V[1], h2 = V[2], h4 = V[4], h11 = V[11];
   // GetTotalManagedNodes (common_manager.go:715-730): 11 buckets — not 6, 7, other
   const long long total = h0 + h1 + h2 + V[3] + h4 + V[5] + V[8] + V[9] + V[10] + h11 + V[12];
@@ -184,109 +193,144 @@ __device__ inline void derive_scalars(const UstParams& P, DecideShared& D) {
   }
   // SchedulePodEviction with a nil DeletionSpec (pod_manager.go:125-134)
   if (P.active && P.pd_enabled && !P.pd_spec_present && h4 > 0 && UST_KEY(5, 0) < abort_key) abort_key = UST_KEY(5, 0);
-  D.abort_key = abort_key;
-  D.avail = avail;
-  D.max_unav = max_unav;
-  D.budget = avail > 0 ? avail : 0;
-  D.node_offset = my_off;
-  D.cand_before = cand_before;
+  s.abort_key = abort_key;
+  s.total = total;
+  s.in_progress = in_progress;
+  s.avail = avail;
+  s.max_unav = max_unav;
+  s.budget = avail > 0 ? avail : 0;
+  s.node_offset = my_off;
+  s.cand_before = cand_before;
+  return s;
 }
 
-__device__ inline void write_counters(const UstParams& P, const DecideShared& D, long long redone_tiles, bool comm_failed) {
-  ust_counters c;
-  const long long* V = D.V;
-  for (int i = 0; i < 16; i++) c.hist[i] = V[i];
-  c.unavailable = V[UST_V_UNAVAILABLE];
-  c.candidates = V[UST_V_CANDIDATES];
-  c.total_managed = V[0] + V[1] + V[2] + V[3] + V[4] + V[5] + V[8] + V[9] + V[10] + V[11] + V[12];
-  c.in_progress = c.total_managed - V[0] - V[11] - V[1];
-  c.error_code = UST_OK;
-  c.error_index = -1;
-  c.error_pass = -1;
-  if (D.abort_key != ~0ull) {
-    const int pass = (int)(D.abort_key >> 56);
-    const long long idx1 = (long long)(D.abort_key & 0x00FFFFFFFFFFFFFFull);
-    c.error_pass = pass;
-    c.error_index = idx1 - 1;
-    c.error_code = idx1 ? UST_ERR_REVISION_HASH : (pass == 2 ? UST_ERR_MAX_UNAVAILABLE : UST_ERR_POD_DELETION_SPEC);
+// ust_counters, one field per lane of a warp (31 int64 fields)
+__device__ inline void write_counters(const UstParams& P, const long long* V, const Scalars& s, long long redone_tiles, bool comm_failed) {
+  const int lane = threadIdx.x & 31;
+  long long code = UST_OK, index = -1, pass = -1;
+  if (s.abort_key != ~0ull) {
+    pass = (long long)(s.abort_key >> 56);
+    const long long idx1 = (long long)(s.abort_key & 0x00FFFFFFFFFFFFFFull);
+    index = idx1 - 1;
+    code = idx1 ? UST_ERR_REVISION_HASH : (pass == 2 ? UST_ERR_MAX_UNAVAILABLE : UST_ERR_POD_DELETION_SPEC);
   }
-  const bool slots = P.active && !P.requestor && !(c.error_code && c.error_pass < 2) && c.error_code != UST_ERR_MAX_UNAVAILABLE;
-  c.max_unavailable = slots ? D.max_unav : 0;
-  c.upgrades_available = slots ? D.avail : 0;
-  for (int i = 0; i < 7; i++) c.reserved[i] = 0;
-  if (comm_failed) { c.error_code = UST_ERR_COMM; c.error_index = -1; c.error_pass = -1; }
-  c.reserved[0] = redone_tiles;  // tiles the verification kernel re-evaluates (diagnostic; the pipelined host path re-downloads when != 0)
-  *P.out = c;
+  const bool slots = P.active && !P.requestor && !(code && pass < 2) && code != UST_ERR_MAX_UNAVAILABLE;
+  if (comm_failed) { code = UST_ERR_COMM; index = -1; pass = -1; }
+  long long v = 0;
+  if (lane < 16) v = V[lane];
+  else if (lane == 16) v = V[UST_V_UNAVAILABLE];
+  else if (lane == 17) v = V[UST_V_CANDIDATES];
+  else if (lane == 18) v = s.total;
+  else if (lane == 19) v = s.in_progress;
+  else if (lane == 20) v = slots ? s.max_unav : 0;
+  else if (lane == 21) v = slots ? s.avail : 0;
+  else if (lane == 22) v = code;
+  else if (lane == 23) v = index;
+  else if (lane == 24) v = pass;
+  else if (lane == 25) v = redone_tiles;  // reserved[0]: tiles the verification kernel re-evaluates (diagnostic; the pipelined host path re-downloads when != 0)
+  static_assert(sizeof(ust_counters) == 32 * 8, "one field per lane");
+  reinterpret_cast<long long*>(P.out)[lane] = v;
 }
 
-// The decision, made by every thread of a CTA once the cluster-wide vector is in D.V (every CTA of the verification
-// kernel makes it for itself - it is a few hundred instructions on 42 numbers): derive the slot budget, check the
-// speculation in O(1) (rank-local: "nobody gets a slot" only fails if this shard has a budget, "everybody" only if
-// the budget is smaller than its candidates), and only when that cannot tell - or the call aborts - scan the per-tile
-// candidate counts for the tile where the budget cuts. Tiles before the cut are fully granted, tiles behind it get
-// nothing, the cut tile hands out `slots_left` in slice order (upgrade_inplace.go:71-109). `write_global`: this CTA
-// also publishes the counters and the next call's speculation hint. `comm_failed`: a peer never showed up - the call
-// fails, nothing is re-evaluated.
+// The decision, made by every CTA of the verification kernel for itself once the cluster-wide vector is in D.V (it is
+// a few hundred instructions on 42 numbers): warp 0 derives the slot budget and checks the speculation in O(1)
+// (rank-local: "nobody gets a slot" only fails if this shard has a budget, "everybody" only if the budget is smaller
+// than its candidates); only when that cannot tell - or the call aborts - the CTA searches the per-tile candidate
+// counts for the tile where the budget cuts (two block-wide passes, every load in flight at once). Tiles before the
+// cut are fully granted, tiles behind it get nothing, the cut tile hands out `slots_left` in slice order
+// (upgrade_inplace.go:71-109). `write_global`: this CTA also publishes the counters and the next call's speculation
+// hint. `comm_failed`: a peer never showed up - the call fails, nothing is re-evaluated.
 __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_global, bool comm_failed) {
   const int t = threadIdx.x, nt = blockDim.x, nT = P.n_tiles;
-  if (t == 0) derive_scalars(P, D);
-  __syncthreads();
   const bool slotted = P.active && !P.requestor;
-  const bool aborting = D.abort_key != ~0ull;
-  const long long lc = D.V[UST_V_RANK_CAND + P.rank];   // this shard's candidates
-  const long long lb = D.budget - D.cand_before;         // slots left when slice order reaches this shard
-  const int sc = D.spec_cut < 0 ? 0 : (D.spec_cut > nT ? nT : D.spec_cut);
-  bool need = false;
-  if (slotted && lc > 0) need = sc <= 0 ? lb > 0 : (sc >= nT ? lb < lc : true);
-  if (t == 0) { D.cut = nT; D.slots_left = 0; }
-  __syncthreads();
-  if (slotted && lc > 0 && (need || aborting) && !comm_failed) {
-    if (lb <= 0) {
-      if (t == 0) D.cut = 0;
-    } else if (lb < lc) {
-      // thread t owns tiles [c0, c1): sum, block-wide exclusive scan, then the one thread whose run contains the
-      // crossing walks it
-      const int per = (nT + nt - 1) / nt;
-      const int c0 = t * per < nT ? t * per : nT, c1 = c0 + per < nT ? c0 + per : nT;
-      long long mine = 0;
-#pragma unroll 8
-      for (int c = c0; c < c1; c++) mine += __ldcg(&P.cand_tile[c]);
-      long long incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const long long v = __shfl_up_sync(kFull, incl, o);
-        if ((t & 31) >= o) incl += v;
-      }
-      if ((t & 31) == 31) D.part[t >> 5] = incl;
-      __syncthreads();
-      long long before = incl - mine;
-      for (int w = 0; w < (t >> 5); w++) before += D.part[w];
-      if (before <= lb && lb < before + mine) {
-        long long local = before;
-        for (int c = c0; c < c1; c++) {
-          const long long cand = __ldcg(&P.cand_tile[c]);
-          if (local + cand > lb) { D.cut = c; D.slots_left = lb - local; break; }
-          local += cand;
-        }
+  if (t < 32) {
+    const Scalars s = derive_scalars(P, D.V);
+    const bool aborting = s.abort_key != ~0ull;
+    const long long lc = D.V[UST_V_RANK_CAND + P.rank];   // this shard's candidates
+    const long long lb = s.budget - s.cand_before;         // slots left when slice order reaches this shard
+    const int sc = D.spec_cut < 0 ? 0 : (D.spec_cut > nT ? nT : D.spec_cut);
+    bool need = false;
+    if (slotted && lc > 0) need = sc <= 0 ? lb > 0 : (sc >= nT ? lb < lc : true);
+    int cut = nT, scan = 0;
+    if (slotted && lc > 0 && (need || aborting) && !comm_failed) {
+      if (lb <= 0) cut = 0;
+      else if (lb < lc) scan = 1;   // the cut lies inside this shard: find it
+    }
+    const int redo = comm_failed ? 0 : (aborting ? 2 : (need ? 1 : 0));  // need: final once the cut is known
+    if (t == 0) {
+      D.abort_key = s.abort_key; D.budget = s.budget; D.avail = s.avail; D.max_unav = s.max_unav;
+      D.node_offset = s.node_offset; D.cand_before = s.cand_before;
+      D.cut = cut; D.slots_left = 0; D.scan = scan; D.redo = redo; D.lo = 1; D.hi = 0;
+      D.run0 = D.run1 = 0; D.run_before = 0;
+    }
+    if (write_global && !scan && !(redo == 1)) {  // the common case ends here: counters out, no tile is redone
+      write_counters(P, D.V, s, redo == 2 ? (long long)nT : 0, comm_failed);
+      if (t == 0 && P.spec_sig != 0 && slotted && !aborting && !comm_failed) {
+        P.ws->hint_cut = D.spec_cut;  // the all-or-nothing guess held
+        P.ws->hint_sig = P.spec_sig;
       }
     }
   }
   __syncthreads();
-  if (t == 0) {
+  if (D.redo != 1 && !D.scan) return;
+  const long long lb = D.budget - D.cand_before;
+  if (D.scan) {
+    // pass 1: thread t sums the tiles [c0, c1); block-wide exclusive scan; the run that contains the crossing is
+    // published. pass 2: the whole CTA loads that run (<= per tiles) and scans again.
+    const int per = (nT + nt - 1) / nt;
+    const int c0 = t * per < nT ? t * per : nT, c1 = c0 + per < nT ? c0 + per : nT;
+    long long mine = 0;
+#pragma unroll 8
+    for (int c = c0; c < c1; c++) mine += __ldcg(&P.cand_tile[c]);
+    long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long v = __shfl_up_sync(kFull, incl, o);
+      if ((t & 31) >= o) incl += v;
+    }
+    if ((t & 31) == 31) D.part[t >> 5] = incl;
+    __syncthreads();
+    long long before = incl - mine;
+    for (int w = 0; w < (t >> 5); w++) before += D.part[w];
+    if (before <= lb && lb < before + mine) { D.run0 = c0; D.run1 = c1; D.run_before = before; }
+    __syncthreads();
+    const int r0 = D.run0, r1 = D.run1;
+    long long run_before = D.run_before;
+    for (int b = r0; b < r1; b += nt) {   // one round unless a thread owns more than nt tiles
+      const int c = b + t;
+      const long long cand = c < r1 ? (long long)__ldcg(&P.cand_tile[c]) : 0;
+      long long inc2 = cand;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long v = __shfl_up_sync(kFull, inc2, o);
+        if ((t & 31) >= o) inc2 += v;
+      }
+      __syncthreads();
+      if ((t & 31) == 31) D.part[t >> 5] = inc2;
+      __syncthreads();
+      long long pre = run_before + inc2 - cand, tot = 0;
+      for (int w = 0; w < (nt >> 5); w++) { const long long v = D.part[w]; if (w < (t >> 5)) pre += v; tot += v; }
+      if (c < r1 && pre <= lb && lb < pre + cand) { D.cut = c; D.slots_left = lb - pre; }
+      run_before += tot;
+    }
+    __syncthreads();
+  }
+  if (t < 32) {
+    const bool aborting = D.abort_key != ~0ull;
     const int cut = D.cut;
+    const int sc = D.spec_cut < 0 ? 0 : (D.spec_cut > nT ? nT : D.spec_cut);
     int lo = 1, hi = 0;
-    if (!aborting && need) {
+    if (!aborting) {
       if (sc <= cut) { lo = sc; hi = (cut < nT && D.slots_left > 0) ? cut : cut - 1; }
       else { lo = cut; hi = sc - 1; }
     }
-    int redo = aborting ? 2 : (lo <= hi ? 1 : 0);
-    if (comm_failed) redo = 0;
-    D.redo = redo; D.lo = lo; D.hi = hi;
+    const int redo = aborting ? 2 : (lo <= hi ? 1 : 0);
+    if (t == 0) { D.redo = redo; D.lo = lo; D.hi = hi; }
     if (write_global) {
-      write_counters(P, D, redo == 2 ? (long long)nT : (redo == 1 ? (long long)(hi - lo + 1) : 0), comm_failed);
-      if (P.spec_sig != 0 && slotted && !aborting && !comm_failed) {
-        // where the budget really cut this time = next call's speculation (else: the all-or-nothing guess that held)
-        P.ws->hint_cut = need ? cut : D.spec_cut;
+      const Scalars s = derive_scalars(P, D.V);
+      write_counters(P, D.V, s, redo == 2 ? (long long)nT : (redo == 1 ? (long long)(hi - lo + 1) : 0), false);
+      if (t == 0 && P.spec_sig != 0 && slotted && !aborting) {
+        P.ws->hint_cut = cut;  // where the budget really cut this time = next call's speculation
         P.ws->hint_sig = P.spec_sig;
       }
     }

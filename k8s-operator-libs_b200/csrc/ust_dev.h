@@ -14,10 +14,10 @@
 // stage, and the slot speculation is made for. Tiles of fewer nodes (a power of two >= 128) are used for small
 // snapshots so that every SM gets work; the ring stages are sized for the largest.
 #ifndef UST_TILE_NODES
-#define UST_TILE_NODES 2048
+#define UST_TILE_NODES 4096
 #endif
 #ifndef UST_STAGES
-#define UST_STAGES 5
+#define UST_STAGES 3
 #endif
 #ifndef UST_CONSUMER_WARPS
 #define UST_CONSUMER_WARPS 8

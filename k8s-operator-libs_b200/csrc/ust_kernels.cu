@@ -22,21 +22,18 @@ namespace {
 constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStep = kThreads * 4;   // nodes per CTA step (4 per thread)
-constexpr uint32_t kLutBytes = (UST_LUT_ENTRIES + 32) * sizeof(uint32_t);  // table + 16 {shift, base} pairs
+constexpr int kRedoUnroll = 4;  // steps in flight per thread when whole tiles are re-evaluated
 constexpr int kDsSmem = 64;  // the kernel sits next to the streaming kernel on every SM: keep its shared memory small
 
-struct __align__(128) Shared {
-  uint32_t lut[UST_LUT_ENTRIES];  // + meta directly behind it: filled by ONE bulk (TMA) copy
-  uint2 meta[16];
+struct __align__(16) Shared {
   int dsrev[kDsSmem + 1];         // DaemonSet revisions (larger tables are read from global memory: this is the rare path)
-  unsigned long long mbar;        // mbarrier the bulk copy completes on
   unsigned int warp_tot[kWarps];
   // the verdict, CTA-uniform
   unsigned long long abort_key;   // ~0 = none
   long long node_offset;          // global index of this shard's node 0
   long long slots;                // ordered path: slots left at the start of the tile being evaluated
   int redo, cut, lo, hi;
-  DecideShared D;                 // split mode: the decision is made here
+  DecideShared D;
 };
 
 // byte lanes: B[0] = fields 0,2,4,6  B[1] = fields 1,3,5,7  B[2] = fields 8,10,12,14  B[3] = fields 9,11,13,15
@@ -54,7 +51,9 @@ __device__ __forceinline__ void widen(uint32_t& lo, uint32_t& hi, uint32_t (&B)[
 // ------------------------------------------------------------------------------------------------
 // per-node transition
 // ------------------------------------------------------------------------------------------------
-// table entry for one node. hb = hot byte, extra = derived bits (slot grant, pod-list summaries)
+// table entry for one node. hb = hot byte, extra = derived bits (slot grant, pod-list summaries). The verification
+// kernel keeps no copy of the transition table: it reads the handle's 32 KiB table through the read-only cache, so
+// that the kernel - resident beside the streaming kernel on every SM during every call - costs almost no shared memory.
 __device__ __forceinline__ uint32_t node_entry(const UstParams& P, const Shared& S, bool ds_smem, uint32_t hb, uint32_t fl, int rev,
                                                uint32_t di, uint32_t extra) {
   uint32_t w = (fl & UST_F_INPUT_MASK) | ((hb >> 3) & (UST_W_SKIP | UST_W_UNSCHEDULABLE)) | extra;
@@ -63,9 +62,9 @@ __device__ __forceinline__ uint32_t node_entry(const UstParams& P, const Shared&
   if (ds_smem) synced = (di < (uint32_t)P.n_ds) && (rev == S.dsrev[min(di, (uint32_t)P.n_ds)]);
   else synced = di < (uint32_t)P.n_ds && rev == __ldg(P.ds_rev + di);
   if (synced) w |= UST_W_SYNCED;
-  const uint2 m = S.meta[hb & 15u];
+  const uint2 m = __ldg(reinterpret_cast<const uint2*>(P.lut + UST_LUT_ENTRIES) + (hb & 15u));
   const uint32_t off = (__funnelshift_r(w, 0u, m.x) & 0x7FCu) | m.y;
-  return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(S.lut) + off);
+  return __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(P.lut) + off));
 }
 
 __device__ __forceinline__ uint32_t noop_entry(uint32_t hb) { return ((hb & 15u) << 16) | 0xFF000000u; }
@@ -185,12 +184,12 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
   }
 }
 
-// A span of full steps with a uniform grant and no abort: two steps (2048 nodes) per iteration, all loads of both
+// A span of full steps with a uniform grant and no abort: U steps (U x 1024 nodes) per iteration, all loads of all
 // steps in flight before the first lookup. b0, b1: multiples of kStep apart (the caller peels the ragged end).
+template <int U>
 __device__ void uniform_span(const UstParams& P, Shared& S, long long b0, long long b1, uint32_t grant) {
   const int t = threadIdx.x;
   const bool ds_smem = P.n_ds <= kDsSmem;
-  constexpr int U = 2;
   for (long long base = b0; base < b1; base += (long long)U * kStep) {
     uint32_t h[U], ps[U];
     uint4 f[U], r[U], d[U];
@@ -229,23 +228,47 @@ __device__ void uniform_span(const UstParams& P, Shared& S, long long b0, long l
   }
 }
 
-// Re-evaluate one tile exactly, given where the slot budget cuts.
-__device__ void redo_tile(const UstParams& P, Shared& S, int tile) {
-  const long long b0 = (long long)tile * P.tile_nodes;
-  long long b1 = b0 + P.tile_nodes;
-  if (b1 > P.n) b1 = P.n;
+// candidates (upgrade-required && !skip, upgrade_inplace.go:82) among the nodes [b0, b1) - hot bytes only; b0 and
+// b1 are multiples of kStep apart inside one tile. Whole CTA; every thread returns the total.
+__device__ long long count_candidates(const UstParams& P, Shared& S, long long b0, long long b1) {
+  const int t = threadIdx.x;
+  unsigned c = 0;
+  for (long long i = b0 + 16LL * t; i < b1; i += 16LL * kThreads) {  // b0: multiple of 1024, 16 t < 4096: aligned 16-byte loads
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(P.hot + i));
+    c += __popc(cand_mask4(x.x)) + __popc(cand_mask4(x.y)) + __popc(cand_mask4(x.z)) + __popc(cand_mask4(x.w));
+  }
+  c = __reduce_add_sync(kFull, c);
+  __syncthreads();
+  if ((t & 31) == 0) S.warp_tot[t >> 5] = c;
+  __syncthreads();
+  long long tot = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; w++) tot += S.warp_tot[w];
+  __syncthreads();
+  return tot;
+}
+
+// Re-evaluate the steps [s0, s1) (kStep nodes each) of one tile exactly, given where the slot budget cuts.
+__device__ void redo_steps(const UstParams& P, Shared& S, int tile, int s0, int s1) {
+  const long long t0 = (long long)tile * P.tile_nodes;
+  long long t1 = t0 + P.tile_nodes;
+  if (t1 > P.n) t1 = P.n;
+  const long long b0 = t0 + (long long)s0 * kStep;
+  long long b1 = t0 + (long long)s1 * kStep;
+  if (b1 > t1) b1 = t1;
+  if (b0 >= b1) return;
   const bool slotted = P.active && !P.requestor;
   const bool aborting = S.abort_key != ~0ull;
-  long long running = 0;
   if (slotted && tile == S.cut) {  // the cut tile: S.slots of its candidates get a slot, in slice order
+    long long running = s0 > 0 ? count_candidates(P, S, t0, b0) : 0;  // candidates of the tile before this piece
     for (long long base = b0; base < b1; base += kStep) general_step<true>(P, S, base, b1, 0u, running);
     return;
   }
   const uint32_t grant = (slotted && tile < S.cut) ? UST_W_GRANTED : 0u;
-  long long full_end = b0;
+  long long running = 0, full_end = b0;
   if (!aborting) {
     full_end = b0 + ((b1 - b0) / kStep) * kStep;
-    if (full_end > b0) uniform_span(P, S, b0, full_end, grant);
+    if (full_end > b0) uniform_span<kRedoUnroll>(P, S, b0, full_end, grant);
   }
   for (long long base = full_end; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
 }
@@ -256,14 +279,6 @@ __device__ void redo_tile(const UstParams& P, Shared& S, int tile) {
 __global__ void __launch_bounds__(kThreads, 1) ust_verify_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
   const int t = threadIdx.x;
-  // prologue (overlaps the streaming kernel): the transition table by one TMA bulk copy - uploaded by a copy, not by
-  // a kernel, so it need not wait
-  if (t == 0) {
-    mbar_init(&S.mbar, 1);
-    mbar_fence_init();
-    mbar_arrive_expect_tx(&S.mbar, kLutBytes);
-    bulk_g2s(S.lut, P.lut, kLutBytes, &S.mbar);
-  }
   griddep_launch_dependents();  // the next call's streaming kernel may become resident (it waits for this grid itself)
   griddep_wait();               // the streaming kernel (and, split mode, the collective) has completed
   const bool lead = blockIdx.x == 0;
@@ -273,6 +288,10 @@ __global__ void __launch_bounds__(kThreads, 1) ust_verify_kernel(const __grid_co
     if (t < UST_V_LEN) S.D.V[t] = P.xchg[t];
   } else {
     load_local_vector(P, S.D);
+    if (t < 32) {
+      __syncwarp();
+      if (t == 14) fix_excluded_lane(P, S.D);
+    }
     if (P.fused_exchange) {
       __syncthreads();
       comm_ok = exchange_vector(P, S.D, lead);
@@ -282,23 +301,35 @@ __global__ void __launch_bounds__(kThreads, 1) ust_verify_kernel(const __grid_co
   __syncthreads();
   if (P.stamps && lead && t == 0) P.ws->dbg2[1] = now_ns();
   decide(P, S.D, lead, !comm_ok);
+  if (P.stamps && lead && t == 0) P.ws->dbg2[2] = now_ns();
+  const int redo = S.D.redo;
+  if (redo == 0) return;  // the speculation held: every output of the streaming kernel is final
   if (t == 0) {
-    S.redo = S.D.redo; S.cut = S.D.cut; S.lo = S.D.lo; S.hi = S.D.hi; S.slots = S.D.slots_left;
+    S.redo = redo; S.cut = S.D.cut; S.lo = S.D.lo; S.hi = S.D.hi; S.slots = S.D.slots_left;
     S.abort_key = S.D.abort_key; S.node_offset = S.D.node_offset;
   }
-  __syncthreads();
-  if (P.stamps && lead && t == 0) P.ws->dbg2[2] = now_ns();
-  mbar_wait(&S.mbar, 0);      // never leave with the bulk copy in flight (it landed long ago)
-  if (S.redo == 0) return;    // the speculation held: every output of the streaming kernel is final
-  int first = S.lo, last = S.hi;
-  if (S.redo == 2) { first = 0; last = P.n_tiles - 1; }
-  if (first + (int)blockIdx.x > last) return;
   if (P.n_ds <= kDsSmem)
     for (int i = t; i <= P.n_ds; i += kThreads) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
   __syncthreads();
-  for (int tile = first + (int)blockIdx.x; tile <= last; tile += (int)gridDim.x) {
-    redo_tile(P, S, tile);
-    __syncthreads();
+  int first = S.lo, last = S.hi;
+  if (redo == 2) { first = 0; last = P.n_tiles - 1; }
+  const int m = last - first + 1;
+  const int steps_per_tile = P.tile_nodes / kStep > 0 ? P.tile_nodes / kStep : 1;
+  if (m >= (int)gridDim.x) {
+    // many tiles: whole tiles per CTA
+    for (int tile = first + (int)blockIdx.x; tile <= last; tile += (int)gridDim.x) {
+      redo_steps(P, S, tile, 0, steps_per_tile);
+      __syncthreads();
+    }
+  } else {
+    // a few tiles (the steady state: the one tile the budget cuts through): one step per CTA, so that the redo costs
+    // one load round trip instead of one per step
+    const int items = m * steps_per_tile;
+    for (int it = (int)blockIdx.x; it < items; it += (int)gridDim.x) {
+      const int tile = first + it / steps_per_tile, st = it % steps_per_tile;
+      redo_steps(P, S, tile, st, st + 1);
+      __syncthreads();
+    }
   }
   if (P.stamps && lead && t == 0) P.ws->dbg2[3] = now_ns();
 }

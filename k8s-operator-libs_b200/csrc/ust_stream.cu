@@ -39,7 +39,6 @@ constexpr int kThreads = UST_STREAM_THREADS;
 constexpr int kGroups = kTile / 128;              // 128-node groups per full tile: one per warp instruction (4 nodes per lane)
 constexpr int kGPW = (kGroups + kCW - 1) / kCW;   // groups per consumer warp per full tile
 static_assert(kGroups % kCW == 0 || kCW > kGroups, "consumer warps must divide the groups of a tile");
-static_assert(kGPW <= 3, "nibble counters hold 4 nodes x kGPW groups per tile");
 #ifndef UST_HOT_REP
 #define UST_HOT_REP 8
 #endif
@@ -85,7 +84,7 @@ constexpr unsigned long long kShiftLo = pack_shifts(0), kShiftHi = pack_shifts(8
 
 // Byte-sliced SIMD-in-register counting. The hot-byte table maps a hot byte to sixteen 4-bit one-hot increments packed
 // in 64 bits (fields 0-13: state code, 14: unavailable, 15: upgrade candidate) next to the node's table window; a
-// thread sums the entries of its nodes of a tile (no field can exceed 4 * kGPW), widens the nibbles to byte lanes,
+// thread sums the entries of its nodes of two groups (no field can exceed 8), widens the nibbles to byte lanes,
 // and keeps going. No atomics until the byte lanes fill up or the CTA runs out of tiles.
 __device__ __forceinline__ uint4 hot_entry(unsigned b) {
   // GetCurrentUnavailableNodes (common_manager.go:146-165) counts every snapshot entry that is cordoned or
@@ -315,10 +314,16 @@ __device__ void consume(const UstParams& P, SS<PODS>& S, int cw) {
     unsigned mycand = 0;
     if (valid == kTile) {
 #pragma unroll
-      for (int j = 0; j < kGPW; j++)
+      for (int j = 0; j < kGPW; j++) {
         if (cw + j * kCW < kGroups) eval_group<true, DS_SMEM, OUTCOME, PODS>(P, S, st, cw + j * kCW, base, valid, grant, lo, hi, mycand);
+        if ((j & 1) && j + 1 < kGPW) widen(lo, hi, B);  // a nibble counter holds the 8 nodes of two groups
+      }
     } else {
-      for (int g = cw; g < groups; g += kCW) eval_group<false, DS_SMEM, OUTCOME, PODS>(P, S, st, g, base, valid, grant, lo, hi, mycand);
+      int j = 0;
+      for (int g = cw; g < groups; g += kCW, j++) {
+        eval_group<false, DS_SMEM, OUTCOME, PODS>(P, S, st, g, base, valid, grant, lo, hi, mycand);
+        if (j & 1) widen(lo, hi, B);
+      }
     }
     widen(lo, hi, B);
     // the tile's upgrade candidates (for the ordered slot allocation): the last warp to finish the stage publishes

@@ -12,12 +12,12 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-ffp-contract=off", "--fmad=false"]
 VARIANTS = {
     "w16": ["-DUST_CONSUMER_WARPS=16"],
-    "w16s4": ["-DUST_CONSUMER_WARPS=16", "-DUST_STAGES=4"],
-    "w16s6": ["-DUST_CONSUMER_WARPS=16", "-DUST_STAGES=6"],
-    "t4096w16s3": ["-DUST_TILE_NODES=4096", "-DUST_STAGES=3", "-DUST_CONSUMER_WARPS=16"],
+    "w4": ["-DUST_CONSUMER_WARPS=4"],
+    "t6144w8s2": ["-DUST_TILE_NODES=6144", "-DUST_STAGES=2"],
+    "t6144w16s2": ["-DUST_TILE_NODES=6144", "-DUST_STAGES=2", "-DUST_CONSUMER_WARPS=16"],
+    "t3072w8s4": ["-DUST_TILE_NODES=3072", "-DUST_STAGES=4"],
     "t3072w12s4": ["-DUST_TILE_NODES=3072", "-DUST_STAGES=4", "-DUST_CONSUMER_WARPS=12"],
-    "t3072w24s4": ["-DUST_TILE_NODES=3072", "-DUST_STAGES=4", "-DUST_CONSUMER_WARPS=24"],
-    "t4096w32s3": ["-DUST_TILE_NODES=4096", "-DUST_STAGES=3", "-DUST_CONSUMER_WARPS=32"],
+    "t5120w8s3": ["-DUST_TILE_NODES=5120", "-DUST_STAGES=3", "-DUST_HOT_REP=1"],
 }
 
 

@@ -20,8 +20,6 @@ tail -8 gpurun_out/pytest_gpu.log
 for so in build_variants/*.so; do echo "== $so"; ARGS="" q UST_LIB=$PWD/$so UST_STAMPS=148; done
 echo "== cut mid-array, hinted"; ARGS="--maxpar 0 --maxunav 30%" q UST_STAMPS=148
 echo "== cut mid-array, no hint"; ARGS="--maxpar 0 --maxunav 30%" q UST_NO_HINT=1 UST_STAMPS=148
-echo "== cut mid-array, hinted w16"; ARGS="--maxpar 0 --maxunav 30%" q UST_STAMPS=148 UST_LIB=$PWD/build_variants/w16.so
 echo "== C2 1M"; ARGS="--nodes 1000000" q UST_STAMPS=148
 echo "== 100k"; ARGS="--nodes 100000" q UST_STAMPS=148
 echo "== 10k"; ARGS="--nodes 10000" q UST_STAMPS=148
-echo "== 100k w16"; ARGS="--nodes 100000" q UST_STAMPS=148 UST_LIB=$PWD/build_variants/w16.so
