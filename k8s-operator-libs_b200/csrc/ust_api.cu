@@ -100,7 +100,7 @@ struct ust_handle {
   bool no_hint = false;  // UST_NO_HINT=1 (tuning): every call speculates from the policy default, never from the previous call
 
   UstWorkspace* ws = nullptr;
-  uint32_t* lut_dev = nullptr;      // UST_LUT_ENTRIES + 32 words
+  uint32_t* lut_dev = nullptr;      // UST_LUT_WORDS words
   uint8_t* podlut_dev = nullptr;
   uint32_t* lut_host = nullptr;     // pinned staging copy
   uint8_t* podlut_host = nullptr;   // pinned
@@ -176,15 +176,10 @@ static int ensure_tables(ust_handle* h, const ust_policy* p, cudaStream_t st) {
     ust_build_lut(&key, h->lut_host);
     ust_build_pod_lut(&key, h->podlut_host);
   } else {
-    for (unsigned s = 0; s < 16; s++)
-      for (unsigned k = 0; k < UST_LUT_WINDOW; k++) h->lut_host[s * UST_LUT_WINDOW + k] = ust_lut_pack(s, s, 0, 0xFF);
+    ust_build_lut(nullptr, h->lut_host);
     memset(h->podlut_host, 0, UST_PODLUT_ENTRIES);
   }
-  for (unsigned s = 0; s < 16; s++) {
-    h->lut_host[UST_LUT_ENTRIES + 2 * s] = (uint32_t)(ust_window_shift[s] - 2);
-    h->lut_host[UST_LUT_ENTRIES + 2 * s + 1] = s * UST_LUT_WINDOW * 4u;
-  }
-  UST_CUDA(h, cudaMemcpyAsync(h->lut_dev, h->lut_host, (UST_LUT_ENTRIES + 32) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  UST_CUDA(h, cudaMemcpyAsync(h->lut_dev, h->lut_host, UST_LUT_WORDS * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   UST_CUDA(h, cudaMemcpyAsync(h->podlut_dev, h->podlut_host, UST_PODLUT_ENTRIES, cudaMemcpyHostToDevice, st));
   h->lut_policy = key;
   h->lut_valid = true;
@@ -540,9 +535,9 @@ int ust_create(ust_handle** out, int device) {
   if ((e = cudaEventCreateWithFlags(&h->d2h_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&h->ws, sizeof(UstWorkspace))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(h->ws, 0, sizeof(UstWorkspace))) != cudaSuccess) return bail("cudaMemset", e);
-  if ((e = cudaMalloc(&h->lut_dev, (UST_LUT_ENTRIES + 32) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->lut_dev, UST_LUT_WORDS * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->podlut_dev, UST_PODLUT_ENTRIES)) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMallocHost(&h->lut_host, (UST_LUT_ENTRIES + 32) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost(&h->lut_host, UST_LUT_WORDS * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost(&h->podlut_host, UST_PODLUT_ENTRIES)) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMalloc(&h->counters_dev, sizeof(ust_counters))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMallocHost(&h->counters_host, sizeof(ust_counters))) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -931,12 +926,19 @@ int ust_build_state_uids(ust_handle* h, int64_t n_pods, const uint8_t* state, co
 }
 
 uint32_t ust_table_entry(const ust_policy* policy, unsigned state_code, uint32_t w) {
+  // the very table the kernels stage and the very lookup they make (ust_lut.h), built for `policy` (cached per thread)
+  static thread_local std::vector<uint32_t> lut;
+  static thread_local ust_policy cached;
+  static thread_local bool have = false;
   state_code &= 15u;
-  if (!policy_active(policy)) return ust_lut_pack(state_code, state_code, 0, 0xFF);
   const ust_policy key = table_key(policy);
-  const int sh = ust_window_shift[state_code];
-  const uint32_t window = (uint32_t)(((uint64_t)(UST_LUT_WINDOW - 1) << sh) & 0xFFFFFFFFull);
-  return ust_transition(state_code, w & window, &key);
+  if (!have || memcmp(&key, &cached, sizeof(key)) != 0) {
+    lut.assign(UST_LUT_WORDS, 0u);
+    ust_build_lut(policy_active(policy) ? &key : nullptr, lut.data());
+    cached = key;
+    have = true;
+  }
+  return ust_lut_lookup(lut.data(), state_code, w);
 }
 int ust_table_window_shift(unsigned state_code) { return ust_window_shift[state_code & 15u]; }
 

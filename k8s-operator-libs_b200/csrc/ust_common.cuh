@@ -123,7 +123,9 @@ struct DecideShared {
   long long slots_left;
   long long part[32];
   long long run_before;
+  long long spec_before;         // this shard's candidates in the tiles before the speculative cut (counted while streaming)
   int run0, run1;                // cut search: the run of tiles that contains the crossing
+  int found;
   int spec_cut;                  // effective speculative cut of this call (hint or policy default), in tiles
   int redo, cut, lo, hi, scan;
 };
@@ -139,6 +141,8 @@ __device__ __forceinline__ void load_local_vector(const UstParams& P, DecideShar
     else if (t == UST_V_RANK_NODES + P.rank) v = P.n;
     else if (t == UST_V_RANK_ERRINV + P.rank) v = (long long)__ldcg(&P.ws->errinv[P.parity]);
     D.V[t] = v;
+  } else if (t == UST_V_LEN) {
+    D.spec_before = (long long)__ldcg(&acc[UST_STATE_EXCLUDED]);  // lane 14 of the accumulators: see ust_stream.cu
   }
 }
 // ... lane 14 of the LOCAL vector: everything that is in no bucket - "not in snapshot" (upgrade_state.go:149-152) and
@@ -261,7 +265,7 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
       D.abort_key = s.abort_key; D.budget = s.budget; D.avail = s.avail; D.max_unav = s.max_unav;
       D.node_offset = s.node_offset; D.cand_before = s.cand_before;
       D.cut = cut; D.slots_left = 0; D.scan = scan; D.redo = redo; D.lo = 1; D.hi = 0;
-      D.run0 = D.run1 = 0; D.run_before = 0;
+      D.run0 = D.run1 = 0; D.run_before = 0; D.found = 0;
     }
     if (write_global && !scan && !(redo == 1)) {  // the common case ends here: counters out, no tile is redone
       write_counters(P, D.V, s, redo == 2 ? (long long)nT : 0, comm_failed);
@@ -274,20 +278,53 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
   __syncthreads();
   if (D.redo != 1 && !D.scan) return;
   const long long lb = D.budget - D.cand_before;
-  if (D.scan) {
+  const int sc_mid = D.spec_cut;
+  if (D.scan && sc_mid > 0 && sc_mid < nT && !P.split) {
+    // The speculation came from the previous call's cut, and the streaming pass has counted this shard's candidates in
+    // the tiles before it: the budget most likely cuts in that tile again or next to it. One window of per-tile counts
+    // around it (one load per thread, one round trip) settles that without looking at the other tiles.
+    constexpr int kHalf = 64;
+    const int c = sc_mid - kHalf + t;
+    const bool in = t < 2 * kHalf && c >= 0 && c < nT;
+    const long long cand = in ? (long long)__ldcg(&P.cand_tile[c]) : 0;
+    long long incl = cand;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long v = __shfl_up_sync(kFull, incl, o);
+      if ((t & 31) >= o) incl += v;
+    }
+    if ((t & 31) == 31) D.part[t >> 5] = incl;
+    __syncthreads();
+    long long pre = incl - cand, before_sc = 0;   // pre: candidates of the window before tile c
+    for (int w = 0; w < (nt >> 5); w++) {
+      const long long v = D.part[w];
+      if (w < (t >> 5)) pre += v;
+      if (w < kHalf / 32) before_sc += v;         // the window's tiles before the speculative cut
+    }
+    const long long prefix = D.spec_before - before_sc + pre;  // this shard's candidates before tile c
+    if (in && prefix <= lb && lb < prefix + cand) { D.cut = c; D.slots_left = lb - prefix; D.found = 1; }
+    __syncthreads();
+  }
+  if (D.scan && !D.found) {
     // pass 1: thread t sums the tiles [c0, c1); block-wide exclusive scan; the run that contains the crossing is
     // published. pass 2: the whole CTA loads that run (<= per tiles) and scans again.
     const int per = (nT + nt - 1) / nt;
     const int c0 = t * per < nT ? t * per : nT, c1 = c0 + per < nT ? c0 + per : nT;
     long long mine = 0;
-#pragma unroll 8
-    for (int c = c0; c < c1; c++) mine += __ldcg(&P.cand_tile[c]);
+    for (int cb = c0; cb < c1; cb += 16) {   // 16 loads in flight
+      unsigned v[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) v[k] = cb + k < c1 ? __ldcg(&P.cand_tile[cb + k]) : 0u;
+#pragma unroll
+      for (int k = 0; k < 16; k++) mine += v[k];
+    }
     long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const long long v = __shfl_up_sync(kFull, incl, o);
       if ((t & 31) >= o) incl += v;
     }
+    __syncthreads();
     if ((t & 31) == 31) D.part[t >> 5] = incl;
     __syncthreads();
     long long before = incl - mine;

@@ -20,7 +20,7 @@
 #define UST_STAGES 3
 #endif
 #ifndef UST_CONSUMER_WARPS
-#define UST_CONSUMER_WARPS 8
+#define UST_CONSUMER_WARPS 16
 #endif
 #define UST_STREAM_THREADS (32 * (1 + UST_CONSUMER_WARPS))
 
@@ -80,7 +80,7 @@ struct UstParams {
   uint8_t* next;
   uint16_t* actions;
   uint8_t* outcome;  // nullable
-  const uint32_t* lut;    // UST_LUT_ENTRIES words, then 16 uint2 {shift-2, state*2048}
+  const uint32_t* lut;    // UST_LUT_ENTRIES words, then 16 uint2 lookup constants (ust_lut.h)
   const uint8_t* podlut;  // UST_PODLUT_ENTRIES bytes
   uint8_t* podsum;        // per-node pod-list summary (written by the pod-summary kernel, read by the streaming pass); null = no pod lists
   UstWorkspace* ws;

@@ -1,7 +1,7 @@
 // ust_kernels.cu — the verification kernel of ApplyState and the auxiliary kernels of libust.so (sm_100a).
 //
 // ust_verify_kernel runs behind ust_stream_kernel (ust_stream.cu) on the same stream, launched with programmatic
-// dependent launch: one small CTA per SM, resident (asleep in griddepcontrol.wait, transition table already staged)
+// dependent launch: one small CTA per SM, resident (asleep in griddepcontrol.wait, 4.4 KiB transition table staged)
 // while the streaming kernel runs. When that ends every CTA reads the shard's counters - on several GPUs: exchanges
 // them through NVLink mailboxes, or takes the result of a host-launched NCCL all-reduce - derives the slot budget
 // (GetUpgradesAvailable, common_manager.go:748-776) and judges the speculation the streaming kernel made. CTA 0 writes
@@ -22,10 +22,14 @@ namespace {
 constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStep = kThreads * 4;   // nodes per CTA step (4 per thread)
+constexpr uint32_t kLutBytes = UST_LUT_WORDS * sizeof(uint32_t);  // table + 16 {x, y} meta pairs
 constexpr int kRedoUnroll = 4;  // steps in flight per thread when whole tiles are re-evaluated
 constexpr int kDsSmem = 64;  // the kernel sits next to the streaming kernel on every SM: keep its shared memory small
 
-struct __align__(16) Shared {
+struct __align__(128) Shared {
+  uint32_t lut[UST_LUT_ENTRIES];  // + meta directly behind it: filled by ONE bulk (TMA) copy
+  uint2 meta[16];
+  unsigned long long mbar;        // mbarrier the bulk copy completes on
   int dsrev[kDsSmem + 1];         // DaemonSet revisions (larger tables are read from global memory: this is the rare path)
   unsigned int warp_tot[kWarps];
   // the verdict, CTA-uniform
@@ -51,9 +55,7 @@ __device__ __forceinline__ void widen(uint32_t& lo, uint32_t& hi, uint32_t (&B)[
 // ------------------------------------------------------------------------------------------------
 // per-node transition
 // ------------------------------------------------------------------------------------------------
-// table entry for one node. hb = hot byte, extra = derived bits (slot grant, pod-list summaries). The verification
-// kernel keeps no copy of the transition table: it reads the handle's 32 KiB table through the read-only cache, so
-// that the kernel - resident beside the streaming kernel on every SM during every call - costs almost no shared memory.
+// table entry for one node. hb = hot byte, extra = derived bits (slot grant, pod-list summaries)
 __device__ __forceinline__ uint32_t node_entry(const UstParams& P, const Shared& S, bool ds_smem, uint32_t hb, uint32_t fl, int rev,
                                                uint32_t di, uint32_t extra) {
   uint32_t w = (fl & UST_F_INPUT_MASK) | ((hb >> 3) & (UST_W_SKIP | UST_W_UNSCHEDULABLE)) | extra;
@@ -62,9 +64,9 @@ __device__ __forceinline__ uint32_t node_entry(const UstParams& P, const Shared&
   if (ds_smem) synced = (di < (uint32_t)P.n_ds) && (rev == S.dsrev[min(di, (uint32_t)P.n_ds)]);
   else synced = di < (uint32_t)P.n_ds && rev == __ldg(P.ds_rev + di);
   if (synced) w |= UST_W_SYNCED;
-  const uint2 m = __ldg(reinterpret_cast<const uint2*>(P.lut + UST_LUT_ENTRIES) + (hb & 15u));
-  const uint32_t off = (__funnelshift_r(w, 0u, m.x) & 0x7FCu) | m.y;
-  return __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(P.lut) + off));
+  const uint2 m = S.meta[hb & 15u];
+  const uint32_t off = (__funnelshift_r(w, 0u, m.x) & (m.x >> 16)) | m.y;
+  return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(S.lut) + off);
 }
 
 __device__ __forceinline__ uint32_t noop_entry(uint32_t hb) { return ((hb & 15u) << 16) | 0xFF000000u; }
@@ -276,9 +278,17 @@ __device__ void redo_steps(const UstParams& P, Shared& S, int tile, int s0, int 
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) ust_verify_kernel(const __grid_constant__ UstParams P) {
+__global__ void __maxnreg__(96) ust_verify_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
   const int t = threadIdx.x;
+  // prologue (overlaps the streaming kernel): the transition table (4.4 KiB) by one TMA bulk copy - it was uploaded by
+  // a copy, not by a kernel, so it need not wait
+  if (t == 0) {
+    mbar_init(&S.mbar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&S.mbar, kLutBytes);
+    bulk_g2s(S.lut, P.lut, kLutBytes, &S.mbar);
+  }
   griddep_launch_dependents();  // the next call's streaming kernel may become resident (it waits for this grid itself)
   griddep_wait();               // the streaming kernel (and, split mode, the collective) has completed
   const bool lead = blockIdx.x == 0;
@@ -303,6 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) ust_verify_kernel(const __grid_co
   decide(P, S.D, lead, !comm_ok);
   if (P.stamps && lead && t == 0) P.ws->dbg2[2] = now_ns();
   const int redo = S.D.redo;
+  mbar_wait(&S.mbar, 0);  // never leave with the bulk copy in flight (it landed long ago)
   if (redo == 0) return;  // the speculation held: every output of the streaming kernel is final
   if (t == 0) {
     S.redo = redo; S.cut = S.D.cut; S.lo = S.D.lo; S.hi = S.D.hi; S.slots = S.D.slots_left;

@@ -2,10 +2,10 @@
 //
 // The kernel never branches on a node's state. For every node it forms a 32-bit predicate word
 //   w = (flags & UST_F_INPUT_MASK) | skip/unschedulable from the hot byte | derived bits
-// and looks the result up in a table indexed by (state code, 9-bit window of w). Which window a state
-// reads is fixed by the bit layout in include/ust.h; WHAT each (state, window) maps to depends on the
-// policy and the manager options, so the table is rebuilt whenever those change (8192 entries, built
-// on the host in microseconds, cached in the handle, 32 KiB in shared memory per CTA).
+// and looks the result up in a table indexed by (state code, the window of w that state reads: up to 9 bits). Which
+// window a state reads is fixed by the bit layout in include/ust.h; WHAT each (state, window) maps to depends on the
+// policy and the manager options, so the table is rebuilt whenever those change (1105 entries packed widest window
+// first, built on the host in microseconds, cached in the handle, 4.4 KiB in shared memory per CTA).
 //
 // Entry layout:  bits 0-15 actions (UST_A_*), bits 16-23 next state, bits 24-31 actuator outcome
 // (UST_OUTCOME_NONE = no actuator ran) — byte-aligned so the kernel packs four nodes with PRMT.
@@ -14,9 +14,11 @@
 
 #include "../../include/ust.h"
 
-#define UST_LUT_WINDOW_BITS 9
-#define UST_LUT_WINDOW (1u << UST_LUT_WINDOW_BITS)
-#define UST_LUT_ENTRIES (16u * UST_LUT_WINDOW)
+#ifdef __CUDACC__
+#define UST_HD __host__ __device__
+#else
+#define UST_HD
+#endif
 
 // bits of w that the kernel derives (never taken from the caller's flags word)
 #define UST_W_SKIP (1u << 2)
@@ -27,23 +29,63 @@
 #define UST_W_PD_MISMATCH (1u << 23) /* numPodsCanDelete != numPodsToDelete    pod_manager.go:194 */
 #define UST_W_DRAIN_ERROR (1u << 24) /* drain helper reports an error pod      drain_manager.go:121-128 */
 
-// first bit of the window each state's transition reads (always >= 2: the kernel shifts by sh-2 so the
-// table index comes out pre-multiplied by 4)
-static constexpr int ust_window_shift[16] = {
-    /* 0 unknown            */ 3,   // UNSCHED, UPG_REQ, SAFE_LOAD, ORPHANED, SYNCED
-    /* 1 upgrade-required   */ 2,   // SKIP, UNSCHED, GRANTED, UPG_REQ
-    /* 2 cordon-required    */ 2,
-    /* 3 wait-for-jobs      */ 16,  // WAIT_*
-    /* 4 pod-deletion       */ 22,  // PD_HAS, PD_MISMATCH
-    /* 5 drain-required     */ 24,  // DRAIN_ERROR
-    /* 6 node-maintenance   */ 20,  // NM_PRESENT, NM_READY
-    /* 7 post-maintenance   */ 2,
-    /* 8 pod-restart        */ 7,   // SAFE_LOAD, ORPHANED, SYNCED, POD_READY, INITIAL, REQUESTOR, TERMINATING, FAILING
-    /* 9 validation         */ 6,   // VALIDATION_DONE, SAFE_LOAD, INITIAL, REQUESTOR
-    /* 10 uncordon          */ 13,  // REQUESTOR
-    /* 11 upgrade-done      */ 3,
-    /* 12 upgrade-failed    */ 8,   // ORPHANED, SYNCED, POD_READY, INITIAL
-    /* 13 other, 14 excluded, 15 reserved */ 2, 2, 2};
+// The window of w each state's transition reads: first bit (always >= 2: the kernel shifts by sh-2 so the table index
+// comes out pre-multiplied by 4) and width. Only these bits can change what ust_transition() returns for the state -
+// tests/test_abi_cpu.py::test_transition_table_matches_oracle checks that against the oracle for every 9-bit key.
+UST_HD constexpr int ust_shift_of(int s) {
+  switch (s) {
+    case 0: case 11: return 3;   // unknown / upgrade-done: UNSCHED, UPG_REQ, SAFE_LOAD, ORPHANED, SYNCED
+    case 1: return 2;            // upgrade-required: SKIP, UNSCHED, GRANTED, UPG_REQ
+    case 3: return 16;           // wait-for-jobs: WAIT_*
+    case 4: return 22;           // pod-deletion: PD_HAS, PD_MISMATCH
+    case 5: return 24;           // drain-required: DRAIN_ERROR
+    case 6: return 20;           // node-maintenance: NM_PRESENT, NM_READY
+    case 8: return 7;            // pod-restart: SAFE_LOAD, ORPHANED, SYNCED, POD_READY, INITIAL, REQUESTOR, TERMINATING, FAILING
+    case 9: return 6;            // validation: VALIDATION_DONE, SAFE_LOAD, INITIAL, REQUESTOR
+    case 10: return 13;          // uncordon: REQUESTOR
+    case 12: return 8;           // upgrade-failed: ORPHANED, SYNCED, POD_READY, INITIAL
+    default: return 2;           // cordon-required, post-maintenance, other, excluded, reserved: read nothing
+  }
+}
+UST_HD constexpr int ust_bits_of(int s) {
+  switch (s) {
+    case 0: case 11: return 7;   // bits 3..9
+    case 1: return 4;            // bits 2..5
+    case 3: return 4;            // bits 16..19
+    case 4: return 2;            // bits 22..23
+    case 5: return 1;            // bit 24
+    case 6: return 2;            // bits 20..21
+    case 8: return 9;            // bits 7..15
+    case 9: return 8;            // bits 6..13
+    case 10: return 1;           // bit 13
+    case 12: return 5;           // bits 8..12
+    default: return 0;
+  }
+}
+#define UST_LUT_WINDOW_BITS 9    /* the widest window */
+#define UST_LUT_WINDOW (1u << UST_LUT_WINDOW_BITS)
+// Compact layout: the windows are packed widest first, so every window starts at a multiple of its own size and the
+// kernel can OR the index into the base. 1105 entries instead of 16 x 512.
+UST_HD constexpr int ust_base_of(int s) {
+  int b = 0;
+  for (int q = 0; q < 16; q++)
+    if (ust_bits_of(q) > ust_bits_of(s) || (ust_bits_of(q) == ust_bits_of(s) && q < s)) b += 1 << ust_bits_of(q);
+  return b;
+}
+UST_HD constexpr int ust_lut_used() {
+  int b = 0;
+  for (int q = 0; q < 16; q++) b += 1 << ust_bits_of(q);
+  return b;
+}
+#define UST_LUT_ENTRIES ((unsigned)((ust_lut_used() + 3) & ~3))   /* 1108 words; + 16 {x, y} meta pairs behind it */
+#define UST_LUT_WORDS (UST_LUT_ENTRIES + 32u)
+// per-state lookup constants: byte offset of a node's entry = (funnelshift_r(w, 0, x) & (x >> 16)) | y
+UST_HD constexpr uint32_t ust_meta_x(int s) { return (uint32_t)(ust_shift_of(s) - 2) | ((((1u << ust_bits_of(s)) - 1u) << 2) << 16); }
+UST_HD constexpr uint32_t ust_meta_y(int s) { return (uint32_t)ust_base_of(s) * 4u; }
+
+static constexpr int ust_window_shift[16] = {ust_shift_of(0), ust_shift_of(1), ust_shift_of(2), ust_shift_of(3), ust_shift_of(4), ust_shift_of(5),
+                                             ust_shift_of(6), ust_shift_of(7), ust_shift_of(8), ust_shift_of(9), ust_shift_of(10), ust_shift_of(11),
+                                             ust_shift_of(12), ust_shift_of(13), ust_shift_of(14), ust_shift_of(15)};
 
 // position of each state's Process* pass in ApplyState's call order (upgrade_state.go:205-274);
 // -1 = the state is never processed
@@ -170,15 +212,26 @@ static inline uint32_t ust_transition(unsigned s, uint32_t w, const ust_policy* 
   return ust_lut_pack(s, next, a, outcome);
 }
 
-// lut[s * 512 + key] for key = (w >> ust_window_shift[s]) & 511
+// lut[ust_base_of(s) + key] for key = (w >> ust_shift_of(s)) & (2^ust_bits_of(s) - 1); then the 16 {x, y} meta pairs.
+// `p` == NULL: the table of an inactive policy (every node is a no-op).
 static inline void ust_build_lut(const ust_policy* p, uint32_t* lut) {
-  for (unsigned s = 0; s < 16; s++) {
-    const int sh = ust_window_shift[s];
-    for (uint32_t key = 0; key < UST_LUT_WINDOW; key++) {
-      uint32_t w = (sh + UST_LUT_WINDOW_BITS >= 32) ? (uint32_t)(((uint64_t)key << sh) & 0xFFFFFFFFull) : (key << sh);
-      lut[s * UST_LUT_WINDOW + key] = ust_transition(s, w, p);
+  for (unsigned i = 0; i < UST_LUT_WORDS; i++) lut[i] = 0;
+  for (int s = 0; s < 16; s++) {
+    const int sh = ust_shift_of(s), base = ust_base_of(s);
+    for (uint32_t key = 0; key < (1u << ust_bits_of(s)); key++) {
+      const uint32_t w = (uint32_t)(((uint64_t)key << sh) & 0xFFFFFFFFull);
+      lut[base + (int)key] = p ? ust_transition((unsigned)s, w, p) : ust_lut_pack((unsigned)s, (unsigned)s, 0, 0xFF);
     }
+    lut[UST_LUT_ENTRIES + 2 * s] = ust_meta_x(s);
+    lut[UST_LUT_ENTRIES + 2 * s + 1] = ust_meta_y(s);
   }
+}
+// the lookup the kernels make, on the host (audit / tests)
+static inline uint32_t ust_lut_lookup(const uint32_t* lut, unsigned s, uint32_t w) {
+  const uint32_t x = lut[UST_LUT_ENTRIES + 2 * s], y = lut[UST_LUT_ENTRIES + 2 * s + 1];
+  const uint32_t sh = x & 31u;
+  const uint32_t fs = (uint32_t)(((uint64_t)w << 32) >> (32 + sh));  // __funnelshift_r(w, 0, sh)
+  return lut[((fs & (x >> 16)) | y) >> 2];
 }
 
 // Pod-list table: for one workload pod, which actuator conditions it raises (index = pod_flags & 0x7FF).

@@ -13,7 +13,7 @@
 //     flags (4), pod_rev (4), ds_idx (4) per node - into one stage of a shared-memory ring with TMA bulk copies
 //     (cp.async.bulk, UBLKCP in SASS) that complete on the stage's "full" mbarrier. Bytes in flight are bounded by
 //     the ring (UST_STAGES x 26 KiB per SM), not by registers;
-//   * the per-policy transition table (32 KiB, built by the host: ust_lut.h) arrives the same way, once per CTA;
+//   * the per-policy transition table (4.4 KiB, built by the host: ust_lut.h) arrives the same way, once per CTA;
 //   * consumer warps wait on "full", evaluate 128-node groups straight out of shared memory - one 16-byte lookup
 //     indexed by the node's hot byte (table window + byte-sliced counter increments; the table is replicated per bank
 //     group, so the lookup never conflicts), one lookup in the transition table - write next_state (1 B) + actions
@@ -46,7 +46,8 @@ constexpr int kHotRep = UST_HOT_REP;              // replicas of the hot-byte ta
 static_assert(kHotRep == 1 || kHotRep == 8, "hot-byte table: plain or one replica per bank group");
 constexpr int kHotShift = kHotRep == 8 ? 7 : 4;   // byte offset of entry b (replica 0) = b << kHotShift
 constexpr uint32_t kHotMask = 0x7Fu << kHotShift;
-constexpr uint32_t kLutBytes = (UST_LUT_ENTRIES + 32) * sizeof(uint32_t);  // table + 16 {shift, base} pairs
+constexpr uint32_t kLutBytes = UST_LUT_WORDS * sizeof(uint32_t);  // table + 16 {x, y} meta pairs
+static_assert(kLutBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 template <bool PODS>
 struct Stage {            // one tile's input columns as the TMA engine lays them down
@@ -61,26 +62,19 @@ template <bool PODS>
 struct __align__(128) SS {
   uint32_t lut[UST_LUT_ENTRIES];   // + meta directly behind it: filled by ONE bulk copy
   uint2 meta[16];
-  uint4 hotent[128 * kHotRep];     // per hot byte (bit 7 ignored): {window shift - 2, table base, sixteen 4-bit one-hot count increments}
+  uint4 hotent[128 * kHotRep];     // per hot byte (bit 7 ignored): {window shift - 2 | index mask << 16, table base, sixteen 4-bit one-hot count increments}
   Stage<PODS> st[kStages];
   int dsrev[UST_DS_SMEM_MAX + 1];
   unsigned long long full[kStages], empty[kStages], lutbar;
   int tile_of[kStages];            // tile held by the stage; -1 = end of stream
   unsigned int stage_acc[kStages]; // (consumer warps done << 16) | upgrade candidates of the tile so far
   unsigned int cnt[16];
+  unsigned int spec_before;
   unsigned long long errinv;
   int spec_cut;
   int last;
   long long V[UST_V_LEN];          // split mode: the vector the last CTA publishes
 };
-
-// window shift (minus 2) of every state code, 8 bits each — compile-time copy of ust_window_shift[]
-constexpr unsigned long long pack_shifts(int from) {
-  unsigned long long v = 0;
-  for (int i = 0; i < 8; i++) v |= (unsigned long long)(ust_window_shift[from + i] - 2) << (8 * i);
-  return v;
-}
-constexpr unsigned long long kShiftLo = pack_shifts(0), kShiftHi = pack_shifts(8);
 
 // Byte-sliced SIMD-in-register counting. The hot-byte table maps a hot byte to sixteen 4-bit one-hot increments packed
 // in 64 bits (fields 0-13: state code, 14: unavailable, 15: upgrade candidate) next to the node's table window; a
@@ -96,8 +90,11 @@ __device__ __forceinline__ uint4 hot_entry(unsigned b) {
     if (b & (UST_HOT_UNSCHEDULABLE | UST_HOT_NOT_READY)) v |= 1ull << 56;
     if (code == UST_STATE_UPGRADE_REQUIRED && !(b & UST_HOT_SKIP)) v |= 1ull << 60;
   }
-  const unsigned shift = (unsigned)(((code < 8 ? kShiftLo : kShiftHi) >> (8 * (code & 7))) & 0xFFull);
-  return make_uint4(shift, code * (UST_LUT_WINDOW * 4u), (uint32_t)v, (uint32_t)(v >> 32));
+  uint32_t x = 0, y = 0;  // the state's lookup constants (ust_lut.h): 16 compile-time pairs
+#pragma unroll
+  for (int s = 0; s < 16; s++)
+    if (code == (unsigned)s) { x = ust_meta_x(s); y = ust_meta_y(s); }
+  return make_uint4(x, y, (uint32_t)v, (uint32_t)(v >> 32));
 }
 
 // byte lanes: B[0] = fields 0,2,4,6  B[1] = fields 1,3,5,7  B[2] = fields 8,10,12,14  B[3] = fields 9,11,13,15
@@ -146,7 +143,7 @@ __device__ __forceinline__ uint32_t eval_node(const UstParams& P, const SS<PODS>
   if (DS_SMEM) synced = (di < (uint32_t)P.n_ds) && (rev == S.dsrev[min(di, (uint32_t)P.n_ds)]);
   else synced = di < (uint32_t)P.n_ds && rev == __ldg(P.ds_rev + di);
   if (synced) w |= UST_W_SYNCED;
-  const uint32_t off = (__funnelshift_r(w, 0u, m.x) & 0x7FCu) | m.y;
+  const uint32_t off = (__funnelshift_r(w, 0u, m.x) & (m.x >> 16)) | m.y;
   return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(S.lut) + off);
 }
 
@@ -297,6 +294,7 @@ __device__ void consume(const UstParams& P, SS<PODS>& S, int cw) {
   const int spec_cut = S.spec_cut;
   uint32_t B[4] = {0, 0, 0, 0};
   int pending = 0;  // upper bound of any byte lane of B
+  unsigned spec_before = 0;  // this thread's upgrade candidates in tiles before the speculative cut
   for (uint32_t it = 0;; it++) {
     const int s = (int)(it % kStages);
     const uint32_t ph = (it / kStages) & 1u;
@@ -326,6 +324,7 @@ __device__ void consume(const UstParams& P, SS<PODS>& S, int cw) {
       }
     }
     widen(lo, hi, B);
+    if (tile < spec_cut) spec_before += mycand;
     // the tile's upgrade candidates (for the ordered slot allocation): the last warp to finish the stage publishes
     const unsigned wc = __reduce_add_sync(kFull, mycand);
     if (lane == 0) {
@@ -341,10 +340,14 @@ __device__ void consume(const UstParams& P, SS<PODS>& S, int cw) {
     if (pending > 255 - 4 * kGPW) { flush_counts(S, B); pending = 0; }
   }
   flush_counts(S, B);
+  // candidates before the speculative cut: with them the verification kernel finds a cut that stayed in (or near) the
+  // tile of the previous call's without scanning the per-tile counts
+  spec_before = __reduce_add_sync(kFull, spec_before);
+  if (lane == 0 && spec_before) atomicAdd(&S.spec_before, spec_before);
 }
 
 template <bool DS_SMEM, bool OUTCOME, bool PODS>
-__global__ void __launch_bounds__(kThreads, 1) ust_stream_kernel(const __grid_constant__ UstParams P) {
+__global__ void __maxnreg__(72) ust_stream_kernel(const __grid_constant__ UstParams P) {
   extern __shared__ __align__(128) unsigned char ust_smem[];
   SS<PODS>& S = *reinterpret_cast<SS<PODS>*>(ust_smem);
   const int t = threadIdx.x, warp = t >> 5;
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) ust_stream_kernel(const __grid_co
       for (int s = 0; s < kStages; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], kCW); }
       mbar_init(&S.lutbar, 1);
       mbar_fence_init();
-      // the per-policy transition table (DriverUpgradePolicySpec + manager options, compiled to 32 KiB by ust_lut.h):
+      // the per-policy transition table (DriverUpgradePolicySpec + manager options, compiled to 4.4 KiB by ust_lut.h):
       // one bulk copy; it was uploaded by a copy, not by a kernel, so it does not have to wait for the previous grid
       mbar_arrive_expect_tx(&S.lutbar, kLutBytes);
       bulk_g2s(S.lut, P.lut, kLutBytes, &S.lutbar);
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) ust_stream_kernel(const __grid_co
       for (int i = ct; i <= P.n_ds; i += cn) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
     if (ct == 0) {
       S.errinv = 0;
+      S.spec_before = 0;
       // speculative cut: the previous call's, when it was made under the same signature; else the policy default
       const bool slotted = P.active && !P.requestor;
       const bool hinted = P.spec_sig != 0 && __ldcg(&ws->hint_sig) == P.spec_sig;
@@ -401,6 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) ust_stream_kernel(const __grid_co
   else if (t == 14) { if (S.cnt[14]) atomicAdd(&acc[UST_V_UNAVAILABLE], (unsigned long long)S.cnt[14]); }
   else if (t == 15) { if (S.cnt[15]) atomicAdd(&acc[UST_V_CANDIDATES], (unsigned long long)S.cnt[15]); }
   else if (t == 32) { if (S.errinv) atomicMax(&ws->errinv[P.parity], S.errinv); }
+  else if (t == 33) { if (S.spec_before) atomicAdd(&acc[UST_STATE_EXCLUDED], (unsigned long long)S.spec_before); }  // lane 14 is free: "not in snapshot" is derived
   if (P.stamps && t == 0) ws->dbg[blockIdx.x][3] = now_ns();
   if (!(P.split && P.publish)) return;
   // ---- split mode (a host-launched collective follows): the last CTA of the call's last streaming launch publishes

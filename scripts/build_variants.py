@@ -11,13 +11,12 @@ OUT = os.path.join(ROOT, "build_variants")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-ffp-contract=off", "--fmad=false"]
 VARIANTS = {
-    "w16": ["-DUST_CONSUMER_WARPS=16"],
-    "w4": ["-DUST_CONSUMER_WARPS=4"],
-    "t6144w8s2": ["-DUST_TILE_NODES=6144", "-DUST_STAGES=2"],
-    "t6144w16s2": ["-DUST_TILE_NODES=6144", "-DUST_STAGES=2", "-DUST_CONSUMER_WARPS=16"],
-    "t3072w8s4": ["-DUST_TILE_NODES=3072", "-DUST_STAGES=4"],
+    "w8": ["-DUST_CONSUMER_WARPS=8"],
+    "rep1": ["-DUST_HOT_REP=1"],
+    "t5120w20s3": ["-DUST_TILE_NODES=5120", "-DUST_STAGES=3", "-DUST_CONSUMER_WARPS=20"],
+    "t5120w10s3": ["-DUST_TILE_NODES=5120", "-DUST_STAGES=3", "-DUST_CONSUMER_WARPS=10"],
     "t3072w12s4": ["-DUST_TILE_NODES=3072", "-DUST_STAGES=4", "-DUST_CONSUMER_WARPS=12"],
-    "t5120w8s3": ["-DUST_TILE_NODES=5120", "-DUST_STAGES=3", "-DUST_HOT_REP=1"],
+    "t3072w12s5": ["-DUST_TILE_NODES=3072", "-DUST_STAGES=5", "-DUST_CONSUMER_WARPS=12"],
 }
 
 

@@ -13,7 +13,7 @@ for l in sys.stdin:
 }
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3
 echo "== default C3"; ARGS="" q UST_STAMPS=148
-echo "== no PDL"; ARGS="" q UST_PDL=0 UST_STAMPS=148
+echo "== static 100"; ARGS="" q UST_STATIC_PCT=100 UST_STAMPS=148
 echo "== parity tests"
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -8 gpurun_out/pytest_gpu.log
