@@ -7,13 +7,25 @@ shard of an N x 10 M-node cluster (config C5 at N=8): weak scaling, one exchange
 per step.
 
   value      device-resident inputs, CUDA-event time of K steps, max over ranks, whole-job nodes/s
-  e2e        the same step through the host-pointer C ABI, pinned host arrays in, H2D + kernel + D2H inside the
-             timed region. N=1: ust_apply_state_packed (uint16 revisions / int8 DaemonSet indices on the host side,
-             8 B/node up; --e2e-format wide = ust_apply_state, 13 B/node up); N>1: ust_apply_state
+  e2e        the same step through the host-pointer C ABI, pinned host arrays in, H2D + kernels + D2H inside the
+             timed region: ust_apply_state_packed (uint16 revisions / int8 DaemonSet indices on the host side,
+             8 B/node up; --e2e-format wide = ust_apply_state, 13 B/node up)
   e2e_delta  (N=1, informative) ust_apply_state_delta: the snapshot stays resident, 1 % of the nodes are
              re-encoded and uploaded per step, everything is evaluated, all outputs come back
-  roofline   dominant kernel (ust_fused_kernel): 16 algorithmic bytes per node / its CUDA-event duration,
-             against the measured HBM copy bandwidth of MEASURED_PEAKS.json
+  roofline   dominant kernel (ust_stream_kernel): 16 algorithmic bytes per node / average step duration
+             (CUDA events), against the measured HBM copy bandwidth of MEASURED_PEAKS.json
+  by_config  (N=1) the other BASELINE configurations and the paths the headline does not take, each timed the same
+             way and each verified against the SoA oracle on the timed buffers:
+               C2      1 M nodes, no limits
+               C3_cut  C3's data under MaxParallelUpgrades=0 / MaxUnavailable=30 %: the slot budget cuts in the
+                       middle of the array. first_call_us: every call under a policy the previous call did not
+                       have (no speculation hint); steady_us: same policy, every buffer set perturbed (0.1 % of
+                       the state bytes differ from set to set), so the hint is stale but close
+               C4      10 M nodes + ~300 M workload pods in CSR lists, pod deletion and drain enabled
+               small   100 k and 10 k nodes (what a reconcile of a real cluster sees): us per call
+  N>1        parity_checked: after the timed region the shards' outputs are gathered on rank 0 and compared with the
+             SoA oracle on the unsharded cluster, for the timed policy and for one whose budget cuts mid-cluster;
+             exchange_us = step time minus the step time of the same shard on a handle without a communicator
   cpu_baseline / --impl reference   the oracle's reference-shaped restatement of the Go loop (1 thread —
              the reference's ApplyState is strictly sequential), bounded sample of the same workload
 """
@@ -39,18 +51,18 @@ L2_BYTES = 126 * 1024 * 1024
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
-    ncu capture (profiles/rNN_ncu_traffic.json); None when there is none."""
+    """(dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, name of the committed ncu
+    capture it comes from). This run does not measure it (a number taken under ncu is never a bench value)."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
     if not files:
-        return None
+        return None, None
     try:
         with open(files[-1]) as f:
             d = json.load(f)
-        return d["dram_bytes_read"] + d["dram_bytes_write"]
+        return d["dram_bytes_read"] + d["dram_bytes_write"], "profiles/" + os.path.basename(files[-1]) + " (" + d.get("kernel", "?") + ")"
     except Exception:
-        return None
+        return None, None
 
 
 def peaks():
@@ -151,6 +163,116 @@ def workload_name(world):
             f"MaxUnavailable=25%, one exchange of the constraint counters per ApplyState")
 
 
+class DeviceBench:
+    """Device-resident timing of ust_apply_state_device over rotating buffer sets (the same protocol for every
+    configuration): warm-up, then `steps` back-to-back calls queued behind a GPU-side spin, bracketed by CUDA events
+    on the launching stream."""
+
+    def __init__(self, torch, dist, ustlib, abi, dev, world):
+        self.torch, self.dist, self.ustlib, self.abi, self.dev, self.world = torch, dist, ustlib, abi, dev, world
+        # a dedicated stream: torch's default stream has handle 0, which the C ABI reads as "use the handle's own
+        # stream" — events recorded on torch's stream would then not bracket the kernels (round-1 lesson)
+        self.tstream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(self.tstream)
+        self.stream = self.tstream.cuda_stream
+        assert self.stream != 0
+        self.counters = torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)
+        self.fn = ustlib.load().ust_apply_state_device
+
+    def upload(self, soa, sets, outcome=False):
+        torch = self.torch
+        n = int(soa["state"].shape[0])
+        bufs = []
+        for _ in range(sets):
+            d = {k: torch.from_numpy(v).to(self.dev) for k, v in soa.items()}
+            d["next"] = torch.empty(n, dtype=torch.uint8, device=self.dev)
+            d["actions"] = torch.empty(n, dtype=torch.int16, device=self.dev)
+            d["outcome"] = torch.empty(n, dtype=torch.uint8, device=self.dev) if outcome else None
+            bufs.append(d)
+        return bufs
+
+    def bind(self, h, pol, bufs, pods_struct=None):
+        """pre-bound ctypes arguments per buffer set: the launch loop must not be the bottleneck (a step is ~30 us)"""
+        n = int(bufs[0]["state"].shape[0])
+        n_ds = int(bufs[0]["ds_rev"].shape[0])
+        pol_p = C.c_void_p(C.addressof(pol))
+        cnt_p = C.c_void_p(self.counters.data_ptr())
+        st_p = C.c_void_p(self.stream)
+        bound = []
+        for b in bufs:
+            bound.append((h._h, pol_p, C.c_int64(n), C.c_void_p(b["state"].data_ptr()), C.c_void_p(b["flags"].data_ptr()),
+                          C.c_void_p(b["pod_rev"].data_ptr()), C.c_void_p(b["ds_idx"].data_ptr()), C.c_int32(n_ds),
+                          C.c_void_p(b["ds_rev"].data_ptr()), C.byref(pods_struct) if pods_struct is not None else None,
+                          C.c_void_p(b["next"].data_ptr()), C.c_void_p(b["actions"].data_ptr()),
+                          C.c_void_p(b["outcome"].data_ptr()) if b["outcome"] is not None else None, cnt_p, st_p))
+        return bound
+
+    def call(self, h, args):
+        rc = self.fn(*args)
+        if rc:
+            raise self.ustlib.UstError(rc, h.last_error())
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def blocker(self):
+        # ~1.5 ms of GPU spinning: the host queues the timed launches behind it, so the CUDA events bracket
+        # back-to-back GPU execution rather than the Python launch rate
+        self.torch.cuda._sleep(3_000_000)
+
+    def time_steps(self, h, seq, steps, warmup):
+        """seq(i) -> bound argument tuple of step i. Returns total milliseconds of `steps` steps (this rank)."""
+        torch = self.torch
+        for i in range(warmup):
+            self.call(h, seq(i))
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.blocker()
+        e0.record()
+        for i in range(steps):
+            self.call(h, seq(warmup + i))
+        e1.record()
+        self.barrier()
+        return e0.elapsed_time(e1)
+
+    def counters_struct(self):
+        return self.abi.Counters.from_buffer_copy(self.counters.cpu().numpy().tobytes())
+
+    def counters_dict(self):
+        return self.counters_struct().as_dict()
+
+    def redone_tiles(self):
+        return int(self.counters_struct().reserved[0])
+
+
+def same_as_oracle(helpers, pol, soa, buf, pods=None):
+    """next_state / actions (/ actuator_outcome) of one timed buffer set against the SoA oracle, bit for bit."""
+    ref = helpers.oracle_apply(pol, soa, pods, variant=1)
+    ok = np.array_equal(buf["next"].cpu().numpy(), ref[1]) and np.array_equal(buf["actions"].cpu().numpy().view(np.uint16), ref[2])
+    if buf.get("outcome") is not None and ref[3] is not None:
+        ok = ok and np.array_equal(buf["outcome"].cpu().numpy(), ref[3])
+    return bool(ok)
+
+
+def print_stamps(ustlib, h):
+    g = min(int(os.environ["UST_STAMPS"]), 148)
+    st = (C.c_uint64 * (4 * g + 8))()
+    ustlib.load().ust_debug_stamps(h._h, st, g)
+    a = np.array(st, dtype=np.int64)
+    v = a[4 * g:]
+    a = a[:4 * g].reshape(g, 4)
+    a = a[a[:, 0] > a[:, 0].max() - 1_000_000]   # CTAs of the last launch only (a small snapshot uses fewer)
+    t0 = a[:, 0].min()
+    rel = (a - t0) / 1e3
+    v = (v - t0) / 1e3
+    print("stamps us: entry[min,max]=%.1f,%.1f first_tile[min,med,max]=%.1f,%.1f,%.1f stream_end[min,med,max]=%.1f,%.1f,%.1f "
+          "exit[max]=%.1f | verify kernel CTA 0: woken %.1f vector %.1f decided %.1f redo done %.1f | decide: begin %.2f derived %.2f written %.2f synced %.2f" % (
+              rel[:, 0].min(), rel[:, 0].max(), rel[:, 1].min(), np.median(rel[:, 1]), rel[:, 1].max(),
+              rel[:, 2].min(), np.median(rel[:, 2]), rel[:, 2].max(), rel[:, 3].max(), v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,11 +285,12 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="N>1: counter exchange mechanism")
     ap.add_argument("--maxpar", type=int, default=None, help="tuning: override MaxParallelUpgrades")
     ap.add_argument("--maxunav", default=None, help="tuning: override MaxUnavailable ('nil', int or 'NN%%')")
-    ap.add_argument("--quick", action="store_true", help="tuning: device-resident timing only (no e2e / cpu baseline)")
+    ap.add_argument("--quick", action="store_true", help="tuning: device-resident timing of one configuration only")
     ap.add_argument("--e2e-format", default="packed", choices=["wide", "packed"],
                     help="host format of the e2e leg: wide = ust_apply_state (int32 pod_rev / ds_idx), packed = "
                          "ust_apply_state_packed (uint16 / int8: 8 instead of 13 bytes per node over PCIe)")
-    ap.add_argument("--pods", action="store_true", help="tuning (with --quick): the C4 workload - CSR pod lists, pod deletion and drain enabled")
+    ap.add_argument("--pods", action="store_true", help="tuning (with --quick): the C4 workload as the timed configuration")
+    ap.add_argument("--no-by-config", action="store_true", help="skip the by_config legs (C2, C3_cut, C4, small)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,6 +302,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    import helpers
     from ust import abi, lib as ustlib, synth
 
     if not torch.cuda.is_available():
@@ -200,23 +324,19 @@ def main():
         pol = abi.make_policy(max_parallel_upgrades=args.maxpar if args.maxpar is not None else 100, max_unavailable=mu)
     if args.pods:
         if not args.quick:
-            raise SystemExit("--pods is a tuning option: use it with --quick")
+            raise SystemExit("--pods selects C4 as the timed configuration of a --quick run; the full run reports C4 under by_config")
         cfg = synth.CONFIGS["C4"]
         pol = synth.config_policy("C4")
     soa = synth.make_nodes(n, cfg["seed"], start=rank * n)
     n_ds = int(soa["ds_rev"].shape[0])
-    pods_dev = pods_struct = None
-    if args.pods:
-        pods = synth.make_pods_blocked(n, cfg["seed"], start=rank * n)
-        pods_dev = {k: torch.from_numpy(v).to(dev) for k, v in pods.items()}
-        pods_struct = abi.Pods(pods_dev["pod_off"].data_ptr(), pods_dev["pod_flags"].data_ptr(), int(pods["pod_flags"].shape[0]))
 
     h = ustlib.Handle(local_rank)
+    exchange = "none"
     if world > 1:
         uid = [ustlib.get_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         h.comm_init(rank, world, uid[0])
-        exchange = "ncclAllReduce of 42 int64 lanes between two kernels"
+        exchange = "ncclAllReduce of 42 int64 lanes between the streaming and the verification kernel"
         if args.exchange == "fused":
             # every rank must end up in the same mode: agree on whether all of them mapped their peers
             ok = torch.ones(1, device=dev)
@@ -226,145 +346,77 @@ def main():
                 ok.zero_()
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() > 0:
-                exchange = "fused in-kernel NVLink mailbox exchange (CUDA IPC peer memory), one kernel per rank"
+                exchange = "in-kernel NVLink mailbox exchange (CUDA IPC peer memory) inside the verification kernel"
             else:
                 h.comm_set_mode(0)
 
+    B = DeviceBench(torch, dist, ustlib, abi, dev, world)
     # Rotating buffer sets: a step never finds more than 126 MB / (SETS x 160 MB) of its inputs in L2.
     # (Two sets are NOT enough: the streaming loads are evict-first, so L2 keeps a fixed ~126 MB subset of
     # the 320 MB alive and half of every step would be L2 hits — measured in round 1, profiles/README.md.)
     SETS = max(2, args.sets)
-    bufs = []
-    for _ in range(SETS):
-        d = {k: torch.from_numpy(v).to(dev) for k, v in soa.items()}
-        d["next"] = torch.empty(n, dtype=torch.uint8, device=dev)
-        d["actions"] = torch.empty(n, dtype=torch.int16, device=dev)
-        d["outcome"] = torch.empty(n, dtype=torch.uint8, device=dev) if args.pods else None
-        bufs.append(d)
-    counters = torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)
-    # a dedicated stream: torch's default stream has handle 0, which the C ABI reads as "use the handle's own
-    # stream" — events recorded on torch's stream would then not bracket the kernels (round-1 lesson)
-    tstream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
-
-    # pre-bound ctypes arguments per buffer set: the launch loop must not be the bottleneck (a step is ~40 us)
-    fn = ustlib.load().ust_apply_state_device
-    pol_p = C.c_void_p(C.addressof(pol))
-    cnt_p = C.c_void_p(counters.data_ptr())
-    st_p = C.c_void_p(stream)
-    bound = []
-    for b in bufs:
-        bound.append((h._h, pol_p, C.c_int64(n), C.c_void_p(b["state"].data_ptr()), C.c_void_p(b["flags"].data_ptr()),
-                      C.c_void_p(b["pod_rev"].data_ptr()), C.c_void_p(b["ds_idx"].data_ptr()), C.c_int32(n_ds),
-                      C.c_void_p(b["ds_rev"].data_ptr()), C.byref(pods_struct) if pods_struct is not None else None,
-                      C.c_void_p(b["next"].data_ptr()), C.c_void_p(b["actions"].data_ptr()),
-                      C.c_void_p(b["outcome"].data_ptr()) if b["outcome"] is not None else None, cnt_p, st_p))
-
-    def step(i):
-        rc = fn(*bound[i % SETS])
-        if rc:
-            raise ustlib.UstError(rc, h.last_error())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def blocker():
-        # ~1.5 ms of GPU spinning: the host queues the timed launches behind it, so the CUDA events bracket
-        # back-to-back GPU execution rather than the Python launch rate
-        torch.cuda._sleep(3_000_000)
-
-    for i in range(warmup):
-        step(i)
-    barrier()
+    pods_dev = pods_struct = pods = None
+    if args.pods:
+        pods = synth.make_pods_blocked(n, cfg["seed"], start=rank * n)
+        pods_dev = {k: torch.from_numpy(v).to(dev) for k, v in pods.items()}
+        pods_struct = abi.Pods(pods_dev["pod_off"].data_ptr(), pods_dev["pod_flags"].data_ptr(), int(pods["pod_flags"].shape[0]))
+        SETS = min(SETS, 4)
+    bufs = B.upload(soa, SETS, outcome=args.pods)
+    bound = B.bind(h, pol, bufs, pods_struct)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = h.launch_count()
-    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     t_wall0 = time.time()
-    blocker()
-    e_start.record()
-    for i in range(args.steps):
-        step(i)
-    e_end.record()
-    barrier()
+    total_ms = B.time_steps(h, lambda i: bound[i % SETS], args.steps, warmup)
     t_wall = time.time() - t_wall0
     launches = h.launch_count() - launches0
-    total_ms = e_start.elapsed_time(e_end)
-    # dominant-kernel duration: per-step event pairs over a second, shorter run of the same steps
-    ksteps = min(args.steps, 20)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
-    blocker()
-    for i in range(ksteps):
-        ev[i][0].record()
-        step(i)
-        ev[i][1].record()
-    barrier()
-    per_step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     clocks = sampler.stop()
+    launches_per_step = launches / float(args.steps + warmup)
 
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms = float(tmax.item())
     value = world * n * args.steps / (total_ms * 1e-3)
-
-    # verify the outputs of the timed buffers (rank-local properties; full parity lives in tests/)
-    cnt = abi.Counters.from_buffer_copy(counters.cpu().numpy().tobytes()).as_dict()
-    nxt = bufs[0]["next"].cpu().numpy()
-    code = soa["state"] & 15
+    cnt = B.counters_dict()
     assert cnt["error_code"] == 0
-    assert cnt["total_managed"] == world * n or world > 1
-    assert np.array_equal(nxt[code == 2], np.full(int((code == 2).sum()), 3, np.uint8)), "cordon-required -> wait-for-jobs"
-    if args.quick and rank == 0:
-        print("counters:", {k: cnt[k] for k in ("candidates", "upgrades_available", "max_unavailable")},
-              "redone chunks:", abi.Counters.from_buffer_copy(counters.cpu().numpy().tobytes()).reserved[0], flush=True)
+    verified = None
+    if world == 1:
+        last = (warmup + args.steps - 1) % SETS
+        verified = same_as_oracle(helpers, pol, soa, bufs[last], pods)
+        assert verified, "timed outputs differ from the oracle"
 
     line = None
     if rank == 0:
         peak, peak_src = peaks()
-        # one step == one launch of the dominant kernel: its average duration over the timed region; the
-        # per-step event pairs (each pair adds ~2 us of event latency) are reported alongside
         kern_ms = total_ms / args.steps
         achieved = BYTES_PER_NODE * n / (kern_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic() if (world == 1 and n == SHARD_NODES and not args.pods) else (None, None)
         line = {
             "metric": "node state-transitions/sec", "value": value, "unit": "nodes/s", "n_gpus": world,
-            "steps": args.steps, "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": kern_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32", "data": "synthetic",
             "config": {"workload": workload_name(world), "nodes_per_gpu": n, "bytes_per_node": BYTES_PER_NODE,
                        "l2": f"inputs larger than L2: {SETS} rotating buffer sets of {BYTES_PER_NODE * n / 1e6:.0f} MB each "
                              f"({SETS * BYTES_PER_NODE * n / 1e9:.2f} GB vs 126 MB L2, at most {100 * 126e6 / (SETS * BYTES_PER_NODE * n):.0f}% of a step can hit)",
-                       "exchange": "none" if world == 1 else exchange},
+                       "exchange": exchange},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic() if (world == 1 and n == SHARD_NODES) else None, "peak_source": peak_src,
-                         "kernel": "ust_stream_kernel",
-                         "kernel_ms": kern_ms, "kernel_ms_event_pairs_median": float(np.median(per_step_ms)),
-                         "frac_of_8TBs": achieved / 8000.0},
-            "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "ust_stream_kernel", "kernel_ms": kern_ms, "frac_of_8TBs": achieved / 8000.0,
+                         "note": "kernel_ms = the step (streaming kernel + the verification kernel that follows it under "
+                                 "programmatic dependent launch) averaged over the timed region"},
+            "clocks": clocks, "gpu_launches": int(round(launches_per_step * args.steps)), "wall_s_timed_region": t_wall,
             "counters": {k: cnt[k] for k in ("total_managed", "in_progress", "unavailable", "max_unavailable", "upgrades_available")},
+            "verified_vs_oracle": verified,
         }
 
     if args.quick:
+        if rank == 0:
+            print("counters:", {k: cnt[k] for k in ("candidates", "upgrades_available", "max_unavailable")},
+                  "redone tiles:", B.redone_tiles(), flush=True)
         if rank == 0 and os.environ.get("UST_STAMPS"):
-            g = min(int(os.environ["UST_STAMPS"]), 148)
-            st = (C.c_uint64 * (4 * g + 4))()
-            ustlib.load().ust_debug_stamps(h._h, st, g)
-            a = np.array(st, dtype=np.int64)
-            v = a[4 * g:]
-            a = a[:4 * g].reshape(g, 4)
-            a = a[a[:, 0] > a[:, 0].max() - 1_000_000]   # CTAs of the last launch only (a small snapshot uses fewer)
-            t0 = a[:, 0].min()
-            rel = (a - t0) / 1e3
-            v = (v - t0) / 1e3
-            print("stamps us: entry[min,max]=%.1f,%.1f first_tile[min,med,max]=%.1f,%.1f,%.1f stream_end[min,med,max]=%.1f,%.1f,%.1f "
-                  "exit[max]=%.1f | verify kernel CTA 0: woken %.1f vector %.1f decided %.1f redo done %.1f" % (
-                      rel[:, 0].min(), rel[:, 0].max(), rel[:, 1].min(), np.median(rel[:, 1]), rel[:, 1].max(),
-                      rel[:, 2].min(), np.median(rel[:, 2]), rel[:, 2].max(), rel[:, 3].max(), v[0], v[1], v[2], v[3]), flush=True)
+            print_stamps(ustlib, h)
         if rank == 0:
             print(json.dumps({k: line[k] for k in ("value", "ms_per_step", "roofline", "clocks")}), flush=True)
         h.close()
@@ -372,12 +424,53 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- e2e: host-pointer C ABI with pinned host buffers, H2D + kernel + D2H inside the timed region ----
+    # ---- N > 1: parity of the sharded run against the unsharded oracle, and what the exchange costs ----------------
+    if world > 1:
+        def gathered(policy):
+            B.call(h, B.bind(h, policy, bufs[:1])[0])
+            B.barrier()
+            nx = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+            ac = [torch.empty(n, dtype=torch.int16, device=dev) for _ in range(world)] if rank == 0 else None
+            dist.gather(bufs[0]["next"], nx, dst=0)
+            dist.gather(bufs[0]["actions"], ac, dst=0)
+            if rank != 0:
+                return None
+            return (np.concatenate([t.cpu().numpy() for t in nx]), np.concatenate([t.cpu().numpy() for t in ac]).view(np.uint16),
+                    B.counters_dict())
+        cut_pol = abi.make_policy(max_parallel_upgrades=0, max_unavailable="30%")
+        got = [gathered(pol), gathered(cut_pol)]
+        # the exchange: the same shard on a handle without a communicator
+        h_local = ustlib.Handle(local_rank)
+        bound_l = B.bind(h_local, pol, bufs)
+        loc_ms = B.time_steps(h_local, lambda i: bound_l[i % SETS], args.steps, warmup)
+        tl = torch.tensor([loc_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        h_local.close()
+        if rank == 0:
+            whole = synth.make_nodes(world * n, cfg["seed"])
+            mism = 0
+            for policy, g in zip((pol, cut_pol), got):
+                ref = helpers.oracle_apply(policy, whole, variant=1)
+                mism += int(np.sum(g[0] != ref[1])) + int(np.sum(g[1] != ref[2])) + (0 if g[2] == ref[4] else 1)
+            gr = (got[1][0] == 2) & ((whole["state"] & 15) == 1) & ((whole["state"] & abi.UST_HOT_UNSCHEDULABLE) == 0)
+            line["parity_checked"] = True
+            line["mismatches"] = mism
+            line["parity"] = {"policies": ["timed policy (C3/C5)", "MaxParallelUpgrades=0, MaxUnavailable=30% (budget cuts mid-cluster)"],
+                              "nodes": world * n, "slots_granted_cut_policy": int(gr.sum()),
+                              "ranks_with_grants": int(len(set((np.nonzero(gr)[0] // n).tolist()))),
+                              "against": "SoA oracle on the unsharded cluster (next_state, actions, every counter)"}
+            line["exchange_us"] = (total_ms - float(tl.item())) / args.steps * 1e3
+            line["local_ms_per_step"] = float(tl.item()) / args.steps
+            assert mism == 0, f"sharded outputs differ from the unsharded oracle in {mism} places"
+            del whole
+        B.barrier()
+
+    # ---- e2e: host-pointer C ABI with pinned host buffers, H2D + kernels + D2H inside the timed region ----
     host = {k: ustlib.pinned_array(v.shape, v.dtype) for k, v in soa.items()}
     for k in soa:
         host[k][...] = soa[k]
     out = (ustlib.pinned_array(n, np.uint8), ustlib.pinned_array(n, np.uint16), None)
-    packed = args.e2e_format == "packed" and world == 1   # N > 1 keeps the int32 host format
+    packed = args.e2e_format == "packed"
     if packed:
         assert soa["pod_rev"].min() >= 0 and soa["pod_rev"].max() < 65536 and soa["ds_idx"].min() >= -128 and n_ds <= 127
         pk = (ustlib.pinned_array(n, np.uint16), ustlib.pinned_array(n, np.int8))
@@ -392,17 +485,18 @@ def main():
 
     for _ in range(2):
         e2e_step()
-    barrier()
+    B.barrier()
     t0 = time.time()
     for _ in range(args.e2e_steps):
         e2e_step()
-    barrier()
+    B.barrier()
     e2e_s = time.time() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.e2e_steps / float(te.item())
-    assert np.array_equal(out[0], nxt), "e2e result differs from the device-resident result"
+    if world == 1:
+        assert np.array_equal(out[0], bufs[(warmup + args.steps - 1) % SETS]["next"].cpu().numpy()), "e2e result differs from the device-resident result"
 
     # ---- the same through the delta entry point: the snapshot stays resident, 1 % of the nodes are re-encoded and
     # re-uploaded per step (a reconcile that watches resourceVersions), the whole snapshot is evaluated, all outputs
@@ -428,9 +522,101 @@ def main():
         delta = {"value": n * steps_d / d_s, "unit": "nodes/s", "ms_per_step": d_s / steps_d * 1e3, "changed_nodes_per_step": m,
                  "h2d_bytes_per_step": 21 * m + 4 * n_ds, "d2h_bytes_per_step": 3 * n + C.sizeof(abi.Counters), "steps": steps_d}
 
+    # ---- by_config (N = 1): the other configurations, same timing protocol, each verified on the timed buffers ------
+    by_config = None
+    if world == 1 and not args.no_by_config and n == SHARD_NODES:
+        peak, _ = peaks()
+        by_config = {"C3": {"ms": line["ms_per_step"], "frac": line["roofline"]["frac"], "bytes_per_node": BYTES_PER_NODE,
+                            "verified_vs_oracle": verified, "redone_tiles_per_call": 0}}
+
+        def frac_of(nbytes, ms):
+            return nbytes / (ms * 1e-3) / 1e9 / peak
+
+        # C3_cut: the budget cuts mid-array. Buffer sets perturbed: 0.1 % of the state bytes differ from set to set.
+        rng = np.random.default_rng(11)
+        variants = []
+        for k in range(SETS):
+            st = soa["state"].copy()
+            idx = rng.choice(n, size=n // 1000, replace=False)
+            st[idx] = soa["state"][rng.integers(0, n, size=idx.shape[0])]
+            variants.append(st)
+            bufs[k]["state"].copy_(torch.from_numpy(st))
+        torch.cuda.synchronize()
+        pol_a = abi.make_policy(max_parallel_upgrades=0, max_unavailable="30%")
+        pol_b = abi.make_policy(max_parallel_upgrades=0, max_unavailable="31%")
+        bound_a, bound_b = B.bind(h, pol_a, bufs), B.bind(h, pol_b, bufs)
+        steps_c = max(10, args.steps // 2)
+        # first call: the policy alternates, so no call finds a hint made under its own signature
+        ms_first = B.time_steps(h, lambda i: (bound_a if i % 2 == 0 else bound_b)[i % SETS], steps_c, warmup)
+        i_last = warmup + steps_c - 1
+        redone_first = B.redone_tiles()
+        v_first = same_as_oracle(helpers, pol_a if i_last % 2 == 0 else pol_b, dict(soa, state=variants[i_last % SETS]), bufs[i_last % SETS])
+        ms_steady = B.time_steps(h, lambda i: bound_a[i % SETS], args.steps, warmup)
+        i_last = warmup + args.steps - 1
+        redone_steady = B.redone_tiles()
+        v_steady = same_as_oracle(helpers, pol_a, dict(soa, state=variants[i_last % SETS]), bufs[i_last % SETS])
+        by_config["C3_cut"] = {
+            "policy": "MaxParallelUpgrades=0, MaxUnavailable=30% on C3's data: the slot budget cuts mid-array",
+            "first_call_us": ms_first / steps_c * 1e3, "steady_us": ms_steady / args.steps * 1e3,
+            "frac_first": frac_of(BYTES_PER_NODE * n, ms_first / steps_c), "frac_steady": frac_of(BYTES_PER_NODE * n, ms_steady / args.steps),
+            "redone_tiles_first_call": redone_first, "redone_tiles_steady": redone_steady,
+            "perturbation": "every buffer set differs from the base snapshot in 0.1 % of its state bytes (stale-but-close hint)",
+            "verified_vs_oracle": bool(v_first and v_steady)}
+        del bound_a, bound_b, variants
+
+        # C2 and the small snapshots: what a reconcile of a real cluster sees
+        small = {}
+        for name, nn, sets in (("C2", 1_000_000, 32), ("100k", 100_000, 64), ("10k", 10_000, 64)):
+            c = synth.CONFIGS["C2"]
+            s2 = synth.make_nodes(nn, c["seed"])
+            p2 = synth.config_policy("C2")
+            b2 = B.upload(s2, sets)
+            bd2 = B.bind(h, p2, b2)
+            steps2 = max(args.steps, 100)
+            ms2 = B.time_steps(h, lambda i: bd2[i % sets], steps2, warmup)
+            v2 = same_as_oracle(helpers, p2, s2, b2[(warmup + steps2 - 1) % sets])
+            entry = {"nodes": nn, "us_per_call": ms2 / steps2 * 1e3, "ms": ms2 / steps2, "frac": frac_of(BYTES_PER_NODE * nn, ms2 / steps2),
+                     "bytes_per_node": BYTES_PER_NODE, "buffer_sets": sets, "verified_vs_oracle": v2}
+            if name == "C2":
+                by_config["C2"] = entry
+            else:
+                small[name] = entry
+            del b2, bd2
+        by_config["small"] = small
+
+        # C4: pod lists. Bytes the configuration moves: the five node streams + outputs, the hot byte and the summary byte
+        # of the pod pass, and the CSR offsets + lists of the nodes whose actuator looks at its pods.
+        del bufs, bound
+        torch.cuda.empty_cache()
+        c4 = synth.CONFIGS["C4"]
+        s4 = synth.make_nodes(n, c4["seed"])
+        pods4 = synth.make_pods_blocked(n, c4["seed"])
+        p4 = synth.config_policy("C4")
+        pd = {k: torch.from_numpy(v).to(dev) for k, v in pods4.items()}
+        ps4 = abi.Pods(pd["pod_off"].data_ptr(), pd["pod_flags"].data_ptr(), int(pods4["pod_flags"].shape[0]))
+        sets4 = 4
+        b4 = B.upload(s4, sets4, outcome=True)
+        bd4 = B.bind(h, p4, b4, ps4)
+        steps4 = max(10, args.steps // 2)
+        launches0 = h.launch_count()
+        ms4 = B.time_steps(h, lambda i: bd4[i % sets4], steps4, warmup)
+        l4 = (h.launch_count() - launches0) / float(steps4 + warmup)
+        v4 = same_as_oracle(helpers, p4, s4, b4[(warmup + steps4 - 1) % sets4], pods4)
+        code = s4["state"] & 15
+        need = (code >= 3) & (code <= 5)
+        lens = np.diff(pods4["pod_off"].astype(np.int64))
+        moved = (14 + 4 + 2) * n + int(np.sum(2 * lens[need] + 8))  # streaming pass 14 read + 4 written, pod pass 1 + 1
+        by_config["C4"] = {"nodes": n, "pods": int(pods4["pod_flags"].shape[0]), "ms": ms4 / steps4, "us_per_call": ms4 / steps4 * 1e3,
+                           "bytes_moved_per_call": moved, "bytes_per_node_moved": moved / n, "frac": frac_of(moved, ms4 / steps4),
+                           "frac_of_81B_budget": frac_of(81 * n, ms4 / steps4), "launches_per_call": l4,
+                           "nodes_whose_lists_are_read": int(need.sum()), "verified_vs_oracle": v4}
+        del b4, bd4, pd
+
     if rank == 0:
         if delta is not None:
             line["e2e_delta"] = delta
+        if by_config is not None:
+            line["by_config"] = by_config
         line["e2e"] = {"value": e2e_value, "unit": "nodes/s", "h2d_bytes_per_step": (8 if packed else 13) * n + 4 * n_ds,
                        "entry_point": "ust_apply_state_packed" if packed else "ust_apply_state",
                        "d2h_bytes_per_step": 3 * n + C.sizeof(abi.Counters), "steps": args.e2e_steps,

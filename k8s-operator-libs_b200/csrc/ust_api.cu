@@ -186,11 +186,11 @@ static int ensure_tables(ust_handle* h, const ust_policy* p, cudaStream_t st) {
   return UST_OK;
 }
 
-// Tiling of a shard: tiles of UST_TILE_NODES nodes; smaller (power-of-two) tiles when the snapshot is so small that
+// Tiling of a shard: tiles of UST_TILE_NODES nodes; smaller tiles (halved, multiples of 128) when the snapshot is so small that
 // full-size tiles would leave SMs without work. One persistent CTA per SM, never more CTAs than tiles.
 static int pick_tile_nodes(const ust_handle* h, int64_t n) {
   int tn = UST_TILE_NODES;
-  while (tn > 128 && n / tn < 2LL * h->num_sms) tn >>= 1;
+  while (tn > 128 && n / tn < 2LL * h->num_sms) { tn = (tn / 2) & ~127; if (tn < 128) tn = 128; }  // multiples of 128 nodes
   return tn;
 }
 static int pick_grid(const ust_handle* h, int tiles) {
@@ -949,7 +949,7 @@ int ust_debug_stamps(ust_handle* h, unsigned long long* out, int n_ctas) {
   UST_CUDA(h, cudaSetDevice(h->device));
   UST_CUDA(h, cudaDeviceSynchronize());
   UST_CUDA(h, cudaMemcpy(out, h->ws->dbg, (size_t)n_ctas * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  UST_CUDA(h, cudaMemcpy(out + (size_t)n_ctas * 4, h->ws->dbg2, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));  // verification kernel
+  UST_CUDA(h, cudaMemcpy(out + (size_t)n_ctas * 4, h->ws->dbg2, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));  // verification kernel
   return UST_OK;
 }
 

@@ -120,6 +120,7 @@ struct DecideShared {
   long long max_unav;
   long long node_offset;         // global index of this shard's node 0
   long long cand_before;         // upgrade candidates on lower ranks
+  long long total, in_progress;
   long long slots_left;
   long long part[32];
   long long run_before;
@@ -186,8 +187,18 @@ __device__ inline Scalars derive_scalars(const UstParams& P, const long long* V)
     if (P.max_unav_kind == UST_MAXUNAVAIL_INVALID && UST_KEY(2, 0) < abort_key) abort_key = UST_KEY(2, 0);
     max_unav = total;
     if (P.max_unav_kind == UST_MAXUNAVAIL_INT) max_unav = P.max_unav_value;
-    else if (P.max_unav_kind == UST_MAXUNAVAIL_PERCENT)
-      max_unav = (long long)ceil(__ddiv_rn(__dmul_rn((double)P.max_unav_value, (double)total), 100.0));
+    else if (P.max_unav_kind == UST_MAXUNAVAIL_PERCENT) {
+      // int(math.Ceil(float64(v) * float64(total) / 100)). While |v * total| < 2^52 the product is exact in float64 and
+      // the correctly rounded quotient is closer than 2^-7 to the true one, which is an integer or at least 1/100 away
+      // from one: the ceiling is the integer one. Beyond that, float64 as the reference computes it.
+      const long long v = P.max_unav_value;
+      if (v > -(1LL << 20) && v < (1LL << 20) && total < (1LL << 31)) {
+        const long long x = v * total, q = x / 100;
+        max_unav = q + ((x % 100) > 0 ? 1 : 0);
+      } else {
+        max_unav = (long long)ceil(__ddiv_rn(__dmul_rn((double)v, (double)total), 100.0));
+      }
+    }
     // GetUpgradesAvailable (common_manager.go:748-776)
     avail = (P.max_parallel == 0) ? h1 : P.max_parallel - in_progress;
     const long long cur_unav = V[UST_V_UNAVAILABLE] + h2;
@@ -248,7 +259,9 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
   const int t = threadIdx.x, nt = blockDim.x, nT = P.n_tiles;
   const bool slotted = P.active && !P.requestor;
   if (t < 32) {
+    if (P.stamps && write_global && t == 0) P.ws->dbg2[4] = now_ns();
     const Scalars s = derive_scalars(P, D.V);
+    if (P.stamps && write_global && t == 0) P.ws->dbg2[5] = now_ns() + (s.total & 1);
     const bool aborting = s.abort_key != ~0ull;
     const long long lc = D.V[UST_V_RANK_CAND + P.rank];   // this shard's candidates
     const long long lb = s.budget - s.cand_before;         // slots left when slice order reaches this shard
@@ -263,7 +276,7 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
     const int redo = comm_failed ? 0 : (aborting ? 2 : (need ? 1 : 0));  // need: final once the cut is known
     if (t == 0) {
       D.abort_key = s.abort_key; D.budget = s.budget; D.avail = s.avail; D.max_unav = s.max_unav;
-      D.node_offset = s.node_offset; D.cand_before = s.cand_before;
+      D.node_offset = s.node_offset; D.cand_before = s.cand_before; D.total = s.total; D.in_progress = s.in_progress;
       D.cut = cut; D.slots_left = 0; D.scan = scan; D.redo = redo; D.lo = 1; D.hi = 0;
       D.run0 = D.run1 = 0; D.run_before = 0; D.found = 0;
     }
@@ -274,8 +287,10 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
         P.ws->hint_sig = P.spec_sig;
       }
     }
+    if (P.stamps && write_global && t == 0) P.ws->dbg2[6] = now_ns();
   }
   __syncthreads();
+  if (P.stamps && write_global && t == 0) P.ws->dbg2[7] = now_ns();
   if (D.redo != 1 && !D.scan) return;
   const long long lb = D.budget - D.cand_before;
   const int sc_mid = D.spec_cut;
@@ -364,7 +379,9 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
     const int redo = aborting ? 2 : (lo <= hi ? 1 : 0);
     if (t == 0) { D.redo = redo; D.lo = lo; D.hi = hi; }
     if (write_global) {
-      const Scalars s = derive_scalars(P, D.V);
+      Scalars s;
+      s.abort_key = D.abort_key; s.total = D.total; s.in_progress = D.in_progress; s.budget = D.budget; s.avail = D.avail;
+      s.max_unav = D.max_unav; s.node_offset = D.node_offset; s.cand_before = D.cand_before;
       write_counters(P, D.V, s, redo == 2 ? (long long)nT : (redo == 1 ? (long long)(hi - lo + 1) : 0), false);
       if (t == 0 && P.spec_sig != 0 && slotted && !aborting) {
         P.ws->hint_cut = cut;  // where the budget really cut this time = next call's speculation

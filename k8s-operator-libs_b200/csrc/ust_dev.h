@@ -11,16 +11,16 @@
 #define UST_DS_SMEM_MAX 1024
 
 // Streaming kernel geometry (ust_stream.cu): a tile is the unit a CTA claims, the TMA engine copies into one ring
-// stage, and the slot speculation is made for. Tiles of fewer nodes (a power of two >= 128) are used for small
+// stage, and the slot speculation is made for. Tiles of fewer nodes (a multiple of 128) are used for small
 // snapshots so that every SM gets work; the ring stages are sized for the largest.
 #ifndef UST_TILE_NODES
-#define UST_TILE_NODES 4096
+#define UST_TILE_NODES 3072
 #endif
 #ifndef UST_STAGES
-#define UST_STAGES 3
+#define UST_STAGES 4
 #endif
 #ifndef UST_CONSUMER_WARPS
-#define UST_CONSUMER_WARPS 16
+#define UST_CONSUMER_WARPS 12
 #endif
 #define UST_STREAM_THREADS (32 * (1 + UST_CONSUMER_WARPS))
 
@@ -61,7 +61,7 @@ struct UstWorkspace {
   int hint_cut;
   int pad_;
   unsigned long long dbg[UST_MAX_CTAS][4];  // %globaltimer stamps per streaming CTA: entry, first tile landed, stream end, exit
-  unsigned long long dbg2[4];               // verification kernel, CTA 0: woken, vector loaded, decided, done
+  unsigned long long dbg2[8];               // verification kernel, CTA 0: woken, vector loaded, decided, done; 4..: inside the decision
 };
 
 // abort key: (pass << 56) | (global node index + 1); policy-level aborts use index part 0
@@ -102,7 +102,7 @@ struct UstParams {
   int rank;
   int world;
   // tiling
-  int tile_nodes;         // nodes per tile (power of two, 128 .. UST_TILE_NODES)
+  int tile_nodes;         // nodes per tile (a multiple of 128, 128 .. UST_TILE_NODES)
   int n_tiles;            // tiles of the shard
   int tile_begin;         // streaming sub-range launches (pipelined uploads): tiles [tile_begin, tile_end)
   int tile_end;

@@ -325,7 +325,7 @@ __global__ void __maxnreg__(96) ust_verify_kernel(const __grid_constant__ UstPar
   int first = S.lo, last = S.hi;
   if (redo == 2) { first = 0; last = P.n_tiles - 1; }
   const int m = last - first + 1;
-  const int steps_per_tile = P.tile_nodes / kStep > 0 ? P.tile_nodes / kStep : 1;
+  const int steps_per_tile = (P.tile_nodes + kStep - 1) / kStep;
   if (m >= (int)gridDim.x) {
     // many tiles: whole tiles per CTA
     for (int tile = first + (int)blockIdx.x; tile <= last; tile += (int)gridDim.x) {
