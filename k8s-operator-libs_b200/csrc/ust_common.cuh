@@ -231,18 +231,18 @@ __device__ inline void write_counters(const UstParams& P, const long long* V, co
   }
   const bool slots = P.active && !P.requestor && !(code && pass < 2) && code != UST_ERR_MAX_UNAVAILABLE;
   if (comm_failed) { code = UST_ERR_COMM; index = -1; pass = -1; }
-  long long v = 0;
-  if (lane < 16) v = V[lane];
-  else if (lane == 16) v = V[UST_V_UNAVAILABLE];
-  else if (lane == 17) v = V[UST_V_CANDIDATES];
-  else if (lane == 18) v = s.total;
-  else if (lane == 19) v = s.in_progress;
-  else if (lane == 20) v = slots ? s.max_unav : 0;
-  else if (lane == 21) v = slots ? s.avail : 0;
-  else if (lane == 22) v = code;
-  else if (lane == 23) v = index;
-  else if (lane == 24) v = pass;
-  else if (lane == 25) v = redone_tiles;  // reserved[0]: tiles the verification kernel re-evaluates (diagnostic; the pipelined host path re-downloads when != 0)
+  // one field per lane, picked with selects (a branchy pick would run its ten arms one after the other)
+  long long v = V[lane < 18 ? lane : 0];   // hist[0..15], unavailable, candidates: lanes 0..17 of the vector
+  v = lane == 18 ? s.total : v;
+  v = lane == 19 ? s.in_progress : v;
+  v = lane == 20 ? (slots ? s.max_unav : 0) : v;
+  v = lane == 21 ? (slots ? s.avail : 0) : v;
+  v = lane == 22 ? code : v;
+  v = lane == 23 ? index : v;
+  v = lane == 24 ? pass : v;
+  v = lane == 25 ? redone_tiles : v;  // reserved[0]: tiles the verification kernel re-evaluates (diagnostic; the pipelined host path re-downloads when != 0)
+  v = lane > 25 ? 0 : v;
+  static_assert(UST_V_UNAVAILABLE == 16 && UST_V_CANDIDATES == 17, "counter fields 16, 17 mirror the vector");
   static_assert(sizeof(ust_counters) == 32 * 8, "one field per lane");
   reinterpret_cast<long long*>(P.out)[lane] = v;
 }

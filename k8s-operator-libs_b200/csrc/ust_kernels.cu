@@ -23,7 +23,6 @@ constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStep = kThreads * 4;   // nodes per CTA step (4 per thread)
 constexpr uint32_t kLutBytes = UST_LUT_WORDS * sizeof(uint32_t);  // table + 16 {x, y} meta pairs
-constexpr int kRedoUnroll = 4;  // steps in flight per thread when whole tiles are re-evaluated
 constexpr int kDsSmem = 64;  // the kernel sits next to the streaming kernel on every SM: keep its shared memory small
 
 struct __align__(128) Shared {
@@ -186,47 +185,62 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
   }
 }
 
-// A span of full steps with a uniform grant and no abort: U steps (U x 1024 nodes) per iteration, all loads of all
-// steps in flight before the first lookup. b0, b1: multiples of kStep apart (the caller peels the ragged end).
-template <int U>
-__device__ void uniform_span(const UstParams& P, Shared& S, long long b0, long long b1, uint32_t grant) {
+// A span of full steps with a uniform grant and no abort, software-pipelined: while the two steps (2048 nodes) of one
+// iteration are evaluated, the loads of the next two are already in flight (two register buffers, the loop is unrolled
+// over them). b0, b1: multiples of kStep apart (the caller peels the ragged end).
+struct SpanTile {
+  uint32_t h[2], ps[2];
+  uint4 f[2], r[2], d[2];
+};
+__device__ __forceinline__ void span_load(const UstParams& P, SpanTile& T, long long base, long long b1) {
   const int t = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const long long i = base + (long long)j * kStep + 4 * t;
+    const bool v = i < b1;   // warp-uniform: spans are multiples of kStep
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    T.h[j] = v ? __ldg(reinterpret_cast<const uint32_t*>(P.hot + i)) : 0x0E0E0E0Eu;
+    T.ps[j] = (v && P.podsum) ? __ldcs(reinterpret_cast<const uint32_t*>(P.podsum + i)) : 0u;
+    T.f[j] = v ? __ldcs(reinterpret_cast<const uint4*>(P.flags + i)) : zero;
+    T.r[j] = v ? __ldcs(reinterpret_cast<const uint4*>(P.pod_rev + i)) : zero;
+    T.d[j] = v ? __ldcs(reinterpret_cast<const uint4*>(P.ds_idx + i)) : zero;
+  }
+}
+__device__ __forceinline__ void span_eval(const UstParams& P, Shared& S, const SpanTile& T, long long base, long long b1, uint32_t grant,
+                                          bool ds_smem) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const long long i = base + (long long)j * kStep + 4 * t;
+    if (i >= b1) continue;
+    const uint32_t fl[4] = {T.f[j].x, T.f[j].y, T.f[j].z, T.f[j].w};
+    const uint32_t rv[4] = {T.r[j].x, T.r[j].y, T.r[j].z, T.r[j].w};
+    const uint32_t dv[4] = {T.d[j].x, T.d[j].y, T.d[j].z, T.d[j].w};
+    uint32_t e[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t hb = (T.h[j] >> (8 * k)) & 0xFFu, p = (T.ps[j] >> (8 * k)) & 0xFFu;
+      const uint32_t fk = fl[k] & ~((p & 0x10u) << 12);
+      e[k] = node_entry(P, S, ds_smem, hb, fk, (int)rv[k], dv[k], grant | ((p & 1u) << 16) | ((p & 0xEu) << 21));
+    }
+    uint32_t next4, out4;
+    uint2 act4;
+    pack4(e, next4, act4, out4);
+    __stcs(reinterpret_cast<uint32_t*>(P.next + i), next4);
+    __stcs(reinterpret_cast<uint2*>(P.actions + i), act4);
+    if (P.outcome) __stcs(reinterpret_cast<uint32_t*>(P.outcome + i), out4);
+  }
+}
+__device__ void uniform_span(const UstParams& P, Shared& S, long long b0, long long b1, uint32_t grant) {
   const bool ds_smem = P.n_ds <= kDsSmem;
-  for (long long base = b0; base < b1; base += (long long)U * kStep) {
-    uint32_t h[U], ps[U];
-    uint4 f[U], r[U], d[U];
-#pragma unroll
-    for (int j = 0; j < U; j++) {
-      const long long i = base + (long long)j * kStep + 4 * t;
-      const bool v = i < b1;   // warp-uniform: spans are multiples of kStep
-      h[j] = v ? __ldg(reinterpret_cast<const uint32_t*>(P.hot + i)) : 0x0E0E0E0Eu;
-      ps[j] = (v && P.podsum) ? __ldcs(reinterpret_cast<const uint32_t*>(P.podsum + i)) : 0u;
-      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-      f[j] = v ? __ldcs(reinterpret_cast<const uint4*>(P.flags + i)) : zero;
-      r[j] = v ? __ldcs(reinterpret_cast<const uint4*>(P.pod_rev + i)) : zero;
-      d[j] = v ? __ldcs(reinterpret_cast<const uint4*>(P.ds_idx + i)) : zero;
-    }
-#pragma unroll
-    for (int j = 0; j < U; j++) {
-      const long long i = base + (long long)j * kStep + 4 * t;
-      if (i >= b1) continue;
-      const uint32_t fl[4] = {f[j].x, f[j].y, f[j].z, f[j].w};
-      const uint32_t rv[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
-      const uint32_t dv[4] = {d[j].x, d[j].y, d[j].z, d[j].w};
-      uint32_t e[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t hb = (h[j] >> (8 * k)) & 0xFFu, p = (ps[j] >> (8 * k)) & 0xFFu;
-        const uint32_t fk = fl[k] & ~((p & 0x10u) << 12);
-        e[k] = node_entry(P, S, ds_smem, hb, fk, (int)rv[k], dv[k], grant | ((p & 1u) << 16) | ((p & 0xEu) << 21));
-      }
-      uint32_t next4, out4;
-      uint2 act4;
-      pack4(e, next4, act4, out4);
-      __stcs(reinterpret_cast<uint32_t*>(P.next + i), next4);
-      __stcs(reinterpret_cast<uint2*>(P.actions + i), act4);
-      if (P.outcome) __stcs(reinterpret_cast<uint32_t*>(P.outcome + i), out4);
-    }
+  constexpr long long kIter = 2LL * kStep;
+  SpanTile A, B;
+  span_load(P, A, b0, b1);
+  for (long long base = b0; base < b1; base += 2 * kIter) {
+    span_load(P, B, base + kIter, b1);           // (all-invalid past the end: no loads are issued)
+    span_eval(P, S, A, base, b1, grant, ds_smem);
+    span_load(P, A, base + 2 * kIter, b1);
+    span_eval(P, S, B, base + kIter, b1, grant, ds_smem);
   }
 }
 
@@ -270,9 +284,38 @@ __device__ void redo_steps(const UstParams& P, Shared& S, int tile, int s0, int 
   long long running = 0, full_end = b0;
   if (!aborting) {
     full_end = b0 + ((b1 - b0) / kStep) * kStep;
-    if (full_end > b0) uniform_span<kRedoUnroll>(P, S, b0, full_end, grant);
+    if (full_end > b0) uniform_span(P, S, b0, full_end, grant);
   }
   for (long long base = full_end; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
+}
+
+// Re-evaluate the tiles [ta, tb) - a contiguous run owned by one CTA when many tiles are redone. Without an abort and
+// with tiles that are whole steps, the tiles before the cut and the tiles behind it are two node ranges that go
+// through the pipelined span as a whole; the cut tile takes the ordered path.
+__device__ void redo_range(const UstParams& P, Shared& S, int ta, int tb) {
+  const int tn = P.tile_nodes;
+  const int steps_per_tile = (tn + kStep - 1) / kStep;
+  const bool aborting = S.abort_key != ~0ull;
+  if (aborting || tn % kStep != 0) {
+    for (int tile = ta; tile < tb; tile++) { redo_steps(P, S, tile, 0, steps_per_tile); __syncthreads(); }
+    return;
+  }
+  const bool slotted = P.active && !P.requestor;
+  const int cut = slotted ? S.cut : 0x7FFFFFFF;
+  for (int part = 0; part < 2; part++) {
+    const int x = part == 0 ? ta : (cut + 1 > ta ? cut + 1 : ta);
+    const int y = part == 0 ? (cut < tb ? cut : tb) : tb;
+    if (x >= y) continue;
+    const uint32_t grant = (slotted && part == 0) ? UST_W_GRANTED : 0u;
+    const long long b0 = (long long)x * tn;
+    long long b1 = (long long)y * tn;
+    if (b1 > P.n) b1 = P.n;
+    const long long full_end = b0 + ((b1 - b0) / kStep) * kStep;
+    if (full_end > b0) uniform_span(P, S, b0, full_end, grant);
+    long long running = 0;
+    for (long long base = full_end; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
+  }
+  if (cut >= ta && cut < tb) { __syncthreads(); redo_steps(P, S, cut, 0, steps_per_tile); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -327,11 +370,10 @@ __global__ void __maxnreg__(96) ust_verify_kernel(const __grid_constant__ UstPar
   const int m = last - first + 1;
   const int steps_per_tile = (P.tile_nodes + kStep - 1) / kStep;
   if (m >= (int)gridDim.x) {
-    // many tiles: whole tiles per CTA
-    for (int tile = first + (int)blockIdx.x; tile <= last; tile += (int)gridDim.x) {
-      redo_steps(P, S, tile, 0, steps_per_tile);
-      __syncthreads();
-    }
+    // many tiles: a contiguous run per CTA
+    const int per = (m + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int ta = first + (int)blockIdx.x * per, tb = ta + per < last + 1 ? ta + per : last + 1;
+    if (ta < tb) redo_range(P, S, ta, tb);
   } else {
     // a few tiles (the steady state: the one tile the budget cuts through): one step per CTA, so that the redo costs
     // one load round trip instead of one per step

@@ -15,15 +15,13 @@ timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&
 tail -5 gpurun_out/pytest_gpu.log
 echo "== quick, no stamps"; ARGS="" q X=1
 echo "== quick, stamps"; ARGS="" q UST_STAMPS=148
-echo "== quick, no stamps again"; ARGS="" q X=1
 echo "== cut hinted, no stamps"; ARGS="--maxpar 0 --maxunav 30%" q X=1
 echo "== cut no hint, stamps"; ARGS="--maxpar 0 --maxunav 30%" q UST_NO_HINT=1 UST_STAMPS=148
-echo "== 100k stamps"; ARGS="--nodes 100000" q UST_STAMPS=148
 echo "== 100k no stamps"; ARGS="--nodes 100000" q X=1
 echo "== full bench"
-/usr/bin/time -v timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench exit $?"
-grep -E "Elapsed|Maximum resident" gpurun_out/bench_full.err; tail -3 gpurun_out/bench_full.err | cut -c1-300
-cut -c1-600 gpurun_out/bench_full.json
+T0=$(date +%s); timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench exit $? in $(( $(date +%s) - T0 )) s"
+tail -3 gpurun_out/bench_full.err | cut -c1-300
+python -c "import json;d=json.load(open('gpurun_out/bench_full.json'));print({k:d[k] for k in ('value','ms_per_step','gpu_launches','verified_vs_oracle')}, d['roofline']['frac'], d['e2e'], d.get('e2e_delta')); print(json.dumps(d.get('by_config'), indent=1))"
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench_full.err
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
