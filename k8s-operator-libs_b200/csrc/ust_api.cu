@@ -190,7 +190,9 @@ static int ensure_tables(ust_handle* h, const ust_policy* p, cudaStream_t st) {
 // full-size tiles would leave SMs without work. One persistent CTA per SM, never more CTAs than tiles.
 static int pick_tile_nodes(const ust_handle* h, int64_t n) {
   int tn = UST_TILE_NODES;
-  while (tn > 128 && n / tn < 2LL * h->num_sms) { tn = (tn / 2) & ~127; if (tn < 128) tn = 128; }  // multiples of 128 nodes
+  // at least one tile per SM; a CTA keeps up to UST_STAGES tiles in flight at once, so a small snapshot is one load
+  // round trip whatever its tile size - and larger tiles mean larger (more efficient) bulk copies
+  while (tn > 128 && n / tn < (int64_t)h->num_sms) { tn = (tn / 2) & ~127; if (tn < 128) tn = 128; }  // multiples of 128 nodes
   return tn;
 }
 static int pick_grid(const ust_handle* h, int tiles) {
