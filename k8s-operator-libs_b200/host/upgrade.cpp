@@ -295,15 +295,13 @@ Error ClusterUpgradeStateManagerImpl::Encode(const ClusterUpgradeState& s, const
     if (!isNodeConditionReady(n)) hot |= UST_HOT_NOT_READY;
     if (SkipNodeUpgrade(n)) hot |= UST_HOT_SKIP;
     if (IsUpgradeRequested(n)) f |= UST_F_UPGRADE_REQUESTED;
-    bool waiting = false;
-    if (Error err = SafeDriverLoadManager->IsWaitingForSafeDriverLoad(&n, &waiting)) return err;
-    if (waiting) f |= UST_F_SAFE_LOAD;
     if (n.Annotations.count(GetUpgradeInitialStateAnnotationKey())) f |= UST_F_INITIAL_STATE_ANNO;
     if (IsNodeInRequestorMode(n)) f |= UST_F_REQUESTOR_MODE;
     // ValidationManager.Validate is an actuator with side effects: Replay calls it, at the reference's point in
     // the pass order, and drops the transition when it reports "not done" (common_manager.go:587-596)
     f |= UST_F_VALIDATION_DONE;
     int32_t rev = 0, ds = -1;
+    bool synced = false;
     if (ns->IsOrphanedPod()) {
       f |= UST_F_POD_ORPHANED;
     } else {
@@ -319,8 +317,28 @@ Error ClusterUpgradeStateManagerImpl::Encode(const ClusterUpgradeState& s, const
       std::string podHash;
       if (ns->DriverPod == nullptr || PodManager->GetPodControllerRevisionHash(ns->DriverPod, &podHash) || dsHashError[(size_t)ds])
         hot |= UST_HOT_REVISION_HASH_ERROR;  // pod_manager.go:84-89, :108-110
-      else
+      else {
         rev = internHash(podHash);
+        synced = rev == e.ds_rev[(size_t)ds];
+      }
+    }
+    // IsWaitingForSafeDriverLoad: the reference consults it in the unknown / upgrade-done passes only
+    // (common_manager.go:240) and returns its error there; the pod-restart and validation passes call UnblockLoading
+    // unconditionally (:477, :581), a no-op unless the node is waiting - there the predicate only selects whether the
+    // call is replayed, and an error from it selects "replay".
+    if (code == UST_STATE_UNKNOWN || code == UST_STATE_DONE) {
+      bool waiting = false;
+      if (Error err = SafeDriverLoadManager->IsWaitingForSafeDriverLoad(&n, &waiting)) {
+        if (!(hot & UST_HOT_REVISION_HASH_ERROR)) {  // podInSyncWithDS fails first (:234-238)
+          e.deferred[e.entries.size()] = *err;
+          hot |= UST_HOT_REVISION_HASH_ERROR;         // same abort point: before any action on the node
+        }
+      } else if (waiting) {
+        f |= UST_F_SAFE_LOAD;
+      }
+    } else if (code == UST_STATE_VALIDATION_REQUIRED || (code == UST_STATE_POD_RESTART_REQUIRED && synced)) {
+      bool waiting = false;
+      if (SafeDriverLoadManager->IsWaitingForSafeDriverLoad(&n, &waiting) || waiting) f |= UST_F_SAFE_LOAD;
     }
     if (const Pod* p = ns->DriverPod) {
       bool ready = p->Phase == "Running" && !p->ContainerStatuses.empty();  // common_manager.go:617-630
@@ -366,7 +384,10 @@ Error ClusterUpgradeStateManagerImpl::Replay(const EncodedSnapshot& enc, const D
   const bool requestor = opts_.Requestor.UseMaintenanceOperator;
   auto setState = [&](size_t i) { return NodeUpgradeStateProvider->ChangeNodeUpgradeState(enc.entries[i]->Node, StateNameOfCode(next_state[i])); };
   auto anno = [&](size_t i, const std::string& k, const char* v) { return NodeUpgradeStateProvider->ChangeNodeUpgradeAnnotation(enc.entries[i]->Node, k, v); };
-  auto abortError = [&]() -> Error { return Errorf(ust_last_error(handle_)); };
+  auto abortError = [&](long long idx = -1) -> Error {
+    if (idx >= 0) { auto it = enc.deferred.find((size_t)idx); if (it != enc.deferred.end()) return Errorf(it->second); }
+    return Errorf(ust_last_error(handle_));
+  };
 
   size_t i = 0;
   for (int pass = 0; pass < 12; pass++) {
@@ -384,7 +405,7 @@ Error ClusterUpgradeStateManagerImpl::Replay(const EncodedSnapshot& enc, const D
       if (code == UST_STATE_UNCORDON_REQUIRED) continue;  // two sub-passes below
       const unsigned a = actions[i];
       Node* node = enc.entries[i]->Node;
-      if (a & UST_A_ERROR) return abortError();
+      if (a & UST_A_ERROR) return abortError((long long)i);
       if (a & UST_A_CLEAR_UPGRADE_REQUESTED)
         if (Error e = anno(i, GetUpgradeRequestedAnnotationKey(), kNullString)) return e;
       if (a & UST_A_SET_INITIAL_STATE_ANNO)
@@ -398,7 +419,9 @@ Error ClusterUpgradeStateManagerImpl::Replay(const EncodedSnapshot& enc, const D
         if (Error e = ValidationManager->Validate(node, &done)) return e;
         if (!done) continue;  // "Validations not complete on the node"
       }
-      if (a & UST_A_NM_CREATE_OR_DELETE) {}  // NodeMaintenance CRUD is the requestor's own client call (upgrade_requestor.go:296)
+      if ((a & UST_A_NM_CREATE_OR_DELETE) && code == UST_STATE_UPGRADE_REQUIRED)  // upgrade_requestor.go:296
+        if (K8sClient != nullptr)
+          if (Error e = K8sClient->CreateOrUpdateNodeMaintenance(enc.entries[i])) return e;
       if ((a & UST_A_REQUESTOR_ANNO_CHANGE) && code == UST_STATE_UPGRADE_REQUIRED)
         if (Error e = anno(i, GetUpgradeRequestorModeAnnotationKey(), kTrueString)) return Errorf("failed annotate node for 'upgrade-requestor-mode'. " + *e);
       if (a & UST_A_SET_STATE) {
@@ -455,13 +478,15 @@ Error ClusterUpgradeStateManagerImpl::Replay(const EncodedSnapshot& enc, const D
             if (Error e = setState(k)) return e;
             if (Error e = anno(k, GetUpgradeRequestorModeAnnotationKey(), kNullString))
               return Errorf("failed to remove '" + GetUpgradeRequestorModeAnnotationKey() + "' annotation . " + *e);
+            if (K8sClient != nullptr)
+              if (Error e = K8sClient->DeleteOrUpdateNodeMaintenance(enc.entries[k])) return e;  // upgrade_requestor.go:482
           }
         }
       } break;
       default: break;
     }
   }
-  if (abi_rc != UST_OK) return abortError();
+  if (abi_rc != UST_OK) return abortError(counters.error_index);
   return std::nullopt;
 }
 

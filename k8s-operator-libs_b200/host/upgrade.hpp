@@ -169,6 +169,10 @@ struct K8sClient {
   virtual Error ListDaemonSets(const std::string& ns, const StringMap& labels, std::vector<DaemonSet*>* out) = 0;
   virtual Error ListPods(const std::string& ns, const StringMap& labels, std::vector<Pod*>* out) = 0;
   virtual Error GetNodeMaintenance(const std::string& nodeName, NodeMaintenance** out) { *out = nullptr; return std::nullopt; }
+  // requestor mode: createOrUpdateNodeMaintenance (upgrade_requestor.go:320-368) / deleteOrUpdateNodeMaintenance
+  // (:370-414), the NodeMaintenance CRUD of the upgrade-required and uncordon-required passes
+  virtual Error CreateOrUpdateNodeMaintenance(NodeUpgradeState* nodeState) { (void)nodeState; return std::nullopt; }
+  virtual Error DeleteOrUpdateNodeMaintenance(NodeUpgradeState* nodeState) { (void)nodeState; return std::nullopt; }
 };
 
 struct RequestorOptions { bool UseMaintenanceOperator = false; };  // upgrade_requestor.go:527-546 (the switch only)
@@ -180,6 +184,7 @@ struct EncodedSnapshot {
   std::vector<uint8_t> state;
   std::vector<uint32_t> flags;
   std::vector<int32_t> pod_rev, ds_idx, ds_rev;
+  std::map<size_t, std::string> deferred;  // an error the reference raises when it reaches the node (IsWaitingForSafeDriverLoad)
   ust_policy policy{};
 };
 
