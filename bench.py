@@ -521,6 +521,42 @@ def main():
         d_s = time.time() - t0
         delta = {"value": n * steps_d / d_s, "unit": "nodes/s", "ms_per_step": d_s / steps_d * 1e3, "changed_nodes_per_step": m,
                  "h2d_bytes_per_step": 21 * m + 4 * n_ds, "d2h_bytes_per_step": 3 * n + C.sizeof(abi.Counters), "steps": steps_d}
+        # ... and with sparse outputs (ust_apply_state_delta_sparse): only the outputs that differ from the previous
+        # call's come back. The caller's full arrays, patched with them, are checked against the dense result.
+        cap = n // 8
+        sp = (ustlib.pinned_array(cap + 1, np.int64), ustlib.pinned_array(cap + 1, np.uint8), ustlib.pinned_array(cap + 1, np.uint16))
+        full_next, full_act = out[0].copy(), out[1].copy()
+        cur = {k: soa[k].copy() for k in ("state", "flags", "pod_rev", "ds_idx")}
+        for idx, ch in deltas:   # the dense leg applied these in order: replay them on the host copy
+            for k in cur:
+                cur[k][idx] = ch[k]
+        more = []
+        for _ in range(steps_d + 1):
+            idx = rng.choice(n, size=m, replace=False).astype(np.int64)
+            src = rng.integers(0, n, size=m)
+            more.append((idx, {k: np.ascontiguousarray(soa[k][src]) for k in ("state", "flags", "pod_rev", "ds_idx")}))
+        n_outs = []
+        t_sparse = 0.0
+        for j, (idx, ch) in enumerate(more):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            rc, n_out, oi, on, oa, _ = h.apply_state_delta_sparse(pol, idx, ch, soa["ds_rev"], cap, out=sp)
+            dt = time.time() - t0
+            assert rc == 0 and n_out <= cap, (rc, n_out, h.last_error())
+            full_next[oi[:n_out]] = on[:n_out]
+            full_act[oi[:n_out]] = oa[:n_out]
+            for k in cur:
+                cur[k][idx] = ch[k]
+            if j > 0:      # the first call warms the buffers up
+                t_sparse += dt
+                n_outs.append(n_out)
+        ref = helpers.oracle_apply(pol, dict(cur, ds_rev=soa["ds_rev"]), variant=1)
+        sparse_ok = bool(np.array_equal(full_next, ref[1]) and np.array_equal(full_act, ref[2]))
+        assert sparse_ok, "sparse delta outputs, patched into the previous outputs, differ from the oracle"
+        delta["sparse_outputs"] = {"ms_per_step": t_sparse / steps_d * 1e3, "value": n * steps_d / t_sparse, "unit": "nodes/s",
+                                   "changed_outputs_per_step": float(np.mean(n_outs)), "h2d_bytes_per_step": 21 * m + 4 * n_ds,
+                                   "d2h_bytes_per_step": int(11 * np.mean(n_outs)) + 8 + C.sizeof(abi.Counters),
+                                   "entry_point": "ust_apply_state_delta_sparse", "verified_vs_oracle": sparse_ok}
 
     # ---- by_config (N = 1): the other configurations, same timing protocol, each verified on the timed buffers ------
     by_config = None

@@ -169,7 +169,8 @@ enum {
   UST_ERR_MAX_UNAVAILABLE = -5, /* intstr.GetScaledValueFromIntOrPercent fails   upgrade_inplace.go:54-60 */
   UST_ERR_POD_DELETION_SPEC = -6, /* "pod deletion spec should not be empty"     pod_manager.go:132-134 */
   UST_ERR_DS_UNSCHEDULED = -7,  /* "driver DaemonSet should not have Unscheduled pods"  upgrade_state.go:128-131 */
-  UST_ERR_COMM = -8             /* multi-GPU exchange failed */
+  UST_ERR_COMM = -8,            /* multi-GPU exchange failed */
+  UST_ERR_TRUNCATED = -9        /* ust_apply_state_delta_sparse: more changed outputs than the caller's arrays hold */
 };
 
 typedef struct ust_counters {
@@ -264,6 +265,21 @@ int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_cha
                           const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx,
                           int32_t n_ds, const int32_t* ds_rev, uint8_t* next_state, uint16_t* actions,
                           uint8_t* actuator_outcome, ust_counters* out);
+
+/* Delta in, delta out: ust_apply_state_delta with sparse outputs. The previous call on this handle (ust_apply_state,
+ * _packed, _delta or _delta_sparse - whose full next_state / actions the caller still holds) left its outputs on the
+ * device; this call returns only the nodes whose (next_state, actions) differ from them, in node order:
+ * out_idx[k], out_next_state[k], out_actions[k] for k < *n_out. Patching the caller's arrays with them gives exactly what
+ * ust_apply_state_delta would have written - a reconcile with 1 % churn moves ~1 % of the 3 bytes per node back over
+ * PCIe instead of all of them. When more than max_out outputs changed, *n_out holds the count, nothing is written to
+ * the out_* arrays and UST_ERR_TRUNCATED is returned: fetch everything with ust_fetch_outputs. No actuator_outcome.
+ * Reference-level aborts are reported like in ust_apply_state_delta (the sparse outputs are still delivered). */
+int ust_apply_state_delta_sparse(ust_handle* h, const ust_policy* policy, int64_t n_changed, const int64_t* idx,
+                                 const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx,
+                                 int32_t n_ds, const int32_t* ds_rev, int64_t max_out, int64_t* out_idx,
+                                 uint8_t* out_next_state, uint16_t* out_actions, int64_t* n_out, ust_counters* out);
+/* The full outputs of the last call on the resident snapshot (n_nodes entries each). */
+int ust_fetch_outputs(ust_handle* h, uint8_t* next_state, uint16_t* actions);
 
 /* Rollout simulation on the resident snapshot (see ust_apply_state_delta): `steps` reconciles in a row,
  * entirely on the device. After each ApplyState the decisions are fed back into the snapshot under "ideal

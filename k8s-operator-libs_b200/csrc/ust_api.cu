@@ -121,6 +121,14 @@ struct ust_handle {
   DevBuf<uint16_t> s_actions, s_podflags;
   DevBuf<uint8_t> s_podsum;
   DevBuf<unsigned int> s_candtile;   // upgrade candidates per tile of the current call
+  // sparse delta outputs: the previous call's outputs, block counts, compacted entries
+  DevBuf<uint8_t> s_next_prev, sp_next;
+  DevBuf<uint16_t> s_actions_prev, sp_actions;
+  DevBuf<unsigned int> sp_blocks;
+  DevBuf<long long> sp_idx;
+  long long* sp_count_dev = nullptr;
+  long long* sp_count_host = nullptr;  // pinned
+  bool outputs_resident = false;       // s_next / s_actions hold the outputs of the last call on the resident snapshot
   DevBuf<uint64_t> s_uid, s_dsuid;   // BuildState owner join: pod owner UIDs, DaemonSet UID hash table (+ s_dsorder: slot -> index)
   DevBuf<int32_t> s_dsorder;
   DevBuf<long long> d_idx;           // delta updates: indices and values of the changed nodes
@@ -544,6 +552,8 @@ int ust_create(ust_handle** out, int device) {
   if ((e = cudaMalloc(&h->counters_dev, sizeof(ust_counters))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMallocHost(&h->counters_host, sizeof(ust_counters))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMalloc(&h->xchg_dev, UST_V_LEN * sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->sp_count_dev, sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMallocHost(&h->sp_count_host, sizeof(long long))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMemset(h->xchg_dev, 0, UST_V_LEN * sizeof(long long))) != cudaSuccess) return bail("cudaMemset", e);
   if (const char* v = getenv("UST_PDL")) h->pdl = atoi(v) != 0;
   if (const char* v = getenv("UST_STATIC_PCT")) { h->static_pct = atoi(v); if (h->static_pct < 0) h->static_pct = 0; if (h->static_pct > 100) h->static_pct = 100; }
@@ -578,6 +588,9 @@ void ust_destroy(ust_handle* h) {
   if (h->counters_dev) cudaFree(h->counters_dev);
   if (h->counters_host) cudaFreeHost(h->counters_host);
   if (h->xchg_dev) cudaFree(h->xchg_dev);
+  if (h->sp_count_dev) cudaFree(h->sp_count_dev);
+  if (h->sp_count_host) cudaFreeHost(h->sp_count_host);
+  h->s_next_prev.release(); h->sp_next.release(); h->s_actions_prev.release(); h->sp_actions.release(); h->sp_blocks.release(); h->sp_idx.release();
   if (h->ds_count_dev) cudaFree(h->ds_count_dev);
   h->s_hot.release(); h->s_next.release(); h->s_outcome.release(); h->s_flags.release();
   h->s_rev.release(); h->s_ds.release(); h->s_dsrev.release(); h->s_podoff.release(); h->s_dsdesired.release();
@@ -652,8 +665,9 @@ int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const ui
   }
   if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsrev.p, ds_rev, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
   h->resident_n = -1;
+  h->outputs_resident = false;
   auto keep = [&](int rc) {  // the uploaded snapshot stays usable unless the call itself failed (not the policy / the data)
-    if (rc != UST_ERR_CUDA && rc != UST_ERR_INVALID_ARGUMENT && rc != UST_ERR_COMM && rc != UST_ERR_NIL_STATE && !pods) { h->resident_n = n; h->resident_n_ds = n_ds; }
+    if (rc != UST_ERR_CUDA && rc != UST_ERR_INVALID_ARGUMENT && rc != UST_ERR_COMM && rc != UST_ERR_NIL_STATE && !pods) { h->resident_n = n; h->resident_n_ds = n_ds; h->outputs_resident = true; }
     return rc;
   };
   if (!pods && n >= (1 << 19))
@@ -680,15 +694,20 @@ int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const ui
   return keep(finish_with_counters(h, st, out));
 }
 
-int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_changed, const int64_t* idx, const uint8_t* state,
-                          const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds,
-                          const int32_t* ds_rev, uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome,
-                          ust_counters* out) {
-  if (!h) return UST_ERR_INVALID_ARGUMENT;
-  std::lock_guard<std::mutex> g(h->mu);
+// ust_apply_state_delta and ust_apply_state_delta_sparse: scatter the re-encoded nodes into the resident snapshot,
+// evaluate everything, return all outputs (dense) or the outputs that differ from the previous call's (sparse).
+static int delta_common(ust_handle* h, const ust_policy* policy, int64_t n_changed, const int64_t* idx, const uint8_t* state,
+                        const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                        bool sparse, uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome, int64_t max_out,
+                        int64_t* out_idx, int64_t* n_out, ust_counters* out) {
   const int64_t n = h->resident_n;
   if (n < 0) return h->fail(UST_ERR_INVALID_ARGUMENT, "no resident snapshot: call ust_apply_state (without pod lists) first");
-  if (n_changed < 0 || (n_changed > 0 && (!idx || !state || !flags || !pod_rev || !ds_idx)) || (n > 0 && (!next_state || !actions)))
+  if (sparse && !h->outputs_resident)
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "no resident outputs to compare with: the previous call must be an ApplyState on this snapshot");
+  if (n_changed < 0 || (n_changed > 0 && (!idx || !state || !flags || !pod_rev || !ds_idx)))
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (!sparse && n > 0 && (!next_state || !actions)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (sparse && (max_out < 0 || !n_out || (max_out > 0 && (!out_idx || !next_state || !actions))))
     return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
   if (n_ds < 0 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table");
   for (int64_t k = 0; k < n_changed; k++)
@@ -701,7 +720,16 @@ int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_cha
   if (actuator_outcome) UST_CUDA(h, h->s_outcome.reserve(N + 16));
   UST_CUDA(h, h->d_idx.reserve(M + 1)); UST_CUDA(h, h->d_state.reserve(M + 16)); UST_CUDA(h, h->d_flags.reserve(M + 4));
   UST_CUDA(h, h->d_rev.reserve(M + 4)); UST_CUDA(h, h->d_ds.reserve(M + 4));
+  if (sparse) {
+    UST_CUDA(h, h->s_next_prev.reserve(h->s_next.cap));
+    UST_CUDA(h, h->s_actions_prev.reserve(h->s_actions.cap));
+    UST_CUDA(h, h->sp_blocks.reserve((size_t)ust_diff_blocks(n) + 1));
+    UST_CUDA(h, h->sp_idx.reserve((size_t)max_out + 1));
+    UST_CUDA(h, h->sp_next.reserve((size_t)max_out + 16));
+    UST_CUDA(h, h->sp_actions.reserve((size_t)max_out + 8));
+  }
   h->resident_n = -1;  // until the patched snapshot has been evaluated
+  h->outputs_resident = false;
   if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsrev.p, ds_rev, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
   if (M) {
     static_assert(sizeof(long long) == sizeof(int64_t), "index width");
@@ -715,17 +743,74 @@ int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_cha
     if (e) return h->fail(UST_ERR_CUDA, "patch kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
     h->launches += 1;
   }
+  if (sparse) {  // the previous call's outputs step aside; this call writes the other pair of arrays
+    std::swap(h->s_next, h->s_next_prev);
+    std::swap(h->s_actions, h->s_actions_prev);
+  }
   int rc = apply_device(h, policy, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, n_ds, h->s_dsrev.p, nullptr, nullptr, 0,
                         h->s_next.p, h->s_actions.p, actuator_outcome ? h->s_outcome.p : nullptr, nullptr, st);
   if (rc) return rc;
-  if (N) {
-    UST_CUDA(h, cudaMemcpyAsync(next_state, h->s_next.p, N, cudaMemcpyDeviceToHost, st));
-    UST_CUDA(h, cudaMemcpyAsync(actions, h->s_actions.p, N * 2, cudaMemcpyDeviceToHost, st));
-    if (actuator_outcome) UST_CUDA(h, cudaMemcpyAsync(actuator_outcome, h->s_outcome.p, N, cudaMemcpyDeviceToHost, st));
+  if (!sparse) {
+    if (N) {
+      UST_CUDA(h, cudaMemcpyAsync(next_state, h->s_next.p, N, cudaMemcpyDeviceToHost, st));
+      UST_CUDA(h, cudaMemcpyAsync(actions, h->s_actions.p, N * 2, cudaMemcpyDeviceToHost, st));
+      if (actuator_outcome) UST_CUDA(h, cudaMemcpyAsync(actuator_outcome, h->s_outcome.p, N, cudaMemcpyDeviceToHost, st));
+    }
+  } else {
+    int e = ust_launch_diff((long long)n, h->s_next.p, h->s_actions.p, h->s_next_prev.p, h->s_actions_prev.p, h->sp_blocks.p,
+                            h->sp_count_dev, (long long)max_out, h->sp_idx.p, h->sp_next.p, h->sp_actions.p, st);
+    if (e) return h->fail(UST_ERR_CUDA, "diff kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->launches += 3;
+    UST_CUDA(h, cudaMemcpyAsync(h->sp_count_host, h->sp_count_dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    UST_CUDA(h, cudaStreamSynchronize(st));
+    const int64_t cnt = *h->sp_count_host;
+    *n_out = cnt;
+    if (cnt <= max_out && cnt > 0) {
+      UST_CUDA(h, cudaMemcpyAsync(out_idx, h->sp_idx.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+      UST_CUDA(h, cudaMemcpyAsync(next_state, h->sp_next.p, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+      UST_CUDA(h, cudaMemcpyAsync(actions, h->sp_actions.p, (size_t)cnt * 2, cudaMemcpyDeviceToHost, st));
+    }
   }
   rc = finish_with_counters(h, st, out);
-  if (rc != UST_ERR_CUDA && rc != UST_ERR_COMM) { h->resident_n = n; h->resident_n_ds = n_ds; }
+  if (rc != UST_ERR_CUDA && rc != UST_ERR_COMM) { h->resident_n = n; h->resident_n_ds = n_ds; h->outputs_resident = true; }
+  if (sparse && (rc == UST_OK) && *n_out > max_out)
+    return h->fail(UST_ERR_TRUNCATED, "%lld outputs changed, the caller's arrays hold %lld: fetch them with ust_fetch_outputs", (long long)*n_out, (long long)max_out);
   return rc;
+}
+
+int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_changed, const int64_t* idx, const uint8_t* state,
+                          const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds,
+                          const int32_t* ds_rev, uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome,
+                          ust_counters* out) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  return delta_common(h, policy, n_changed, idx, state, flags, pod_rev, ds_idx, n_ds, ds_rev, false, next_state, actions,
+                      actuator_outcome, 0, nullptr, nullptr, out);
+}
+
+int ust_apply_state_delta_sparse(ust_handle* h, const ust_policy* policy, int64_t n_changed, const int64_t* idx,
+                                 const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx,
+                                 int32_t n_ds, const int32_t* ds_rev, int64_t max_out, int64_t* out_idx,
+                                 uint8_t* out_next_state, uint16_t* out_actions, int64_t* n_out, ust_counters* out) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  return delta_common(h, policy, n_changed, idx, state, flags, pod_rev, ds_idx, n_ds, ds_rev, true, out_next_state, out_actions,
+                      nullptr, max_out, out_idx, n_out, out);
+}
+
+int ust_fetch_outputs(ust_handle* h, uint8_t* next_state, uint16_t* actions) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  if (h->resident_n < 0 || !h->outputs_resident) return h->fail(UST_ERR_INVALID_ARGUMENT, "no resident outputs");
+  if (h->resident_n > 0 && (!next_state || !actions)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
+  UST_CUDA(h, cudaSetDevice(h->device));
+  const size_t N = (size_t)h->resident_n;
+  if (N) {
+    UST_CUDA(h, cudaMemcpyAsync(next_state, h->s_next.p, N, cudaMemcpyDeviceToHost, h->stream));
+    UST_CUDA(h, cudaMemcpyAsync(actions, h->s_actions.p, N * 2, cudaMemcpyDeviceToHost, h->stream));
+  }
+  UST_CUDA(h, cudaStreamSynchronize(h->stream));
+  return UST_OK;
 }
 
 int ust_apply_state_packed(ust_handle* h, const ust_policy* policy, int64_t n, const uint8_t* state, const uint32_t* flags,
@@ -752,8 +837,9 @@ int ust_apply_state_packed(ust_handle* h, const ust_policy* policy, int64_t n, c
   if (actuator_outcome) UST_CUDA(h, h->s_outcome.reserve(N + 16));
   if (n_ds) UST_CUDA(h, cudaMemcpyAsync(h->s_dsrev.p, ds_rev, (size_t)n_ds * 4, cudaMemcpyHostToDevice, st));
   h->resident_n = -1;
+  h->outputs_resident = false;
   auto keep = [&](int rc) {
-    if (rc != UST_ERR_CUDA && rc != UST_ERR_INVALID_ARGUMENT && rc != UST_ERR_COMM && rc != UST_ERR_NIL_STATE) { h->resident_n = n; h->resident_n_ds = n_ds; }
+    if (rc != UST_ERR_CUDA && rc != UST_ERR_INVALID_ARGUMENT && rc != UST_ERR_COMM && rc != UST_ERR_NIL_STATE) { h->resident_n = n; h->resident_n_ds = n_ds; h->outputs_resident = true; }
     return rc;
   };
   if (n >= (1 << 19))
@@ -802,6 +888,7 @@ int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps,
     UST_CUDA(h, cudaMalloc(&h->hist_dev, h->hist_cap * sizeof(ust_counters)));
   }
   h->resident_n = -1;
+  h->outputs_resident = false;
   int grid = 8 * h->num_sms;
   for (int32_t k = 0; k < steps; k++) {
     int rc = apply_device(h, policy ? &pol : nullptr, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, h->resident_n_ds,
@@ -820,6 +907,7 @@ int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps,
   cudaError_t ce = cudaStreamSynchronize(st);
   if (ce != cudaSuccess) { h->ws_dirty = true; return h->fail(UST_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(ce)); }
   h->resident_n = n;  // the snapshot now holds the simulated state
+  h->outputs_resident = false;
   int32_t done = steps;
   int rc = UST_OK;
   for (int32_t k = 0; k < steps; k++)
@@ -837,6 +925,7 @@ int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const i
   if (n_pods < 0 || (n_pods > 0 && (!state || !ds_idx)) || n_ds < 0 || (n_ds > 0 && !ds_desired))
     return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
   h->resident_n = -1;  // shares the staging arrays
+  h->outputs_resident = false;
   UST_CUDA(h, cudaSetDevice(h->device));
   StreamDrain drain(h);
   cudaStream_t st = h->stream;
@@ -890,6 +979,7 @@ int ust_build_state_uids(ust_handle* h, int64_t n_pods, const uint8_t* state, co
     tab[2 * s] = x; tab[2 * s + 1] = y; tab_idx[s] = d;
   }
   h->resident_n = -1;  // shares the staging arrays
+  h->outputs_resident = false;
   UST_CUDA(h, cudaSetDevice(h->device));
   StreamDrain drain(h);
   cudaStream_t st = h->stream;

@@ -144,3 +144,8 @@ int ust_launch_feedback(long long n, uint8_t* hot, uint32_t* flags, int32_t* pod
                         const ust_counters* step, int grid, void* stream);
 int ust_launch_widen(long long n, const uint16_t* rev16, const int8_t* ds8, int32_t* rev_out, int32_t* ds_out, int grid,
                      void* stream);
+// sparse outputs of a delta call: nodes whose (next_state, actions) differ from the previous call's, in node order
+int ust_launch_diff(long long n, const uint8_t* next, const uint16_t* actions, const uint8_t* prev_next, const uint16_t* prev_actions,
+                    unsigned int* block_count, long long* n_out, long long cap, long long* out_idx, uint8_t* out_next,
+                    uint16_t* out_actions, void* stream);
+int ust_diff_blocks(long long n);

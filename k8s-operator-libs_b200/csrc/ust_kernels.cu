@@ -771,6 +771,106 @@ __global__ void __launch_bounds__(kThreads) ust_widen_kernel(long long n, const 
     ds_out[i] = (int32_t)__ldcs(ds8 + i);
   }
 }
+// Sparse outputs of a delta call: the nodes whose (next_state, actions) differ from the previous call's,
+// compacted in node order. Three launches: per-block counts, a one-CTA scan of the block counts, the ordered write.
+// 6 B/node read twice; the alternative is 3 B/node over PCIe.
+constexpr int kDiffBlock = 4096;  // nodes per CTA: 16 per thread
+__device__ __forceinline__ unsigned diff_mask16(const uint8_t* next, const uint16_t* act, const uint8_t* pnext, const uint16_t* pact,
+                                                long long i0, long long n) {
+  unsigned m = 0;
+  if (i0 + 16 <= n) {
+    const uint4 a = __ldcs(reinterpret_cast<const uint4*>(next + i0)), b = __ldcs(reinterpret_cast<const uint4*>(pnext + i0));
+    const uint4 c0 = __ldcs(reinterpret_cast<const uint4*>(act + i0)), c1 = __ldcs(reinterpret_cast<const uint4*>(act + i0 + 8));
+    const uint4 d0 = __ldcs(reinterpret_cast<const uint4*>(pact + i0)), d1 = __ldcs(reinterpret_cast<const uint4*>(pact + i0 + 8));
+    const uint32_t x[4] = {a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w};
+    const uint32_t y[8] = {c0.x ^ d0.x, c0.y ^ d0.y, c0.z ^ d0.z, c0.w ^ d0.w, c1.x ^ d1.x, c1.y ^ d1.y, c1.z ^ d1.z, c1.w ^ d1.w};
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const bool dn = ((x[k >> 2] >> (8 * (k & 3))) & 0xFFu) != 0;
+      const bool da = ((y[k >> 1] >> (16 * (k & 1))) & 0xFFFFu) != 0;
+      m |= (dn || da ? 1u : 0u) << k;
+    }
+  } else {
+    for (int k = 0; k < 16; k++)
+      if (i0 + k < n && (next[i0 + k] != pnext[i0 + k] || act[i0 + k] != pact[i0 + k])) m |= 1u << k;
+  }
+  return m;
+}
+__global__ void __launch_bounds__(kThreads) ust_diff_count_kernel(long long n, const uint8_t* __restrict__ next, const uint16_t* __restrict__ act,
+                                                                  const uint8_t* __restrict__ pnext, const uint16_t* __restrict__ pact,
+                                                                  unsigned int* __restrict__ block_count) {
+  __shared__ unsigned int tot;
+  if (threadIdx.x == 0) tot = 0;
+  __syncthreads();
+  const long long i0 = (long long)blockIdx.x * kDiffBlock + 16 * threadIdx.x;
+  unsigned c = i0 < n ? __popc(diff_mask16(next, act, pnext, pact, i0, n)) : 0u;
+  c = __reduce_add_sync(kFull, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&tot, c);
+  __syncthreads();
+  if (threadIdx.x == 0) block_count[blockIdx.x] = tot;
+}
+// exclusive scan of the block counts in place (one CTA); total -> *n_out
+__global__ void __launch_bounds__(1024) ust_diff_scan_kernel(int blocks, unsigned int* block_count, long long* n_out) {
+  __shared__ unsigned long long part[32];
+  __shared__ unsigned long long carry;
+  const int t = threadIdx.x;
+  if (t == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < blocks; b0 += 1024) {
+    const int b = b0 + t;
+    const unsigned long long v = b < blocks ? block_count[b] : 0ull;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(kFull, incl, o);
+      if ((t & 31) >= o) incl += u;
+    }
+    if ((t & 31) == 31) part[t >> 5] = incl;
+    __syncthreads();
+    unsigned long long before = carry, tot = 0;
+    for (int w = 0; w < 32; w++) { if (w < (t >> 5)) before += part[w]; tot += part[w]; }
+    // offsets fit 32 bits per launch range: the API caps a sparse call at 2^31 changed outputs
+    if (b < blocks) block_count[b] = (unsigned int)(before + incl - v);
+    __syncthreads();
+    if (t == 0) carry += tot;
+    __syncthreads();
+  }
+  if (t == 0) *n_out = (long long)carry;
+}
+__global__ void __launch_bounds__(kThreads) ust_diff_write_kernel(long long n, const uint8_t* __restrict__ next, const uint16_t* __restrict__ act,
+                                                                  const uint8_t* __restrict__ pnext, const uint16_t* __restrict__ pact,
+                                                                  const unsigned int* __restrict__ block_off, long long cap,
+                                                                  long long* __restrict__ out_idx, uint8_t* __restrict__ out_next,
+                                                                  uint16_t* __restrict__ out_act) {
+  __shared__ unsigned int wtot[kWarps];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const long long i0 = (long long)blockIdx.x * kDiffBlock + 16 * t;
+  const unsigned m = i0 < n ? diff_mask16(next, act, pnext, pact, i0, n) : 0u;
+  const unsigned c = __popc(m);
+  unsigned incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned u = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  unsigned before = 0;
+  for (int w = 0; w < warp; w++) before += wtot[w];
+  long long pos = (long long)block_off[blockIdx.x] + before + incl - c;
+  unsigned mm = m;
+  while (mm) {
+    const int k = __ffs(mm) - 1;
+    mm &= mm - 1;
+    if (pos < cap) {
+      out_idx[pos] = i0 + k;
+      out_next[pos] = next[i0 + k];
+      out_act[pos] = act[i0 + k];
+    }
+    pos++;
+  }
+}
+
 }  // namespace
 
 int ust_launch_verify(const UstParams& p, int grid, void* stream, int pdl) {
@@ -832,3 +932,15 @@ int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* own
   ust_build_state_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_ds, ds_desired, ds_count, ws, out);
   return (int)cudaGetLastError();
 }
+int ust_launch_diff(long long n, const uint8_t* next, const uint16_t* actions, const uint8_t* prev_next, const uint16_t* prev_actions,
+                    unsigned int* block_count, long long* n_out, long long cap, long long* out_idx, uint8_t* out_next,
+                    uint16_t* out_actions, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long blocks = (n + kDiffBlock - 1) / kDiffBlock;
+  if (blocks > 0) ust_diff_count_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(n, next, actions, prev_next, prev_actions, block_count);
+  ust_diff_scan_kernel<<<1, 1024, 0, st>>>((int)blocks, block_count, n_out);
+  if (blocks > 0)
+    ust_diff_write_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(n, next, actions, prev_next, prev_actions, block_count, cap, out_idx, out_next, out_actions);
+  return (int)cudaGetLastError();
+}
+int ust_diff_blocks(long long n) { return (int)((n + kDiffBlock - 1) / kDiffBlock); }

@@ -2,6 +2,7 @@
 #include "upgrade.hpp"
 
 #include <algorithm>
+#include <unordered_map>
 #include <cstring>
 
 namespace upgrade {
@@ -233,6 +234,7 @@ Error ClusterUpgradeStateManagerImpl::BuildState(const std::string& ns, const St
     auto nus = std::make_unique<NodeUpgradeState>();
     nus->Node = node;
     nus->DriverPod = pod;
+    nus->ListIndex = (int64_t)i;
     nus->DriverDaemonSet = IsOrphanedPod(*pod) ? nullptr : daemonSets[pod->OwnerReferences[0].UID];
     if (opts_.Requestor.UseMaintenanceOperator)
       if (Error e = K8sClient->GetNodeMaintenance(node->Name, &nus->NodeMaintenance)) return Errorf("failed while trying to fetch nodeMaintennace obj: " + *e);
@@ -279,6 +281,73 @@ static void flatten_policy(const DriverUpgradePolicySpec& p, bool podDeletionEna
   c->use_maintenance_operator = useMaintenanceOperator;
 }
 
+// One snapshot entry -> its four SoA values. `ds` / `dsErr`: index of its DaemonSet in the table (-1 = orphaned) and
+// whether that DaemonSet's revision-hash lookup failed; `deferred` receives an error the reference would raise when
+// its pass reaches the node.
+Error ClusterUpgradeStateManagerImpl::encodeOne(const NodeUpgradeState* ns, int code, int32_t ds, bool dsErr,
+                                                std::map<std::string, int32_t>* intern, const std::vector<int32_t>& ds_rev,
+                                                uint8_t* hot_out, uint32_t* flags_out, int32_t* rev_out, std::string* deferred) {
+  auto internHash = [&](const std::string& h) { return intern->emplace(h, (int32_t)intern->size() + 1).first->second; };
+  const Node& n = *ns->Node;
+  uint8_t hot = (uint8_t)code;
+  uint32_t f = 0;
+  if (IsNodeUnschedulable(n)) hot |= UST_HOT_UNSCHEDULABLE;
+  if (!isNodeConditionReady(n)) hot |= UST_HOT_NOT_READY;
+  if (SkipNodeUpgrade(n)) hot |= UST_HOT_SKIP;
+  if (IsUpgradeRequested(n)) f |= UST_F_UPGRADE_REQUESTED;
+  if (n.Annotations.count(GetUpgradeInitialStateAnnotationKey())) f |= UST_F_INITIAL_STATE_ANNO;
+  if (IsNodeInRequestorMode(n)) f |= UST_F_REQUESTOR_MODE;
+  // ValidationManager.Validate is an actuator with side effects: Replay calls it, at the reference's point in
+  // the pass order, and drops the transition when it reports "not done" (common_manager.go:587-596)
+  f |= UST_F_VALIDATION_DONE;
+  int32_t rev = 0;
+  bool synced = false;
+  if (ns->IsOrphanedPod()) {
+    f |= UST_F_POD_ORPHANED;
+  } else {
+    std::string podHash;
+    if (ns->DriverPod == nullptr || PodManager->GetPodControllerRevisionHash(ns->DriverPod, &podHash) || dsErr)
+      hot |= UST_HOT_REVISION_HASH_ERROR;  // pod_manager.go:84-89, :108-110
+    else {
+      rev = internHash(podHash);
+      synced = rev == ds_rev[(size_t)ds];
+    }
+  }
+  // IsWaitingForSafeDriverLoad: the reference consults it in the unknown / upgrade-done passes only
+  // (common_manager.go:240) and returns its error there; the pod-restart and validation passes call UnblockLoading
+  // unconditionally (:477, :581), a no-op unless the node is waiting - there the predicate only selects whether the
+  // call is replayed, and an error from it selects "replay".
+  if (code == UST_STATE_UNKNOWN || code == UST_STATE_DONE) {
+    bool waiting = false;
+    if (Error err = SafeDriverLoadManager->IsWaitingForSafeDriverLoad(&n, &waiting)) {
+      if (!(hot & UST_HOT_REVISION_HASH_ERROR)) {  // podInSyncWithDS fails first (:234-238)
+        *deferred = *err;
+        hot |= UST_HOT_REVISION_HASH_ERROR;         // same abort point: before any action on the node
+      }
+    } else if (waiting) {
+      f |= UST_F_SAFE_LOAD;
+    }
+  } else if (code == UST_STATE_VALIDATION_REQUIRED || (code == UST_STATE_POD_RESTART_REQUIRED && synced)) {
+    bool waiting = false;
+    if (SafeDriverLoadManager->IsWaitingForSafeDriverLoad(&n, &waiting) || waiting) f |= UST_F_SAFE_LOAD;
+  }
+  if (const Pod* p = ns->DriverPod) {
+    bool ready = p->Phase == "Running" && !p->ContainerStatuses.empty();  // common_manager.go:617-630
+    for (const auto& cs : p->ContainerStatuses) ready = ready && cs.Ready;
+    if (ready) f |= UST_F_POD_READY;
+    if (isDriverPodFailing(*p)) f |= UST_F_POD_FAILING;
+    if (p->DeletionTimestampSet) f |= UST_F_POD_TERMINATING;
+  }
+  if (ns->NodeMaintenance) {
+    f |= UST_F_NM_PRESENT;
+    if (ns->NodeMaintenance->ReadyConditionWithReasonReady) f |= UST_F_NM_READY;
+  }
+  *hot_out = hot;
+  *flags_out = f;
+  *rev_out = rev;
+  return std::nullopt;
+}
+
 Error ClusterUpgradeStateManagerImpl::Encode(const ClusterUpgradeState& s, const DriverUpgradePolicySpec& policy, EncodedSnapshot* out) {
   EncodedSnapshot& e = *out;
   e = EncodedSnapshot();
@@ -286,71 +355,24 @@ Error ClusterUpgradeStateManagerImpl::Encode(const ClusterUpgradeState& s, const
   std::map<std::string, int32_t> intern;
   std::map<const DaemonSet*, int32_t> dsIndex;
   std::vector<bool> dsHashError;
-  auto internHash = [&](const std::string& h) { return intern.emplace(h, (int32_t)intern.size() + 1).first->second; };
   auto add = [&](NodeUpgradeState* ns, int code) -> Error {
-    const Node& n = *ns->Node;
-    uint8_t hot = (uint8_t)code;
-    uint32_t f = 0;
-    if (IsNodeUnschedulable(n)) hot |= UST_HOT_UNSCHEDULABLE;
-    if (!isNodeConditionReady(n)) hot |= UST_HOT_NOT_READY;
-    if (SkipNodeUpgrade(n)) hot |= UST_HOT_SKIP;
-    if (IsUpgradeRequested(n)) f |= UST_F_UPGRADE_REQUESTED;
-    if (n.Annotations.count(GetUpgradeInitialStateAnnotationKey())) f |= UST_F_INITIAL_STATE_ANNO;
-    if (IsNodeInRequestorMode(n)) f |= UST_F_REQUESTOR_MODE;
-    // ValidationManager.Validate is an actuator with side effects: Replay calls it, at the reference's point in
-    // the pass order, and drops the transition when it reports "not done" (common_manager.go:587-596)
-    f |= UST_F_VALIDATION_DONE;
-    int32_t rev = 0, ds = -1;
-    bool synced = false;
-    if (ns->IsOrphanedPod()) {
-      f |= UST_F_POD_ORPHANED;
-    } else {
+    int32_t ds = -1;
+    bool dsErr = false;
+    if (!ns->IsOrphanedPod()) {
       auto it = dsIndex.find(ns->DriverDaemonSet);
       if (it == dsIndex.end()) {
         std::string dsHash;
         const bool bad = (bool)PodManager->GetDaemonsetControllerRevisionHash(ns->DriverDaemonSet, &dsHash);  // once per DaemonSet
         it = dsIndex.emplace(ns->DriverDaemonSet, (int32_t)e.ds_rev.size()).first;
-        e.ds_rev.push_back(bad ? 0 : internHash(dsHash));
+        e.ds_rev.push_back(bad ? 0 : intern.emplace(dsHash, (int32_t)intern.size() + 1).first->second);
         dsHashError.push_back(bad);
       }
       ds = it->second;
-      std::string podHash;
-      if (ns->DriverPod == nullptr || PodManager->GetPodControllerRevisionHash(ns->DriverPod, &podHash) || dsHashError[(size_t)ds])
-        hot |= UST_HOT_REVISION_HASH_ERROR;  // pod_manager.go:84-89, :108-110
-      else {
-        rev = internHash(podHash);
-        synced = rev == e.ds_rev[(size_t)ds];
-      }
+      dsErr = dsHashError[(size_t)ds];
     }
-    // IsWaitingForSafeDriverLoad: the reference consults it in the unknown / upgrade-done passes only
-    // (common_manager.go:240) and returns its error there; the pod-restart and validation passes call UnblockLoading
-    // unconditionally (:477, :581), a no-op unless the node is waiting - there the predicate only selects whether the
-    // call is replayed, and an error from it selects "replay".
-    if (code == UST_STATE_UNKNOWN || code == UST_STATE_DONE) {
-      bool waiting = false;
-      if (Error err = SafeDriverLoadManager->IsWaitingForSafeDriverLoad(&n, &waiting)) {
-        if (!(hot & UST_HOT_REVISION_HASH_ERROR)) {  // podInSyncWithDS fails first (:234-238)
-          e.deferred[e.entries.size()] = *err;
-          hot |= UST_HOT_REVISION_HASH_ERROR;         // same abort point: before any action on the node
-        }
-      } else if (waiting) {
-        f |= UST_F_SAFE_LOAD;
-      }
-    } else if (code == UST_STATE_VALIDATION_REQUIRED || (code == UST_STATE_POD_RESTART_REQUIRED && synced)) {
-      bool waiting = false;
-      if (SafeDriverLoadManager->IsWaitingForSafeDriverLoad(&n, &waiting) || waiting) f |= UST_F_SAFE_LOAD;
-    }
-    if (const Pod* p = ns->DriverPod) {
-      bool ready = p->Phase == "Running" && !p->ContainerStatuses.empty();  // common_manager.go:617-630
-      for (const auto& cs : p->ContainerStatuses) ready = ready && cs.Ready;
-      if (ready) f |= UST_F_POD_READY;
-      if (isDriverPodFailing(*p)) f |= UST_F_POD_FAILING;
-      if (p->DeletionTimestampSet) f |= UST_F_POD_TERMINATING;
-    }
-    if (ns->NodeMaintenance) {
-      f |= UST_F_NM_PRESENT;
-      if (ns->NodeMaintenance->ReadyConditionWithReasonReady) f |= UST_F_NM_READY;
-    }
+    uint8_t hot; uint32_t f; int32_t rev; std::string deferred;
+    if (Error err = encodeOne(ns, code, ds, dsErr, &intern, e.ds_rev, &hot, &f, &rev, &deferred)) return err;
+    if (!deferred.empty()) e.deferred[e.entries.size()] = deferred;
     e.entries.push_back(ns);
     e.state.push_back(hot);
     e.flags.push_back(f);
@@ -506,6 +528,209 @@ Error ClusterUpgradeStateManagerImpl::ApplyState(ClusterUpgradeState* currentSta
                                  actions.data(), nullptr, &last_);
   if (rc == UST_ERR_CUDA || rc == UST_ERR_INVALID_ARGUMENT || rc == UST_ERR_NIL_STATE) return Errorf(ust_last_error(handle_));
   return Replay(enc, *upgradePolicy, next.data(), actions.data(), rc, last_);
+}
+
+// ---- incremental ApplyState: the resourceVersion-keyed encode cache (upgrade.hpp) --------------------------------------
+void ClusterUpgradeStateManagerImpl::ResetIncremental() { cache_ = Cache(); }
+
+int ClusterUpgradeStateManagerImpl::EvaluateCached(const ust_policy& policy, bool full, const std::vector<int64_t>& changed,
+                                                   Cache* cache, ust_counters* c) {
+  Cache& k = *cache;
+  const size_t n = k.slots.size();
+  if (handle_ == nullptr) return UST_ERR_CUDA;
+  // never pass NULL for empty arrays
+  std::vector<int32_t> dsrev = k.ds_rev;
+  dsrev.push_back(0);
+  if (full) {
+    k.next.assign(n + 1, 0);
+    k.actions.assign(n + 1, 0);
+    std::vector<uint8_t> st = k.state; st.push_back(0);
+    std::vector<uint32_t> fl = k.flags; fl.push_back(0);
+    std::vector<int32_t> rv = k.pod_rev; rv.push_back(0);
+    std::vector<int32_t> di = k.ds_idx; di.push_back(0);
+    return ust_apply_state(handle_, &policy, (int64_t)n, st.data(), fl.data(), rv.data(), di.data(), (int32_t)k.ds_rev.size(),
+                           dsrev.data(), nullptr, k.next.data(), k.actions.data(), nullptr, c);
+  }
+  const size_t m = changed.size();
+  std::vector<uint8_t> st(m + 1);
+  std::vector<uint32_t> fl(m + 1);
+  std::vector<int32_t> rv(m + 1), di(m + 1);
+  std::vector<int64_t> ix(changed);
+  ix.push_back(0);
+  for (size_t j = 0; j < m; j++) {
+    const size_t i = (size_t)changed[j];
+    st[j] = k.state[i]; fl[j] = k.flags[i]; rv[j] = k.pod_rev[i]; di[j] = k.ds_idx[i];
+  }
+  const int64_t cap = (int64_t)(n / 4 + 1024);
+  std::vector<int64_t> oi((size_t)cap + 1);
+  std::vector<uint8_t> on((size_t)cap + 1);
+  std::vector<uint16_t> oa((size_t)cap + 1);
+  int64_t n_out = 0;
+  int rc = ust_apply_state_delta_sparse(handle_, &policy, (int64_t)m, ix.data(), st.data(), fl.data(), rv.data(), di.data(),
+                                        (int32_t)k.ds_rev.size(), dsrev.data(), cap, oi.data(), on.data(), oa.data(), &n_out, c);
+  if (rc == UST_ERR_TRUNCATED) {
+    stats_.outputs_received += (int64_t)n;
+    return ust_fetch_outputs(handle_, k.next.data(), k.actions.data());
+  }
+  if (rc == UST_ERR_CUDA || rc == UST_ERR_INVALID_ARGUMENT || rc == UST_ERR_COMM) return rc;
+  for (int64_t j = 0; j < n_out; j++) { k.next[(size_t)oi[(size_t)j]] = on[(size_t)j]; k.actions[(size_t)oi[(size_t)j]] = oa[(size_t)j]; }
+  stats_.outputs_received += n_out;
+  return rc;
+}
+
+Error ClusterUpgradeStateManagerImpl::ApplyStateIncremental(ClusterUpgradeState* currentState, const DriverUpgradePolicySpec* upgradePolicy) {
+  if (currentState == nullptr) return Errorf("currentState should not be empty");  // upgrade_state.go:175-177
+  if (upgradePolicy == nullptr || !upgradePolicy->AutoUpgrade) return std::nullopt;  // upgrade_state.go:179-182
+  ust_policy pol;
+  flatten_policy(*upgradePolicy, podDeletionStateEnabled_, validationStateEnabled_, opts_.Requestor.UseMaintenanceOperator, &pol);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    Cache& k = cache_;
+    stats_.reconciles += attempt == 0 ? 1 : 0;
+    bool full = !k.valid;
+    for (auto& sl : k.slots) sl.seen = false;
+    // the DaemonSet table: identities are cached by UID, revision hashes are looked up once per DaemonSet per reconcile
+    std::map<const DaemonSet*, int32_t> dsOf;
+    auto dsIndexOf = [&](const DaemonSet* d) -> int32_t {
+      auto it = dsOf.find(d);
+      if (it != dsOf.end()) return it->second;
+      auto ins = k.dsIndexByUID.emplace(d->UID, (int32_t)k.dsIndexByUID.size());
+      const int32_t idx = ins.first->second;
+      if ((size_t)idx >= k.ds_rev.size()) { k.ds_rev.resize((size_t)idx + 1, 0); k.dsHashError.resize((size_t)idx + 1, false); }
+      std::string dsHash;
+      const bool bad = (bool)PodManager->GetDaemonsetControllerRevisionHash(d, &dsHash);
+      k.ds_rev[(size_t)idx] = bad ? 0 : k.intern.emplace(dsHash, (int32_t)k.intern.size() + 1).first->second;
+      k.dsHashError[(size_t)idx] = bad;
+      dsOf.emplace(d, idx);
+      return idx;
+    };
+    std::vector<int64_t> changed;
+    // Slots follow BuildState's list order (NodeUpgradeState::ListIndex), of which every bucket's slice order is a
+    // subsequence: walk the entries in that order, check that the cached slots still increase along it, append the
+    // nodes the cache has not seen. Entries without a ListIndex take their position in the bucket walk instead.
+    bool orderBroken = false;
+    {
+      std::vector<std::pair<int64_t, const NodeUpgradeState*>> order;
+      int64_t pos = 0;
+      bool haveIndex = true;
+      auto collect = [&](const std::vector<NodeUpgradeState*>& v) {
+        for (const NodeUpgradeState* ns : v) { haveIndex = haveIndex && ns->ListIndex >= 0; order.emplace_back(ns->ListIndex, ns); pos++; }
+      };
+      for (int code : kPassOrder) {
+        auto it = currentState->NodeStates.find(kStateNames[code]);
+        if (it != currentState->NodeStates.end()) collect(it->second);
+      }
+      for (const auto& kv : currentState->NodeStates) {
+        const int code = StateCodeOfLabel(kv.first);
+        if (code == UST_STATE_OTHER || code == UST_STATE_POST_MAINTENANCE_REQUIRED) collect(kv.second);
+      }
+      if (haveIndex) std::stable_sort(order.begin(), order.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+      long long lastSlot = -1;
+      for (const auto& o : order) {
+        auto ins = k.slotOf.emplace(o.second->Node->Name, k.slots.size());
+        if (ins.second) {  // a node the cache has not seen: the snapshot grows
+          k.slots.emplace_back();
+          k.state.push_back(UST_STATE_EXCLUDED); k.flags.push_back(0); k.pod_rev.push_back(0); k.ds_idx.push_back(-1);
+          k.deferredMsg.emplace_back();
+          full = true;
+        }
+        const long long slot = (long long)ins.first->second;
+        if (slot < lastSlot) orderBroken = true;
+        lastSlot = slot;
+      }
+    }
+    if (orderBroken && attempt == 0) { ResetIncremental(); continue; }  // re-encode in this snapshot's order
+    // this reconcile's view in pass order (what Replay walks): entry, its slot
+    EncodedSnapshot view;
+    view.policy = pol;
+    std::vector<size_t> slotOfView;
+    auto visit = [&](NodeUpgradeState* ns, int code) -> Error {
+      const Node& n = *ns->Node;
+      const size_t i = k.slotOf.at(n.Name);
+      Cache::Slot& sl = k.slots[i];
+      if (sl.seen) return Errorf("node " + n.Name + " appears twice in the snapshot");
+      sl.seen = true;
+      int32_t ds = -1;
+      bool dsErr = false;
+      if (!ns->IsOrphanedPod()) { ds = dsIndexOf(ns->DriverDaemonSet); dsErr = k.dsHashError[(size_t)ds]; }
+      // everything the encoding of the entry depends on
+      const bool versioned = !n.ResourceVersion.empty() && (ns->DriverPod == nullptr || !ns->DriverPod->ResourceVersion.empty());
+      std::string sig = std::to_string(code) + "|" + n.ResourceVersion + "|" + (ns->DriverPod ? ns->DriverPod->ResourceVersion : "-") + "|" +
+                        std::to_string(ds) + (dsErr ? "!" : "") + "|" + std::to_string(ds >= 0 ? k.ds_rev[(size_t)ds] : 0) + "|" +
+                        (ns->NodeMaintenance ? (ns->NodeMaintenance->ReadyConditionWithReasonReady ? "R" : "P") : "-");
+      if (!versioned || sig != sl.sig || sl.code != code) {
+        uint8_t hot; uint32_t f; int32_t rev; std::string deferred;
+        if (Error err = encodeOne(ns, code, ds, dsErr, &k.intern, k.ds_rev, &hot, &f, &rev, &deferred)) return err;
+        stats_.encoded++;
+        if (hot != k.state[i] || f != k.flags[i] || rev != k.pod_rev[i] || ds != k.ds_idx[i]) {
+          k.state[i] = hot; k.flags[i] = f; k.pod_rev[i] = rev; k.ds_idx[i] = ds;
+          changed.push_back((int64_t)i);
+        }
+        k.deferredMsg[i] = deferred;
+        sl.sig = versioned ? sig : std::string();
+        sl.code = code;
+      } else {
+        stats_.reused++;
+      }
+      if (!slotOfView.empty() && (int)(view.state.back() & UST_HOT_STATE_MASK) == code && slotOfView.back() > i)
+        orderBroken = true;  // within a bucket, slot order must be the slice order: slots are handed out in it
+                             // (upgrade_inplace.go:71) and the first error in it ends the pass
+      view.entries.push_back(ns);
+      view.state.push_back(k.state[i]);
+      slotOfView.push_back(i);
+      return std::nullopt;
+    };
+    Error walkErr;
+    for (int code : kPassOrder) {
+      auto it = currentState->NodeStates.find(kStateNames[code]);
+      if (it == currentState->NodeStates.end()) continue;
+      for (NodeUpgradeState* ns : it->second)
+        if ((walkErr = visit(ns, code))) break;
+      if (walkErr) break;
+    }
+    if (!walkErr)
+      for (const auto& kv : currentState->NodeStates) {
+        const int code = StateCodeOfLabel(kv.first);
+        if (code != UST_STATE_OTHER && code != UST_STATE_POST_MAINTENANCE_REQUIRED) continue;
+        for (NodeUpgradeState* ns : kv.second)
+          if ((walkErr = visit(ns, code))) break;
+        if (walkErr) break;
+      }
+    if (walkErr) { ResetIncremental(); return walkErr; }
+    if (orderBroken) {  // a bucket's slice order contradicts the cached order (entries without a ListIndex): start over
+      ResetIncremental();
+      if (attempt == 0) continue;
+      return Errorf("incremental ApplyState: a bucket's slice order contradicts the list order");
+    }
+    // nodes that left the snapshot keep their slot, as "not in snapshot"
+    for (size_t i = 0; i < k.slots.size(); i++)
+      if (!k.slots[i].seen && (k.state[i] & UST_HOT_STATE_MASK) != UST_STATE_EXCLUDED) {
+        k.state[i] = UST_STATE_EXCLUDED; k.flags[i] = 0; k.pod_rev[i] = 0; k.ds_idx[i] = -1;
+        k.slots[i].sig.clear(); k.slots[i].code = UST_STATE_EXCLUDED;
+        changed.push_back((int64_t)i);
+      }
+    std::sort(changed.begin(), changed.end());
+    if (full) stats_.full_uploads++;
+    const int rc = EvaluateCached(pol, full, changed, &k, &last_);
+    if (rc == UST_ERR_CUDA || rc == UST_ERR_INVALID_ARGUMENT || rc == UST_ERR_NIL_STATE || rc == UST_ERR_COMM) {
+      ResetIncremental();
+      return Errorf(handle_ ? ust_last_error(handle_) : "no B200 device bound to this manager: ApplyState has no CPU path");
+    }
+    k.valid = true;
+    // Replay walks this reconcile's view: gather its outputs, translate the abort position
+    const size_t nv = view.entries.size();
+    std::vector<uint8_t> next(nv + 1);
+    std::vector<uint16_t> actions(nv + 1);
+    ust_counters c = last_;
+    for (size_t v = 0; v < nv; v++) {
+      const size_t i = slotOfView[v];
+      next[v] = k.next[i];
+      actions[v] = k.actions[i];
+      if (!k.deferredMsg[i].empty()) view.deferred[v] = k.deferredMsg[i];
+      if (last_.error_index == (int64_t)i) c.error_index = (int64_t)v;
+    }
+    return Replay(view, *upgradePolicy, next.data(), actions.data(), rc, c);
+  }
+  return Errorf("incremental ApplyState could not settle on a node order");
 }
 
 }  // namespace upgrade

@@ -21,6 +21,7 @@
 #include <memory>
 #include <optional>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ust.h"
@@ -62,6 +63,7 @@ using StringMap = std::map<std::string, std::string>;
 struct NodeCondition { std::string Type, Status; };
 struct Node {
   std::string Name;
+  std::string ResourceVersion;           // metadata.resourceVersion ("" = unknown: the object is re-encoded every reconcile)
   StringMap Labels, Annotations;
   bool Unschedulable = false;            // Spec.Unschedulable
   std::vector<NodeCondition> Conditions;  // Status.Conditions
@@ -70,6 +72,7 @@ struct ContainerStatus { bool Ready = false; int RestartCount = 0; };
 struct OwnerReference { std::string Kind, Name, UID; };
 struct Pod {
   std::string Name, Namespace, NodeName;  // Spec.NodeName
+  std::string ResourceVersion;
   StringMap Labels;
   std::vector<OwnerReference> OwnerReferences;
   std::string Phase;                      // Status.Phase
@@ -78,6 +81,7 @@ struct Pod {
 };
 struct DaemonSet {
   std::string Name, Namespace, UID;
+  std::string ResourceVersion;
   int DesiredNumberScheduled = 0;         // Status.DesiredNumberScheduled
 };
 struct NodeMaintenance {                   // maintenance-operator api v0.3.0, the fields the path reads
@@ -113,6 +117,10 @@ struct NodeUpgradeState {
   Pod* DriverPod = nullptr;
   DaemonSet* DriverDaemonSet = nullptr;
   upgrade::NodeMaintenance* NodeMaintenance = nullptr;
+  // Position of the entry's driver pod in BuildState's filteredPodList (upgrade_state.go:126-136), -1 = unknown. Not in
+  // the reference's struct: ApplyStateIncremental uses it as the one node order every bucket's slice order is a
+  // subsequence of, so that cached entries keep their place when a node changes bucket.
+  int64_t ListIndex = -1;
   bool IsOrphanedPod() const { return DriverDaemonSet == nullptr; }
 };
 struct ClusterUpgradeState {
@@ -259,8 +267,49 @@ class ClusterUpgradeStateManagerImpl : public ClusterUpgradeStateManager {
 
   const ust_counters& LastCounters() const { return last_; }
 
- private:
+  // ---- incremental ApplyState: the resourceVersion-keyed encode cache -------------------------------
+  // The same contract as ApplyState for a reconcile loop that calls it again and again with fresh BuildState
+  // snapshots. The manager keeps the encoded snapshot (host and device) from call to call, in a node order that does
+  // not move when a node changes bucket (first-seen order = BuildState's pod-list order); an entry is re-encoded only
+  // when the resourceVersion of its node, its driver pod or its DaemonSet changed (or is unknown), only the re-encoded
+  // entries are uploaded (ust_apply_state_delta_sparse) and only the outputs that differ from the previous reconcile's
+  // come back. The reference re-derives everything from node.Labels / Annotations on every reconcile
+  // (upgrade_state.go:140-161, common_manager.go:229-604); the provider calls skipped for an unchanged object are
+  // GetPodControllerRevisionHash and IsWaitingForSafeDriverLoad, both pure functions of the object in the reference's
+  // own implementations (pod_manager.go:84-89, safe_driver_load_manager.go:51-53).
+  // Falls back to a full encode + upload when the snapshot grew, when a bucket's slice order no longer follows the
+  // cached order (slots are handed out in slice order, upgrade_inplace.go:71), or on the first call.
+  Error ApplyStateIncremental(ClusterUpgradeState* currentState, const DriverUpgradePolicySpec* upgradePolicy);
+  struct IncrementalStats { int64_t reconciles = 0, full_uploads = 0, encoded = 0, reused = 0, outputs_received = 0; };
+  const IncrementalStats& Stats() const { return stats_; }
+  void ResetIncremental();
+
+ protected:
+  // The device half of ApplyStateIncremental: evaluate the cached snapshot. full: upload all of it and fetch all
+  // outputs; else upload the entries `changed` and patch the outputs that differ into cache_.next / cache_.actions.
+  // Returns the ABI's return code. (Virtual so that the host-logic test can put the oracle behind the same cache.)
+  struct Cache {
+    struct Slot { std::string sig; int code = UST_STATE_EXCLUDED; bool seen = false; };
+    std::unordered_map<std::string, size_t> slotOf;  // node name -> SoA index
+    std::vector<Slot> slots;
+    std::vector<uint8_t> state, next;
+    std::vector<uint32_t> flags;
+    std::vector<int32_t> pod_rev, ds_idx, ds_rev;
+    std::vector<uint16_t> actions;
+    std::vector<std::string> deferredMsg;            // per slot: the error the reference raises when it reaches the node
+    std::map<std::string, int32_t> intern;           // revision hash -> id
+    std::map<std::string, int32_t> dsIndexByUID;
+    std::vector<bool> dsHashError;
+    bool valid = false;
+  };
+  virtual int EvaluateCached(const ust_policy& policy, bool full, const std::vector<int64_t>& changed, Cache* cache, ust_counters* c);
   ClusterUpgradeStateManagerImpl() = default;
+
+ private:
+  Error encodeOne(const NodeUpgradeState* ns, int code, int32_t ds, bool dsErr, std::map<std::string, int32_t>* intern,
+                  const std::vector<int32_t>& ds_rev, uint8_t* hot, uint32_t* flags, int32_t* rev, std::string* deferred);
+  Cache cache_;
+  IncrementalStats stats_;
   ust_handle* handle_ = nullptr;
   StateOptions opts_;
   bool podDeletionStateEnabled_ = false, validationStateEnabled_ = false;

@@ -61,7 +61,7 @@ def load():
 
 
 EXPORTS = ["ust_abi_version", "ust_create", "ust_destroy", "ust_last_error", "ust_create_error", "ust_launch_count",
-           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_apply_state_packed", "ust_apply_state_delta", "ust_simulate_rollout", "ust_sync",
+           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_apply_state_packed", "ust_apply_state_delta", "ust_apply_state_delta_sparse", "ust_fetch_outputs", "ust_simulate_rollout", "ust_sync",
            "ust_build_state", "ust_build_state_uids", "ust_get_unique_id", "ust_comm_init", "ust_comm_set_mode", "ust_table_entry",
            "ust_table_window_shift"]
 
@@ -197,6 +197,32 @@ class Handle:
             _p(ch["flags"]), _p(ch["pod_rev"]), _p(ch["ds_idx"]), int(ds_rev.shape[0]), _p(ds_rev), _p(nxt), _p(act), _p(oc),
             C.addressof(cnt))
         return rc, nxt, act, oc, cnt.as_dict()
+
+    def apply_state_delta_sparse(self, policy, idx, changed, ds_rev, max_out, out=None):
+        """ust_apply_state_delta_sparse: like apply_state_delta, but only the outputs that differ from the previous call's
+        come back. Returns (rc, n_out, out_idx, out_next, out_actions, counters-dict); the arrays hold n_out entries
+        when n_out <= max_out."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        ch = {"state": np.ascontiguousarray(changed["state"], dtype=np.uint8),
+              "flags": np.ascontiguousarray(changed["flags"], dtype=np.uint32),
+              "pod_rev": np.ascontiguousarray(changed["pod_rev"], dtype=np.int32),
+              "ds_idx": np.ascontiguousarray(changed["ds_idx"], dtype=np.int32)}
+        ds_rev = np.ascontiguousarray(ds_rev, dtype=np.int32)
+        if out is None:
+            out = (np.zeros(max_out + 1, np.int64), np.zeros(max_out + 1, np.uint8), np.zeros(max_out + 1, np.uint16))
+        n_out = C.c_int64(0)
+        cnt = abi.Counters()
+        rc = self._lib.ust_apply_state_delta_sparse(
+            self._h, C.addressof(policy) if policy is not None else None, int(idx.shape[0]), _p(idx), _p(ch["state"]),
+            _p(ch["flags"]), _p(ch["pod_rev"]), _p(ch["ds_idx"]), int(ds_rev.shape[0]), _p(ds_rev), C.c_int64(int(max_out)),
+            _p(out[0]), _p(out[1]), _p(out[2]), C.addressof(n_out), C.addressof(cnt))
+        return rc, int(n_out.value), out[0], out[1], out[2], cnt.as_dict()
+
+    def fetch_outputs(self, n):
+        nxt = np.zeros(n, np.uint8)
+        act = np.zeros(n, np.uint16)
+        rc = self._lib.ust_fetch_outputs(self._h, _p(nxt), _p(act))
+        return rc, nxt, act
 
     def simulate_rollout(self, policy, n, steps, want_final=True):
         """ust_simulate_rollout on the resident snapshot. Returns (rc, steps_done, [counters-dict per step], final dict)."""

@@ -2,7 +2,7 @@
 // checker of the encoder / replayer logic; the product's ApplyState never does this (it fails without a device).
 #include <cstring>
 
-#include "upgrade_state_spec.hpp"
+#include "incremental_spec.hpp"
 
 extern "C" int ust_oracle_apply_state(int variant, const ust_policy* policy, int64_t n, const uint8_t* state,
                                       const uint32_t* flags, const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds,
@@ -37,6 +37,37 @@ int main() {
     auto err = m->ApplyState(&s, &p);
     EXPECT(R, err.has_value());
   });
+  // the incremental path with the oracle behind the cache (the product evaluates the cache on the device)
+  struct OracleBacked : upgrade::ClusterUpgradeStateManagerImpl {
+    int EvaluateCached(const ust_policy& policy, bool, const std::vector<int64_t>&, Cache* cache, ust_counters* c) override {
+      Cache& k = *cache;
+      const size_t n = k.slots.size();
+      k.next.assign(n + 1, 0);
+      k.actions.assign(n + 1, 0);
+      std::vector<uint8_t> st = k.state; st.push_back(0);
+      std::vector<uint32_t> fl = k.flags; fl.push_back(0);
+      std::vector<int32_t> rv = k.pod_rev, di = k.ds_idx, dr = k.ds_rev;
+      rv.push_back(0); di.push_back(0); dr.push_back(0);
+      return ust_oracle_apply_state(0, &policy, (int64_t)n, st.data(), fl.data(), rv.data(), di.data(), (int32_t)k.ds_rev.size(),
+                                    dr.data(), nullptr, k.next.data(), k.actions.data(), nullptr, c);
+    }
+  };
+  spec::MakeFn makeIncr = [](upgrade::StateOptions) { return std::unique_ptr<upgrade::ClusterUpgradeStateManagerImpl>(new OracleBacked()); };
+  spec::WorldApplyFn wfull = [&](spec::World& w, const upgrade::DriverUpgradePolicySpec* p) -> upgrade::Error {
+    upgrade::EncodedSnapshot enc;
+    if (auto err = w.m->Encode(w.state, *p, &enc)) return err;
+    const size_t n = enc.entries.size();
+    std::vector<uint8_t> next(n + 1);
+    std::vector<uint16_t> actions(n + 1);
+    enc.state.push_back(0); enc.flags.push_back(0); enc.pod_rev.push_back(0); enc.ds_idx.push_back(0); enc.ds_rev.push_back(0);
+    ust_counters c;
+    const int rc = ust_oracle_apply_state(0, &enc.policy, (int64_t)n, enc.state.data(), enc.flags.data(), enc.pod_rev.data(),
+                                          enc.ds_idx.data(), (int32_t)enc.ds_rev.size() - 1, enc.ds_rev.data(), nullptr,
+                                          next.data(), actions.data(), nullptr, &c);
+    return w.m->Replay(enc, *p, next.data(), actions.data(), rc, c);
+  };
+  spec::WorldApplyFn wincr = [](spec::World& w, const upgrade::DriverUpgradePolicySpec* p) { return w.m->ApplyStateIncremental(&w.state, p); };
+  spec::run_incremental(R, make, wfull, makeIncr, wincr, 400);
   std::printf("# %d passed, %d failed\n", R.passed, R.failed);
   return R.failed == 0 ? 0 : 1;
 }

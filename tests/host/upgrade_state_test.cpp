@@ -1,6 +1,6 @@
 // The reference's ApplyState specs through ClusterUpgradeStateManagerImpl::ApplyState — i.e. through the C ABI and
 // the B200 kernel. Needs a GPU; run by tests/test_host_mirror.py::test_reference_specs_on_gpu.
-#include "upgrade_state_spec.hpp"
+#include "incremental_spec.hpp"
 
 int main() {
   mocks::Runner R;
@@ -49,6 +49,10 @@ int main() {
     auto err = e.m->BuildState("ns", {}, &st);
     EXPECT(R, err.has_value() && *err == "driver DaemonSet should not have Unscheduled pods");
   });
+  // the resourceVersion-keyed encode cache over ust_apply_state_delta_sparse, against ApplyState from scratch
+  spec::WorldApplyFn wfull = [](spec::World& w, const upgrade::DriverUpgradePolicySpec* p) { return w.m->ApplyState(&w.state, p); };
+  spec::WorldApplyFn wincr = [](spec::World& w, const upgrade::DriverUpgradePolicySpec* p) { return w.m->ApplyStateIncremental(&w.state, p); };
+  spec::run_incremental(R, make, wfull, make, wincr, 3000);
   std::printf("# %d passed, %d failed\n", R.passed, R.failed);
   return (R.failed == 0 && device_ok) ? 0 : 1;
 }

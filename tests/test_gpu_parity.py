@@ -249,6 +249,47 @@ def test_delta_updates_of_the_resident_snapshot(handle, n):
     assert gone[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]
 
 
+@pytest.mark.parametrize("n", [4097, 700_001])
+def test_sparse_delta_outputs(handle, n):
+    """ust_apply_state_delta_sparse: patching the previous call's outputs with the returned (index, next_state, actions)
+    entries gives exactly the oracle's outputs on the updated snapshot - over several reconciles, with policy changes,
+    a slot budget that moves, an abort, an overflow of the caller's arrays (then ust_fetch_outputs)."""
+    rng = np.random.default_rng(31 + n)
+    soa, _ = helpers.random_soa(rng, n, wild=True)
+    pol = abi.make_policy(max_parallel_upgrades=0, max_unavailable="30%")
+    rc, nxt, act, _, _ = handle.apply_state(pol, soa, want_outcome=False)
+    helpers.assert_same((rc, nxt, act, None, None), helpers.oracle_apply(pol, soa, variant=1)[:3] + (None, None), "full call")
+    cap = n // 4 + 16
+    for rep, frac in enumerate((0.0, 0.001, 0.01, 0.05, 0.01, 0.6)):
+        m = int(n * frac)
+        idx = np.sort(rng.choice(n, size=m, replace=False)).astype(np.int64)
+        fresh, _ = helpers.random_soa(rng, m, wild=True, p_err=2e-4 if rep == 4 else 0.0)
+        for k in ("state", "flags", "pod_rev", "ds_idx"):
+            soa[k][idx] = fresh[k]
+        if rep == 3:
+            pol = abi.make_policy(max_parallel_upgrades=int(n // 7), max_unavailable="55%")
+        rc, n_out, oi, on, oa, cnt = handle.apply_state_delta_sparse(pol, idx, {k: fresh[k] for k in ("state", "flags", "pod_rev", "ds_idx")},
+                                                                    soa["ds_rev"], cap)
+        ref = helpers.oracle_apply(pol, soa, variant=1)
+        expect_changed = int(np.sum((ref[1] != nxt) | (ref[2] != act)))
+        assert n_out == expect_changed, (rep, n_out, expect_changed)
+        if n_out > cap:
+            assert rc == abi.K["UST_ERR_TRUNCATED"]
+            frc, nxt, act = handle.fetch_outputs(n)
+            assert frc == 0
+        else:
+            assert rc == ref[0], (rep, rc, ref[0])
+            assert np.all(np.diff(oi[:n_out]) > 0)          # node order
+            nxt[oi[:n_out]] = on[:n_out]
+            act[oi[:n_out]] = oa[:n_out]
+        assert np.array_equal(nxt, ref[1]) and np.array_equal(act, ref[2]), f"rep={rep}"
+        assert cnt == ref[4] or n_out > cap
+    handle.build_state(soa["state"][:10], np.zeros(10, np.int32), np.array([10], np.int32))   # drops the resident snapshot
+    rc = handle.apply_state_delta_sparse(pol, np.zeros(0, np.int64), {k: soa[k][:0] for k in ("state", "flags", "pod_rev", "ds_idx")},
+                                         soa["ds_rev"], 16)[0]
+    assert rc == abi.K["UST_ERR_INVALID_ARGUMENT"]
+
+
 @pytest.mark.parametrize("n,steps", [(3000, 25), (120_000, 30), (700_001, 8)])
 def test_simulated_rollout_matches_the_cpu_simulation(handle, n, steps):
     """ust_simulate_rollout (ApplyState + feedback kernel, `steps` times on the device) against the oracle's

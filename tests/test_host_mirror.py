@@ -21,7 +21,7 @@ def _run(exe):
     out = p.stdout + p.stderr
     assert p.returncode == 0, out
     ok = [line for line in out.splitlines() if line.startswith("ok ")]
-    assert len(ok) >= 39, out
+    assert len(ok) >= 40, out
     assert "not ok" not in out, out
     return out
 
