@@ -290,10 +290,41 @@ int ust_fetch_outputs(ust_handle* h, uint8_t* next_state, uint16_t* actions);
  * reconcile - so the only thing that paces the rollout is the MaxParallelUpgrades / MaxUnavailable budget, which is
  * the planning question. history[k] (nullable, `steps` entries) receives the counters of reconcile k; final_*
  * (nullable) the snapshot afterwards; *steps_done the number of reconciles fed back. A reconcile that returns a
- * reference-level error stops the feedback: its code is returned, the state before it is kept. In-place mode, one
- * GPU, no pod lists. */
+ * reference-level error stops the feedback: its code is returned, the state before it is kept. One GPU, no pod
+ * lists; in-place and requestor mode (see ust_simulate_rollout_timed for what the maintenance operator is taken to do). */
 int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps, ust_counters* history,
                          uint8_t* final_state, uint32_t* final_flags, int32_t* final_pod_rev, int32_t* steps_done);
+
+/* The same simulation with a clock: reconcile k runs at simulated time k * seconds_per_reconcile, and the things a
+ * node waits for take time instead of having happened by the next reconcile. Per node the device keeps the time it
+ * entered its state, its wait-for-pod-completion start time (the annotation of pod_manager.go:336-345) and its
+ * validation start time (validation_manager.go:139-175):
+ *   wait-for-jobs-required  the wait-selector pods of a node run until job_seconds after the node entered the state
+ *                           (nodes already there at time 0: from time 0, if their UST_F_WAIT_PODS_RUNNING is set). While
+ *                           they run: no start annotation => it is set to `now`; present and now > start +
+ *                           wait_timeout_seconds => pod-deletion-required, annotation removed (pod_manager.go:331-368;
+ *                           the policy's wait_timeout_nonzero must say whether wait_timeout_seconds != 0).
+ *   validation-required     the validation pod is ready validation_seconds after the node entered the state (< 0: never).
+ *                           Until then Validate() runs handleTimeout: no start annotation => set to `now`; present and
+ *                           now > start + validation_timeout_seconds (600 in the reference, validation_manager.go:32) =>
+ *                           upgrade-failed, annotation removed.
+ *   requestor mode (policy->use_maintenance_operator, accepted by both simulation entry points): an upgrade-required
+ *                           node gets its NodeMaintenance and the requestor-mode annotation (upgrade_requestor.go:277-319);
+ *                           the maintenance operator cordons it and reports Ready maintenance_seconds after the object
+ *                           was created (=> pod-restart-required, :416-452); the uncordon pass removes annotation and
+ *                           object, the maintenance operator uncordons (:454-488).
+ * With every field 0 (validation_timeout_seconds aside) this is ust_simulate_rollout. */
+typedef struct ust_sim_options {
+  int64_t seconds_per_reconcile;
+  int64_t wait_timeout_seconds;
+  int64_t job_seconds;
+  int64_t validation_seconds;
+  int64_t validation_timeout_seconds;
+  int64_t maintenance_seconds;
+} ust_sim_options;
+int ust_simulate_rollout_timed(ust_handle* h, const ust_policy* policy, const ust_sim_options* options, int32_t steps,
+                               ust_counters* history, uint8_t* final_state, uint32_t* final_flags, int32_t* final_pod_rev,
+                               int32_t* steps_done);
 
 /* ---- BuildState -------------------------------------------------------------------------------- */
 

@@ -134,7 +134,8 @@ struct ust_handle {
   DevBuf<long long> d_idx;           // delta updates: indices and values of the changed nodes
   DevBuf<uint8_t> d_state;
   DevBuf<uint32_t> d_flags;
-  DevBuf<int32_t> d_rev, d_ds;  // per-node pod-list summaries (ust_pod_summary_kernel -> streaming pass)
+  DevBuf<int32_t> d_rev, d_ds;
+  DevBuf<int32_t> sim_entered, sim_wait, sim_valid;  // timed rollout simulation: per-node clocks
 
   // multi-GPU
   int rank = 0, world = 1, comm_mode = 0;
@@ -594,7 +595,7 @@ void ust_destroy(ust_handle* h) {
   if (h->ds_count_dev) cudaFree(h->ds_count_dev);
   h->s_hot.release(); h->s_next.release(); h->s_outcome.release(); h->s_flags.release();
   h->s_rev.release(); h->s_ds.release(); h->s_dsrev.release(); h->s_podoff.release(); h->s_dsdesired.release();
-  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_candtile.release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release(); h->s_rev16.release(); h->s_ds8.release(); h->d_idx.release(); h->d_state.release(); h->d_flags.release(); h->d_rev.release(); h->d_ds.release();
+  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_candtile.release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release(); h->s_rev16.release(); h->s_ds8.release(); h->d_idx.release(); h->d_state.release(); h->d_flags.release(); h->d_rev.release(); h->d_ds.release(); h->sim_entered.release(); h->sim_wait.release(); h->sim_valid.release();
   for (auto& ev : h->seg_done) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->seg_up) if (ev) cudaEventDestroy(ev);
   if (h->stream_h2d) cudaStreamDestroy(h->stream_h2d);
@@ -865,16 +866,17 @@ int ust_apply_state_packed(ust_handle* h, const ust_policy* policy, int64_t n, c
   return keep(finish_with_counters(h, st, out));
 }
 
-int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps, ust_counters* history, uint8_t* final_state,
-                         uint32_t* final_flags, int32_t* final_pod_rev, int32_t* steps_done) {
-  if (!h) return UST_ERR_INVALID_ARGUMENT;
-  std::lock_guard<std::mutex> g(h->mu);
+static int simulate_common(ust_handle* h, const ust_policy* policy, const ust_sim_options* opt, int32_t steps, ust_counters* history,
+                           uint8_t* final_state, uint32_t* final_flags, int32_t* final_pod_rev, int32_t* steps_done) {
   const int64_t n = h->resident_n;
   if (n < 0) return h->fail(UST_ERR_INVALID_ARGUMENT, "no resident snapshot: call ust_apply_state (without pod lists) first");
   if (steps < 0 || steps > (1 << 20)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad step count");
   if (h->world > 1) return h->fail(UST_ERR_INVALID_ARGUMENT, "rollout simulation runs on one GPU");
-  if (policy && policy->use_maintenance_operator)
-    return h->fail(UST_ERR_INVALID_ARGUMENT, "rollout simulation models the in-place mode only");
+  if (opt && (opt->seconds_per_reconcile < 0 || opt->wait_timeout_seconds < 0 || opt->job_seconds < 0 || opt->validation_timeout_seconds < 0 ||
+              opt->maintenance_seconds < 0 || (int64_t)steps * opt->seconds_per_reconcile >= (1LL << 29)))
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "bad simulation options (times are non-negative; the horizon stays below 2^29 seconds)");
+  if (opt && policy && (policy->wait_timeout_nonzero != 0) != (opt->wait_timeout_seconds != 0))
+    return h->fail(UST_ERR_INVALID_ARGUMENT, "policy.wait_timeout_nonzero must say whether wait_timeout_seconds != 0");
   ust_policy pol;
   if (policy) { pol = *policy; pol.evaluate_actuators = 1; }  // the asynchronous actuators' results are what is fed back
   UST_CUDA(h, cudaSetDevice(h->device));
@@ -890,12 +892,26 @@ int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps,
   h->resident_n = -1;
   h->outputs_resident = false;
   int grid = 8 * h->num_sms;
+  UstSimParams sp;
+  memset(&sp, 0, sizeof(sp));
+  if (opt) {
+    sp.timed = 1;
+    sp.dt = opt->seconds_per_reconcile;
+    sp.wait_timeout = opt->wait_timeout_seconds; sp.job_seconds = opt->job_seconds; sp.validation_seconds = opt->validation_seconds;
+    sp.validation_timeout = opt->validation_timeout_seconds; sp.maintenance_seconds = opt->maintenance_seconds;
+    UST_CUDA(h, h->sim_entered.reserve(N + 1)); UST_CUDA(h, h->sim_wait.reserve(N + 1)); UST_CUDA(h, h->sim_valid.reserve(N + 1));
+    int e = ust_launch_sim_init(n, h->s_flags.p, h->sim_entered.p, h->sim_wait.p, h->sim_valid.p, grid, st);
+    if (e) return h->fail(UST_ERR_CUDA, "simulation init kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->launches += 1;
+  }
   for (int32_t k = 0; k < steps; k++) {
     int rc = apply_device(h, policy ? &pol : nullptr, n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, h->resident_n_ds,
                           h->s_dsrev.p, nullptr, nullptr, 0, h->s_next.p, h->s_actions.p, h->s_outcome.p, h->hist_dev + k, st);
     if (rc) return rc;
+    sp.now = (long long)k * sp.dt;
     int e = ust_launch_feedback(n, h->s_hot.p, h->s_flags.p, h->s_rev.p, h->s_ds.p, h->resident_n_ds, h->s_dsrev.p, h->s_next.p,
-                                h->s_actions.p, h->s_outcome.p, h->hist_dev + k, grid, st);
+                                h->s_actions.p, h->s_outcome.p, h->hist_dev + k, sp, h->sim_entered.p, h->sim_wait.p, h->sim_valid.p,
+                                grid, st);
     if (e) return h->fail(UST_ERR_CUDA, "feedback kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
     h->launches += 1;
   }
@@ -916,6 +932,21 @@ int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps,
   if (steps_done) *steps_done = done;
   if (rc) return h->fail(rc, "the simulated reconcile %d returned an error (code %d); the state before it is kept", (int)done, rc);
   return UST_OK;
+}
+
+int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps, ust_counters* history, uint8_t* final_state,
+                         uint32_t* final_flags, int32_t* final_pod_rev, int32_t* steps_done) {
+  if (!h) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  return simulate_common(h, policy, nullptr, steps, history, final_state, final_flags, final_pod_rev, steps_done);
+}
+
+int ust_simulate_rollout_timed(ust_handle* h, const ust_policy* policy, const ust_sim_options* options, int32_t steps,
+                               ust_counters* history, uint8_t* final_state, uint32_t* final_flags, int32_t* final_pod_rev,
+                               int32_t* steps_done) {
+  if (!h || !options) return UST_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(h->mu);
+  return simulate_common(h, policy, options, steps, history, final_state, final_flags, final_pod_rev, steps_done);
 }
 
 int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const int32_t* ds_idx, int32_t n_ds,

@@ -139,9 +139,18 @@ int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* own
                                 unsigned long long* ds_count, UstWorkspace* ws, ust_counters* out, int grid, void* stream);
 int ust_launch_patch(long long m, const long long* idx, const uint8_t* state, const uint32_t* flags, const int32_t* pod_rev,
                      const int32_t* ds_idx, uint8_t* hot_out, uint32_t* flags_out, int32_t* rev_out, int32_t* ds_out, void* stream);
+// rollout simulation: the clock of the feedback between two reconciles (include/ust.h, ust_sim_options)
+struct UstSimParams {
+  int timed;            // 0: whatever a node waits for has happened by the next reconcile
+  long long now, dt;    // time of the reconcile that was just evaluated, seconds to the next one
+  long long wait_timeout, job_seconds, validation_seconds, validation_timeout, maintenance_seconds;
+};
 int ust_launch_feedback(long long n, uint8_t* hot, uint32_t* flags, int32_t* pod_rev, const int32_t* ds_idx, int n_ds,
                         const int32_t* ds_rev, const uint8_t* next, const uint16_t* actions, const uint8_t* outcome,
-                        const ust_counters* step, int grid, void* stream);
+                        const ust_counters* step, const UstSimParams& sp, int32_t* entered, int32_t* wait_start,
+                        int32_t* valid_start, int grid, void* stream);
+int ust_launch_sim_init(long long n, const uint32_t* flags, int32_t* entered, int32_t* wait_start, int32_t* valid_start, int grid,
+                        void* stream);
 int ust_launch_widen(long long n, const uint16_t* rev16, const int8_t* ds8, int32_t* rev_out, int32_t* ds_out, int grid,
                      void* stream);
 // sparse outputs of a delta call: nodes whose (next_state, actions) differ from the previous call's, in node order

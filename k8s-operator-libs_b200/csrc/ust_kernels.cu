@@ -13,6 +13,8 @@
 // common_manager.go:462-523).
 // Around it: ust_pod_summary_kernel (pod lists -> one byte per node), ust_build_state*_kernel (BuildState),
 // ust_patch_kernel / ust_feedback_kernel (delta updates, rollout simulation), ust_widen_kernel (packed host format).
+#include <climits>
+
 #include "ust_common.cuh"
 
 using namespace ustd;
@@ -23,6 +25,8 @@ constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStep = kThreads * 4;   // nodes per CTA step (4 per thread)
 constexpr uint32_t kLutBytes = UST_LUT_WORDS * sizeof(uint32_t);  // table + 16 {x, y} meta pairs
+constexpr int kSimNone = INT32_MIN;        // rollout simulation: no start-time annotation
+constexpr int kSimLongAgo = -(1 << 30);    // ... one that timed out before the simulation began
 constexpr int kDsSmem = 64;  // the kernel sits next to the streaming kernel on every SM: keep its shared memory small
 
 struct __align__(128) Shared {
@@ -701,7 +705,7 @@ __global__ void __launch_bounds__(kThreads) ust_patch_kernel(long long m, const 
   }
 }
 
-// Rollout simulation: the state feedback between two reconciles under "ideal actuators" - every call
+// Rollout simulation: the state feedback between two reconciles. Untimed (sp.timed == 0): "ideal actuators" - every call
 // the reference makes through its providers takes effect, every asynchronous actuator succeeds, and whatever a node
 // is waiting for (jobs, pod readiness, validation) has happened by the next reconcile. One streaming pass, in place:
 // 13 B read + up to 9 B written per node.
@@ -717,9 +721,12 @@ __global__ void __launch_bounds__(kThreads) ust_feedback_kernel(long long n, uin
                                                                 const int32_t* __restrict__ ds_idx, int n_ds,
                                                                 const int32_t* __restrict__ ds_rev,
                                                                 const uint8_t* __restrict__ next, const uint16_t* __restrict__ actions,
-                                                                const uint8_t* __restrict__ outcome, const ust_counters* step) {
+                                                                const uint8_t* __restrict__ outcome, const ust_counters* step,
+                                                                const UstSimParams sp, int32_t* entered, int32_t* wait_start,
+                                                                int32_t* valid_start) {
   if (step->error_code != UST_OK) return;  // the reconcile returned an error: nothing it decided is fed back
   const long long stride = (long long)gridDim.x * kThreads;
+  const long long now = sp.now, now_next = sp.now + sp.dt;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     unsigned b = hot[i];
     const unsigned s = b & 15u;
@@ -737,6 +744,16 @@ __global__ void __launch_bounds__(kThreads) ust_feedback_kernel(long long n, uin
     if (a & UST_A_UNBLOCK_SAFE_LOAD) f &= ~UST_F_SAFE_LOAD;
     if (a & UST_A_SET_WAIT_START) f |= UST_F_WAIT_START_ANNO;
     if (a & UST_A_CLEAR_WAIT_START) f &= ~(UST_F_WAIT_START_ANNO | UST_F_WAIT_TIMED_OUT | UST_F_WAIT_START_INVALID);
+    // requestor mode (upgrade_requestor.go:277-319, :454-488): the annotation and the NodeMaintenance object
+    if (a & UST_A_REQUESTOR_ANNO_CHANGE) f = s == UST_STATE_UPGRADE_REQUIRED ? (f | UST_F_REQUESTOR_MODE) : (f & ~UST_F_REQUESTOR_MODE);
+    if (a & UST_A_NM_CREATE_OR_DELETE) {
+      if (s == UST_STATE_UPGRADE_REQUIRED) {
+        f |= UST_F_NM_PRESENT;
+      } else {  // the object goes, and with it the maintenance operator's cordon
+        f &= ~(UST_F_NM_PRESENT | UST_F_NM_READY);
+        b &= ~UST_HOT_UNSCHEDULABLE;
+      }
+    }
     int rev = pod_rev[i];
     if (a & UST_A_RESTART_DRIVER_POD) {
       const int d = ds_idx[i];
@@ -747,15 +764,61 @@ __global__ void __launch_bounds__(kThreads) ust_feedback_kernel(long long n, uin
         f = (f | UST_F_POD_READY) & ~(UST_F_POD_FAILING | UST_F_POD_TERMINATING);
       }
     }
-    if (ns == UST_STATE_WAIT_FOR_JOBS_REQUIRED) f &= ~UST_F_WAIT_PODS_RUNNING;
+    int ent = 0, ws = 0, vs = 0;
+    if (sp.timed) {
+      ent = entered[i]; ws = wait_start[i]; vs = valid_start[i];
+      if (a & UST_A_SET_WAIT_START) ws = (int)now;                 // annotation = currentTime (pod_manager.go:339)
+      if (a & UST_A_CLEAR_WAIT_START) ws = kSimNone;
+      // Validate() of a node whose validation pod is not ready runs handleTimeout (validation_manager.go:139-175)
+      if (s == UST_STATE_VALIDATION_REQUIRED && ns == UST_STATE_VALIDATION_REQUIRED && !(f & UST_F_VALIDATION_DONE)) {
+        if (vs == kSimNone) vs = (int)now;
+        else if (now > (long long)vs + sp.validation_timeout) { ns = UST_STATE_FAILED; vs = kSimNone; }
+      }
+      if (ns != UST_STATE_VALIDATION_REQUIRED) vs = kSimNone;      // the annotation is removed once the pod is ready (:104-110)
+      if (ns != s) ent = (int)now;
+    }
+    if (ns == UST_STATE_WAIT_FOR_JOBS_REQUIRED) {
+      if (!sp.timed) f &= ~UST_F_WAIT_PODS_RUNNING;
+      else {
+        if (ns != s) f = sp.job_seconds > 0 ? (f | UST_F_WAIT_PODS_RUNNING) : (f & ~UST_F_WAIT_PODS_RUNNING);
+        if (now_next >= (long long)ent + sp.job_seconds) f &= ~UST_F_WAIT_PODS_RUNNING;
+        const bool timed_out = ws != kSimNone && now_next > (long long)ws + sp.wait_timeout;
+        f = timed_out ? (f | UST_F_WAIT_TIMED_OUT) : (f & ~UST_F_WAIT_TIMED_OUT);
+      }
+    }
     if (ns == UST_STATE_POD_RESTART_REQUIRED) {
       f &= ~UST_F_POD_TERMINATING;
       if (!(f & UST_F_POD_FAILING)) f |= UST_F_POD_READY;
     }
-    if (ns == UST_STATE_VALIDATION_REQUIRED) f |= UST_F_VALIDATION_DONE;
+    if (ns == UST_STATE_VALIDATION_REQUIRED) {
+      if (!sp.timed) f |= UST_F_VALIDATION_DONE;
+      else {
+        const bool ready = sp.validation_seconds >= 0 && now_next >= (long long)ent + sp.validation_seconds;
+        f = ready ? (f | UST_F_VALIDATION_DONE) : (f & ~UST_F_VALIDATION_DONE);
+      }
+    }
+    if (ns == UST_STATE_NODE_MAINTENANCE_REQUIRED && (f & UST_F_NM_PRESENT)) {
+      // the maintenance operator: cordon + drain, then Ready (maintenance_seconds after the object was created)
+      const bool ready = !sp.timed || now_next >= (long long)ent + sp.maintenance_seconds;
+      if (ready) { f |= UST_F_NM_READY; b |= UST_HOT_UNSCHEDULABLE; }
+    }
     hot[i] = (uint8_t)((b & 0xF0u) | (ns & 15u));
     flags[i] = f;
     pod_rev[i] = rev;
+    if (sp.timed) { entered[i] = ent; wait_start[i] = ws; valid_start[i] = vs; }
+  }
+}
+
+// the per-node clocks of a timed simulation at time 0: every node "entered" its state then; a wait-start annotation that
+// is already there started then, or - when the snapshot says it has timed out - long ago
+__global__ void __launch_bounds__(kThreads) ust_sim_init_kernel(long long n, const uint32_t* __restrict__ flags, int32_t* entered,
+                                                                int32_t* wait_start, int32_t* valid_start) {
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const uint32_t f = flags[i];
+    entered[i] = 0;
+    wait_start[i] = !(f & UST_F_WAIT_START_ANNO) ? kSimNone : ((f & UST_F_WAIT_TIMED_OUT) ? kSimLongAgo : 0);
+    valid_start[i] = kSimNone;
   }
 }
 
@@ -918,9 +981,17 @@ int ust_launch_patch(long long m, const long long* idx, const uint8_t* state, co
 }
 int ust_launch_feedback(long long n, uint8_t* hot, uint32_t* flags, int32_t* pod_rev, const int32_t* ds_idx, int n_ds,
                         const int32_t* ds_rev, const uint8_t* next, const uint16_t* actions, const uint8_t* outcome,
-                        const ust_counters* step, int grid, void* stream) {
+                        const ust_counters* step, const UstSimParams& sp, int32_t* entered, int32_t* wait_start,
+                        int32_t* valid_start, int grid, void* stream) {
   if (n <= 0) return 0;
-  ust_feedback_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, hot, flags, pod_rev, ds_idx, n_ds, ds_rev, next, actions, outcome, step);
+  ust_feedback_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, hot, flags, pod_rev, ds_idx, n_ds, ds_rev, next, actions, outcome, step,
+                                                                   sp, entered, wait_start, valid_start);
+  return (int)cudaGetLastError();
+}
+int ust_launch_sim_init(long long n, const uint32_t* flags, int32_t* entered, int32_t* wait_start, int32_t* valid_start, int grid,
+                        void* stream) {
+  if (n <= 0) return 0;
+  ust_sim_init_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, flags, entered, wait_start, valid_start);
   return (int)cudaGetLastError();
 }
 int ust_launch_build_state_uids(long long n, const uint8_t* hot, const void* owner_uid, int n_ds, const void* ds_tab,

@@ -78,6 +78,11 @@ class Counters(C.Structure):
         return d
 
 
+class SimOptions(C.Structure):
+    _fields_ = [("seconds_per_reconcile", C.c_int64), ("wait_timeout_seconds", C.c_int64), ("job_seconds", C.c_int64),
+                ("validation_seconds", C.c_int64), ("validation_timeout_seconds", C.c_int64), ("maintenance_seconds", C.c_int64)]
+
+
 class Pods(C.Structure):
     _fields_ = [("pod_off", C.c_void_p), ("pod_flags", C.c_void_p), ("n_pods", C.c_int64)]
 

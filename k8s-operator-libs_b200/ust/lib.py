@@ -61,7 +61,7 @@ def load():
 
 
 EXPORTS = ["ust_abi_version", "ust_create", "ust_destroy", "ust_last_error", "ust_create_error", "ust_launch_count",
-           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_apply_state_packed", "ust_apply_state_delta", "ust_apply_state_delta_sparse", "ust_fetch_outputs", "ust_simulate_rollout", "ust_sync",
+           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_apply_state_packed", "ust_apply_state_delta", "ust_apply_state_delta_sparse", "ust_fetch_outputs", "ust_simulate_rollout", "ust_simulate_rollout_timed", "ust_sync",
            "ust_build_state", "ust_build_state_uids", "ust_get_unique_id", "ust_comm_init", "ust_comm_set_mode", "ust_table_entry",
            "ust_table_window_shift"]
 
@@ -231,6 +231,17 @@ class Handle:
         done = C.c_int32(0)
         rc = self._lib.ust_simulate_rollout(
             self._h, C.addressof(policy) if policy is not None else None, int(steps), C.addressof(hist),
+            _p(fin["state"]) if fin else None, _p(fin["flags"]) if fin else None, _p(fin["pod_rev"]) if fin else None,
+            C.addressof(done))
+        return rc, int(done.value), [hist[k].as_dict() for k in range(steps)], fin
+
+    def simulate_rollout_timed(self, policy, options, n, steps, want_final=True):
+        """ust_simulate_rollout_timed on the resident snapshot (options: abi.SimOptions)."""
+        hist = (abi.Counters * max(steps, 1))()
+        fin = {"state": np.zeros(n, np.uint8), "flags": np.zeros(n, np.uint32), "pod_rev": np.zeros(n, np.int32)} if want_final else None
+        done = C.c_int32(0)
+        rc = self._lib.ust_simulate_rollout_timed(
+            self._h, C.addressof(policy) if policy is not None else None, C.addressof(options), int(steps), C.addressof(hist),
             _p(fin["state"]) if fin else None, _p(fin["flags"]) if fin else None, _p(fin["pod_rev"]) if fin else None,
             C.addressof(done))
         return rc, int(done.value), [hist[k].as_dict() for k in range(steps)], fin

@@ -1296,12 +1296,16 @@ int ust_oracle_build_state_uids(int64_t n_pods, const uint8_t* state, const uint
 //   a deleted driver pod is recreated by its DaemonSet at the current revision and becomes ready; an orphaned pod
 //       (common_manager.go:225-227) has no controller: the node has no driver pod any more and leaves the snapshot
 //   whatever the node still waits for - wait-for-jobs pods, pod readiness, validation - has happened by then.
+int ust_oracle_simulate_timed(int variant, const ust_policy* policy, const ust_sim_options* opt, int64_t n, uint8_t* state,
+                              uint32_t* flags, int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                              int32_t steps, ust_counters* history, int32_t* steps_done);
 int ust_oracle_simulate(int variant, const ust_policy* policy, int64_t n, uint8_t* state, uint32_t* flags, int32_t* pod_rev,
                         const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev, int32_t steps, ust_counters* history,
                         int32_t* steps_done) {
+  if (policy && policy->use_maintenance_operator)  // requestor mode: the restatement below, without a clock
+    return ust_oracle_simulate_timed(variant, policy, nullptr, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, steps, history, steps_done);
   ust_policy pol;
   if (policy) {
-    if (policy->use_maintenance_operator) return UST_ERR_INVALID_ARGUMENT;
     pol = *policy;
     pol.evaluate_actuators = 1;
   }
@@ -1356,6 +1360,121 @@ int ust_oracle_simulate(int variant, const ust_policy* policy, int64_t n, uint8_
         default: break;
       }
       state[i] = (uint8_t)((hb & 0xF0u) | (ns & UST_HOT_STATE_MASK));
+      flags[i] = f;
+    }
+  }
+  if (steps_done) *steps_done = done;
+  return rc;
+}
+
+
+// The timed simulation (ust_simulate_rollout_timed; also the requestor-mode feedback of both entry points), restated
+// on its own: per node a small record of annotations-with-times, advanced reconcile by reconcile. The reconcile itself
+// is the oracle's ApplyState (pinned by the reference's vectors, including the wait-start ones of
+// pod_manager_test.go:183-229); the clock model around it is this repository's (include/ust.h spells it out):
+//   pod_manager.go:331-368        HandleTimeoutOnPodCompletions: start annotation = now; now > start + timeout => pod-deletion
+//   validation_manager.go:139-175 handleTimeout: start annotation = now; now > start + 600 => upgrade-failed
+//   upgrade_requestor.go:277-319, :416-488   NodeMaintenance created / Ready / deleted
+struct SimNode {
+  bool has_wait_start = false, has_valid_start = false;
+  int64_t wait_start = 0, valid_start = 0, entered = 0;
+};
+int ust_oracle_simulate_timed(int variant, const ust_policy* policy, const ust_sim_options* opt, int64_t n, uint8_t* state,
+                              uint32_t* flags, int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
+                              int32_t steps, ust_counters* history, int32_t* steps_done) {
+  ust_policy pol;
+  if (policy) { pol = *policy; pol.evaluate_actuators = 1; }
+  const bool timed = opt != nullptr;
+  std::vector<SimNode> clk((size_t)n);
+  if (timed)
+    for (int64_t i = 0; i < n; i++)
+      if (flags[i] & UST_F_WAIT_START_ANNO) {
+        clk[(size_t)i].has_wait_start = true;
+        clk[(size_t)i].wait_start = (flags[i] & UST_F_WAIT_TIMED_OUT) ? -(1LL << 30) : 0;
+      }
+  std::vector<uint8_t> next((size_t)n + 1), outcome((size_t)n + 1);
+  std::vector<uint16_t> actions((size_t)n + 1);
+  int32_t done = 0;
+  int rc = UST_OK;
+  for (int32_t k = 0; k < steps; k++) {
+    const int64_t now = timed ? (int64_t)k * opt->seconds_per_reconcile : 0;
+    const int64_t then = timed ? now + opt->seconds_per_reconcile : 0;  // time of the next reconcile
+    ust_counters c;
+    rc = ust_oracle_apply_state(variant, policy ? &pol : nullptr, n, state, flags, pod_rev, ds_idx, n_ds, ds_rev, nullptr,
+                                next.data(), actions.data(), outcome.data(), &c);
+    if (history) history[k] = c;
+    if (rc != UST_OK) {
+      if (history) for (int32_t j = k + 1; j < steps; j++) history[j] = c;
+      break;
+    }
+    done = k + 1;
+    for (int64_t i = 0; i < n; i++) {
+      const unsigned code = state[i] & UST_HOT_STATE_MASK;
+      if (code >= UST_STATE_OTHER) continue;
+      SimNode& t = clk[(size_t)i];
+      const unsigned a = actions[i];
+      unsigned to = next[i];
+      if ((a & (UST_A_SCHEDULE_WAIT_CHECK | UST_A_SCHEDULE_POD_EVICTION | UST_A_SCHEDULE_DRAIN)) && outcome[i] != UST_OUTCOME_NONE)
+        to = outcome[i];  // what the asynchronous actuator ends in
+      uint32_t f = flags[i];
+      bool unschedulable = (state[i] & UST_HOT_UNSCHEDULABLE) != 0;
+      // provider calls (ChangeNodeUpgradeAnnotation / Cordon / Uncordon)
+      if (a & UST_A_CLEAR_UPGRADE_REQUESTED) f &= ~UST_F_UPGRADE_REQUESTED;
+      if (a & UST_A_SET_INITIAL_STATE_ANNO) f |= UST_F_INITIAL_STATE_ANNO;
+      if (a & UST_A_CLEAR_INITIAL_STATE_ANNO) f &= ~UST_F_INITIAL_STATE_ANNO;
+      if (a & UST_A_CORDON) unschedulable = true;
+      if (a & UST_A_UNCORDON) unschedulable = false;
+      if (a & UST_A_UNBLOCK_SAFE_LOAD) f &= ~UST_F_SAFE_LOAD;
+      if (a & UST_A_SET_WAIT_START) { f |= UST_F_WAIT_START_ANNO; t.has_wait_start = true; t.wait_start = now; }
+      if (a & UST_A_CLEAR_WAIT_START) {
+        f &= ~(UST_F_WAIT_START_ANNO | UST_F_WAIT_TIMED_OUT | UST_F_WAIT_START_INVALID);
+        t.has_wait_start = false;
+      }
+      if (a & UST_A_REQUESTOR_ANNO_CHANGE) {
+        if (code == UST_STATE_UPGRADE_REQUIRED) f |= UST_F_REQUESTOR_MODE; else f &= ~UST_F_REQUESTOR_MODE;
+      }
+      if (a & UST_A_NM_CREATE_OR_DELETE) {
+        if (code == UST_STATE_UPGRADE_REQUIRED) f |= UST_F_NM_PRESENT;
+        else { f &= ~(UST_F_NM_PRESENT | UST_F_NM_READY); unschedulable = false; }
+      }
+      if (a & UST_A_RESTART_DRIVER_POD) {
+        const bool owned = !(f & UST_F_POD_ORPHANED) && ds_idx[i] >= 0 && ds_idx[i] < n_ds;
+        if (!owned) to = UST_STATE_EXCLUDED;
+        else { pod_rev[i] = ds_rev[ds_idx[i]]; f |= UST_F_POD_READY; f &= ~(UST_F_POD_FAILING | UST_F_POD_TERMINATING); }
+      }
+      if (timed) {
+        // ValidationManager.Validate on a node whose validation pod is not ready
+        if (code == UST_STATE_VALIDATION_REQUIRED && to == UST_STATE_VALIDATION_REQUIRED && !(f & UST_F_VALIDATION_DONE)) {
+          if (!t.has_valid_start) { t.has_valid_start = true; t.valid_start = now; }
+          else if (now > t.valid_start + opt->validation_timeout_seconds) { to = UST_STATE_FAILED; t.has_valid_start = false; }
+        }
+        if (to != UST_STATE_VALIDATION_REQUIRED) t.has_valid_start = false;
+        if (to != code) t.entered = now;
+      }
+      // what the node is waiting for, as the next reconcile will see it
+      if (to == UST_STATE_WAIT_FOR_JOBS_REQUIRED) {
+        if (!timed) {
+          f &= ~UST_F_WAIT_PODS_RUNNING;
+        } else {
+          if (to != code) { if (opt->job_seconds > 0) f |= UST_F_WAIT_PODS_RUNNING; else f &= ~UST_F_WAIT_PODS_RUNNING; }
+          if (then >= t.entered + opt->job_seconds) f &= ~UST_F_WAIT_PODS_RUNNING;
+          if (t.has_wait_start && then > t.wait_start + opt->wait_timeout_seconds) f |= UST_F_WAIT_TIMED_OUT; else f &= ~UST_F_WAIT_TIMED_OUT;
+        }
+      }
+      if (to == UST_STATE_POD_RESTART_REQUIRED) {
+        f &= ~UST_F_POD_TERMINATING;
+        if (!(f & UST_F_POD_FAILING)) f |= UST_F_POD_READY;
+      }
+      if (to == UST_STATE_VALIDATION_REQUIRED) {
+        const bool ready = !timed || (opt->validation_seconds >= 0 && then >= t.entered + opt->validation_seconds);
+        if (ready) f |= UST_F_VALIDATION_DONE; else f &= ~UST_F_VALIDATION_DONE;
+      }
+      if (to == UST_STATE_NODE_MAINTENANCE_REQUIRED && (f & UST_F_NM_PRESENT)) {
+        if (!timed || then >= t.entered + opt->maintenance_seconds) { f |= UST_F_NM_READY; unschedulable = true; }
+      }
+      uint8_t hb = (uint8_t)(state[i] & 0xF0u);
+      hb = unschedulable ? (uint8_t)(hb | UST_HOT_UNSCHEDULABLE) : (uint8_t)(hb & ~UST_HOT_UNSCHEDULABLE);
+      state[i] = (uint8_t)(hb | (to & UST_HOT_STATE_MASK));
       flags[i] = f;
     }
   }

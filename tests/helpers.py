@@ -385,3 +385,52 @@ def oracle_simulate(policy, soa, steps, variant=1):
         _ptr(fin["pod_rev"]), _ptr(soa["ds_idx"]), C.c_int32(int(soa["ds_rev"].shape[0])), _ptr(soa["ds_rev"]), C.c_int32(steps),
         hist, C.byref(done))
     return rc, int(done.value), [hist[k].as_dict() for k in range(steps)], fin
+
+
+def oracle_simulate_timed(policy, options, soa, steps, variant=1):
+    """CPU restatement of ust_simulate_rollout_timed (options None: the untimed feedback, incl. requestor mode)."""
+    n = int(soa["state"].shape[0])
+    fin = {"state": soa["state"].copy(), "flags": soa["flags"].copy(), "pod_rev": soa["pod_rev"].copy()}
+    hist = (abi.Counters * max(steps, 1))()
+    done = C.c_int32(0)
+    rc = oracle().ust_oracle_simulate_timed(
+        C.c_int(variant), C.byref(policy) if policy is not None else None, C.byref(options) if options is not None else None,
+        C.c_int64(n), _ptr(fin["state"]), _ptr(fin["flags"]), _ptr(fin["pod_rev"]), _ptr(soa["ds_idx"]),
+        C.c_int32(int(soa["ds_rev"].shape[0])), _ptr(soa["ds_rev"]), C.c_int32(steps), hist, C.byref(done))
+    return rc, int(done.value), [hist[k].as_dict() for k in range(steps)], fin
+
+
+def wait_timeout_timeline(golden_hash, timeout, dt, steps, n_nodes=3):
+    """What the reference's HandleTimeoutOnPodCompletions (pod_manager.go:331-368) does to nodes whose wait-selector pods
+    keep running, reconcile by reconcile at times k * dt: the annotation bookkeeping is done here, every reconcile is
+    evaluated by the golden-vector encoder (the "wait-start": "now-N" rule of pod_manager_test.go:183-229) and the
+    oracle's vector-pinned ApplyState. Returns (policy, initial soa, final state names, final start annotations)."""
+    pol = abi.make_policy(max_parallel_upgrades=0, wait_for_completion={"podSelector": "app=job", "timeoutSeconds": timeout})
+    pol.evaluate_actuators = 1
+    nodes = [{"state": "wait-for-jobs-required", "ds": True, "pod": {"hash": golden_hash, "phase": "Running", "containers": [[True, 0]]}}
+             for _ in range(n_nodes)]
+    pdict = {"waitForCompletion": {"timeoutSeconds": timeout}}
+    soa, _ = encode_nodes(nodes, golden_hash, pdict)
+    soa["flags"] = (soa["flags"] | np.uint32(abi.UST_F_WAIT_PODS_RUNNING)).astype(np.uint32)   # the jobs keep running
+    start = [None] * n_nodes
+    state = ["wait-for-jobs-required"] * n_nodes
+    for k in range(steps):
+        now = k * dt
+        vec = []
+        for i in range(n_nodes):
+            nd = dict(nodes[i], state=state[i])
+            if start[i] is not None:
+                nd["anno"] = {"wait-start": f"now-{now - start[i]}"}
+            vec.append(nd)
+        s2, _ = encode_nodes(vec, golden_hash, pdict)
+        s2["flags"] = np.where((s2["state"] & 15) == 3, s2["flags"] | np.uint32(abi.UST_F_WAIT_PODS_RUNNING), s2["flags"]).astype(np.uint32)
+        rc, nxt, act, oc, _ = oracle_apply(pol, s2, variant=0)
+        assert rc == 0
+        for i in range(n_nodes):
+            if act[i] & abi.UST_A_SET_WAIT_START:
+                start[i] = now
+            if act[i] & abi.UST_A_CLEAR_WAIT_START:
+                start[i] = None
+            new = oc[i] if ((act[i] & abi.UST_A_SCHEDULE_WAIT_CHECK) and oc[i] != 0xFF) else nxt[i]
+            state[i] = abi.STATE_NAMES[new]
+    return pol, soa, state, start

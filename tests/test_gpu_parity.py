@@ -320,7 +320,68 @@ def test_simulated_rollout_matches_the_cpu_simulation(handle, n, steps):
     orc, odone, ohist, ofin = helpers.oracle_simulate(bad, soa, 3, variant=1)
     assert rc == orc == abi.K["UST_ERR_MAX_UNAVAILABLE"] and done == odone == 0
     assert all(np.array_equal(fin[k], soa[k]) for k in ("state", "flags", "pod_rev"))
-    assert handle.simulate_rollout(abi.make_policy(use_maintenance_operator=True), n, 1)[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]
+
+
+@pytest.mark.parametrize("n,steps", [(4000, 40), (300_001, 16)])
+def test_timed_and_requestor_rollout_simulation(handle, n, steps):
+    """ust_simulate_rollout_timed (a clock: wait-for-completion and validation timeouts, jobs and validation pods that
+    take time) and requestor mode, against the oracle's independent restatement: every reconcile's counters and the
+    final snapshot, bit for bit."""
+    rng = np.random.default_rng(n + steps)
+    soa = synth.make_nodes(n, 0xDEF + n, requestor_pct=3.0)
+    soa["flags"] = (soa["flags"] | np.where(rng.random(n) < 0.3, np.uint32(abi.UST_F_WAIT_PODS_RUNNING), np.uint32(0))
+                    | np.where(rng.random(n) < 0.05, np.uint32(abi.UST_F_WAIT_START_ANNO), np.uint32(0))).astype(np.uint32)
+    soa["flags"] = (soa["flags"] | np.where((rng.random(n) < 0.3) & ((soa["flags"] & abi.UST_F_WAIT_START_ANNO) != 0),
+                                            np.uint32(abi.UST_F_WAIT_TIMED_OUT), np.uint32(0))).astype(np.uint32)
+    wfc = {"podSelector": "app=job", "timeoutSeconds": 90}
+    cases = [
+        (abi.make_policy(max_parallel_upgrades=max(1, n // 40), max_unavailable="40%", validation_enabled=True, drain={"enable": True},
+                         wait_for_completion=wfc), abi.SimOptions(30, 90, 200, 75, 600, 0)),
+        (abi.make_policy(max_parallel_upgrades=0, max_unavailable="20%", validation_enabled=True, wait_for_completion=wfc),
+         abi.SimOptions(60, 90, 45, -1, 300, 0)),                 # validation pods never become ready: nodes time out into upgrade-failed
+        (abi.make_policy(max_parallel_upgrades=max(1, n // 40), validation_enabled=True, use_maintenance_operator=True,
+                         wait_for_completion={"podSelector": "app=job"}), abi.SimOptions(20, 0, 50, 30, 600, 70)),
+        (abi.make_policy(max_parallel_upgrades=5, use_maintenance_operator=True), None),   # requestor mode without a clock
+    ]
+    for pol, opt in cases:
+        assert gpu_apply(handle, pol, soa)[0] == 0          # makes the snapshot resident
+        if opt is None:
+            rc, done, hist, fin = handle.simulate_rollout(pol, n, steps)
+        else:
+            rc, done, hist, fin = handle.simulate_rollout_timed(pol, opt, n, steps)
+        orc, odone, ohist, ofin = helpers.oracle_simulate_timed(pol, opt, soa, steps, variant=1)
+        assert rc == orc == 0 and done == odone == steps, (rc, orc, handle.last_error())
+        for k in range(steps):
+            assert hist[k] == ohist[k], f"counters of reconcile {k}"
+        for key in ("state", "flags", "pod_rev"):
+            assert np.array_equal(fin[key], ofin[key]), key
+    # the clock did something: with validation pods that never come up, nodes end in upgrade-failed through the timeout
+    pol, opt = cases[1]
+    gpu_apply(handle, pol, soa)
+    _, _, hist, _ = handle.simulate_rollout_timed(pol, opt, n, steps)
+    assert hist[-1]["hist"][abi.UST_STATE_FAILED] > hist[0]["hist"][abi.UST_STATE_FAILED]
+    bad = abi.SimOptions(30, 0, 0, 0, 600, 0)
+    assert handle.simulate_rollout_timed(cases[0][0], bad, n, 1)[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]   # timeout flag / value disagree
+
+
+def test_simulated_wait_timeout_follows_the_reference_vectors(handle):
+    """The wait-for-completion timeout of the simulation, pinned: a node whose wait-selector pods keep running is driven
+    through the device simulation, and reconcile by reconcile the result must be what the reference's
+    HandleTimeoutOnPodCompletions does (pod_manager.go:331-368; golden vectors pod_manager_test.go:183-229): no start
+    annotation -> the annotation is set; within the timeout -> nothing; now > start + timeout -> pod-deletion-required
+    and the annotation is gone. The expectation is computed here from the annotation rules alone, with the oracle's
+    (vector-pinned) ApplyState evaluating each reconcile."""
+    timeout, dt, steps = 100, 30, 8
+    pol, soa, state, start = helpers.wait_timeout_timeline(G["daemonset_hash"], timeout, dt, steps)
+    assert gpu_apply(handle, pol, soa)[0] == 0
+    opt = abi.SimOptions(dt, timeout, 10 ** 6, 0, 600, 0)
+    rc, done, hist, fin = handle.simulate_rollout_timed(pol, opt, 3, steps)
+    assert rc == 0 and done == steps
+    # annotation set at t=0, timeout exceeded at the first reconcile with now > 100 (t=120, reconcile 4): pod deletion is
+    # not enabled, so the node goes on from pod-deletion-required to drain-required and further
+    assert [abi.STATE_NAMES[c & 15] for c in fin["state"]] == state
+    assert all(((fin["flags"][i] & abi.UST_F_WAIT_START_ANNO) != 0) == (start[i] is not None) for i in range(3))
+    assert hist[4]["hist"][abi.UST_STATE_WAIT_FOR_JOBS_REQUIRED] == 3 and hist[5]["hist"][abi.UST_STATE_WAIT_FOR_JOBS_REQUIRED] == 0
 
 
 @pytest.mark.parametrize("n", [0, 1, 5000, 700_001])

@@ -105,3 +105,24 @@ def test_simulated_rollout_converges_and_respects_the_budget():
         assert moved <= max(hist[k - 1]["upgrades_available"], 0) + hist[k - 1]["unavailable"], k
         if hist[k]["max_unavailable"] < hist[k]["total_managed"] and k > 8:
             assert hist[k]["unavailable"] <= max(hist[0]["unavailable"], hist[k]["max_unavailable"]), k
+
+
+def test_oracle_timed_simulation_follows_the_wait_start_vectors():
+    """The oracle's restatement of the timed rollout simulation against the reference's wait-for-completion timeout rule
+    (pod_manager.go:331-368, vectors pod_manager_test.go:183-229), reconcile by reconcile (helpers.wait_timeout_timeline):
+    annotation set on the first reconcile, nothing until now > start + timeout, then pod-deletion-required."""
+    G = helpers.load_golden()
+    for timeout, dt, steps in ((100, 30, 8), (45, 45, 5), (10, 60, 3)):
+        pol, soa, state, start = helpers.wait_timeout_timeline(G["daemonset_hash"], timeout, dt, steps)
+        opt = abi.SimOptions(dt, timeout, 10 ** 6, 0, 600, 0)
+        for variant in (0, 1):
+            rc, done, hist, fin = helpers.oracle_simulate_timed(pol, opt, soa, steps, variant=variant)
+            assert rc == 0 and done == steps
+            assert [abi.STATE_NAMES[c & 15] for c in fin["state"]] == state, (timeout, dt, state)
+            assert all(((fin["flags"][i] & abi.UST_F_WAIT_START_ANNO) != 0) == (start[i] is not None) for i in range(3))
+        # first reconcile with now > start + timeout
+        k_out = next(k for k in range(steps + 50) if k * dt > timeout)
+        if k_out < steps:
+            assert hist[k_out]["hist"][abi.UST_STATE_WAIT_FOR_JOBS_REQUIRED] == 3
+            if k_out + 1 < steps:
+                assert hist[k_out + 1]["hist"][abi.UST_STATE_WAIT_FOR_JOBS_REQUIRED] == 0
