@@ -24,6 +24,10 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libust.so does not export {name}"
     assert sorted(ustlib.EXPORTS) == declared
+    # every entry point that takes arguments has its ctypes signature declared (a missing one passes pointers as 32-bit ints)
+    for name in declared:
+        if name not in ("ust_abi_version", "ust_create_error"):
+            assert getattr(lib, name).argtypes is not None, f"{name}: argtypes not declared in ust/lib.py"
     assert lib.ust_abi_version() == abi.UST_ABI_VERSION
 
 
