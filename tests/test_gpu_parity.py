@@ -355,11 +355,16 @@ def test_timed_and_requestor_rollout_simulation(handle, n, steps):
             assert hist[k] == ohist[k], f"counters of reconcile {k}"
         for key in ("state", "flags", "pod_rev"):
             assert np.array_equal(fin[key], ofin[key]), key
-    # the clock did something: with validation pods that never come up, nodes end in upgrade-failed through the timeout
+    # the clock does something: validation pods that never come up hold their nodes in validation-required until the
+    # validation timeout (start annotation at t = 0, now > 0 + 300 first at t = 360 = reconcile 6), then the nodes fail
+    v = synth.make_nodes(64, 0x77)
+    v["state"] = ((v["state"] & 0xF0) | abi.UST_STATE_VALIDATION_REQUIRED).astype(np.uint8)
+    v["flags"] = (v["flags"] & ~np.uint32(abi.UST_F_VALIDATION_DONE | abi.UST_F_SAFE_LOAD)).astype(np.uint32)
     pol, opt = cases[1]
-    gpu_apply(handle, pol, soa)
-    _, _, hist, _ = handle.simulate_rollout_timed(pol, opt, n, steps)
-    assert hist[-1]["hist"][abi.UST_STATE_FAILED] > hist[0]["hist"][abi.UST_STATE_FAILED]
+    gpu_apply(handle, pol, v)
+    rc, _, hist, _ = handle.simulate_rollout_timed(pol, opt, 64, 9)
+    assert rc == 0
+    assert [h["hist"][abi.UST_STATE_VALIDATION_REQUIRED] for h in hist] == [64] * 7 + [0, 0]
     bad = abi.SimOptions(30, 0, 0, 0, 600, 0)
     assert handle.simulate_rollout_timed(cases[0][0], bad, n, 1)[0] == abi.K["UST_ERR_INVALID_ARGUMENT"]   # timeout flag / value disagree
 
