@@ -430,9 +430,9 @@ def main():
             B.call(h, B.bind(h, policy, bufs[:1])[0])
             B.barrier()
             nx = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
-            ac = [torch.empty(n, dtype=torch.int16, device=dev) for _ in range(world)] if rank == 0 else None
+            ac = [torch.empty(2 * n, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None   # NCCL has no int16
             dist.gather(bufs[0]["next"], nx, dst=0)
-            dist.gather(bufs[0]["actions"], ac, dst=0)
+            dist.gather(bufs[0]["actions"].view(torch.uint8), ac, dst=0)
             if rank != 0:
                 return None
             return (np.concatenate([t.cpu().numpy() for t in nx]), np.concatenate([t.cpu().numpy() for t in ac]).view(np.uint16),
