@@ -393,39 +393,55 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
 }
 
 // Cluster-wide vector for world > 1 without a host-launched collective (verification kernel, every CTA): CTA 0 pushes
-// this shard's lanes into every rank's mailbox over NVLink (all lanes of all peers in parallel) and releases a flag per
-// peer; every CTA waits for every rank's flag in the OWN mailbox (local memory) and sums for itself - no intra-GPU
-// broadcast, no CTA waits for another CTA of its grid. One-hot per-rank lanes make the sum an all-gather. Returns
-// false when a peer did not show up in time.
+// this shard's lanes into every rank's mailbox over NVLink - one 8-byte store per half lane and peer, all of them in
+// flight at once, each word tagged with the call number, so nothing has to be fenced or flagged; every CTA polls the
+// words of every rank in the OWN mailbox (local memory) until they carry this call's number, and sums for itself - no
+// intra-GPU broadcast, no CTA waits for another CTA of its grid. One-hot per-rank lanes make the sum an all-gather.
+// Returns false when a peer did not show up in time.
+__device__ __forceinline__ void st_mbox(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_mbox(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ inline bool exchange_vector(const UstParams& P, DecideShared& D, bool pusher) {
   const int t = threadIdx.x, nt = blockDim.x;
   const int par = (int)(P.epoch & 1);
+  const unsigned long long tag = (unsigned long long)(unsigned)P.epoch << 32;
   if (pusher) {
-    for (int i = t; i < P.world * UST_V_LEN; i += nt) {
-      const int r = i / UST_V_LEN, l = i - r * UST_V_LEN;
-      st_relaxed_sys(&P.mbox[r]->slot[par][P.rank][l], D.V[l]);
+    for (int i = t; i < P.world * UST_MBOX_WORDS; i += nt) {
+      const int r = i / UST_MBOX_WORDS, w = i - r * UST_MBOX_WORDS;
+      const unsigned long long lane = (unsigned long long)D.V[w >> 1];
+      const unsigned long long half = (w & 1) ? (lane >> 32) : (lane & 0xFFFFFFFFull);
+      st_mbox(&P.mbox[r]->slot[par][P.rank][w], tag | half);
     }
-    __threadfence_system();
-    __syncthreads();
-    if (t < P.world) st_release_sys(&P.mbox[t]->slot[par][P.rank][UST_MBOX_FLAG], P.epoch);
   }
+  __syncthreads();  // D.V is about to be overwritten with the sum
+  // word w of rank r: thread (r * WORDS + w) when the block is wide enough, else a strided loop
   int ok = 1;
-  if (t < P.world) {
-    const unsigned long long t0 = now_ns();
-    while (ld_acquire_sys(&P.mbox[P.rank]->slot[par][t][UST_MBOX_FLAG]) != P.epoch) {
+  const unsigned long long t0 = now_ns();
+  long long mine[(UST_MAX_WORLD * UST_MBOX_WORDS + UST_THREADS - 1) / UST_THREADS];
+  int k = 0;
+  for (int i = t; i < P.world * UST_MBOX_WORDS; i += nt, k++) {
+    const int r = i / UST_MBOX_WORDS, w = i - r * UST_MBOX_WORDS;
+    const unsigned long long* src = &P.mbox[P.rank]->slot[par][r][w];
+    unsigned long long v = ld_mbox(src);
+    while ((v >> 32) != (tag >> 32)) {
       if (now_ns() - t0 > kCommTimeoutNs) { ok = 0; break; }
-      __nanosleep(40);
+      __nanosleep(20);
+      v = ld_mbox(src);
     }
+    mine[k] = (long long)(v & 0xFFFFFFFFull);
   }
+  if (t < UST_V_LEN) D.V[t] = 0;
   ok = __syncthreads_and(ok);
-  if (t < UST_V_LEN) {
-    long long v[UST_MAX_WORLD];
-#pragma unroll
-    for (int r = 0; r < UST_MAX_WORLD; r++) v[r] = r < P.world ? ld_relaxed_sys(&P.mbox[P.rank]->slot[par][r][t]) : 0;
-    long long sum = 0;
-#pragma unroll
-    for (int r = 0; r < UST_MAX_WORLD; r++) sum += v[r];
-    D.V[t] = sum;
+  // sum the halves into the lanes (shared-memory atomics: 84 x world adds)
+  k = 0;
+  for (int i = t; i < P.world * UST_MBOX_WORDS; i += nt, k++) {
+    const int w = i % UST_MBOX_WORDS;
+    atomicAdd(reinterpret_cast<unsigned long long*>(&D.V[w >> 1]), (unsigned long long)mine[k] << (32 * (w & 1)));
   }
   __syncthreads();
   return ok != 0;

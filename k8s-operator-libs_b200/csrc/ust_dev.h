@@ -36,11 +36,12 @@
 #define UST_V_LEN (18 + 3 * UST_MAX_WORLD)
 
 // Peer mailboxes of the fused multi-GPU exchange: rank s writes its lanes into slot[epoch & 1][s] of EVERY rank's
-// mailbox over NVLink (CUDA IPC mapping), then releases the flag lane with the epoch number.
-#define UST_MBOX_FLAG UST_V_LEN
-#define UST_MBOX_LANES (UST_V_LEN + 6)  /* 48 lanes = 384 B per slot */
+// mailbox over NVLink (CUDA IPC mapping). Every 8-byte word carries half a lane and the call number
+// ({data:32, epoch:32}, one 8-byte store each - delivered whole), so the data is its own flag: no fence, no separate
+// flag store, the reader polls the words it needs.
+#define UST_MBOX_WORDS (2 * UST_V_LEN)   /* 84 words = 672 B per slot */
 struct UstMailbox {
-  long long slot[2][UST_MAX_WORLD][UST_MBOX_LANES];
+  unsigned long long slot[2][UST_MAX_WORLD][UST_MBOX_WORDS + 12];
 };
 
 // Device workspace owned by a handle. The per-call accumulators exist twice: call k uses set (k & 1); the streaming
