@@ -189,7 +189,10 @@ typedef struct ust_counters {
 
 /* Optional per-node workload pod lists (CSR). pod_off has n_nodes+1 entries; for device-resident calls
  * pod_flags must be 16-byte aligned like every other array (the list reader uses 16-byte loads, never past
- * pod_flags + n_pods). */
+ * pod_flags + n_pods). pod_off is int32: one call (one shard) holds fewer than 2^31 workload pods - at BASELINE's 30
+ * pods per node that is 71 M nodes per GPU; shard further before that. The host entry points check the offsets
+ * (pod_off[0] == 0, non-decreasing, pod_off[n_nodes] == n_pods => UST_ERR_INVALID_ARGUMENT otherwise);
+ * ust_apply_state_device trusts the caller's device arrays. */
 typedef struct ust_pods {
   const int32_t* pod_off;
   const uint16_t* pod_flags;

@@ -422,7 +422,7 @@ __device__ inline bool exchange_vector(const UstParams& P, DecideShared& D, bool
   // word w of rank r: thread (r * WORDS + w) when the block is wide enough, else a strided loop
   int ok = 1;
   const unsigned long long t0 = now_ns();
-  long long mine[(UST_MAX_WORLD * UST_MBOX_WORDS + UST_THREADS - 1) / UST_THREADS];
+  long long mine[(UST_MAX_WORLD * UST_MBOX_WORDS + 255) / 256];   // the kernel runs at least 256 threads
   int k = 0;
   for (int i = t; i < P.world * UST_MBOX_WORDS; i += nt, k++) {
     const int r = i / UST_MBOX_WORDS, w = i - r * UST_MBOX_WORDS;

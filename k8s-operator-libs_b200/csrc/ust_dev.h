@@ -5,7 +5,10 @@
 #include "../../include/ust.h"
 #include "ust_lut.h"
 
-#define UST_THREADS 256          /* verification / auxiliary kernels */
+#define UST_THREADS 256          /* auxiliary kernels */
+#ifndef UST_VERIFY_THREADS
+#define UST_VERIFY_THREADS 384   /* verification kernel */
+#endif
 #define UST_MAX_CTAS 1024        /* per-CTA diagnostic stamps */
 #define UST_MAX_WORLD 8
 #define UST_DS_SMEM_MAX 1024

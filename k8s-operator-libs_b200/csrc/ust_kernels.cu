@@ -24,6 +24,10 @@ namespace {
 constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStep = kThreads * 4;   // nodes per CTA step (4 per thread)
+// the verification kernel: 12 warps per CTA (one CTA per SM beside the resident streaming kernel: 384 x 96 registers fit)
+constexpr int kVThreads = UST_VERIFY_THREADS;
+constexpr int kVWarps = kVThreads / 32;
+constexpr int kVStep = kVThreads * 4;
 constexpr uint32_t kLutBytes = UST_LUT_WORDS * sizeof(uint32_t);  // table + 16 {x, y} meta pairs
 constexpr int kSimNone = INT32_MIN;        // rollout simulation: no start-time annotation
 constexpr int kSimLongAgo = -(1 << 30);    // ... one that timed out before the simulation began
@@ -34,7 +38,7 @@ struct __align__(128) Shared {
   uint2 meta[16];
   unsigned long long mbar;        // mbarrier the bulk copy completes on
   int dsrev[kDsSmem + 1];         // DaemonSet revisions (larger tables are read from global memory: this is the rare path)
-  unsigned int warp_tot[kWarps];
+  unsigned int warp_tot[kVWarps];
   // the verdict, CTA-uniform
   unsigned long long abort_key;   // ~0 = none
   long long node_offset;          // global index of this shard's node 0
@@ -91,7 +95,7 @@ __device__ __forceinline__ uint32_t apply_abort(const Shared& S, uint32_t ent, u
   return ent;
 }
 
-// One step of kStep nodes starting at `base`, bounds-checked against b1 (the end of the tile / the shard).
+// One step of kVStep nodes starting at `base`, bounds-checked against b1 (the end of the tile / the shard).
 // EXACT: the ordered slot allocation - candidate = upgrade-required && !skip; rank = exclusive count of candidates in
 // slice order from the start of the tile (`running` carries it from step to step); granted iff rank < S.slots
 // (upgrade_inplace.go:71-109). Otherwise the grant is uniform. Abort masking and pod-list summaries as in the
@@ -144,7 +148,7 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
     __syncthreads();
     unsigned before = 0, step_total = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; w++) {
+    for (int w = 0; w < kVWarps; w++) {
       const unsigned v = S.warp_tot[w];
       if (w < (t >> 5)) before += v;
       step_total += v;
@@ -191,7 +195,7 @@ __device__ void general_step(const UstParams& P, Shared& S, long long base, long
 
 // A span of full steps with a uniform grant and no abort, software-pipelined: while the two steps (2048 nodes) of one
 // iteration are evaluated, the loads of the next two are already in flight (two register buffers, the loop is unrolled
-// over them). b0, b1: multiples of kStep apart (the caller peels the ragged end).
+// over them). b0, b1: multiples of kVStep apart (the caller peels the ragged end).
 struct SpanTile {
   uint32_t h[2], ps[2];
   uint4 f[2], r[2], d[2];
@@ -200,8 +204,8 @@ __device__ __forceinline__ void span_load(const UstParams& P, SpanTile& T, long 
   const int t = threadIdx.x;
 #pragma unroll
   for (int j = 0; j < 2; j++) {
-    const long long i = base + (long long)j * kStep + 4 * t;
-    const bool v = i < b1;   // warp-uniform: spans are multiples of kStep
+    const long long i = base + (long long)j * kVStep + 4 * t;
+    const bool v = i < b1;   // warp-uniform: spans are multiples of kVStep
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     T.h[j] = v ? __ldg(reinterpret_cast<const uint32_t*>(P.hot + i)) : 0x0E0E0E0Eu;
     T.ps[j] = (v && P.podsum) ? __ldcs(reinterpret_cast<const uint32_t*>(P.podsum + i)) : 0u;
@@ -215,7 +219,7 @@ __device__ __forceinline__ void span_eval(const UstParams& P, Shared& S, const S
   const int t = threadIdx.x;
 #pragma unroll
   for (int j = 0; j < 2; j++) {
-    const long long i = base + (long long)j * kStep + 4 * t;
+    const long long i = base + (long long)j * kVStep + 4 * t;
     if (i >= b1) continue;
     const uint32_t fl[4] = {T.f[j].x, T.f[j].y, T.f[j].z, T.f[j].w};
     const uint32_t rv[4] = {T.r[j].x, T.r[j].y, T.r[j].z, T.r[j].w};
@@ -237,7 +241,7 @@ __device__ __forceinline__ void span_eval(const UstParams& P, Shared& S, const S
 }
 __device__ void uniform_span(const UstParams& P, Shared& S, long long b0, long long b1, uint32_t grant) {
   const bool ds_smem = P.n_ds <= kDsSmem;
-  constexpr long long kIter = 2LL * kStep;
+  constexpr long long kIter = 2LL * kVStep;
   SpanTile A, B;
   span_load(P, A, b0, b1);
   for (long long base = b0; base < b1; base += 2 * kIter) {
@@ -249,11 +253,11 @@ __device__ void uniform_span(const UstParams& P, Shared& S, long long b0, long l
 }
 
 // candidates (upgrade-required && !skip, upgrade_inplace.go:82) among the nodes [b0, b1) - hot bytes only; b0 and
-// b1 are multiples of kStep apart inside one tile. Whole CTA; every thread returns the total.
+// b1 are multiples of kVStep apart inside one tile. Whole CTA; every thread returns the total.
 __device__ long long count_candidates(const UstParams& P, Shared& S, long long b0, long long b1) {
   const int t = threadIdx.x;
   unsigned c = 0;
-  for (long long i = b0 + 16LL * t; i < b1; i += 16LL * kThreads) {  // b0: multiple of 1024, 16 t < 4096: aligned 16-byte loads
+  for (long long i = b0 + 16LL * t; i < b1; i += 16LL * kVThreads) {  // b0: multiple of 1024, 16 t < 4096: aligned 16-byte loads
     const uint4 x = __ldg(reinterpret_cast<const uint4*>(P.hot + i));
     c += __popc(cand_mask4(x.x)) + __popc(cand_mask4(x.y)) + __popc(cand_mask4(x.z)) + __popc(cand_mask4(x.w));
   }
@@ -263,34 +267,34 @@ __device__ long long count_candidates(const UstParams& P, Shared& S, long long b
   __syncthreads();
   long long tot = 0;
 #pragma unroll
-  for (int w = 0; w < kWarps; w++) tot += S.warp_tot[w];
+  for (int w = 0; w < kVWarps; w++) tot += S.warp_tot[w];
   __syncthreads();
   return tot;
 }
 
-// Re-evaluate the steps [s0, s1) (kStep nodes each) of one tile exactly, given where the slot budget cuts.
+// Re-evaluate the steps [s0, s1) (kVStep nodes each) of one tile exactly, given where the slot budget cuts.
 __device__ void redo_steps(const UstParams& P, Shared& S, int tile, int s0, int s1) {
   const long long t0 = (long long)tile * P.tile_nodes;
   long long t1 = t0 + P.tile_nodes;
   if (t1 > P.n) t1 = P.n;
-  const long long b0 = t0 + (long long)s0 * kStep;
-  long long b1 = t0 + (long long)s1 * kStep;
+  const long long b0 = t0 + (long long)s0 * kVStep;
+  long long b1 = t0 + (long long)s1 * kVStep;
   if (b1 > t1) b1 = t1;
   if (b0 >= b1) return;
   const bool slotted = P.active && !P.requestor;
   const bool aborting = S.abort_key != ~0ull;
   if (slotted && tile == S.cut) {  // the cut tile: S.slots of its candidates get a slot, in slice order
     long long running = s0 > 0 ? count_candidates(P, S, t0, b0) : 0;  // candidates of the tile before this piece
-    for (long long base = b0; base < b1; base += kStep) general_step<true>(P, S, base, b1, 0u, running);
+    for (long long base = b0; base < b1; base += kVStep) general_step<true>(P, S, base, b1, 0u, running);
     return;
   }
   const uint32_t grant = (slotted && tile < S.cut) ? UST_W_GRANTED : 0u;
   long long running = 0, full_end = b0;
   if (!aborting) {
-    full_end = b0 + ((b1 - b0) / kStep) * kStep;
+    full_end = b0 + ((b1 - b0) / kVStep) * kVStep;
     if (full_end > b0) uniform_span(P, S, b0, full_end, grant);
   }
-  for (long long base = full_end; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
+  for (long long base = full_end; base < b1; base += kVStep) general_step<false>(P, S, base, b1, grant, running);
 }
 
 // Re-evaluate the tiles [ta, tb) - a contiguous run owned by one CTA when many tiles are redone. Without an abort and
@@ -298,9 +302,9 @@ __device__ void redo_steps(const UstParams& P, Shared& S, int tile, int s0, int 
 // through the pipelined span as a whole; the cut tile takes the ordered path.
 __device__ void redo_range(const UstParams& P, Shared& S, int ta, int tb) {
   const int tn = P.tile_nodes;
-  const int steps_per_tile = (tn + kStep - 1) / kStep;
+  const int steps_per_tile = (tn + kVStep - 1) / kVStep;
   const bool aborting = S.abort_key != ~0ull;
-  if (aborting || tn % kStep != 0) {
+  if (aborting || tn % kVStep != 0) {
     for (int tile = ta; tile < tb; tile++) { redo_steps(P, S, tile, 0, steps_per_tile); __syncthreads(); }
     return;
   }
@@ -314,10 +318,10 @@ __device__ void redo_range(const UstParams& P, Shared& S, int ta, int tb) {
     const long long b0 = (long long)x * tn;
     long long b1 = (long long)y * tn;
     if (b1 > P.n) b1 = P.n;
-    const long long full_end = b0 + ((b1 - b0) / kStep) * kStep;
+    const long long full_end = b0 + ((b1 - b0) / kVStep) * kVStep;
     if (full_end > b0) uniform_span(P, S, b0, full_end, grant);
     long long running = 0;
-    for (long long base = full_end; base < b1; base += kStep) general_step<false>(P, S, base, b1, grant, running);
+    for (long long base = full_end; base < b1; base += kVStep) general_step<false>(P, S, base, b1, grant, running);
   }
   if (cut >= ta && cut < tb) { __syncthreads(); redo_steps(P, S, cut, 0, steps_per_tile); }
 }
@@ -367,12 +371,12 @@ __global__ void __maxnreg__(96) ust_verify_kernel(const __grid_constant__ UstPar
     S.abort_key = S.D.abort_key; S.node_offset = S.D.node_offset;
   }
   if (P.n_ds <= kDsSmem)
-    for (int i = t; i <= P.n_ds; i += kThreads) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
+    for (int i = t; i <= P.n_ds; i += kVThreads) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
   __syncthreads();
   int first = S.lo, last = S.hi;
   if (redo == 2) { first = 0; last = P.n_tiles - 1; }
   const int m = last - first + 1;
-  const int steps_per_tile = (P.tile_nodes + kStep - 1) / kStep;
+  const int steps_per_tile = (P.tile_nodes + kVStep - 1) / kVStep;
   if (m >= (int)gridDim.x) {
     // many tiles: a contiguous run per CTA
     const int per = (m + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -939,7 +943,7 @@ __global__ void __launch_bounds__(kThreads) ust_diff_write_kernel(long long n, c
 int ust_launch_verify(const UstParams& p, int grid, void* stream, int pdl) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kVThreads);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
