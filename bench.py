@@ -170,14 +170,16 @@ class DeviceBench:
 
     def __init__(self, torch, dist, ustlib, abi, dev, world):
         self.torch, self.dist, self.ustlib, self.abi, self.dev, self.world = torch, dist, ustlib, abi, dev, world
-        # a dedicated stream: torch's default stream has handle 0, which the C ABI reads as "use the handle's own
-        # stream" — events recorded on torch's stream would then not bracket the kernels (round-1 lesson)
-        self.tstream = torch.cuda.Stream(device=dev)
-        torch.cuda.set_stream(self.tstream)
-        self.stream = self.tstream.cuda_stream
-        assert self.stream != 0
         self.counters = torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)
         self.fn = ustlib.load().ust_apply_state_device
+
+    def on(self, h):
+        """Time calls of handle `h`: they run on the handle's own stream (stream argument NULL), and so do the CUDA events
+        and the launch-queue blocker - torch is made to treat that stream as current. (Events recorded on any other stream
+        would not bracket the kernels: round-1 lesson.)"""
+        ext = self.torch.cuda.ExternalStream(h.stream(), device=self.dev)
+        self.torch.cuda.set_stream(ext)
+        self._ext = ext
 
     def upload(self, soa, sets, outcome=False):
         torch = self.torch
@@ -197,7 +199,7 @@ class DeviceBench:
         n_ds = int(bufs[0]["ds_rev"].shape[0])
         pol_p = C.c_void_p(C.addressof(pol))
         cnt_p = C.c_void_p(self.counters.data_ptr())
-        st_p = C.c_void_p(self.stream)
+        st_p = None   # the handle's own stream
         bound = []
         for b in bufs:
             bound.append((h._h, pol_p, C.c_int64(n), C.c_void_p(b["state"].data_ptr()), C.c_void_p(b["flags"].data_ptr()),
@@ -225,6 +227,7 @@ class DeviceBench:
     def time_steps(self, h, seq, steps, warmup):
         """seq(i) -> bound argument tuple of step i. Returns total milliseconds of `steps` steps (this rank)."""
         torch = self.torch
+        self.on(h)
         for i in range(warmup):
             self.call(h, seq(i))
         self.barrier()
@@ -564,6 +567,19 @@ def main():
         peak, _ = peaks()
         by_config = {"C3": {"ms": line["ms_per_step"], "frac": line["roofline"]["frac"], "bytes_per_node": BYTES_PER_NODE,
                             "verified_vs_oracle": verified, "redone_tiles_per_call": 0}}
+        # the same steps in strict order (UST_OVERLAP=0: every call waits for the previous call's verification kernel, as
+        # calls that share buffers always do): the time of ONE call, where the headline is the rate of a pipeline of them
+        os.environ["UST_OVERLAP"] = "0"
+        h_serial = ustlib.Handle(local_rank)
+        del os.environ["UST_OVERLAP"]
+        bound_s = B.bind(h_serial, pol, bufs)
+        ms_serial = B.time_steps(h_serial, lambda i: bound_s[i % SETS], args.steps, warmup)
+        by_config["C3"]["serial_ms"] = ms_serial / args.steps
+        by_config["C3"]["serial_frac"] = BYTES_PER_NODE * n / (ms_serial / args.steps * 1e-3) / 1e9 / peak
+        by_config["C3"]["note"] = ("ms: back-to-back calls on separate buffer sets overlap (a call's streaming kernel starts while the "
+                                   "previous call is being decided); serial_ms: strict order, one call at a time")
+        h_serial.close()
+        del bound_s
 
         def frac_of(nbytes, ms):
             return nbytes / (ms * 1e-3) / 1e9 / peak

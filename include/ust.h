@@ -246,6 +246,13 @@ int ust_apply_state_device(ust_handle* h, const ust_policy* policy, int64_t n_no
                            uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome,
                            ust_counters* out_device, void* stream);
 int ust_sync(ust_handle* h);
+/* The handle's own CUDA stream (a cudaStream_t), the one calls with stream == NULL run on - to record events on it.
+ * Back-to-back ust_apply_state_device calls on this stream that share no buffer with one another except read-only
+ * inputs (different snapshots, different output arrays - a batch of clusters, a sweep of what-if policies) overlap: a
+ * call's streaming kernel starts as the previous call's runs out of work, and that call's decision (and multi-GPU
+ * exchange) runs beside it. Calls that share an output or feed on the previous call's outputs, calls with pod lists
+ * and calls on any other stream keep the strict order. Results are the same either way. */
+void* ust_stream(ust_handle* h);
 
 /* Packed host format: ust_apply_state with the two interned columns at the width they need - pod_rev16[i] is the
  * interned driver-pod revision hash (0 = none) as uint16, ds_idx8[i] the DaemonSet index as int8 (< 0 = orphaned),

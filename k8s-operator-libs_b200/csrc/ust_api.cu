@@ -92,6 +92,12 @@ struct ust_handle {
   bool stamps = false;      // UST_STAMPS: per-CTA %globaltimer stamps (diagnostics)
   int static_pct = 75;      // share of a launch's tile rounds taken in stride order before the ticket (UST_STATIC_PCT: tuning)
   unsigned call_seq = 0;    // calls whose kernels were launched: call k uses accumulator set k & 1 of the workspace
+  // the previous call's buffers, when its kernels are the last thing enqueued on the handle's own stream (else n = -1):
+  // a call that touches none of them does not wait for it (UstParams::relaxed)
+  struct Span { const char* p; size_t len; };
+  Span prev_in[4] = {}, prev_out[3] = {};
+  int64_t prev_n = -1;
+  bool overlap_calls = true;  // UST_OVERLAP=0 turns the overlap of independent back-to-back calls off (tuning)
   cudaStream_t last_stream = nullptr;  // stream of the previous device-resident call (calls on another stream are ordered behind it)
   int64_t resident_n = -1;  // nodes of the snapshot the last ust_apply_state left in the staging arrays (-1 = none)
   int32_t resident_n_ds = 0;  // ... and the size of its DaemonSet table
@@ -120,7 +126,8 @@ struct ust_handle {
   DevBuf<int8_t> s_ds8;
   DevBuf<uint16_t> s_actions, s_podflags;
   DevBuf<uint8_t> s_podsum;
-  DevBuf<unsigned int> s_candtile;   // upgrade candidates per tile of the current call
+  DevBuf<unsigned int> s_candtile[2];   // upgrade candidates per tile of the current call (by call parity: the previous
+                                        // call's verification kernel may still be reading its own)
   // sparse delta outputs: the previous call's outputs, block counts, compacted entries
   DevBuf<uint8_t> s_next_prev, sp_next;
   DevBuf<uint16_t> s_actions_prev, sp_actions;
@@ -277,9 +284,12 @@ static int fill_params(ust_handle* h, const ust_policy* policy, int64_t n, const
   P.static_rounds = pick_static_rounds(h, tiles, grid);
   P.publish = 1;
   P.stamps = (h->stamps && grid <= UST_MAX_CTAS) ? 1 : 0;
-  cudaError_t ce = h->s_candtile.reserve((size_t)tiles + 1);
-  if (ce != cudaSuccess) return h->fail(UST_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(ce));
-  P.cand_tile = h->s_candtile.p;
+  for (auto& b : h->s_candtile) {
+    // growing a buffer frees the old one: nothing of an earlier call may still be using it
+    if ((size_t)tiles + 1 > b.cap && h->last_stream) cudaStreamSynchronize(h->last_stream);
+    cudaError_t ce = b.reserve((size_t)tiles + 1);
+    if (ce != cudaSuccess) return h->fail(UST_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(ce));
+  }
   *out = P;
   *grid_out = grid;
   return UST_OK;
@@ -352,12 +362,40 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
   }
   if (P.fused_exchange) P.epoch = ++h->epoch;  // collective call number: identical on every rank
   P.parity = (int)(h->call_seq++ & 1u);
+  P.cand_tile = h->s_candtile[P.parity].p;
+  // Independent back-to-back calls overlap: when the last thing enqueued on the handle's own stream is the previous
+  // call's verification kernel and this call reads nothing that call writes and writes nothing that call reads or
+  // writes, its streaming kernel does not wait for it (programmatic dependent launch without the initial wait: the
+  // CTAs of this call take over the SMs as the CTAs of that one run out of tiles, and that call's decision and exchange
+  // run beside them). Everything else - another stream, pod lists, shared output arrays - keeps the strict order.
+  ust_handle::Span in[4] = {{(const char*)state, (size_t)n}, {(const char*)flags, (size_t)n * 4}, {(const char*)pod_rev, (size_t)n * 4},
+                            {(const char*)ds_idx, (size_t)n * 4}};
+  ust_handle::Span outs[3] = {{(const char*)next_state, (size_t)n}, {(const char*)actions, (size_t)n * 2},
+                             {(const char*)outcome, outcome ? (size_t)n : 0}};
+  auto overlaps = [](const ust_handle::Span& a, const ust_handle::Span& b) {
+    return a.len && b.len && a.p < b.p + b.len && b.p < a.p + a.len;
+  };
+  bool relaxed = h->pdl && h->overlap_calls && st == h->stream && h->prev_n >= 0 && !P.eval_pods && !P.split && !P.stamps;
+  for (int i = 0; relaxed && i < 3; i++) {
+    for (int j = 0; j < 3; j++) relaxed = relaxed && !overlaps(outs[i], h->prev_out[j]);   // write / write
+    for (int j = 0; j < 4; j++) relaxed = relaxed && !overlaps(outs[i], h->prev_in[j]);    // write / read (that call's redo)
+  }
+  for (int i = 0; relaxed && i < 4; i++)
+    for (int j = 0; j < 3; j++) relaxed = relaxed && !overlaps(in[i], h->prev_out[j]);     // read / write
+  P.relaxed = relaxed ? 1 : 0;
+  if (relaxed) P.static_rounds = P.n_tiles / grid + 3;  // no tickets: a CTA's tiles are fixed, the next call fills the tail
+  h->prev_n = -1;
   int e = ust_launch_stream(P, grid, st, h->pdl ? 1 : 0);
   if (e) return h->fail(UST_ERR_CUDA, "streaming kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
   h->launches += 1;
   rc = launch_verify(h, P, st, h->pdl);
   if (rc) return rc;
   h->ws_dirty = false;
+  if (st == h->stream && !P.eval_pods) {
+    for (int i = 0; i < 4; i++) h->prev_in[i] = in[i];
+    for (int i = 0; i < 3; i++) h->prev_out[i] = outs[i];
+    h->prev_n = n;
+  }
   return UST_OK;
 }
 
@@ -425,6 +463,8 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
   if (rc) return rc;
   if (P.fused_exchange) P.epoch = ++h->epoch;
   P.parity = (int)(h->call_seq++ & 1u);
+  P.cand_tile = h->s_candtile[P.parity].p;
+  h->prev_n = -1;
   const int tiles = P.n_tiles;
   const int kSegments = 8;
   static_assert(kSegments <= UST_MAX_SEGMENTS, "one ticket per streaming launch");
@@ -559,6 +599,7 @@ int ust_create(ust_handle** out, int device) {
   if (const char* v = getenv("UST_PDL")) h->pdl = atoi(v) != 0;
   if (const char* v = getenv("UST_STATIC_PCT")) { h->static_pct = atoi(v); if (h->static_pct < 0) h->static_pct = 0; if (h->static_pct > 100) h->static_pct = 100; }
   h->stamps = getenv("UST_STAMPS") != nullptr;
+  if (const char* v = getenv("UST_OVERLAP")) h->overlap_calls = atoi(v) != 0;
   int rc = ust_stream_config(device, &h->num_sms, &h->stream_smem);
   if (rc != 0 || h->num_sms < 1) {
     g_create_error = std::string("no sm_100a kernel image usable on this device: ") + cudaGetErrorString((cudaError_t)rc);
@@ -595,7 +636,7 @@ void ust_destroy(ust_handle* h) {
   if (h->ds_count_dev) cudaFree(h->ds_count_dev);
   h->s_hot.release(); h->s_next.release(); h->s_outcome.release(); h->s_flags.release();
   h->s_rev.release(); h->s_ds.release(); h->s_dsrev.release(); h->s_podoff.release(); h->s_dsdesired.release();
-  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_candtile.release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release(); h->s_rev16.release(); h->s_ds8.release(); h->d_idx.release(); h->d_state.release(); h->d_flags.release(); h->d_rev.release(); h->d_ds.release(); h->sim_entered.release(); h->sim_wait.release(); h->sim_valid.release();
+  h->s_actions.release(); h->s_podflags.release(); h->s_podsum.release(); h->s_candtile[0].release(); h->s_candtile[1].release(); h->s_uid.release(); h->s_dsuid.release(); h->s_dsorder.release(); h->s_rev16.release(); h->s_ds8.release(); h->d_idx.release(); h->d_state.release(); h->d_flags.release(); h->d_rev.release(); h->d_ds.release(); h->sim_entered.release(); h->sim_wait.release(); h->sim_valid.release();
   for (auto& ev : h->seg_done) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->seg_up) if (ev) cudaEventDestroy(ev);
   if (h->stream_h2d) cudaStreamDestroy(h->stream_h2d);
@@ -611,6 +652,8 @@ void* ust_host_alloc(size_t bytes) {
   return p;
 }
 void ust_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void* ust_stream(ust_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int ust_sync(ust_handle* h) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;

@@ -115,6 +115,8 @@ struct UstParams {
   int seg;                // index of this streaming launch within the call (its ticket counter)
   int publish;            // split mode: this streaming launch is the last one of the call, its last CTA publishes P.xchg
   int split;              // split mode: a host-launched collective reduces P.xchg between the two kernels
+  int relaxed;            // the call does not depend on the previous call of the handle (see apply_device): its streaming kernel
+                          // starts without waiting for that call's verification kernel and overlaps its tail
   int stamps;             // diagnostics: write %globaltimer stamps
   // fused multi-GPU exchange (world > 1): mailboxes of all ranks as mapped into this process, call number
   int fused_exchange;

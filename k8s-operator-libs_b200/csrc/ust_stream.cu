@@ -366,14 +366,17 @@ __global__ void __maxnreg__(72) ust_stream_kernel(const __grid_constant__ UstPar
       bulk_g2s(S.lut, P.lut, kLutBytes, &S.lutbar);
     }
     __syncwarp();
-    griddep_wait();  // everything before this line overlapped the tail of the previous kernel of the stream
+    // everything before this line overlapped the tail of the previous kernel of the stream. A call that does not depend
+    // on the previous one (P.relaxed: the host has checked that no buffer of this call is written by it) streams on at
+    // once and waits at its end, before it touches the workspace.
+    if (!P.relaxed) griddep_wait();
     produce<PODS>(P, S);
   } else {
     const int ct = t - 32, cn = kThreads - 32;
     for (int i = ct; i < 128 * kHotRep; i += cn) S.hotent[i] = hot_entry((unsigned)(kHotRep == 8 ? i >> 3 : i));
     if (ct < 16) S.cnt[ct] = 0;
     if (ct >= 32 && ct < 32 + kStages) S.stage_acc[ct - 32] = 0;
-    griddep_wait();
+    if (!P.relaxed) griddep_wait();
     if (DS_SMEM)
       for (int i = ct; i <= P.n_ds; i += cn) S.dsrev[i] = i < P.n_ds ? __ldg(P.ds_rev + i) : 0;
     if (ct == 0) {
@@ -386,21 +389,24 @@ __global__ void __maxnreg__(72) ust_stream_kernel(const __grid_constant__ UstPar
       S.spec_cut = cut;
       if (blockIdx.x == 0) ws->spec_used[P.parity] = cut;  // the verification kernel judges the speculation that was made
     }
-    if (blockIdx.x == 0 && P.seg == 0 && ct >= 32 && ct < 32 + 18 + 1 + UST_MAX_SEGMENTS) {
-      // clear the previous call's accumulator set: its only reader, that call's verification kernel, has completed
-      const int o = ct - 32, q = P.parity ^ 1;
-      if (o < 18) ws->acc[q][o] = 0;
-      else if (o == 18) ws->errinv[q] = 0;
-      else ws->ticket[q][o - 19] = 0;
-    }
     __syncthreads();
     mbar_wait(&S.lutbar, 0);
     consume<DS_SMEM, OUTCOME, PODS>(P, S, warp - 1);
   }
   if (P.stamps && t == 32) ws->dbg[blockIdx.x][2] = now_ns();
-  // this CTA has run out of tiles: add its counts to the shard's (reductions, nobody waits for them) and leave
+  // this CTA has run out of tiles: add its counts to the shard's (reductions, nobody waits for them) and leave.
+  // The previous call's verification kernel must be through with the workspace first (it is, unless this call started
+  // early: then this is where it waits).
   __syncthreads();
+  griddep_wait();
   unsigned long long* acc = ws->acc[P.parity];
+  if (blockIdx.x == 0 && P.seg == 0 && t >= 64 && t < 64 + 18 + 1 + UST_MAX_SEGMENTS) {
+    // clear the previous call's accumulator set (the next call's): its only reader has completed
+    const int o = t - 64, q = P.parity ^ 1;
+    if (o < 18) ws->acc[q][o] = 0;
+    else if (o == 18) ws->errinv[q] = 0;
+    else ws->ticket[q][o - 19] = 0;
+  }
   if (t < 14) { if (S.cnt[t]) atomicAdd(&acc[t], (unsigned long long)S.cnt[t]); }
   else if (t == 14) { if (S.cnt[14]) atomicAdd(&acc[UST_V_UNAVAILABLE], (unsigned long long)S.cnt[14]); }
   else if (t == 15) { if (S.cnt[15]) atomicAdd(&acc[UST_V_CANDIDATES], (unsigned long long)S.cnt[15]); }

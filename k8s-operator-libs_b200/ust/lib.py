@@ -38,6 +38,8 @@ def load():
         lib.ust_host_free.argtypes = [C.c_void_p]
         lib.ust_host_free.restype = None
         lib.ust_sync.argtypes = [C.c_void_p]
+        lib.ust_stream.argtypes = [C.c_void_p]
+        lib.ust_stream.restype = C.c_void_p
         apply_args = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ust_apply_state.argtypes = apply_args
@@ -67,7 +69,7 @@ def load():
 
 
 EXPORTS = ["ust_abi_version", "ust_create", "ust_destroy", "ust_last_error", "ust_create_error", "ust_launch_count",
-           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_apply_state_packed", "ust_apply_state_delta", "ust_apply_state_delta_sparse", "ust_fetch_outputs", "ust_simulate_rollout", "ust_simulate_rollout_timed", "ust_sync",
+           "ust_host_alloc", "ust_host_free", "ust_apply_state", "ust_apply_state_device", "ust_stream", "ust_apply_state_packed", "ust_apply_state_delta", "ust_apply_state_delta_sparse", "ust_fetch_outputs", "ust_simulate_rollout", "ust_simulate_rollout_timed", "ust_sync",
            "ust_build_state", "ust_build_state_uids", "ust_get_unique_id", "ust_comm_init", "ust_comm_set_mode", "ust_table_entry",
            "ust_table_window_shift"]
 
@@ -132,6 +134,10 @@ class Handle:
 
     def launch_count(self):
         return int(self._lib.ust_launch_count(self._h))
+
+    def stream(self):
+        """cudaStream_t of the handle's own stream (as an int)."""
+        return int(self._lib.ust_stream(self._h))
 
     def sync(self):
         rc = self._lib.ust_sync(self._h)

@@ -11,8 +11,10 @@ for l in sys.stdin:
 }
 timeout 1800 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
-echo "== default"; ARGS="" q X=1
+echo "== default (overlapped)"; ARGS="" q X=1
+echo "== strict order"; ARGS="" q UST_OVERLAP=0
 echo "== cut hinted"; ARGS="--maxpar 0 --maxunav 30%" q X=1
 echo "== cut no hint"; ARGS="--maxpar 0 --maxunav 30%" q UST_NO_HINT=1 UST_STAMPS=148
 echo "== 100k"; ARGS="--nodes 100000" q UST_STAMPS=148
-echo "== pods quick"; ARGS="--pods" q X=1
+echo "== C2"; ARGS="--nodes 1000000 --sets 32" q X=1
+echo "== 100k strict"; ARGS="--nodes 100000 --sets 64" q UST_OVERLAP=0

@@ -526,6 +526,50 @@ def test_device_resident_entry_point(handle):
     assert c.as_dict() == ref[4]
 
 
+@pytest.mark.parametrize("shared_outputs", [False, True])
+def test_back_to_back_device_calls_overlap_or_not(handle, shared_outputs):
+    """Device-resident calls enqueued back to back on the handle's own stream, without a sync in between. With separate
+    buffers per call they overlap (the next call streams while the previous one is still being decided, its tiles redone,
+    its abort masked); with shared output arrays they run in strict order. Either way every call's outputs and counters
+    are the oracle's."""
+    import torch
+    dev = torch.device("cuda:0")
+    n = 1_200_037
+    sets = 3
+    rng = np.random.default_rng(99)
+    snaps, bufs = [], []
+    for k in range(sets):
+        soa, _ = helpers.random_soa(rng, n, all_states=True, wild=True, p_err=(0.0, 0.0, 2e-6)[k])
+        snaps.append(soa)
+        t = {key: torch.from_numpy(v).to(dev) for key, v in soa.items()}
+        t["next"] = torch.empty(n, dtype=torch.uint8, device=dev)
+        t["actions"] = torch.empty(n, dtype=torch.int16, device=dev)
+        t["cnt"] = torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)
+        bufs.append(t)
+    if shared_outputs:
+        for t in bufs[1:]:
+            t["next"], t["actions"] = bufs[0]["next"], bufs[0]["actions"]
+    pols = [abi.make_policy(max_parallel_upgrades=0, max_unavailable="30%"), abi.make_policy(max_parallel_upgrades=100, max_unavailable="25%"),
+            abi.make_policy(max_parallel_upgrades=0), abi.make_policy(max_parallel_upgrades=n // 9, max_unavailable="60%")]
+    calls = 14
+    for c in range(calls):
+        t, pol = bufs[c % sets], pols[c % len(pols)]
+        handle.apply_state_device(pol, n, t["state"].data_ptr(), t["flags"].data_ptr(), t["pod_rev"].data_ptr(), t["ds_idx"].data_ptr(),
+                                  len(snaps[c % sets]["ds_rev"]), t["ds_rev"].data_ptr(), t["next"].data_ptr(), t["actions"].data_ptr(),
+                                  counters=t["cnt"].data_ptr())
+    handle.sync()
+    last = {}
+    for c in range(calls):
+        last[c % sets] = c
+    for k, c in last.items():
+        if shared_outputs and c != calls - 1:
+            continue   # the shared arrays hold the last call's outputs
+        ref = helpers.oracle_apply(pols[c % len(pols)], snaps[k], variant=1)
+        assert np.array_equal(bufs[k]["next"].cpu().numpy(), ref[1]), (k, c)
+        assert np.array_equal(bufs[k]["actions"].cpu().numpy().view(np.uint16), ref[2]), (k, c)
+        assert abi.Counters.from_buffer_copy(bufs[k]["cnt"].cpu().numpy().tobytes()).as_dict() == ref[4], (k, c)
+
+
 def test_device_entry_point_with_moving_budget_cut(handle):
     """One fused launch over 2.5 M device-resident nodes, the slot budget cutting through the middle of the
     array; consecutive calls share the size and policy (so the second and later ones run on the previous call's
