@@ -227,6 +227,7 @@ class DeviceBench:
     def time_steps(self, h, seq, steps, warmup):
         """seq(i) -> bound argument tuple of step i. Returns total milliseconds of `steps` steps (this rank)."""
         torch = self.torch
+        torch.cuda.synchronize()   # uploads were queued on torch's stream, the calls go to the handle's
         self.on(h)
         for i in range(warmup):
             self.call(h, seq(i))
@@ -238,6 +239,8 @@ class DeviceBench:
             self.call(h, seq(warmup + i))
         e1.record()
         self.barrier()
+        torch.cuda.set_stream(torch.cuda.default_stream(self.dev))   # the handle (and its stream) may be closed next
+        self._ext = None
         return e0.elapsed_time(e1)
 
     def counters_struct(self):
@@ -261,7 +264,7 @@ def same_as_oracle(helpers, pol, soa, buf, pods=None):
 
 def print_stamps(ustlib, h):
     g = min(int(os.environ["UST_STAMPS"]), 148)
-    st = (C.c_uint64 * (4 * g + 8))()
+    st = (C.c_uint64 * (4 * g + 16))()
     ustlib.load().ust_debug_stamps(h._h, st, g)
     a = np.array(st, dtype=np.int64)
     v = a[4 * g:]
@@ -271,9 +274,9 @@ def print_stamps(ustlib, h):
     rel = (a - t0) / 1e3
     v = (v - t0) / 1e3
     print("stamps us: entry[min,max]=%.1f,%.1f first_tile[min,med,max]=%.1f,%.1f,%.1f stream_end[min,med,max]=%.1f,%.1f,%.1f "
-          "exit[max]=%.1f | verify kernel CTA 0: woken %.1f vector %.1f decided %.1f redo done %.1f | decide: begin %.2f derived %.2f written %.2f synced %.2f" % (
+          "exit[max]=%.1f | verify kernel CTA 0: woken %.1f vector %.1f decided %.1f redo done %.1f | decide: begin %.2f derived %.2f written %.2f synced %.2f | verify kernel entry: CTA 0 %.1f last CTA %.1f" % (
               rel[:, 0].min(), rel[:, 0].max(), rel[:, 1].min(), np.median(rel[:, 1]), rel[:, 1].max(),
-              rel[:, 2].min(), np.median(rel[:, 2]), rel[:, 2].max(), rel[:, 3].max(), v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]), flush=True)
+              rel[:, 2].min(), np.median(rel[:, 2]), rel[:, 2].max(), rel[:, 3].max(), v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9]), flush=True)
 
 
 def main():
@@ -416,8 +419,11 @@ def main():
 
     if args.quick:
         if rank == 0:
+            fnr = ustlib.load().ust_debug_relaxed_calls
+            fnr.restype = C.c_longlong
+            fnr.argtypes = [C.c_void_p]
             print("counters:", {k: cnt[k] for k in ("candidates", "upgrades_available", "max_unavailable")},
-                  "redone tiles:", B.redone_tiles(), flush=True)
+                  "redone tiles:", B.redone_tiles(), "overlapped calls:", fnr(h._h), "of", h.launch_count() // 2, flush=True)
         if rank == 0 and os.environ.get("UST_STAMPS"):
             print_stamps(ustlib, h)
         if rank == 0:
@@ -596,13 +602,17 @@ def main():
         torch.cuda.synchronize()
         pol_a = abi.make_policy(max_parallel_upgrades=0, max_unavailable="30%")
         pol_b = abi.make_policy(max_parallel_upgrades=0, max_unavailable="31%")
-        bound_a, bound_b = B.bind(h, pol_a, bufs), B.bind(h, pol_b, bufs)
+        pol_c = abi.make_policy(max_parallel_upgrades=0, max_unavailable="32%")
+        pols3 = (pol_a, pol_b, pol_c)
+        bound3 = tuple(B.bind(h, p_, bufs) for p_ in pols3)
+        bound_a = bound3[0]
         steps_c = max(10, args.steps // 2)
-        # first call: the policy alternates, so no call finds a hint made under its own signature
-        ms_first = B.time_steps(h, lambda i: (bound_a if i % 2 == 0 else bound_b)[i % SETS], steps_c, warmup)
+        # first call: three policies in turn, so no call finds a hint made under its own signature (a call looks at
+        # the hint of the previous call or, when it overlaps that call, of the one before)
+        ms_first = B.time_steps(h, lambda i: bound3[i % 3][i % SETS], steps_c, warmup)
         i_last = warmup + steps_c - 1
         redone_first = B.redone_tiles()
-        v_first = same_as_oracle(helpers, pol_a if i_last % 2 == 0 else pol_b, dict(soa, state=variants[i_last % SETS]), bufs[i_last % SETS])
+        v_first = same_as_oracle(helpers, pols3[i_last % 3], dict(soa, state=variants[i_last % SETS]), bufs[i_last % SETS])
         ms_steady = B.time_steps(h, lambda i: bound_a[i % SETS], args.steps, warmup)
         i_last = warmup + args.steps - 1
         redone_steady = B.redone_tiles()
@@ -614,7 +624,7 @@ def main():
             "redone_tiles_first_call": redone_first, "redone_tiles_steady": redone_steady,
             "perturbation": "every buffer set differs from the base snapshot in 0.1 % of its state bytes (stale-but-close hint)",
             "verified_vs_oracle": bool(v_first and v_steady)}
-        del bound_a, bound_b, variants
+        del bound_a, bound3, variants
 
         # C2 and the small snapshots: what a reconcile of a real cluster sees
         small = {}

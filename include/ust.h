@@ -246,7 +246,10 @@ int ust_apply_state_device(ust_handle* h, const ust_policy* policy, int64_t n_no
                            uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome,
                            ust_counters* out_device, void* stream);
 int ust_sync(ust_handle* h);
-/* The handle's own CUDA stream (a cudaStream_t), the one calls with stream == NULL run on - to record events on it.
+/* The handle's own CUDA stream (a cudaStream_t), the one calls with stream == NULL run on. It belongs to the library:
+ * a caller may record events on it, wait for it and make it wait for events, but must not enqueue kernels or copies
+ * that write a call's arrays on it (produce inputs on a stream of your own and pass that stream, or order the two
+ * streams with an event) - for this reason:
  * Back-to-back ust_apply_state_device calls on this stream that share no buffer with one another except read-only
  * inputs (different snapshots, different output arrays - a batch of clusters, a sweep of what-if policies) overlap: a
  * call's streaming kernel starts as the previous call's runs out of work, and that call's decision (and multi-GPU

@@ -97,6 +97,8 @@ struct ust_handle {
   struct Span { const char* p; size_t len; };
   Span prev_in[4] = {}, prev_out[3] = {};
   int64_t prev_n = -1;
+  bool chain_entry = false;     // set by ust_apply_state_device for the apply_device call it makes
+  int64_t relaxed_calls = 0;   // diagnostics
   bool overlap_calls = true;  // UST_OVERLAP=0 turns the overlap of independent back-to-back calls off (tuning)
   cudaStream_t last_stream = nullptr;  // stream of the previous device-resident call (calls on another stream are ordered behind it)
   int64_t resident_n = -1;  // nodes of the snapshot the last ust_apply_state left in the staging arrays (-1 = none)
@@ -322,6 +324,9 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
                         const int32_t* pod_rev, const int32_t* ds_idx, int32_t n_ds, const int32_t* ds_rev,
                         const int32_t* pod_off, const uint16_t* pod_flags, int64_t n_pods, uint8_t* next_state,
                         uint16_t* actions, uint8_t* outcome, ust_counters* out_dev, cudaStream_t st) {
+  const bool chain = h->chain_entry;  // called by ust_apply_state_device itself: the call may overlap the previous one
+  h->chain_entry = false;
+  if (!chain) h->prev_n = -1;
   if (n < 0) return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
   if (n > 0 && (!state || !flags || !pod_rev || !ds_idx || !next_state || !actions))
     return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
@@ -375,7 +380,7 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
   auto overlaps = [](const ust_handle::Span& a, const ust_handle::Span& b) {
     return a.len && b.len && a.p < b.p + b.len && b.p < a.p + a.len;
   };
-  bool relaxed = h->pdl && h->overlap_calls && st == h->stream && h->prev_n >= 0 && !P.eval_pods && !P.split && !P.stamps;
+  bool relaxed = chain && h->pdl && h->overlap_calls && st == h->stream && h->prev_n >= 0 && !P.eval_pods && !P.split;
   for (int i = 0; relaxed && i < 3; i++) {
     for (int j = 0; j < 3; j++) relaxed = relaxed && !overlaps(outs[i], h->prev_out[j]);   // write / write
     for (int j = 0; j < 4; j++) relaxed = relaxed && !overlaps(outs[i], h->prev_in[j]);    // write / read (that call's redo)
@@ -383,6 +388,7 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
   for (int i = 0; relaxed && i < 4; i++)
     for (int j = 0; j < 3; j++) relaxed = relaxed && !overlaps(in[i], h->prev_out[j]);     // read / write
   P.relaxed = relaxed ? 1 : 0;
+  h->relaxed_calls += relaxed ? 1 : 0;
   if (relaxed) P.static_rounds = P.n_tiles / grid + 3;  // no tickets: a CTA's tiles are fixed, the next call fills the tail
   h->prev_n = -1;
   int e = ust_launch_stream(P, grid, st, h->pdl ? 1 : 0);
@@ -391,7 +397,7 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
   rc = launch_verify(h, P, st, h->pdl);
   if (rc) return rc;
   h->ws_dirty = false;
-  if (st == h->stream && !P.eval_pods) {
+  if (chain && st == h->stream && !P.eval_pods) {
     for (int i = 0; i < 4; i++) h->prev_in[i] = in[i];
     for (int i = 0; i < 3; i++) h->prev_out[i] = outs[i];
     h->prev_n = n;
@@ -658,6 +664,7 @@ void* ust_stream(ust_handle* h) { return h ? (void*)h->stream : nullptr; }
 int ust_sync(ust_handle* h) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   UST_CUDA(h, cudaSetDevice(h->device));
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (e == cudaSuccess && h->last_stream && h->last_stream != h->stream) e = cudaStreamSynchronize(h->last_stream);
@@ -671,6 +678,7 @@ int ust_apply_state_device(ust_handle* h, const ust_policy* policy, int64_t n_no
                            uint8_t* actuator_outcome, ust_counters* out_device, void* stream) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->chain_entry = true;  // the one entry point whose calls may overlap the previous call's tail (apply_device)
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   if (pods && (!pods->pod_off || pods->n_pods < 0 || (pods->n_pods > 0 && !pods->pod_flags)))
     return h->fail(UST_ERR_INVALID_ARGUMENT, "bad pod lists");
@@ -685,6 +693,7 @@ int ust_apply_state(ust_handle* h, const ust_policy* policy, int64_t n, const ui
                     ust_counters* out) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   if (n < 0 || (n > 0 && (!state || !flags || !pod_rev || !ds_idx || !next_state || !actions)))
     return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
   if (n_ds < 0 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table");
@@ -828,6 +837,7 @@ int ust_apply_state_delta(ust_handle* h, const ust_policy* policy, int64_t n_cha
                           ust_counters* out) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   return delta_common(h, policy, n_changed, idx, state, flags, pod_rev, ds_idx, n_ds, ds_rev, false, next_state, actions,
                       actuator_outcome, 0, nullptr, nullptr, out);
 }
@@ -838,6 +848,7 @@ int ust_apply_state_delta_sparse(ust_handle* h, const ust_policy* policy, int64_
                                  uint8_t* out_next_state, uint16_t* out_actions, int64_t* n_out, ust_counters* out) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   return delta_common(h, policy, n_changed, idx, state, flags, pod_rev, ds_idx, n_ds, ds_rev, true, out_next_state, out_actions,
                       nullptr, max_out, out_idx, n_out, out);
 }
@@ -845,6 +856,7 @@ int ust_apply_state_delta_sparse(ust_handle* h, const ust_policy* policy, int64_
 int ust_fetch_outputs(ust_handle* h, uint8_t* next_state, uint16_t* actions) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   if (h->resident_n < 0 || !h->outputs_resident) return h->fail(UST_ERR_INVALID_ARGUMENT, "no resident outputs");
   if (h->resident_n > 0 && (!next_state || !actions)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
   UST_CUDA(h, cudaSetDevice(h->device));
@@ -862,6 +874,7 @@ int ust_apply_state_packed(ust_handle* h, const ust_policy* policy, int64_t n, c
                            uint8_t* next_state, uint16_t* actions, uint8_t* actuator_outcome, ust_counters* out) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   if (n < 0 || (n > 0 && (!state || !flags || !pod_rev16 || !ds_idx8 || !next_state || !actions)))
     return h->fail(UST_ERR_NIL_STATE, "currentState should not be empty");
   if (n_ds < 0 || n_ds > 127 || (n_ds > 0 && !ds_rev)) return h->fail(UST_ERR_INVALID_ARGUMENT, "bad DaemonSet table (the packed format holds at most 127 DaemonSets)");
@@ -981,6 +994,7 @@ int ust_simulate_rollout(ust_handle* h, const ust_policy* policy, int32_t steps,
                          uint32_t* final_flags, int32_t* final_pod_rev, int32_t* steps_done) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   return simulate_common(h, policy, nullptr, steps, history, final_state, final_flags, final_pod_rev, steps_done);
 }
 
@@ -989,6 +1003,7 @@ int ust_simulate_rollout_timed(ust_handle* h, const ust_policy* policy, const us
                                int32_t* steps_done) {
   if (!h || !options) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   return simulate_common(h, policy, options, steps, history, final_state, final_flags, final_pod_rev, steps_done);
 }
 
@@ -996,6 +1011,7 @@ int ust_build_state(ust_handle* h, int64_t n_pods, const uint8_t* state, const i
                     const int32_t* ds_desired, ust_counters* out) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   if (n_pods < 0 || (n_pods > 0 && (!state || !ds_idx)) || n_ds < 0 || (n_ds > 0 && !ds_desired))
     return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
   h->resident_n = -1;  // shares the staging arrays
@@ -1034,6 +1050,7 @@ int ust_build_state_uids(ust_handle* h, int64_t n_pods, const uint8_t* state, co
                          const uint64_t* ds_uid, const int32_t* ds_desired, int32_t* ds_idx_out, ust_counters* out) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   if (n_pods < 0 || (n_pods > 0 && (!state || !owner_uid || !ds_idx_out)) || n_ds < 0 || (n_ds > 0 && (!ds_uid || !ds_desired)))
     return h->fail(UST_ERR_INVALID_ARGUMENT, "bad arguments");
   // the DaemonSet map is keyed by UID (common_manager.go:181-185): an open-addressing table at load factor <= 1/4
@@ -1108,14 +1125,17 @@ uint32_t ust_table_entry(const ust_policy* policy, unsigned state_code, uint32_t
 }
 int ust_table_window_shift(unsigned state_code) { return ust_window_shift[state_code & 15u]; }
 
+long long ust_debug_relaxed_calls(ust_handle* h) { return h ? (long long)h->relaxed_calls : -1; }
+
 // diagnostics (not in include/ust.h): %globaltimer stamps taken by CTA 0 of the last fused launch
 int ust_debug_stamps(ust_handle* h, unsigned long long* out, int n_ctas) {
   if (!h || !out || n_ctas < 1 || n_ctas > UST_MAX_CTAS) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   UST_CUDA(h, cudaSetDevice(h->device));
   UST_CUDA(h, cudaDeviceSynchronize());
   UST_CUDA(h, cudaMemcpy(out, h->ws->dbg, (size_t)n_ctas * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  UST_CUDA(h, cudaMemcpy(out + (size_t)n_ctas * 4, h->ws->dbg2, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));  // verification kernel
+  UST_CUDA(h, cudaMemcpy(out + (size_t)n_ctas * 4, h->ws->dbg2, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));  // verification kernel
   return UST_OK;
 }
 
@@ -1134,6 +1154,7 @@ int ust_get_unique_id(void* out_bytes) {
 int ust_comm_init(ust_handle* h, int rank, int world_size, const void* unique_id_bytes) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   if (world_size < 1 || world_size > UST_MAX_WORLD || rank < 0 || rank >= world_size)
     return h->fail(UST_ERR_INVALID_ARGUMENT, "world size must be 1..%d", UST_MAX_WORLD);
   if (world_size == 1) { h->rank = 0; h->world = 1; return UST_OK; }
@@ -1184,6 +1205,7 @@ int ust_comm_init(ust_handle* h, int rank, int world_size, const void* unique_id
 int ust_comm_set_mode(ust_handle* h, int mode) {
   if (!h) return UST_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(h->mu);
+  h->prev_n = -1;  // whatever this entry point enqueues sits between two device calls: they keep the strict order
   if (mode != 0 && mode != 1) return h->fail(UST_ERR_INVALID_ARGUMENT, "unknown exchange mode %d", mode);
   if (mode == 1 && !(h->world > 1 && h->mbox_ready))
     return h->fail(UST_ERR_COMM, "fused exchange unavailable: peer mailboxes could not be mapped (CUDA IPC)");

@@ -283,8 +283,8 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
     if (write_global && !scan && !(redo == 1)) {  // the common case ends here: counters out, no tile is redone
       write_counters(P, D.V, s, redo == 2 ? (long long)nT : 0, comm_failed);
       if (t == 0 && P.spec_sig != 0 && slotted && !aborting && !comm_failed) {
-        P.ws->hint_cut = D.spec_cut;  // the all-or-nothing guess held
-        P.ws->hint_sig = P.spec_sig;
+        P.ws->hint_cut[P.parity] = D.spec_cut;  // the all-or-nothing guess held
+        P.ws->hint_sig[P.parity] = P.spec_sig;
       }
     }
     if (P.stamps && write_global && t == 0) P.ws->dbg2[6] = now_ns();
@@ -384,8 +384,8 @@ __device__ inline void decide(const UstParams& P, DecideShared& D, bool write_gl
       s.max_unav = D.max_unav; s.node_offset = D.node_offset; s.cand_before = D.cand_before;
       write_counters(P, D.V, s, redo == 2 ? (long long)nT : (redo == 1 ? (long long)(hi - lo + 1) : 0), false);
       if (t == 0 && P.spec_sig != 0 && slotted && !aborting) {
-        P.ws->hint_cut = cut;  // where the budget really cut this time = next call's speculation
-        P.ws->hint_sig = P.spec_sig;
+        P.ws->hint_cut[P.parity] = cut;  // where the budget really cut this time = next call's speculation
+        P.ws->hint_sig[P.parity] = P.spec_sig;
       }
     }
   }

@@ -60,12 +60,14 @@ struct UstWorkspace {
   unsigned int arrive;            // split mode: CTAs of the publishing streaming launch that have finished
   unsigned int comm_timeout;      // set when a peer did not show up (kernel gives up instead of hanging)
   // Speculation hint carried from call to call (results never depend on it, only how many tiles are redone):
-  // the previous call's cut tile, valid for calls with the same signature (size, tiling, slot policy).
-  unsigned long long hint_sig;
-  int hint_cut;
-  int pad_;
+  // an earlier call's cut tile, valid for calls with the same signature (size, tiling, slot policy). One slot per
+  // call parity: the verification kernel writes its own call's slot; a streaming kernel reads the previous call's slot
+  // - or, when it runs beside the previous call's verification kernel (UstParams::relaxed), the slot of the call
+  // before that, which nobody is writing.
+  unsigned long long hint_sig[2];
+  int hint_cut[2];
   unsigned long long dbg[UST_MAX_CTAS][4];  // %globaltimer stamps per streaming CTA: entry, first tile landed, stream end, exit
-  unsigned long long dbg2[8];               // verification kernel, CTA 0: woken, vector loaded, decided, done; 4..: inside the decision
+  unsigned long long dbg2[16];              // verification kernel, CTA 0: woken, vector loaded, decided, done; 4..: inside the decision
 };
 
 // abort key: (pass << 56) | (global node index + 1); policy-level aborts use index part 0

@@ -23,8 +23,7 @@ namespace {
 
 constexpr int kThreads = UST_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kStep = kThreads * 4;   // nodes per CTA step (4 per thread)
-// the verification kernel: 12 warps per CTA (one CTA per SM beside the resident streaming kernel: 384 x 96 registers fit)
+// the verification kernel: 12 warps per CTA, one CTA per SM beside the resident streaming kernel (register bound below)
 constexpr int kVThreads = UST_VERIFY_THREADS;
 constexpr int kVWarps = kVThreads / 32;
 constexpr int kVStep = kVThreads * 4;
@@ -329,7 +328,11 @@ __device__ void redo_range(const UstParams& P, Shared& S, int ta, int tb) {
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void __maxnreg__(96) ust_verify_kernel(const __grid_constant__ UstParams P) {
+// Registers: an SM sub-partition has 16384. The streaming kernel's CTA puts 4 of its 13 warps (64 registers a thread) on
+// one sub-partition = 8192; this kernel's 12 warps come 3 to a sub-partition, so they must stay within 8192 / 96 = 85
+// registers a thread to be resident BESIDE the streaming CTA. At 96 this kernel only got onto an SM when the streaming
+// CTA left it - and the next call's streaming kernel, whose launch waits for every CTA here to have started, with it.
+__global__ void __maxnreg__(80) ust_verify_kernel(const __grid_constant__ UstParams P) {
   __shared__ Shared S;
   const int t = threadIdx.x;
   // prologue (overlaps the streaming kernel): the transition table (4.4 KiB) by one TMA bulk copy - it was uploaded by
@@ -340,6 +343,7 @@ __global__ void __maxnreg__(96) ust_verify_kernel(const __grid_constant__ UstPar
     mbar_arrive_expect_tx(&S.mbar, kLutBytes);
     bulk_g2s(S.lut, P.lut, kLutBytes, &S.mbar);
   }
+  if (P.stamps && t == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) P.ws->dbg2[blockIdx.x == 0 ? 8 : 9] = now_ns();
   griddep_launch_dependents();  // the next call's streaming kernel may become resident (it waits for this grid itself)
   griddep_wait();               // the streaming kernel (and, split mode, the collective) has completed
   const bool lead = blockIdx.x == 0;

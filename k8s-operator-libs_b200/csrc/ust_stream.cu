@@ -347,7 +347,7 @@ __device__ void consume(const UstParams& P, SS<PODS>& S, int cw) {
 }
 
 template <bool DS_SMEM, bool OUTCOME, bool PODS>
-__global__ void __maxnreg__(72) ust_stream_kernel(const __grid_constant__ UstParams P) {
+__global__ void __maxnreg__(64) ust_stream_kernel(const __grid_constant__ UstParams P) {
   extern __shared__ __align__(128) unsigned char ust_smem[];
   SS<PODS>& S = *reinterpret_cast<SS<PODS>*>(ust_smem);
   const int t = threadIdx.x, warp = t >> 5;
@@ -384,8 +384,9 @@ __global__ void __maxnreg__(72) ust_stream_kernel(const __grid_constant__ UstPar
       S.spec_before = 0;
       // speculative cut: the previous call's, when it was made under the same signature; else the policy default
       const bool slotted = P.active && !P.requestor;
-      const bool hinted = P.spec_sig != 0 && __ldcg(&ws->hint_sig) == P.spec_sig;
-      const int cut = !slotted ? 0 : (hinted ? __ldcg(&ws->hint_cut) : P.spec_cut_tile);
+      const int hs = P.relaxed ? P.parity : P.parity ^ 1;  // a slot no running kernel writes (ust_dev.h)
+      const bool hinted = P.spec_sig != 0 && __ldcg(&ws->hint_sig[hs]) == P.spec_sig;
+      const int cut = !slotted ? 0 : (hinted ? __ldcg(&ws->hint_cut[hs]) : P.spec_cut_tile);
       S.spec_cut = cut;
       if (blockIdx.x == 0) ws->spec_used[P.parity] = cut;  // the verification kernel judges the speculation that was made
     }
@@ -460,6 +461,11 @@ cudaError_t launch_variant(const UstParams& p, int grid, cudaStream_t st, int pd
 
 template <bool DS_SMEM, bool OUTCOME, bool PODS>
 cudaError_t config_variant() {
+  // the whole 228 KiB as shared memory: the verification kernel's CTA (7 KiB) must fit beside this kernel's, or it
+  // cannot become resident - and trigger the next call's launch - before this one has left the SM
+  cudaError_t e = cudaFuncSetAttribute(ust_stream_kernel<DS_SMEM, OUTCOME, PODS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(ust_stream_kernel<DS_SMEM, OUTCOME, PODS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sizeof(SS<PODS>));
 }
