@@ -172,6 +172,7 @@ class DeviceBench:
         self.torch, self.dist, self.ustlib, self.abi, self.dev, self.world = torch, dist, ustlib, abi, dev, world
         self.counters = torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)
         self.fn = ustlib.load().ust_apply_state_device
+        self._align = torch.zeros(1, device=dev)
 
     def on(self, h):
         """Time calls of handle `h`: they run on the handle's own stream (stream argument NULL), and so do the CUDA events
@@ -234,6 +235,11 @@ class DeviceBench:
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.blocker()
+        if self.world > 1:
+            # line the ranks' streams up ON THE DEVICE before the clock starts: the host barrier above leaves the ranks
+            # hundreds of microseconds apart (8 Python processes), and with coupled ranks every rank's timed region
+            # would include the wait for the last one to begin (measured: +17 us/step over 50 steps at N=8)
+            self.dist.all_reduce(self._align)
         e0.record()
         for i in range(steps):
             self.call(h, seq(warmup + i))

@@ -59,6 +59,10 @@ struct UstWorkspace {
   unsigned long long bs_acc[18];  // BuildState kernels (zero between calls: their finish kernel clears it)
   unsigned int arrive;            // split mode: CTAs of the publishing streaming launch that have finished
   unsigned int comm_timeout;      // set when a peer did not show up (kernel gives up instead of hanging)
+  // fused exchange: CTA 0 of the verification kernel talks to the peers; it leaves the summed vector here for the
+  // other CTAs of its grid and then sets xflag = (epoch << 32) | ok (by epoch parity, like the mailboxes)
+  long long xsum[2][UST_V_LEN];
+  unsigned long long xflag[2];
   // Speculation hint carried from call to call (results never depend on it, only how many tiles are redone):
   // an earlier call's cut tile, valid for calls with the same signature (size, tiling, slot policy). One slot per
   // call parity: the verification kernel writes its own call's slot; a streaming kernel reads the previous call's slot

@@ -36,6 +36,7 @@ struct __align__(128) Shared {
   uint32_t lut[UST_LUT_ENTRIES];  // + meta directly behind it: filled by ONE bulk (TMA) copy
   uint2 meta[16];
   unsigned long long mbar;        // mbarrier the bulk copy completes on
+  unsigned long long xflag;       // fused exchange: the flag word CTA 0 published (other CTAs)
   int dsrev[kDsSmem + 1];         // DaemonSet revisions (larger tables are read from global memory: this is the rare path)
   unsigned int warp_tot[kVWarps];
   // the verdict, CTA-uniform
@@ -358,8 +359,33 @@ __global__ void __maxnreg__(80) ust_verify_kernel(const __grid_constant__ UstPar
       if (t == 14) fix_excluded_lane(P, S.D);
     }
     if (P.fused_exchange) {
+      // Only CTA 0 polls the peers' mailbox words. (Every CTA polling them - 148 x 84 x world threads spinning on a few
+      // L2 lines that the peers' NVLink writes must get into - cost 17 us a step at 8 GPUs.) The others wait for one
+      // flag, one thread each.
       __syncthreads();
-      comm_ok = exchange_vector(P, S.D, lead);
+      const int par = (int)(P.epoch & 1);
+      const unsigned long long tag = (unsigned long long)(unsigned)P.epoch << 32;
+      if (lead) {
+        comm_ok = exchange_vector(P, S.D, true);
+        if (t < UST_V_LEN) P.ws->xsum[par][t] = S.D.V[t];
+        __threadfence();
+        __syncthreads();
+        if (t == 0) st_release_sys(reinterpret_cast<long long*>(&P.ws->xflag[par]), (long long)(tag | (comm_ok ? 1ull : 0ull)));
+      } else {
+        if (t == 0) {
+          const unsigned long long t0 = now_ns();
+          unsigned long long v = (unsigned long long)ld_acquire_sys(reinterpret_cast<const long long*>(&P.ws->xflag[par]));
+          while ((v >> 32) != (tag >> 32)) {
+            if (now_ns() - t0 > 2 * kCommTimeoutNs) { v = tag; break; }
+            __nanosleep(100);
+            v = (unsigned long long)ld_acquire_sys(reinterpret_cast<const long long*>(&P.ws->xflag[par]));
+          }
+          S.xflag = v;
+        }
+        __syncthreads();
+        comm_ok = (S.xflag & 1ull) != 0;
+        if (t < UST_V_LEN) S.D.V[t] = __ldcg(&P.ws->xsum[par][t]);
+      }
     }
   }
   if (t == 0) S.D.spec_cut = __ldcg(&P.ws->spec_used[P.parity]);
