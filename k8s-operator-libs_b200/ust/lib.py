@@ -135,6 +135,13 @@ class Handle:
     def launch_count(self):
         return int(self._lib.ust_launch_count(self._h))
 
+    def overlapped_calls(self):
+        """diagnostics: how many ust_apply_state_device calls started without waiting for the previous call's tail"""
+        fn = self._lib.ust_debug_relaxed_calls
+        fn.restype = C.c_longlong
+        fn.argtypes = [C.c_void_p]
+        return int(fn(self._h))
+
     def stream(self):
         """cudaStream_t of the handle's own stream (as an int)."""
         return int(self._lib.ust_stream(self._h))

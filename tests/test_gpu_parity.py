@@ -570,6 +570,46 @@ def test_back_to_back_device_calls_overlap_or_not(handle, shared_outputs):
         assert abi.Counters.from_buffer_copy(bufs[k]["cnt"].cpu().numpy().tobytes()).as_dict() == ref[4], (k, c)
 
 
+def test_overlapped_calls_every_call_checked(handle):
+    """24 device calls enqueued without a sync, each with output arrays of its own, over four snapshots (one of them
+    aborting) and six policies: calls k and k+1 share nothing but read-only inputs, so k+1 streams while k is decided,
+    its tiles redone or its abort masked - and EVERY call's outputs and counters must be the oracle's, not only the
+    last ones. The handle must report that calls did overlap (else this test checks nothing new)."""
+    import torch
+    dev = torch.device("cuda:0")
+    n = 700_019
+    rng = np.random.default_rng(4242)
+    snaps, ins = [], []
+    for k in range(4):
+        soa, _ = helpers.random_soa(rng, n, all_states=True, wild=(k % 2 == 1), p_err=(0.0, 0.0, 0.0, 3e-6)[k])
+        snaps.append(soa)
+        ins.append({key: torch.from_numpy(v).to(dev) for key, v in soa.items()})
+    pols = [abi.make_policy(max_parallel_upgrades=0, max_unavailable="30%"), abi.make_policy(max_parallel_upgrades=0, max_unavailable="30%"),
+            abi.make_policy(max_parallel_upgrades=100, max_unavailable="25%"), abi.make_policy(max_parallel_upgrades=0),
+            abi.make_policy(max_parallel_upgrades=n // 7, max_unavailable="55%"), abi.make_policy(max_parallel_upgrades=0, max_unavailable="12%")]
+    calls = 24
+    outs = [{"next": torch.empty(n, dtype=torch.uint8, device=dev), "actions": torch.empty(n, dtype=torch.int16, device=dev),
+             "cnt": torch.zeros(C.sizeof(abi.Counters) // 8, dtype=torch.int64, device=dev)} for _ in range(calls)]
+    torch.cuda.synchronize()
+    before = handle.overlapped_calls()
+    for c in range(calls):
+        t, o = ins[c % 4], outs[c]
+        handle.apply_state_device(pols[c % len(pols)], n, t["state"].data_ptr(), t["flags"].data_ptr(), t["pod_rev"].data_ptr(),
+                                  t["ds_idx"].data_ptr(), len(snaps[c % 4]["ds_rev"]), t["ds_rev"].data_ptr(), o["next"].data_ptr(),
+                                  o["actions"].data_ptr(), counters=o["cnt"].data_ptr())
+    handle.sync()
+    assert handle.overlapped_calls() - before >= calls // 2, "the calls did not overlap: nothing was tested"
+    refs = {}
+    for c in range(calls):
+        key = (c % len(pols), c % 4)
+        if key not in refs:
+            refs[key] = helpers.oracle_apply(pols[key[0]], snaps[key[1]], variant=1)
+        ref = refs[key]
+        assert np.array_equal(outs[c]["next"].cpu().numpy(), ref[1]), c
+        assert np.array_equal(outs[c]["actions"].cpu().numpy().view(np.uint16), ref[2]), c
+        assert abi.Counters.from_buffer_copy(outs[c]["cnt"].cpu().numpy().tobytes()).as_dict() == ref[4], c
+
+
 def test_device_entry_point_with_moving_budget_cut(handle):
     """One fused launch over 2.5 M device-resident nodes, the slot budget cutting through the middle of the
     array; consecutive calls share the size and policy (so the second and later ones run on the previous call's
