@@ -12,7 +12,7 @@
 //     ticket so that every SM runs dry at the same moment) and moves each tile's four input columns - state (1 B),
 //     flags (4), pod_rev (4), ds_idx (4) per node - into one stage of a shared-memory ring with TMA bulk copies
 //     (cp.async.bulk, UBLKCP in SASS) that complete on the stage's "full" mbarrier. Bytes in flight are bounded by
-//     the ring (UST_STAGES x 26 KiB per SM), not by registers;
+//     the ring (UST_STAGES x 39 KiB per SM), not by registers;
 //   * the per-policy transition table (4.4 KiB, built by the host: ust_lut.h) arrives the same way, once per CTA;
 //   * consumer warps wait on "full", evaluate 128-node groups straight out of shared memory - one 16-byte lookup
 //     indexed by the node's hot byte (table window + byte-sliced counter increments; the table is replicated per bank
