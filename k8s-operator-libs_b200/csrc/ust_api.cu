@@ -192,7 +192,7 @@ static int ensure_tables(ust_handle* h, const ust_policy* p, cudaStream_t st) {
   UST_CUDA(h, cudaStreamSynchronize(st));  // the pinned staging copy may still be in flight
   if (policy_active(p)) {
     ust_build_lut(&key, h->lut_host);
-    ust_build_pod_lut(&key, h->podlut_host);
+    ust_build_pod_lut256(&key, h->podlut_host);
   } else {
     ust_build_lut(nullptr, h->lut_host);
     memset(h->podlut_host, 0, UST_PODLUT_ENTRIES);
@@ -1124,6 +1124,17 @@ uint32_t ust_table_entry(const ust_policy* policy, unsigned state_code, uint32_t
   return ust_lut_lookup(lut.data(), state_code, w);
 }
 int ust_table_window_shift(unsigned state_code) { return ust_window_shift[state_code & 15u]; }
+
+// audit: entries of the 2048-entry pod table (ust_build_pod_lut) that T[pf & 255] & gate(pf) disagrees with
+int ust_debug_podlut_mismatches(const ust_policy* p) {
+  if (!p) return -1;
+  uint8_t full[UST_PODLUT_ENTRIES], T[256];
+  ust_build_pod_lut(p, full);
+  ust_build_pod_lut256(p, T);
+  int bad = 0;
+  for (unsigned pf = 0; pf < UST_PODLUT_ENTRIES; pf++) bad += (T[pf & 255u] & ust_pod_gate(pf)) != full[pf];
+  return bad;
+}
 
 long long ust_debug_relaxed_calls(ust_handle* h) { return h ? (long long)h->relaxed_calls : -1; }
 

@@ -442,13 +442,12 @@ __global__ void __launch_bounds__(kThreads, 6) ust_pod_summary_kernel(long long 
                                                                       const int32_t* __restrict__ pod_off,
                                                                       const uint16_t* __restrict__ pod_flags, long long n_pods,
                                                                       const uint8_t* __restrict__ podlut, uint8_t* __restrict__ podsum) {
-  __shared__ __align__(16) uint8_t lut[UST_PODLUT_ENTRIES];
+  __shared__ __align__(16) uint8_t lut[256];   // what a pod raises, by its own eight bits (ust_lut.h: ust_build_pod_lut256)
   __shared__ __align__(16) uint8_t res[kPodBlock];   // summary byte per node of the block (bits 6-7: state - 3 while in work)
   __shared__ unsigned short list[kPodBlock];         // block-local indices of the nodes whose list is read
   __shared__ int cnt;
   const int t = threadIdx.x, lane = t & 31;
-  for (int i = t; i < (int)(UST_PODLUT_ENTRIES / 4); i += kThreads)
-    reinterpret_cast<uint32_t*>(lut)[i] = __ldg(reinterpret_cast<const uint32_t*>(podlut) + i);
+  if (t < 64) reinterpret_cast<uint32_t*>(lut)[t] = __ldg(reinterpret_cast<const uint32_t*>(podlut) + t);
   const unsigned char* bytes = reinterpret_cast<const unsigned char*>(pod_flags);
   const long long total_bytes = 2 * n_pods;
   // hot bytes of this thread's 16 nodes of a block ("excluded" past the end of the array)
@@ -505,6 +504,15 @@ __global__ void __launch_bounds__(kThreads, 6) ust_pod_summary_kernel(long long 
       const int p0 = __ldg(pod_off + i), p1 = __ldg(pod_off + i + 1);
       const int len = p1 - p0;
       unsigned r = 0;
+      // the node's actuator only asks about pods that match ITS selector: wait-for-completion (bit 9), the deletion
+      // filter (bit 8) or the drain selector (bit 10) - the others are not even looked up
+      const unsigned tag = res[li];
+      const unsigned s = UST_STATE_WAIT_FOR_JOBS_REQUIRED + (tag >> 6);
+      const uint32_t sel = s == UST_STATE_WAIT_FOR_JOBS_REQUIRED ? (uint32_t)UST_POD_MATCH_WAIT_SELECTOR
+                         : (s == UST_STATE_POD_DELETION_REQUIRED ? (uint32_t)UST_POD_MATCH_DELETION_FILTER : (uint32_t)UST_POD_MATCH_DRAIN_SELECTOR);
+      // ... and once every bit the node's state reads is set, the rest of the list cannot change the answer
+      const unsigned sat = s == UST_STATE_WAIT_FOR_JOBS_REQUIRED ? UST_PODSUM_WAIT_RUNNING
+                         : (s == UST_STATE_POD_DELETION_REQUIRED ? (UST_PODSUM_TO_DELETE | UST_PODSUM_CANNOT_DELETE) : UST_PODSUM_DRAIN_ERROR);
       // 16-byte chunks covering the list; the last one may reach past the list but, when `safe`, not past the array
       const long long c0 = (2LL * p0) & ~15LL;
       const int nchunks = len > 0 ? (int)((2LL * p1 - c0 + 15) >> 4) : 0;
@@ -518,22 +526,23 @@ __global__ void __launch_bounds__(kThreads, 6) ust_pod_summary_kernel(long long 
           for (int u = 0; u < kPodChunks; u++) x[u] = cb + u < nchunks ? __ldcs(src + cb + u) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int u = 0; u < kPodChunks; u++) {
-            if (cb + u < nchunks) {
+            if (cb + u < nchunks && (r & sat) != sat) {
               const uint32_t wv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
 #pragma unroll
               for (int e = 0; e < 8; e++) {
-                const uint32_t f = (e & 1) ? (wv[e >> 1] >> 16) & (UST_PODLUT_ENTRIES - 1) : wv[e >> 1] & (UST_PODLUT_ENTRIES - 1);
-                if ((unsigned)(rel + e) < (unsigned)len) r |= lut[f];
+                const uint32_t f = (e & 1) ? wv[e >> 1] >> 16 : wv[e >> 1];
+                if ((f & sel) && (unsigned)(rel + e) < (unsigned)len) r |= lut[f & 255u];
               }
             }
             rel += 8;
           }
         }
       } else {  // the list ends within the last 16 bytes of the whole array: plain 2-byte loads
-        for (int p = p0; p < p1; p++) r |= lut[__ldg(pod_flags + p) & (UST_PODLUT_ENTRIES - 1)];
+        for (int p = p0; p < p1; p++) {
+          const uint32_t f = __ldg(pod_flags + p);
+          if (f & sel) r |= lut[f & 255u];
+        }
       }
-      const unsigned tag = res[li];
-      const unsigned s = UST_STATE_WAIT_FOR_JOBS_REQUIRED + (tag >> 6);
       unsigned ps;
       if (s == UST_STATE_WAIT_FOR_JOBS_REQUIRED) ps = 0x10u | (r & UST_PODSUM_WAIT_RUNNING);
       else if (s == UST_STATE_POD_DELETION_REQUIRED) ps = r & (UST_PODSUM_TO_DELETE | UST_PODSUM_CANNOT_DELETE);

@@ -273,3 +273,16 @@ static inline void ust_build_pod_lut(const ust_policy* p, uint8_t* podlut) {
     podlut[pf] = (uint8_t)r;
   }
 }
+
+// The form the pod-summary kernel uses. The three selector-match bits (8-10) only gate output bits - wait-running needs
+// bit 9, to-delete / cannot-delete bit 8, drain-error bit 10 - and everything else is a function of the pod's own eight
+// bits (phase + 5 flags):   podlut[pf] == T[pf & 255] & ust_pod_gate(pf).
+// A node's actuator reads only the output bits of ITS selector (pod_manager.go:263 / :139,179 / drain_manager.go:86), so
+// the kernel skips pods that lack that bit and ORs T[pf & 255] of the others: no gate arithmetic, half the lookups,
+// and a 256-byte table (two words per shared-memory bank) instead of 2 KiB (sixteen).
+static inline unsigned ust_pod_gate(unsigned pf) { return ((pf >> 9) & 1u) | ((pf >> 7) & 0xAu) | ((pf >> 6) & 4u); }
+static inline void ust_build_pod_lut256(const ust_policy* p, uint8_t* T) {
+  uint8_t full[UST_PODLUT_ENTRIES];
+  ust_build_pod_lut(p, full);
+  for (unsigned low = 0; low < 256; low++) T[low] = (uint8_t)(full[low | 0x700u] & 15u);
+}

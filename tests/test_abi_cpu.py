@@ -147,3 +147,19 @@ def test_disabled_policy_table_is_identity():
         for w in (0, 0xFFFFFFFF, 0x12345678):
             for p in (None, C.byref(pol)):
                 assert lib.ust_table_entry(p, s, w) == (s << 16) | 0xFF000000
+
+
+@pytest.mark.parametrize("bits", range(16))
+def test_pod_table_256_equals_full_table(bits):
+    """The pod-summary kernel looks a pod up by its own eight bits in a 256-byte table and lets the node's selector bit
+    decide whether the pod counts (ust_lut.h: ust_build_pod_lut256); gated by the selector-match bits it must say what
+    the 2048-entry table (the restatement of the kubectl drain filter chain, pod_manager.go / drain_manager.go) says,
+    for every pod_flags value and every policy."""
+    fn = ustlib.load().ust_debug_podlut_mismatches
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p]
+    pol = abi.make_policy(pod_deletion_enabled=True,
+                          pod_deletion={"force": bool(bits & 1), "deleteEmptyDir": bool(bits & 2)},
+                          drain={"enable": True, "force": bool(bits & 4), "deleteEmptyDir": bool(bits & 8)},
+                          evaluate_actuators=True)
+    assert fn(C.addressof(pol)) == 0
