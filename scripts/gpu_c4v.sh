@@ -1,5 +1,5 @@
 #!/bin/bash
-for v in pod0 pod1 pod2; do
+for v in podbase podtick; do
 echo "== $v"
 UST_LIB=$PWD/build_variants/$v.so timeout 180 python bench.py --steps 20 --warmup 5 --quick --pods 2>&1 | python -c "
 import json,sys
