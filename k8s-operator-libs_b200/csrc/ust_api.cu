@@ -105,6 +105,7 @@ struct ust_handle {
   int32_t resident_n_ds = 0;  // ... and the size of its DaemonSet table
   ust_counters* hist_dev = nullptr;  // rollout simulation: one ust_counters per simulated reconcile
   size_t hist_cap = 0;
+  int segments = 6;      // upload / compute / download pipeline depth of the host path (UST_SEGMENTS, tuning)
   bool no_hint = false;  // UST_NO_HINT=1 (tuning): every call speculates from the policy default, never from the previous call
 
   UstWorkspace* ws = nullptr;
@@ -405,8 +406,8 @@ static int apply_device(ust_handle* h, const ust_policy* policy, int64_t n, cons
   return UST_OK;
 }
 
-static int finish_with_counters(ust_handle* h, cudaStream_t st, ust_counters* out) {
-  UST_CUDA(h, cudaMemcpyAsync(h->counters_host, h->counters_dev, sizeof(ust_counters), cudaMemcpyDeviceToHost, st));
+static int finish_with_counters(ust_handle* h, cudaStream_t st, ust_counters* out, bool fetched = false) {
+  if (!fetched) UST_CUDA(h, cudaMemcpyAsync(h->counters_host, h->counters_dev, sizeof(ust_counters), cudaMemcpyDeviceToHost, st));
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     h->ws_dirty = true;
@@ -472,9 +473,12 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
   P.cand_tile = h->s_candtile[P.parity].p;
   h->prev_n = -1;
   const int tiles = P.n_tiles;
-  const int kSegments = 8;
-  static_assert(kSegments <= UST_MAX_SEGMENTS, "one ticket per streaming launch");
-  const int per = (tiles + kSegments - 1) / kSegments;
+  // Segments: the uploads are the critical path (PCIe), every segment costs ~25 us of copy-engine turnarounds (measured:
+  // 6 / 8 / 12 / 16 segments -> 1.80 / 1.87 / 1.95 / 2.06 ms at 10 M nodes), and what follows the last upload - its
+  // kernels and the download of its outputs - is exposed. So: few segments, and a last one of 1/16 of the tiles.
+  const int kSegments = h->segments;  // <= UST_MAX_SEGMENTS: one ticket counter and one event pair per streaming launch
+  const int last_tiles = (kSegments > 1 && tiles >= 64) ? tiles / 16 : 0;
+  const int per = last_tiles ? (tiles - last_tiles + kSegments - 2) / (kSegments - 1) : (tiles + kSegments - 1) / kSegments;
   h->ws_dirty = true;
   const bool dbg = getenv("UST_DEBUG_PIPE") != nullptr;
   cudaEvent_t ev[4];
@@ -483,8 +487,8 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
   UST_CUDA(h, cudaEventRecord(h->d2h_done, up));
   UST_CUDA(h, cudaStreamWaitEvent(h2d, h->d2h_done, 0));
   int seg = 0;
-  for (int c0 = 0; c0 < tiles; c0 += per, seg++) {
-    const int c1 = c0 + per < tiles ? c0 + per : tiles;
+  for (int c0 = 0, c1 = 0; c0 < tiles; c0 = c1, seg++) {
+    c1 = c0 + per < tiles - last_tiles ? c0 + per : (c0 < tiles - last_tiles ? tiles - last_tiles : tiles);
     const int64_t n0 = (int64_t)c0 * P.tile_nodes, n1 = c1 == tiles ? n : (int64_t)c1 * P.tile_nodes;
     const size_t len = (size_t)(n1 - n0);
     if (len) {
@@ -547,7 +551,7 @@ static int apply_pipelined(ust_handle* h, const ust_policy* policy, int64_t n, c
     UST_CUDA(h, cudaMemcpyAsync(actions, h->s_actions.p, (size_t)n * 2, cudaMemcpyDeviceToHost, up));
     if (outcome) UST_CUDA(h, cudaMemcpyAsync(outcome, h->s_outcome.p, (size_t)n, cudaMemcpyDeviceToHost, up));
   }
-  return finish_with_counters(h, up, out);
+  return finish_with_counters(h, up, out, h->counters_host->reserved[0] == 0);
 }
 
 extern "C" {
@@ -576,6 +580,7 @@ int ust_create(ust_handle** out, int device) {
   ust_handle* h = new ust_handle();
   h->device = device;
   h->no_hint = getenv("UST_NO_HINT") != nullptr;
+  if (const char* sg = getenv("UST_SEGMENTS")) { int v = atoi(sg); if (v >= 1 && v <= UST_MAX_SEGMENTS) h->segments = v; }
   auto bail = [&](const char* what, cudaError_t err) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
     ust_destroy(h);
