@@ -521,11 +521,18 @@ def main():
         rng = np.random.default_rng(7)
         m = max(1, n // 100)
         steps_d = max(3, args.e2e_steps)
+
+        def pinned(a):
+            # what an encoder writes into: page-locked memory (ust_host_alloc), like the arrays of the full-upload leg
+            p_ = ustlib.pinned_array(a.shape[0], a.dtype)
+            p_[:] = a
+            return p_
+
         deltas = []
         for _ in range(steps_d + 1):
             idx = rng.choice(n, size=m, replace=False).astype(np.int64)
             src = rng.integers(0, n, size=m)
-            deltas.append((idx, {k: np.ascontiguousarray(soa[k][src]) for k in ("state", "flags", "pod_rev", "ds_idx")}))
+            deltas.append((pinned(idx), {k: pinned(soa[k][src]) for k in ("state", "flags", "pod_rev", "ds_idx")}))
         h.apply_state_delta(pol, n, deltas[0][0], deltas[0][1], soa["ds_rev"], want_outcome=False, out=out)
         torch.cuda.synchronize()
         t0 = time.time()
@@ -549,7 +556,7 @@ def main():
         for _ in range(steps_d + 1):
             idx = rng.choice(n, size=m, replace=False).astype(np.int64)
             src = rng.integers(0, n, size=m)
-            more.append((idx, {k: np.ascontiguousarray(soa[k][src]) for k in ("state", "flags", "pod_rev", "ds_idx")}))
+            more.append((pinned(idx), {k: pinned(soa[k][src]) for k in ("state", "flags", "pod_rev", "ds_idx")}))
         n_outs = []
         t_sparse = 0.0
         for j, (idx, ch) in enumerate(more):
