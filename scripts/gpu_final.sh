@@ -21,9 +21,12 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:ust_
    python bench.py --steps 6 --warmup 3 --quick > gpurun_out/ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:ust_verify -s 3 -c 1 -f -o gpurun_out/prof_verify \
    python bench.py --steps 6 --warmup 3 --quick > gpurun_out/ncu_full2.log 2>&1
+echo "== C4 launch list + pod kernel capture"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/c4_launches.csv python bench.py --quick --pods --steps 5 --warmup 3 > gpurun_out/c4_l.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:ust_pod_summary --launch-skip 4 --launch-count 1 -f -o gpurun_out/c4_podsum python bench.py --quick --pods --steps 5 --warmup 3 > gpurun_out/c4_f.log 2>&1
 echo "== memcheck"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q \
-     -k "random_snapshot and (4097 or 8192 or 20000 or 127) or slot_budget_cut_positions and (0 or 1) or many_daemonsets or disabled or speculation_hint and 300000 or long_and_empty and 2 or build_state_vector or delta_updates and 5000 or simulated_rollout and 3000 or sparse" \
+     -k "random_snapshot and (4097 or 8192 or 20000 or 127) or slot_budget_cut_positions and (0 or 1) or many_daemonsets or disabled or speculation_hint and 300000 or long_and_empty and 2 or build_state_vector or delta_updates and 5000 or simulated_rollout and 3000 or sparse or c4_pod_lists_sample" \
      > gpurun_out/sanitizer_memcheck.log 2>&1
 echo "memcheck exit $?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_memcheck.log | tail -3
 ls -la gpurun_out/ | head -30
