@@ -68,6 +68,12 @@ __device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
   asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_release_gpu(long long* p, long long v) { asm volatile("st.release.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ long long ld_acquire_gpu(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ long long ld_relaxed_sys(const long long* p) {
   long long v;
   asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -410,8 +416,10 @@ __device__ inline bool exchange_vector(const UstParams& P, DecideShared& D, bool
   const int t = threadIdx.x, nt = blockDim.x;
   const int par = (int)(P.epoch & 1);
   const unsigned long long tag = (unsigned long long)(unsigned)P.epoch << 32;
-  if (pusher) {
-    for (int i = t; i < P.world * UST_MBOX_WORDS; i += nt) {
+  if (pusher && t >= 64) {
+    // warps 0 and 1 push nothing: they publish the sum to the other CTAs of this grid afterwards (ust_verify_kernel), and
+    // their release must not have to wait for this CTA's NVLink stores to be acknowledged by the peers
+    for (int i = t - 64; i < P.world * UST_MBOX_WORDS; i += nt - 64) {
       const int r = i / UST_MBOX_WORDS, w = i - r * UST_MBOX_WORDS;
       const unsigned long long lane = (unsigned long long)D.V[w >> 1];
       const unsigned long long half = (w & 1) ? (lane >> 32) : (lane & 0xFFFFFFFFull);

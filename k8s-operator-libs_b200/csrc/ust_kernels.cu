@@ -367,18 +367,19 @@ __global__ void __maxnreg__(80) ust_verify_kernel(const __grid_constant__ UstPar
       const unsigned long long tag = (unsigned long long)(unsigned)P.epoch << 32;
       if (lead) {
         comm_ok = exchange_vector(P, S.D, true);
+        // the sum and its flag stay on this GPU: gpu scope, written by warps that issued no NVLink store (a system-scope
+        // release - or a fence by a thread with peer stores in flight - waits for the peers' acknowledgements)
         if (t < UST_V_LEN) P.ws->xsum[par][t] = S.D.V[t];
-        __threadfence();
         __syncthreads();
-        if (t == 0) st_release_sys(reinterpret_cast<long long*>(&P.ws->xflag[par]), (long long)(tag | (comm_ok ? 1ull : 0ull)));
+        if (t == 0) st_release_gpu(reinterpret_cast<long long*>(&P.ws->xflag[par]), (long long)(tag | (comm_ok ? 1ull : 0ull)));
       } else {
         if (t == 0) {
           const unsigned long long t0 = now_ns();
-          unsigned long long v = (unsigned long long)ld_acquire_sys(reinterpret_cast<const long long*>(&P.ws->xflag[par]));
+          unsigned long long v = (unsigned long long)ld_acquire_gpu(reinterpret_cast<const long long*>(&P.ws->xflag[par]));
           while ((v >> 32) != (tag >> 32)) {
             if (now_ns() - t0 > 2 * kCommTimeoutNs) { v = tag; break; }
             __nanosleep(100);
-            v = (unsigned long long)ld_acquire_sys(reinterpret_cast<const long long*>(&P.ws->xflag[par]));
+            v = (unsigned long long)ld_acquire_gpu(reinterpret_cast<const long long*>(&P.ws->xflag[par]));
           }
           S.xflag = v;
         }
