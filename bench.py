@@ -27,7 +27,8 @@ per step.
              SoA oracle on the unsharded cluster, for the timed policy and for one whose budget cuts mid-cluster;
              exchange_us = step time minus the step time of the same shard on a handle without a communicator
   cpu_baseline / --impl reference   the oracle's reference-shaped restatement of the Go loop (1 thread —
-             the reference's ApplyState is strictly sequential), bounded sample of the same workload
+             the reference's ApplyState is strictly sequential), bounded sample of the same workload;
+             cpu_baseline.soa_scalar_1core: the same decisions over the SoA encoding (the generous CPU baseline)
 """
 import argparse
 import ctypes as C
@@ -119,12 +120,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(policy, soa, reps):
-    """Reference-shaped oracle (ApplyState only, objects built untimed) on one host thread. nodes/s."""
+def cpu_reference_rate(policy, soa, reps, variant=0):
+    """variant 0: reference-shaped oracle (ApplyState only, objects built untimed); variant 1: the same decisions over
+    the struct-of-arrays encoding, scalar loop (BASELINE.md §2 `cpu_soa`: the generous CPU baseline). One host thread. nodes/s."""
     import helpers
     n = int(soa["state"].shape[0])
     sec = helpers.oracle().ust_oracle_time_apply_state(
-        C.c_int(0), C.byref(policy), C.c_int64(n), soa["state"].ctypes.data_as(C.c_void_p),
+        C.c_int(variant), C.byref(policy), C.c_int64(n), soa["state"].ctypes.data_as(C.c_void_p),
         soa["flags"].ctypes.data_as(C.c_void_p), soa["pod_rev"].ctypes.data_as(C.c_void_p),
         soa["ds_idx"].ctypes.data_as(C.c_void_p), C.c_int32(int(soa["ds_rev"].shape[0])),
         soa["ds_rev"].ctypes.data_as(C.c_void_p), None, C.c_int(reps))
@@ -700,7 +702,8 @@ def main():
         m = min(CPU_SAMPLE_NODES, n)
         sample = {k: (v[:m].copy() if k != "ds_rev" else v) for k, v in soa.items()}
         rate, sec = cpu_reference_rate(pol, sample, 3)
-        line["cpu_baseline"] = {"value": rate, "unit": "nodes/s", "cores": 1, "kind": "port",
+        rate_soa, _ = cpu_reference_rate(pol, sample, 3, variant=1)
+        line["cpu_baseline"] = {"value": rate, "unit": "nodes/s", "cores": 1, "kind": "port", "soa_scalar_1core": rate_soa,
                                 "sample": f"first {m} nodes of the workload, ApplyState only, median of 3 passes "
                                           f"({sec:.2f} s each), reference-shaped oracle (Go unavailable)"}
         print(json.dumps(line), flush=True)
