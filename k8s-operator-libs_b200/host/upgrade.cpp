@@ -2,6 +2,7 @@
 #include "upgrade.hpp"
 
 #include <algorithm>
+#include <thread>
 #include <unordered_map>
 #include <cstring>
 
@@ -26,18 +27,39 @@ static const char* const kNullString = "null";  // consts.go:90
 static const char* const kTrueString = "true";  // consts.go:92
 static std::string g_driver_name;                 // util.go:91-99
 
-void SetDriverName(const std::string& driver) { g_driver_name = driver; }
+// The seven keys are functions of the driver name only (util.go:101-133). The reference formats them on every use; an
+// encoder that walks a million nodes cannot (six formatted strings per node were a third of Encode's time), so they are
+// built once per SetDriverName.
+struct DriverKeys {
+  bool valid = false;
+  std::string state, skip, safeLoad, requested, requestorMode, initialState, waitStart;
+};
+static DriverKeys g_keys;
 static std::string key(const char* tail) { return "nvidia.com/" + g_driver_name + tail; }
-std::string GetUpgradeStateLabelKey() { return key("-driver-upgrade-state"); }
-std::string GetUpgradeSkipNodeLabelKey() { return key("-driver-upgrade.skip"); }
-std::string GetUpgradeDriverWaitForSafeLoadAnnotationKey() { return key("-driver-upgrade.driver-wait-for-safe-load"); }
-std::string GetUpgradeRequestedAnnotationKey() { return key("-driver-upgrade-requested"); }
-std::string GetUpgradeRequestorModeAnnotationKey() { return key("-driver-upgrade-requestor-mode"); }
-std::string GetUpgradeInitialStateAnnotationKey() { return key("-driver-upgrade.node-initial-state.unschedulable"); }
-std::string GetWaitForPodCompletionStartTimeAnnotationKey() { return key("-driver-upgrade-wait-for-pod-completion-start-time"); }
+static const DriverKeys& keys() {
+  if (!g_keys.valid) {
+    g_keys.state = key("-driver-upgrade-state");
+    g_keys.skip = key("-driver-upgrade.skip");
+    g_keys.safeLoad = key("-driver-upgrade.driver-wait-for-safe-load");
+    g_keys.requested = key("-driver-upgrade-requested");
+    g_keys.requestorMode = key("-driver-upgrade-requestor-mode");
+    g_keys.initialState = key("-driver-upgrade.node-initial-state.unschedulable");
+    g_keys.waitStart = key("-driver-upgrade-wait-for-pod-completion-start-time");
+    g_keys.valid = true;
+  }
+  return g_keys;
+}
+void SetDriverName(const std::string& driver) { g_driver_name = driver; g_keys.valid = false; }
+std::string GetUpgradeStateLabelKey() { return keys().state; }
+std::string GetUpgradeSkipNodeLabelKey() { return keys().skip; }
+std::string GetUpgradeDriverWaitForSafeLoadAnnotationKey() { return keys().safeLoad; }
+std::string GetUpgradeRequestedAnnotationKey() { return keys().requested; }
+std::string GetUpgradeRequestorModeAnnotationKey() { return keys().requestorMode; }
+std::string GetUpgradeInitialStateAnnotationKey() { return keys().initialState; }
+std::string GetWaitForPodCompletionStartTimeAnnotationKey() { return keys().waitStart; }
 
 bool IsOrphanedPod(const Pod& pod) { return pod.OwnerReferences.empty(); }
-bool IsNodeInRequestorMode(const Node& node) { return node.Annotations.count(GetUpgradeRequestorModeAnnotationKey()) != 0; }
+bool IsNodeInRequestorMode(const Node& node) { return node.Annotations.count(keys().requestorMode) != 0; }
 ClusterUpgradeState NewClusterUpgradeState() { return ClusterUpgradeState(); }
 
 static const char* const kStateNames[13] = {
@@ -94,7 +116,7 @@ ClusterUpgradeStateManager& ClusterUpgradeStateManagerImpl::WithValidationEnable
 
 // ---- predicates ---------------------------------------------------------------------------------------------
 bool ClusterUpgradeStateManagerImpl::IsUpgradeRequested(const Node& n) const {
-  auto it = n.Annotations.find(GetUpgradeRequestedAnnotationKey());
+  auto it = n.Annotations.find(keys().requested);
   return it != n.Annotations.end() && it->second == kTrueString;
 }
 bool ClusterUpgradeStateManagerImpl::IsNodeUnschedulable(const Node& n) const { return n.Unschedulable; }
@@ -104,7 +126,7 @@ bool ClusterUpgradeStateManagerImpl::isNodeConditionReady(const Node& n) const {
   return true;
 }
 bool ClusterUpgradeStateManagerImpl::SkipNodeUpgrade(const Node& n) const {
-  auto it = n.Labels.find(GetUpgradeSkipNodeLabelKey());
+  auto it = n.Labels.find(keys().skip);
   return it != n.Labels.end() && it->second == kTrueString;
 }
 bool ClusterUpgradeStateManagerImpl::isDriverPodFailing(const Pod& p) const {
@@ -287,7 +309,10 @@ static void flatten_policy(const DriverUpgradePolicySpec& p, bool podDeletionEna
 Error ClusterUpgradeStateManagerImpl::encodeOne(const NodeUpgradeState* ns, int code, int32_t ds, bool dsErr,
                                                 std::map<std::string, int32_t>* intern, const std::vector<int32_t>& ds_rev,
                                                 uint8_t* hot_out, uint32_t* flags_out, int32_t* rev_out, std::string* deferred) {
-  auto internHash = [&](const std::string& h) { return intern->emplace(h, (int32_t)intern->size() + 1).first->second; };
+  auto internHash = [&](const std::string& h) {  // find first: emplace would build (and throw away) a map node per node
+    auto it = intern->find(h);
+    return it != intern->end() ? it->second : intern->emplace(h, (int32_t)intern->size() + 1).first->second;
+  };
   const Node& n = *ns->Node;
   uint8_t hot = (uint8_t)code;
   uint32_t f = 0;
@@ -295,7 +320,7 @@ Error ClusterUpgradeStateManagerImpl::encodeOne(const NodeUpgradeState* ns, int 
   if (!isNodeConditionReady(n)) hot |= UST_HOT_NOT_READY;
   if (SkipNodeUpgrade(n)) hot |= UST_HOT_SKIP;
   if (IsUpgradeRequested(n)) f |= UST_F_UPGRADE_REQUESTED;
-  if (n.Annotations.count(GetUpgradeInitialStateAnnotationKey())) f |= UST_F_INITIAL_STATE_ANNO;
+  if (n.Annotations.count(keys().initialState)) f |= UST_F_INITIAL_STATE_ANNO;
   if (IsNodeInRequestorMode(n)) f |= UST_F_REQUESTOR_MODE;
   // ValidationManager.Validate is an actuator with side effects: Replay calls it, at the reference's point in
   // the pass order, and drops the transition when it reports "not done" (common_manager.go:587-596)
@@ -351,48 +376,95 @@ Error ClusterUpgradeStateManagerImpl::encodeOne(const NodeUpgradeState* ns, int 
 Error ClusterUpgradeStateManagerImpl::Encode(const ClusterUpgradeState& s, const DriverUpgradePolicySpec& policy, EncodedSnapshot* out) {
   EncodedSnapshot& e = *out;
   e = EncodedSnapshot();
+  (void)keys();  // built before any worker thread reads them
   flatten_policy(policy, podDeletionStateEnabled_, validationStateEnabled_, opts_.Requestor.UseMaintenanceOperator, &e.policy);
-  std::map<std::string, int32_t> intern;
-  std::map<const DaemonSet*, int32_t> dsIndex;
-  std::vector<bool> dsHashError;
-  auto add = [&](NodeUpgradeState* ns, int code) -> Error {
-    int32_t ds = -1;
-    bool dsErr = false;
-    if (!ns->IsOrphanedPod()) {
-      auto it = dsIndex.find(ns->DriverDaemonSet);
-      if (it == dsIndex.end()) {
-        std::string dsHash;
-        const bool bad = (bool)PodManager->GetDaemonsetControllerRevisionHash(ns->DriverDaemonSet, &dsHash);  // once per DaemonSet
-        it = dsIndex.emplace(ns->DriverDaemonSet, (int32_t)e.ds_rev.size()).first;
-        e.ds_rev.push_back(bad ? 0 : intern.emplace(dsHash, (int32_t)intern.size() + 1).first->second);
-        dsHashError.push_back(bad);
-      }
-      ds = it->second;
-      dsErr = dsHashError[(size_t)ds];
-    }
-    uint8_t hot; uint32_t f; int32_t rev; std::string deferred;
-    if (Error err = encodeOne(ns, code, ds, dsErr, &intern, e.ds_rev, &hot, &f, &rev, &deferred)) return err;
-    if (!deferred.empty()) e.deferred[e.entries.size()] = deferred;
-    e.entries.push_back(ns);
-    e.state.push_back(hot);
-    e.flags.push_back(f);
-    e.pod_rev.push_back(rev);
-    e.ds_idx.push_back(ds);
-    return std::nullopt;
+  // 1. the entries, buckets in pass order: SoA index order == replay order, and the upgrade-required bucket keeps its
+  //    slice order
+  std::vector<int8_t> codes;
+  auto take = [&](const std::vector<NodeUpgradeState*>& bucket, int code) {
+    e.entries.insert(e.entries.end(), bucket.begin(), bucket.end());
+    codes.insert(codes.end(), bucket.size(), (int8_t)code);
   };
-  // buckets in pass order: SoA index order == replay order, and the upgrade-required bucket keeps its slice order
   for (int code : kPassOrder) {
     auto it = s.NodeStates.find(kStateNames[code]);
-    if (it == s.NodeStates.end()) continue;
-    for (NodeUpgradeState* ns : it->second)
-      if (Error err = add(ns, code)) return err;
+    if (it != s.NodeStates.end()) take(it->second, code);
   }
   // every other bucket still counts towards GetCurrentUnavailableNodes (common_manager.go:149)
   for (const auto& kv : s.NodeStates) {
     const int code = StateCodeOfLabel(kv.first);
-    if (code != UST_STATE_OTHER && code != UST_STATE_POST_MAINTENANCE_REQUIRED) continue;
-    for (NodeUpgradeState* ns : kv.second)
-      if (Error err = add(ns, code)) return err;
+    if (code == UST_STATE_OTHER || code == UST_STATE_POST_MAINTENANCE_REQUIRED) take(kv.second, code);
+  }
+  const size_t n = e.entries.size();
+  // 2. the DaemonSet table: one revision lookup per DaemonSet (pod_manager.go:92-118), in first-use order
+  std::map<std::string, int32_t> intern;
+  std::map<const DaemonSet*, int32_t> dsIndex;
+  std::vector<char> dsHashError;
+  e.ds_idx.assign(n, -1);
+  for (size_t i = 0; i < n; i++) {
+    const NodeUpgradeState* ns = e.entries[i];
+    if (ns->IsOrphanedPod()) continue;
+    auto it = dsIndex.find(ns->DriverDaemonSet);
+    if (it == dsIndex.end()) {
+      std::string dsHash;
+      const bool bad = (bool)PodManager->GetDaemonsetControllerRevisionHash(ns->DriverDaemonSet, &dsHash);
+      it = dsIndex.emplace(ns->DriverDaemonSet, (int32_t)e.ds_rev.size()).first;
+      e.ds_rev.push_back(bad ? 0 : intern.emplace(dsHash, (int32_t)intern.size() + 1).first->second);
+      dsHashError.push_back(bad ? 1 : 0);
+    }
+    e.ds_idx[i] = it->second;
+  }
+  // 3. the nodes, independent of one another. A worker interns the revision hashes it meets in a copy of the table above
+  //    (so "pod hash == DaemonSet hash" is an id comparison everywhere); hashes no DaemonSet has get provisional ids that
+  //    are made global afterwards.
+  e.state.assign(n, 0);
+  e.flags.assign(n, 0);
+  e.pod_rev.assign(n, 0);
+  const int32_t base = (int32_t)intern.size();
+  const size_t workers = (size_t)std::max(1, std::min(opts_.EncodeThreads, (int)(n / 4096 + 1)));
+  struct Part { std::map<std::string, int32_t> intern; std::vector<std::pair<size_t, std::string>> deferred; Error err; size_t errAt = 0; };
+  std::vector<Part> parts(workers);
+  auto work = [&](size_t w) {
+    Part& p = parts[w];
+    p.intern = intern;
+    const size_t i0 = n * w / workers, i1 = n * (w + 1) / workers;
+    for (size_t i = i0; i < i1; i++) {
+      const int32_t ds = e.ds_idx[i];
+      uint8_t hot; uint32_t f; int32_t rev; std::string deferred;
+      if (Error err = encodeOne(e.entries[i], codes[i], ds, ds >= 0 && dsHashError[(size_t)ds], &p.intern, e.ds_rev, &hot, &f, &rev, &deferred)) {
+        p.err = err; p.errAt = i;
+        return;
+      }
+      if (!deferred.empty()) p.deferred.emplace_back(i, deferred);
+      e.state[i] = hot; e.flags[i] = f; e.pod_rev[i] = rev;
+    }
+  };
+  if (workers == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (size_t w = 1; w < workers; w++) pool.emplace_back(work, w);
+    work(0);
+    for (auto& t : pool) t.join();
+  }
+  for (size_t w = 0; w < workers; w++) {   // first error in index order, like the sequential walk
+    if (parts[w].err) return parts[w].err;
+    for (auto& d : parts[w].deferred) e.deferred[d.first] = d.second;
+  }
+  if (workers > 1) {  // provisional ids (> base, per worker) -> global ids
+    for (size_t w = 0; w < workers; w++) {
+      std::vector<int32_t> remap(parts[w].intern.size() + 1, 0);
+      bool moved = false;
+      for (const auto& kv : parts[w].intern) {
+        if (kv.second <= base) continue;
+        const int32_t g = intern.emplace(kv.first, (int32_t)intern.size() + 1).first->second;
+        remap[(size_t)kv.second] = g;
+        moved = moved || g != kv.second;
+      }
+      if (!moved) continue;
+      const size_t i0 = n * w / workers, i1 = n * (w + 1) / workers;
+      for (size_t i = i0; i < i1; i++)
+        if (e.pod_rev[i] > base) e.pod_rev[i] = remap[(size_t)e.pod_rev[i]];
+    }
   }
   return std::nullopt;
 }

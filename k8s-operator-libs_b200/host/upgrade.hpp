@@ -184,7 +184,14 @@ struct K8sClient {
 };
 
 struct RequestorOptions { bool UseMaintenanceOperator = false; };  // upgrade_requestor.go:527-546 (the switch only)
-struct StateOptions { RequestorOptions Requestor; };               // upgrade_state.go:94-96
+struct StateOptions {                                                 // upgrade_state.go:94-96
+  RequestorOptions Requestor;
+  // Not in the reference: host threads Encode may use (<= 1: the calling thread only). Encoding is the host-side cost of a
+  // call (object walking, string-keyed map lookups: ~1 us per node) and is independent per node; with more than one thread
+  // the injected PodManager::GetPodControllerRevisionHash and SafeDriverLoadManager::IsWaitingForSafeDriverLoad are called
+  // concurrently (they are read-only in the reference: pod_manager.go:84-89, safe_driver_load_manager.go:51-57).
+  int EncodeThreads = 1;
+};
 
 // ---- the encoded snapshot (include/ust.h layout) and its replay ------------------------------------------
 struct EncodedSnapshot {

@@ -68,6 +68,45 @@ int main() {
   };
   spec::WorldApplyFn wincr = [](spec::World& w, const upgrade::DriverUpgradePolicySpec* p) { return w.m->ApplyStateIncremental(&w.state, p); };
   spec::run_incremental(R, make, wfull, makeIncr, wincr, 400);
+  // Encode with several host threads (StateOptions::EncodeThreads) against the single-threaded walk
+  R.it("Encode on several host threads == Encode on one (revision ids up to renaming)", [&] {
+    using namespace upgrade;
+    SetDriverName("gpu");
+    spec::World a, b;
+    StateOptions one, many;
+    many.EncodeThreads = 5;
+    a.m = ClusterUpgradeStateManagerImpl::NewDetached(one); a.wire();
+    b.m = ClusterUpgradeStateManagerImpl::NewDetached(many); b.wire();
+    spec::populate(a, 30000, 77); spec::populate(b, 30000, 77);
+    // revision hashes no DaemonSet has, different ones in different parts of the node list
+    for (size_t i = 0; i < a.podObjs.size(); i += 7) {
+      const std::string h = "stale-" + std::to_string(i / 9000) + "-" + std::to_string(i % 3);
+      a.podObjs[i].Labels[PodControllerRevisionHashLabelKey] = h;
+      b.podObjs[i].Labels[PodControllerRevisionHashLabelKey] = h;
+    }
+    a.snapshot(); b.snapshot();
+    DriverUpgradePolicySpec p;
+    p.AutoUpgrade = true;
+    EncodedSnapshot ea, eb;
+    EXPECT(R, !a.m->Encode(a.state, p, &ea).has_value());
+    EXPECT(R, !b.m->Encode(b.state, p, &eb).has_value());
+    EXPECT(R, ea.entries.size() == eb.entries.size() && ea.entries.size() > 25000);
+    EXPECT(R, ea.state == eb.state && ea.flags == eb.flags && ea.ds_idx == eb.ds_idx && ea.ds_rev == eb.ds_rev);
+    EXPECT(R, ea.deferred == eb.deferred);
+    bool same_nodes = true, renaming = true;
+    std::map<int32_t, int32_t> fwd, back;
+    for (size_t i = 0; i < ea.entries.size() && i < eb.entries.size(); i++) {
+      same_nodes = same_nodes && ea.entries[i]->Node->Name == eb.entries[i]->Node->Name;
+      const int32_t x = ea.pod_rev[i], y = eb.pod_rev[i];
+      auto f = fwd.emplace(x, y).first;
+      auto g = back.emplace(y, x).first;
+      renaming = renaming && f->second == y && g->second == x && (x == 0) == (y == 0);
+      if (ea.ds_idx[i] >= 0) renaming = renaming && (x == ea.ds_rev[(size_t)ea.ds_idx[i]]) == (y == eb.ds_rev[(size_t)eb.ds_idx[i]]);
+    }
+    EXPECT(R, same_nodes);
+    EXPECT(R, renaming);
+    EXPECT(R, fwd.size() >= 10);  // the stale hashes made it into the table
+  });
   std::printf("# %d passed, %d failed\n", R.passed, R.failed);
   return R.failed == 0 ? 0 : 1;
 }
